@@ -1,0 +1,197 @@
+/*
+ * rt_api.h — C ABI of the B200-native path-tracing hot path (librt_b200.so).
+ *
+ * This is the drop-in boundary for felipeagc/sycl-ray-tracer's
+ *   IRenderer::render_frame(const Camera&, const Scene&)        (src/render.hpp:11-18)
+ * and for the pieces of App / Scene / Camera that feed it. Plain pointers and sizes only:
+ * no C++ types, no torch types. The C++ mirror of the reference classes
+ * (sycl-ray-tracer_b200/host/raytracer.hpp) and the Python ctypes binding are thin layers
+ * over exactly these entry points. Each entry point names the reference interface it replaces.
+ *
+ * Conventions
+ *  - every call returns rt_status; on failure rt_last_error(ctx) has the message
+ *    (reference: exceptions ending in std::terminate, src/app.hpp:8-19, src/main.cpp:71-74).
+ *  - "any-space pointer": output/input pointers marked ANY may be host (pageable or pinned) or
+ *    device memory; the library copies with cudaMemcpyDefault on the context stream.
+ *  - all render calls are synchronous on return, like the reference's submit + wait
+ *    (src/render_megakernel.cpp:171).
+ *  - there is no CPU fallback: without a CUDA device rt_context_create fails.
+ */
+#ifndef RT_API_H
+#define RT_API_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RT_API_VERSION 1
+#define RT_TEX_SIZE 512   /* src/image_manager.hpp:14  IMAGE_SIZE  */
+#define RT_MAX_IMAGES 128 /* src/image_manager.hpp:12  MAX_IMAGES  */
+
+typedef enum rt_status {
+    RT_OK = 0,
+    RT_ERR_INVALID = 1,  /* bad argument */
+    RT_ERR_CUDA = 2,     /* CUDA runtime error (message in rt_last_error) */
+    RT_ERR_STATE = 3,    /* call order violated (e.g. render before commit) */
+    RT_ERR_NO_DEVICE = 4 /* no usable CUDA device: there is no CPU path */
+} rt_status;
+
+/* src/material.hpp:61-66 MaterialType */
+typedef enum rt_material_type {
+    RT_MAT_NONE = 0,
+    RT_MAT_DIFFUSE = 1,
+    RT_MAT_METALLIC = 2,
+    RT_MAT_DIELECTRIC = 3
+} rt_material_type;
+
+/* src/main.cpp:57-68: the -m / -w switch */
+typedef enum rt_renderer_kind { RT_MEGAKERNEL = 0, RT_WAVEFRONT = 1 } rt_renderer_kind;
+
+/* src/material.hpp:17-54 (Texture) + :68-238 (Material), flattened to a POD */
+typedef struct rt_material {
+    int32_t type;          /* rt_material_type */
+    int32_t albedo_image;  /* >= 0: ImageRef.index (src/image_manager.hpp:27-29); < 0: albedo_color */
+    float albedo_color[3];
+    float roughness;       /* MaterialMetallic::roughness */
+    float ior;             /* MaterialDielectric::ior */
+    float emissive[3];
+} rt_material;
+
+/* One Embree instance = one glTF node x mesh primitive with its GeometryData
+ * (src/scene.hpp:17-24, src/scene.cpp:483-507). Instance ids are array positions, i.e. the
+ * reference's attach order (src/scene.cpp:101-106). All pointers are HOST memory and are
+ * copied during rt_scene_create. */
+typedef struct rt_instance {
+    const float *positions;  /* 3 * vertex_count   (glm::vec3, src/scene.cpp:286-293) */
+    const float *normals;    /* 3 * vertex_count   (src/scene.cpp:311-318) */
+    const float *uvs;        /* 2 * vertex_count   (src/scene.cpp:337-343) */
+    const uint32_t *indices; /* index_count, u32   (src/scene.cpp:359-401) */
+    uint32_t vertex_count;
+    uint32_t index_count;    /* multiple of 3 */
+    float transform[16];     /* column-major 4x4, node_global_matrix (src/scene.cpp:137-146,491-494) */
+    rt_material material;
+} rt_instance;
+
+/* What Scene hands to the kernels (src/scene.hpp:64-91): instances, sky colour, image array */
+typedef struct rt_scene_desc {
+    const rt_instance *instances;
+    uint32_t instance_count;
+    const uint8_t *texture_layers; /* layer_count * 512 * 512 * 4 RGBA8 (baked array,
+                                      src/image_manager.hpp:76-100); may be NULL */
+    uint32_t texture_layer_count;  /* <= RT_MAX_IMAGES */
+    float sky_color[3];            /* src/scene.hpp:76 default (0.5, 0.7, 1.0) */
+} rt_scene_desc;
+
+/* src/camera.hpp:65-72, by value into the kernels (src/render_megakernel.cpp:95-96) */
+typedef struct rt_camera {
+    float center[3];
+    float pixel00_loc[3];
+    float pixel_delta_u[3];
+    float pixel_delta_v[3];
+    int32_t img_size[2];
+} rt_camera;
+
+/* Multi-GPU sharding of one frame (no reference equivalent: it is single-device). */
+typedef struct rt_shard {
+    uint32_t rank;       /* this context's shard */
+    uint32_t world;      /* number of shards; 0 or 1 = unsharded */
+    uint32_t tile_size;  /* > 0: image-tile sharding. Tiles of tile_size^2 pixels, numbered row
+                            major, tile t belongs to rank t % world. Pixels of other ranks are left
+                            untouched (zero) in accum/rgba8, so a SUM over ranks is the full image,
+                            bit-identical to the unsharded render. */
+    uint32_t seed_salt;  /* XORed into every pixel seed. spp sharding: all ranks render all pixels
+                            with sample_count = spp / world and distinct salts (salt 0 on rank 0
+                            reproduces the reference stream). */
+} rt_shard;
+
+typedef struct rt_render_params {
+    uint32_t max_depth;    /* -d, src/main.cpp:11 */
+    uint32_t sample_count; /* -s, src/main.cpp:13 */
+    rt_shard shard;
+} rt_render_params;
+
+/* Result of one render_frame. Every pointer is optional (NULL = not wanted) and ANY-space. */
+typedef struct rt_frame {
+    uint8_t *rgba8;   /* W*H*4: what the reference writes to out.png (mean, sqrt gamma, unorm8
+                         store + *255 truncating read-back; src/util.hpp:16-22) */
+    float *accum;     /* W*H*4 fp32: linear SUM over samples in rgb, sample count in a
+                         (wavefront: sum of per-sample clamped values, src/render_wavefront.cpp:277) */
+    uint32_t *rng_state; /* W*H: final xorshift32 state per pixel (bit-exact stream check) */
+    uint64_t ray_count;  /* out: ray segments traced = rtcIntersect1 calls
+                            (src/render_megakernel.cpp:32, src/render_wavefront.cpp:407) */
+    float device_ms;     /* out: CUDA-event time of the render on the context stream */
+    uint32_t kernel_launches; /* out: kernels launched by this call */
+} rt_frame;
+
+typedef struct rt_scene_stats {
+    uint64_t triangle_count;
+    uint64_t node_count;      /* 80-byte wide-BVH nodes */
+    uint64_t bvh_bytes;       /* nodes + leaf-ordered triangle records */
+    uint64_t shading_bytes;   /* per-triangle shading records + instance table */
+    float build_ms;           /* device time of rt_scene_commit */
+    uint32_t max_leaf_tris;
+    uint32_t wide_depth;      /* levels of the wide tree */
+} rt_scene_stats;
+
+typedef struct rt_context rt_context;   /* App (src/app.hpp:31-58): device + stream owner */
+typedef struct rt_scene rt_scene;       /* Scene (src/scene.hpp:64-104) */
+typedef struct rt_renderer rt_renderer; /* MegakernelRenderer / WavefrontRenderer */
+
+/* ---- context: replaces raytracer::App (src/app.hpp:43-55) -------------------------------- */
+rt_status rt_context_create(int device, rt_context **out);
+void rt_context_destroy(rt_context *ctx);
+/* the cudaStream_t all work is enqueued on (replaces App::queue, src/app.hpp:33) */
+void *rt_context_stream(rt_context *ctx);
+const char *rt_context_device_name(rt_context *ctx);
+/* last error message of this context (ctx may be NULL for creation failures) */
+const char *rt_last_error(rt_context *ctx);
+uint32_t rt_api_version(void);
+
+/* ---- scene: replaces Scene's device side (src/scene.cpp:101-107,406-439,483-507) --------- */
+/* uploads instances (geometry, GeometryData) and the baked texture array */
+rt_status rt_scene_create(rt_context *ctx, const rt_scene_desc *desc, rt_scene **out);
+/* the rtcCommitScene analogue (src/scene.cpp:107): GPU flatten -> Morton codes -> radix sort
+ * -> LBVH -> 8-wide compressed BVH. The scene is immutable afterwards. */
+rt_status rt_scene_commit(rt_scene *scene);
+rt_status rt_scene_get_stats(const rt_scene *scene, rt_scene_stats *out);
+void rt_scene_destroy(rt_scene *scene);
+
+/* ---- camera: replaces Camera::Camera (src/camera.hpp:74-106); pure host arithmetic ------- */
+void rt_camera_init(rt_camera *cam, int32_t width, int32_t height, const float position[3],
+                    const float direction[3], float focal_length);
+
+/* ---- batch closest hit: replaces rtcIntersect1 (src/trace_ray.hpp:18-22) ------------------
+ * n rays; org/dir are 3 floats per ray (ANY-space); outputs ANY-space, inst/prim = -1 on miss,
+ * u,v in Embree's convention (weights of vertex 1 and 2), t in units of |dir|.
+ * Hit accepted iff tnear < t <= tfar; ties resolve to the lowest (inst, prim). */
+rt_status rt_intersect(rt_context *ctx, const rt_scene *scene, uint64_t n, const float *org,
+                       const float *dir, float tnear, float tfar, int32_t *inst, int32_t *prim,
+                       float *u, float *v, float *t, float *device_ms);
+
+/* ---- renderers: replace MegakernelRenderer / WavefrontRenderer ----------------------------
+ * ctor shape (App&, img_size, image&, max_depth, sample_count): src/render_megakernel.hpp:13-19,
+ * src/render_wavefront.hpp:55-61. The wavefront renderer owns its ray queues and rng buffer
+ * (src/render_wavefront.hpp:18-37,52). */
+rt_status rt_renderer_create(rt_context *ctx, rt_renderer_kind kind, int32_t width, int32_t height,
+                             rt_renderer **out);
+void rt_renderer_destroy(rt_renderer *r);
+/* IRenderer::render_frame (src/render.hpp:12-15). */
+rt_status rt_render_frame(rt_renderer *r, const rt_scene *scene, const rt_camera *camera,
+                          const rt_render_params *params, rt_frame *frame);
+/* device-resident results of the last rt_render_frame (valid until the next call / destroy):
+ * fp32 RGBA accumulation (W*H*4 floats) and RGBA8 image. For zero-copy hand-off to NCCL. */
+float *rt_renderer_device_accum(rt_renderer *r);
+uint8_t *rt_renderer_device_rgba8(rt_renderer *r);
+/* (re)compute the RGBA8 image from an accumulation buffer holding the sum over `sample_count`
+ * samples — used after a cross-GPU reduction (src/render_wavefront.cpp:360-394 + F10).
+ * accum, rgba8: ANY-space. */
+rt_status rt_resolve(rt_context *ctx, const float *accum, uint32_t sample_count, int32_t width,
+                     int32_t height, uint8_t *rgba8);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RT_API_H */

@@ -1,0 +1,574 @@
+/*
+ * rt_api.cu — the C ABI of include/rt_api.h over the CUDA kernels (librt_b200.so).
+ * There is no CPU path in this library: every entry point that computes launches kernels on
+ * the context's stream.
+ */
+#include <cmath>
+#include <cstring>
+#include <new>
+
+#include "rt_internal.h"
+#include "rt_render.h"
+
+static thread_local std::string g_create_error;
+
+rt_status rt_set_error(rt_context *ctx, rt_status st, const char *what, const char *detail) {
+    std::string msg = std::string(what ? what : "") + ": " + (detail ? detail : "");
+    if (ctx) ctx->err = msg;
+    else g_create_error = msg;
+    return st;
+}
+
+struct rt_renderer {
+    rt_context *ctx = nullptr;
+    rt_renderer_kind kind = RT_MEGAKERNEL;
+    int32_t w = 0, h = 0;
+    float4 *d_accum = nullptr;
+    uint32_t *d_rgba8 = nullptr;
+    uint32_t *d_rng = nullptr;
+    uint32_t *d_work = nullptr;             /* megakernel tile counter */
+    unsigned long long *d_rays = nullptr;   /* ray segment counter */
+    RtWavefrontState wf = {};
+    uint32_t *d_counts = nullptr;           /* 2 queue lengths */
+    uint32_t *h_counts = nullptr;           /* pinned mirror */
+    unsigned long long *h_rays = nullptr;   /* pinned */
+    int grid_mega = 0, grid_extend = 0, grid_shade = 0;
+};
+
+namespace {
+
+template <class T>
+cudaError_t dev_alloc(T **p, size_t count) {
+    return cudaMalloc((void **)p, (count ? count : 1) * sizeof(T));
+}
+
+void normal_matrix(const float T[16], float out[9]) {
+    /* transpose(inverse(mat3(T))) with glm's cofactor formula (src/scene.cpp:502) */
+    float m[3][3];
+    for (int c = 0; c < 3; c++)
+        for (int r = 0; r < 3; r++) m[c][r] = T[c * 4 + r];
+    const float ood = 1.0f / (+m[0][0] * (m[1][1] * m[2][2] - m[2][1] * m[1][2]) -
+                              m[1][0] * (m[0][1] * m[2][2] - m[2][1] * m[0][2]) +
+                              m[2][0] * (m[0][1] * m[1][2] - m[1][1] * m[0][2]));
+    float inv[3][3];
+    inv[0][0] = +(m[1][1] * m[2][2] - m[2][1] * m[1][2]) * ood;
+    inv[1][0] = -(m[1][0] * m[2][2] - m[2][0] * m[1][2]) * ood;
+    inv[2][0] = +(m[1][0] * m[2][1] - m[2][0] * m[1][1]) * ood;
+    inv[0][1] = -(m[0][1] * m[2][2] - m[2][1] * m[0][2]) * ood;
+    inv[1][1] = +(m[0][0] * m[2][2] - m[2][0] * m[0][2]) * ood;
+    inv[2][1] = -(m[0][0] * m[2][1] - m[2][0] * m[0][1]) * ood;
+    inv[0][2] = +(m[0][1] * m[1][2] - m[1][1] * m[0][2]) * ood;
+    inv[1][2] = -(m[0][0] * m[1][2] - m[1][0] * m[0][2]) * ood;
+    inv[2][2] = +(m[0][0] * m[1][1] - m[1][0] * m[0][1]) * ood;
+    for (int c = 0; c < 3; c++)
+        for (int r = 0; r < 3; r++) out[c * 3 + r] = inv[r][c];
+}
+
+RtCamera to_device_camera(const rt_camera &c) {
+    RtCamera d;
+    d.center = mk3(c.center[0], c.center[1], c.center[2]);
+    d.pixel00 = mk3(c.pixel00_loc[0], c.pixel00_loc[1], c.pixel00_loc[2]);
+    d.du = mk3(c.pixel_delta_u[0], c.pixel_delta_u[1], c.pixel_delta_u[2]);
+    d.dv = mk3(c.pixel_delta_v[0], c.pixel_delta_v[1], c.pixel_delta_v[2]);
+    d.w = c.img_size[0];
+    d.h = c.img_size[1];
+    return d;
+}
+
+} // namespace
+
+extern "C" {
+
+uint32_t rt_api_version(void) { return RT_API_VERSION; }
+
+const char *rt_last_error(rt_context *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+rt_status rt_context_create(int device, rt_context **out) {
+    if (!out) return rt_set_error(nullptr, RT_ERR_INVALID, "rt_context_create", "out is NULL");
+    *out = nullptr;
+    int n_dev = 0;
+    cudaError_t e = cudaGetDeviceCount(&n_dev);
+    if (e != cudaSuccess || n_dev == 0)
+        return rt_set_error(nullptr, RT_ERR_NO_DEVICE, "rt_context_create",
+                            e != cudaSuccess ? cudaGetErrorString(e) : "no CUDA device (there is no CPU path)");
+    if (device < 0 || device >= n_dev) return rt_set_error(nullptr, RT_ERR_INVALID, "rt_context_create", "bad device index");
+    rt_context *ctx = new (std::nothrow) rt_context();
+    if (!ctx) return rt_set_error(nullptr, RT_ERR_INVALID, "rt_context_create", "out of memory");
+    ctx->device = device;
+    cudaDeviceProp prop;
+    if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess ||
+        (e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaEventCreate(&ctx->ev0)) != cudaSuccess || (e = cudaEventCreate(&ctx->ev1)) != cudaSuccess) {
+        rt_set_error(nullptr, RT_ERR_CUDA, "rt_context_create", cudaGetErrorString(e));
+        delete ctx;
+        return RT_ERR_CUDA;
+    }
+    ctx->sm_count = prop.multiProcessorCount;
+    ctx->name = prop.name;
+    /* arithmetic-contract self test: a*b+c must not be contracted into an FMA */
+    float *d = nullptr, h[2] = {0, 0};
+    /* (1+2^-12)^2 = 1 + 2^-11 + 2^-24 rounds to 1 + 2^-11: unfused a*b+c == 0, fused == 2^-24 */
+    const float a = 1.0f + 1.0f / 4096.0f, b = a, c = -(1.0f + 1.0f / 2048.0f);
+    if ((e = cudaMalloc(&d, 2 * sizeof(float))) != cudaSuccess || (e = rt_launch_selftest(ctx->stream, a, b, c, d)) != cudaSuccess ||
+        (e = cudaMemcpyAsync(h, d, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream)) != cudaSuccess ||
+        (e = cudaStreamSynchronize(ctx->stream)) != cudaSuccess) {
+        rt_set_error(nullptr, RT_ERR_CUDA, "rt_context_create(selftest)", cudaGetErrorString(e));
+        if (d) cudaFree(d);
+        rt_context_destroy(ctx);
+        return RT_ERR_CUDA;
+    }
+    cudaFree(d);
+    if (!(h[0] == 0.0f && h[1] != 0.0f)) {
+        rt_set_error(nullptr, RT_ERR_STATE, "rt_context_create",
+                     "library was built with FMA contraction enabled (needs -fmad=false)");
+        rt_context_destroy(ctx);
+        return RT_ERR_STATE;
+    }
+    *out = ctx;
+    return RT_OK;
+}
+
+void rt_context_destroy(rt_context *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+void *rt_context_stream(rt_context *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+const char *rt_context_device_name(rt_context *ctx) { return ctx ? ctx->name.c_str() : ""; }
+
+void rt_camera_init(rt_camera *cam, int32_t width, int32_t height, const float position[3], const float direction[3],
+                    float focal_length) {
+    /* Camera::Camera, src/camera.hpp:74-106 */
+    cam->img_size[0] = width;
+    cam->img_size[1] = height;
+    const f3 center = mk3(position[0], position[1], position[2]);
+    const f3 dir = normalize3(mk3(direction[0], direction[1], direction[2]));
+    const f3 world_up = mk3(0.0f, 1.0f, 0.0f);
+    auto cross = [](f3 a, f3 b) { return mk3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); };
+    const f3 right = normalize3(cross(dir, world_up));
+    const f3 up = normalize3(cross(right, dir));
+    const float vp0 = 1.0f * ((float)width / (float)height), vp1 = 1.0f;
+    const f3 viewport_u = (-right) * vp0;
+    const f3 viewport_v = up * vp1;
+    const f3 p00 = ((center + viewport_u) + viewport_v) + dir * focal_length;
+    const f3 du = div3(right, (float)width / (vp0 * 2.0f));
+    const f3 dv = div3(-up, (float)height / (vp1 * 2.0f));
+    const f3 v[4] = {center, p00, du, dv};
+    float *dst[4] = {cam->center, cam->pixel00_loc, cam->pixel_delta_u, cam->pixel_delta_v};
+    for (int i = 0; i < 4; i++) {
+        dst[i][0] = v[i].x;
+        dst[i][1] = v[i].y;
+        dst[i][2] = v[i].z;
+    }
+}
+
+/* ------------------------------------------------------------------------------- scene */
+rt_status rt_scene_create(rt_context *ctx, const rt_scene_desc *desc, rt_scene **out) {
+    if (!ctx) return RT_ERR_INVALID;
+    if (!desc || !out) return rt_set_error(ctx, RT_ERR_INVALID, "rt_scene_create", "NULL argument");
+    *out = nullptr;
+    if (desc->instance_count && !desc->instances) return rt_set_error(ctx, RT_ERR_INVALID, "rt_scene_create", "instances is NULL");
+    if (desc->texture_layer_count > RT_MAX_IMAGES)
+        return rt_set_error(ctx, RT_ERR_INVALID, "rt_scene_create", "too many texture layers (MAX_IMAGES = 128)");
+    if (desc->texture_layer_count && !desc->texture_layers)
+        return rt_set_error(ctx, RT_ERR_INVALID, "rt_scene_create", "texture_layers is NULL");
+    RT_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+
+    uint64_t n_verts = 0, n_idx = 0;
+    for (uint32_t i = 0; i < desc->instance_count; i++) {
+        const rt_instance &in = desc->instances[i];
+        if (in.index_count % 3 != 0) return rt_set_error(ctx, RT_ERR_INVALID, "rt_scene_create", "index_count not a multiple of 3");
+        if (in.index_count && (!in.indices || !in.positions || !in.normals || !in.uvs))
+            return rt_set_error(ctx, RT_ERR_INVALID, "rt_scene_create", "instance buffer is NULL (POSITION, NORMAL, TEXCOORD_0 and indices are required)");
+        if (in.material.type < RT_MAT_NONE || in.material.type > RT_MAT_DIELECTRIC)
+            return rt_set_error(ctx, RT_ERR_INVALID, "rt_scene_create", "bad material type");
+        if (in.material.albedo_image >= (int32_t)desc->texture_layer_count)
+            return rt_set_error(ctx, RT_ERR_INVALID, "rt_scene_create", "albedo_image out of range");
+        for (uint32_t k = 0; k < in.index_count; k++)
+            if (in.indices[k] >= in.vertex_count) return rt_set_error(ctx, RT_ERR_INVALID, "rt_scene_create", "index out of range");
+        n_verts += in.vertex_count;
+        n_idx += in.index_count;
+    }
+    if (n_idx / 3 >= 0x7fffffffull || n_verts >= 0xffffffffull)
+        return rt_set_error(ctx, RT_ERR_INVALID, "rt_scene_create", "scene too large (2^31 triangles)");
+
+    rt_scene *s = new (std::nothrow) rt_scene();
+    if (!s) return rt_set_error(ctx, RT_ERR_INVALID, "rt_scene_create", "out of memory");
+    s->ctx = ctx;
+    s->n_inst = desc->instance_count;
+    s->n_verts = (uint32_t)n_verts;
+    s->n_indices = (uint32_t)n_idx;
+    s->n_tris = (uint32_t)(n_idx / 3);
+    memcpy(s->sky, desc->sky_color, sizeof(s->sky));
+
+    std::vector<float> pos(n_verts * 3), nrm(n_verts * 3), uv(n_verts * 2);
+    std::vector<uint32_t> idx(n_idx);
+    s->h_geom.resize(desc->instance_count ? desc->instance_count : 1);
+    s->h_inst.resize(desc->instance_count ? desc->instance_count : 1);
+    uint32_t v0 = 0, i0 = 0;
+    for (uint32_t i = 0; i < desc->instance_count; i++) {
+        const rt_instance &in = desc->instances[i];
+        if (in.vertex_count) {
+            memcpy(&pos[(size_t)v0 * 3], in.positions, (size_t)in.vertex_count * 3 * sizeof(float));
+            memcpy(&nrm[(size_t)v0 * 3], in.normals, (size_t)in.vertex_count * 3 * sizeof(float));
+            memcpy(&uv[(size_t)v0 * 2], in.uvs, (size_t)in.vertex_count * 2 * sizeof(float));
+        }
+        if (in.index_count) memcpy(&idx[i0], in.indices, (size_t)in.index_count * sizeof(uint32_t));
+        RtInstanceGeom &g = s->h_geom[i];
+        memcpy(g.transform, in.transform, sizeof(g.transform));
+        g.first_vertex = v0;
+        g.first_index = i0;
+        g.first_tri = i0 / 3;
+        g.tri_count = in.index_count / 3;
+        RtInstance &m = s->h_inst[i];
+        normal_matrix(in.transform, m.nmat);
+        m.type = in.material.type;
+        m.albedo_image = in.material.albedo_image;
+        memcpy(m.albedo, in.material.albedo_color, sizeof(m.albedo));
+        m.roughness = in.material.roughness;
+        m.ior = in.material.ior;
+        memcpy(m.emissive, in.material.emissive, sizeof(m.emissive));
+        m.first_tri = g.first_tri;
+        v0 += in.vertex_count;
+        i0 += in.index_count;
+    }
+
+    rt_status st = RT_OK;
+    auto fail = [&](cudaError_t e, const char *what) {
+        st = rt_set_error(ctx, RT_ERR_CUDA, what, cudaGetErrorString(e));
+    };
+    cudaError_t e;
+    cudaStream_t stream = ctx->stream;
+    do {
+        if ((e = dev_alloc(&s->d_positions, pos.size())) != cudaSuccess) { fail(e, "alloc positions"); break; }
+        if ((e = dev_alloc(&s->d_normals, nrm.size())) != cudaSuccess) { fail(e, "alloc normals"); break; }
+        if ((e = dev_alloc(&s->d_uvs, uv.size())) != cudaSuccess) { fail(e, "alloc uvs"); break; }
+        if ((e = dev_alloc(&s->d_indices, idx.size())) != cudaSuccess) { fail(e, "alloc indices"); break; }
+        if ((e = dev_alloc(&s->d_geom, s->h_geom.size())) != cudaSuccess) { fail(e, "alloc geom"); break; }
+        if ((e = dev_alloc(&s->d_inst, s->h_inst.size())) != cudaSuccess) { fail(e, "alloc inst"); break; }
+        if (!pos.empty()) {
+            if ((e = cudaMemcpyAsync(s->d_positions, pos.data(), pos.size() * 4, cudaMemcpyHostToDevice, stream)) != cudaSuccess) { fail(e, "copy positions"); break; }
+            if ((e = cudaMemcpyAsync(s->d_normals, nrm.data(), nrm.size() * 4, cudaMemcpyHostToDevice, stream)) != cudaSuccess) { fail(e, "copy normals"); break; }
+            if ((e = cudaMemcpyAsync(s->d_uvs, uv.data(), uv.size() * 4, cudaMemcpyHostToDevice, stream)) != cudaSuccess) { fail(e, "copy uvs"); break; }
+        }
+        if (!idx.empty())
+            if ((e = cudaMemcpyAsync(s->d_indices, idx.data(), idx.size() * 4, cudaMemcpyHostToDevice, stream)) != cudaSuccess) { fail(e, "copy indices"); break; }
+        if ((e = cudaMemcpyAsync(s->d_geom, s->h_geom.data(), s->h_geom.size() * sizeof(RtInstanceGeom), cudaMemcpyHostToDevice, stream)) != cudaSuccess) { fail(e, "copy geom"); break; }
+        if ((e = cudaMemcpyAsync(s->d_inst, s->h_inst.data(), s->h_inst.size() * sizeof(RtInstance), cudaMemcpyHostToDevice, stream)) != cudaSuccess) { fail(e, "copy inst"); break; }
+        /* texture array: RGBA8 512x512xN layered, point sampled, raw element reads (F13) */
+        s->n_layers = desc->texture_layer_count;
+        if (s->n_layers) {
+            cudaChannelFormatDesc cd = cudaCreateChannelDesc<uchar4>();
+            cudaExtent ext = make_cudaExtent(RT_TEX_SIZE, RT_TEX_SIZE, s->n_layers);
+            if ((e = cudaMalloc3DArray(&s->tex_array, &cd, ext, cudaArrayLayered)) != cudaSuccess) { fail(e, "alloc texture array"); break; }
+            cudaMemcpy3DParms cp = {};
+            cp.srcPtr = make_cudaPitchedPtr((void *)desc->texture_layers, RT_TEX_SIZE * 4, RT_TEX_SIZE, RT_TEX_SIZE);
+            cp.dstArray = s->tex_array;
+            cp.extent = ext;
+            cp.kind = cudaMemcpyHostToDevice;
+            if ((e = cudaMemcpy3DAsync(&cp, stream)) != cudaSuccess) { fail(e, "copy textures"); break; }
+            cudaResourceDesc rd = {};
+            rd.resType = cudaResourceTypeArray;
+            rd.res.array.array = s->tex_array;
+            cudaTextureDesc td = {};
+            td.addressMode[0] = td.addressMode[1] = td.addressMode[2] = cudaAddressModeClamp;
+            td.filterMode = cudaFilterModePoint;
+            td.readMode = cudaReadModeElementType;
+            td.normalizedCoords = 0;
+            if ((e = cudaCreateTextureObject(&s->tex, &rd, &td, nullptr)) != cudaSuccess) { fail(e, "create texture object"); break; }
+        }
+        if ((e = cudaStreamSynchronize(stream)) != cudaSuccess) { fail(e, "upload"); break; }
+    } while (0);
+    if (st != RT_OK) {
+        rt_scene_destroy(s);
+        return st;
+    }
+    s->stats.triangle_count = s->n_tris;
+    *out = s;
+    return RT_OK;
+}
+
+rt_status rt_scene_commit(rt_scene *s) {
+    if (!s) return RT_ERR_INVALID;
+    rt_context *ctx = s->ctx;
+    if (s->committed) return rt_set_error(ctx, RT_ERR_STATE, "rt_scene_commit", "scene already committed (immutable)");
+    RT_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    rt_status st = rt_build_bvh(s);
+    if (st != RT_OK) return st;
+    /* the object-space inputs are no longer needed */
+    cudaFree(s->d_positions); s->d_positions = nullptr;
+    cudaFree(s->d_normals); s->d_normals = nullptr;
+    cudaFree(s->d_uvs); s->d_uvs = nullptr;
+    cudaFree(s->d_indices); s->d_indices = nullptr;
+    s->view.bvh.nodes = s->d_nodes;
+    s->view.bvh.tris = s->d_tris;
+    s->view.shade = s->d_shade;
+    s->view.inst = s->d_inst;
+    s->view.tex_raw = nullptr;
+    s->view.tex = s->tex;
+    s->view.n_layers = s->n_layers;
+    s->view.sky = mk3(s->sky[0], s->sky[1], s->sky[2]);
+    s->stats.bvh_bytes = s->stats.node_count * 80ull + (uint64_t)s->n_tris * 48ull;
+    s->stats.shading_bytes = (uint64_t)s->n_tris * 64ull + (uint64_t)s->n_inst * sizeof(RtInstance);
+    s->stats.max_leaf_tris = RT_LEAF_MAX;
+    s->committed = true;
+    return RT_OK;
+}
+
+rt_status rt_scene_get_stats(const rt_scene *s, rt_scene_stats *out) {
+    if (!s || !out) return RT_ERR_INVALID;
+    *out = s->stats;
+    return RT_OK;
+}
+
+void rt_scene_destroy(rt_scene *s) {
+    if (!s) return;
+    cudaSetDevice(s->ctx->device);
+    if (s->tex) cudaDestroyTextureObject(s->tex);
+    if (s->tex_array) cudaFreeArray(s->tex_array);
+    cudaFree(s->d_positions);
+    cudaFree(s->d_normals);
+    cudaFree(s->d_uvs);
+    cudaFree(s->d_indices);
+    cudaFree(s->d_geom);
+    cudaFree(s->d_inst);
+    cudaFree(s->d_nodes);
+    cudaFree(s->d_tris);
+    cudaFree(s->d_shade);
+    delete s;
+}
+
+/* ------------------------------------------------------------------------------- intersect */
+rt_status rt_intersect(rt_context *ctx, const rt_scene *scene, uint64_t n, const float *org, const float *dir,
+                       float tnear, float tfar, int32_t *inst, int32_t *prim, float *u, float *v, float *t,
+                       float *device_ms) {
+    if (!ctx || !scene) return RT_ERR_INVALID;
+    if (!scene->committed) return rt_set_error(ctx, RT_ERR_STATE, "rt_intersect", "scene not committed");
+    if (n && (!org || !dir || !inst || !prim || !u || !v || !t))
+        return rt_set_error(ctx, RT_ERR_INVALID, "rt_intersect", "NULL argument");
+    if (device_ms) *device_ms = 0.0f;
+    if (n == 0) return RT_OK;
+    RT_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    float *d_org = nullptr, *d_dir = nullptr, *d_f = nullptr;
+    int32_t *d_i = nullptr;
+    rt_status rs = RT_OK;
+    cudaError_t e = cudaSuccess;
+    do {
+        if ((e = dev_alloc(&d_org, n * 3)) != cudaSuccess) break;
+        if ((e = dev_alloc(&d_dir, n * 3)) != cudaSuccess) break;
+        if ((e = dev_alloc(&d_f, n * 3)) != cudaSuccess) break;
+        if ((e = dev_alloc(&d_i, n * 2)) != cudaSuccess) break;
+        if ((e = cudaMemcpyAsync(d_org, org, n * 12, cudaMemcpyDefault, st)) != cudaSuccess) break;
+        if ((e = cudaMemcpyAsync(d_dir, dir, n * 12, cudaMemcpyDefault, st)) != cudaSuccess) break;
+        if ((e = cudaEventRecord(ctx->ev0, st)) != cudaSuccess) break;
+        if ((e = rt_launch_intersect(st, scene->view, scene->d_inst, n, d_org, d_dir, tnear, tfar, d_i, d_i + n, d_f,
+                                     d_f + n, d_f + 2 * n)) != cudaSuccess) break;
+        if ((e = cudaEventRecord(ctx->ev1, st)) != cudaSuccess) break;
+        if ((e = cudaMemcpyAsync(inst, d_i, n * 4, cudaMemcpyDefault, st)) != cudaSuccess) break;
+        if ((e = cudaMemcpyAsync(prim, d_i + n, n * 4, cudaMemcpyDefault, st)) != cudaSuccess) break;
+        if ((e = cudaMemcpyAsync(u, d_f, n * 4, cudaMemcpyDefault, st)) != cudaSuccess) break;
+        if ((e = cudaMemcpyAsync(v, d_f + n, n * 4, cudaMemcpyDefault, st)) != cudaSuccess) break;
+        if ((e = cudaMemcpyAsync(t, d_f + 2 * n, n * 4, cudaMemcpyDefault, st)) != cudaSuccess) break;
+        if ((e = cudaStreamSynchronize(st)) != cudaSuccess) break;
+        float ms = 0.0f;
+        if ((e = cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1)) != cudaSuccess) break;
+        if (device_ms) *device_ms = ms;
+    } while (0);
+    if (e != cudaSuccess) rs = rt_set_error(ctx, RT_ERR_CUDA, "rt_intersect", cudaGetErrorString(e));
+    cudaFree(d_org);
+    cudaFree(d_dir);
+    cudaFree(d_f);
+    cudaFree(d_i);
+    return rs;
+}
+
+/* ------------------------------------------------------------------------------- renderers */
+rt_status rt_renderer_create(rt_context *ctx, rt_renderer_kind kind, int32_t width, int32_t height, rt_renderer **out) {
+    if (!ctx) return RT_ERR_INVALID;
+    if (!out) return rt_set_error(ctx, RT_ERR_INVALID, "rt_renderer_create", "out is NULL");
+    *out = nullptr;
+    if (width <= 0 || height <= 0 || (uint64_t)width * (uint64_t)height > 0x7fffffffull)
+        return rt_set_error(ctx, RT_ERR_INVALID, "rt_renderer_create", "bad image size");
+    if (kind != RT_MEGAKERNEL && kind != RT_WAVEFRONT) return rt_set_error(ctx, RT_ERR_INVALID, "rt_renderer_create", "bad renderer kind");
+    RT_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    rt_renderer *r = new (std::nothrow) rt_renderer();
+    if (!r) return rt_set_error(ctx, RT_ERR_INVALID, "rt_renderer_create", "out of memory");
+    r->ctx = ctx;
+    r->kind = kind;
+    r->w = width;
+    r->h = height;
+    const size_t n = (size_t)width * (size_t)height;
+    cudaError_t e = cudaSuccess;
+    do {
+        if ((e = dev_alloc(&r->d_accum, n)) != cudaSuccess) break;
+        if ((e = dev_alloc(&r->d_rgba8, n)) != cudaSuccess) break;
+        if ((e = dev_alloc(&r->d_rng, n)) != cudaSuccess) break;
+        if ((e = dev_alloc(&r->d_work, 1)) != cudaSuccess) break;
+        if ((e = dev_alloc(&r->d_rays, 1)) != cudaSuccess) break;
+        if ((e = dev_alloc(&r->d_counts, 2)) != cudaSuccess) break;
+        if ((e = cudaMallocHost((void **)&r->h_counts, 2 * sizeof(uint32_t))) != cudaSuccess) break;
+        if ((e = cudaMallocHost((void **)&r->h_rays, sizeof(unsigned long long))) != cudaSuccess) break;
+        if (kind == RT_MEGAKERNEL) {
+            if ((e = rt_megakernel_grid(ctx->sm_count, &r->grid_mega)) != cudaSuccess) break;
+        } else {
+            /* Buffers + rng_buffer, src/render_wavefront.hpp:18-37, .cpp:52-54 */
+            if ((e = dev_alloc(&r->wf.org, n)) != cudaSuccess) break;
+            if ((e = dev_alloc(&r->wf.dir, n)) != cudaSuccess) break;
+            if ((e = dev_alloc(&r->wf.att, n)) != cudaSuccess) break;
+            if ((e = dev_alloc(&r->wf.rad, n)) != cudaSuccess) break;
+            if ((e = dev_alloc(&r->wf.hit, n)) != cudaSuccess) break;
+            if ((e = dev_alloc(&r->wf.prog, n)) != cudaSuccess) break;
+            if ((e = dev_alloc(&r->wf.rng, n)) != cudaSuccess) break;
+            if ((e = dev_alloc(&r->wf.queue[0], n)) != cudaSuccess) break;
+            if ((e = dev_alloc(&r->wf.queue[1], n)) != cudaSuccess) break;
+            r->wf.count[0] = r->d_counts;
+            r->wf.count[1] = r->d_counts + 1;
+            if ((e = rt_wavefront_grid(ctx->sm_count, &r->grid_extend, &r->grid_shade)) != cudaSuccess) break;
+        }
+    } while (0);
+    if (e != cudaSuccess) {
+        rt_status st = rt_set_error(ctx, RT_ERR_CUDA, "rt_renderer_create", cudaGetErrorString(e));
+        rt_renderer_destroy(r);
+        return st;
+    }
+    *out = r;
+    return RT_OK;
+}
+
+void rt_renderer_destroy(rt_renderer *r) {
+    if (!r) return;
+    cudaSetDevice(r->ctx->device);
+    cudaFree(r->d_accum);
+    cudaFree(r->d_rgba8);
+    cudaFree(r->d_rng);
+    cudaFree(r->d_work);
+    cudaFree(r->d_rays);
+    cudaFree(r->d_counts);
+    if (r->h_counts) cudaFreeHost(r->h_counts);
+    if (r->h_rays) cudaFreeHost(r->h_rays);
+    cudaFree(r->wf.org);
+    cudaFree(r->wf.dir);
+    cudaFree(r->wf.att);
+    cudaFree(r->wf.rad);
+    cudaFree(r->wf.hit);
+    cudaFree(r->wf.prog);
+    cudaFree(r->wf.rng);
+    cudaFree(r->wf.queue[0]);
+    cudaFree(r->wf.queue[1]);
+    delete r;
+}
+
+float *rt_renderer_device_accum(rt_renderer *r) { return r ? (float *)r->d_accum : nullptr; }
+uint8_t *rt_renderer_device_rgba8(rt_renderer *r) { return r ? (uint8_t *)r->d_rgba8 : nullptr; }
+
+rt_status rt_render_frame(rt_renderer *r, const rt_scene *scene, const rt_camera *camera,
+                          const rt_render_params *params, rt_frame *frame) {
+    if (!r) return RT_ERR_INVALID;
+    rt_context *ctx = r->ctx;
+    if (!scene || !camera || !params || !frame) return rt_set_error(ctx, RT_ERR_INVALID, "rt_render_frame", "NULL argument");
+    if (scene->ctx != ctx) return rt_set_error(ctx, RT_ERR_INVALID, "rt_render_frame", "scene belongs to another context");
+    if (!scene->committed) return rt_set_error(ctx, RT_ERR_STATE, "rt_render_frame", "scene not committed");
+    if (camera->img_size[0] != r->w || camera->img_size[1] != r->h)
+        return rt_set_error(ctx, RT_ERR_INVALID, "rt_render_frame", "camera image size differs from the renderer's");
+    const rt_shard &sh = params->shard;
+    if (sh.world > 1 && sh.rank >= sh.world) return rt_set_error(ctx, RT_ERR_INVALID, "rt_render_frame", "shard rank >= world");
+    if (sh.world > 1 && sh.tile_size % 8 != 0) return rt_set_error(ctx, RT_ERR_INVALID, "rt_render_frame", "tile_size must be a multiple of 8");
+    RT_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+
+    RtFrameParams p;
+    p.cam = to_device_camera(*camera);
+    p.max_depth = params->max_depth;
+    p.spp = params->sample_count;
+    p.seed_salt = sh.seed_salt;
+    p.rank = sh.rank;
+    p.world = sh.world;
+    p.tile_size = sh.tile_size;
+    p.wavefront_seed = r->kind == RT_WAVEFRONT ? 1 : 0;
+    p.clamp_samples = r->kind == RT_WAVEFRONT ? 1 : 0;
+    RtFrameOut out;
+    out.accum = r->d_accum;
+    out.rgba8 = r->d_rgba8;
+    out.rng = r->d_rng;
+    const size_t n = (size_t)r->w * (size_t)r->h;
+    uint32_t launches = 0;
+
+    RT_CUDA_TRY(ctx, cudaEventRecord(ctx->ev0, st));
+    RT_CUDA_TRY(ctx, cudaMemsetAsync(r->d_rays, 0, sizeof(unsigned long long), st));
+    if (r->kind == RT_MEGAKERNEL) {
+        RT_CUDA_TRY(ctx, cudaMemsetAsync(r->d_work, 0, sizeof(uint32_t), st));
+        if (sh.world > 1 && sh.tile_size) { /* pixels of other ranks stay zero */
+            RT_CUDA_TRY(ctx, cudaMemsetAsync(r->d_accum, 0, n * sizeof(float4), st));
+            RT_CUDA_TRY(ctx, cudaMemsetAsync(r->d_rgba8, 0, n * 4, st));
+            RT_CUDA_TRY(ctx, cudaMemsetAsync(r->d_rng, 0, n * 4, st));
+        }
+        RT_CUDA_TRY(ctx, rt_launch_megakernel(st, r->grid_mega, scene->view, p, out, r->d_work, r->d_rays));
+        launches++;
+    } else {
+        RT_CUDA_TRY(ctx, cudaMemsetAsync(r->d_counts, 0, 2 * sizeof(uint32_t), st));
+        RT_CUDA_TRY(ctx, rt_launch_wf_generate(st, r->grid_shade, p, r->wf, out));
+        launches++;
+        /* every pixel traces at most spp * max_depth segments, one per bounce iteration */
+        const uint64_t max_iters = (uint64_t)p.spp * (uint64_t)p.max_depth;
+        int cur = 0;
+        uint64_t it = 0;
+        while (it < max_iters) {
+            const uint64_t batch = (max_iters - it) < 8 ? (max_iters - it) : 8;
+            for (uint64_t k = 0; k < batch; k++) {
+                RT_CUDA_TRY(ctx, rt_launch_wf_extend(st, r->grid_extend, scene->view, r->wf, cur, r->d_rays));
+                RT_CUDA_TRY(ctx, rt_launch_wf_shade(st, r->grid_shade, scene->view, p, r->wf, out, cur));
+                launches += 2;
+                cur ^= 1;
+            }
+            it += batch;
+            RT_CUDA_TRY(ctx, cudaMemcpyAsync(r->h_counts, r->d_counts, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+            RT_CUDA_TRY(ctx, cudaStreamSynchronize(st));
+            if (r->h_counts[cur] == 0) break; /* every pixel has finished its samples */
+        }
+        RT_CUDA_TRY(ctx, rt_launch_resolve_owned(st, p, (const float *)r->d_accum, r->wf.rng, out));
+        launches++;
+    }
+    RT_CUDA_TRY(ctx, cudaEventRecord(ctx->ev1, st));
+    RT_CUDA_TRY(ctx, cudaMemcpyAsync(r->h_rays, r->d_rays, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    if (frame->rgba8) RT_CUDA_TRY(ctx, cudaMemcpyAsync(frame->rgba8, r->d_rgba8, n * 4, cudaMemcpyDefault, st));
+    if (frame->accum) RT_CUDA_TRY(ctx, cudaMemcpyAsync(frame->accum, r->d_accum, n * sizeof(float4), cudaMemcpyDefault, st));
+    if (frame->rng_state) RT_CUDA_TRY(ctx, cudaMemcpyAsync(frame->rng_state, r->d_rng, n * 4, cudaMemcpyDefault, st));
+    RT_CUDA_TRY(ctx, cudaStreamSynchronize(st));
+    float ms = 0.0f;
+    RT_CUDA_TRY(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    frame->device_ms = ms;
+    frame->ray_count = *r->h_rays;
+    frame->kernel_launches = launches;
+    return RT_OK;
+}
+
+rt_status rt_resolve(rt_context *ctx, const float *accum, uint32_t sample_count, int32_t width, int32_t height,
+                     uint8_t *rgba8) {
+    if (!ctx) return RT_ERR_INVALID;
+    if (!accum || !rgba8 || width <= 0 || height <= 0) return rt_set_error(ctx, RT_ERR_INVALID, "rt_resolve", "bad argument");
+    RT_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const size_t n = (size_t)width * (size_t)height;
+    float *d_a = nullptr;
+    uint32_t *d_o = nullptr;
+    cudaError_t e = cudaSuccess;
+    do {
+        if ((e = dev_alloc(&d_a, n * 4)) != cudaSuccess) break;
+        if ((e = dev_alloc(&d_o, n)) != cudaSuccess) break;
+        if ((e = cudaMemcpyAsync(d_a, accum, n * 16, cudaMemcpyDefault, st)) != cudaSuccess) break;
+        if ((e = rt_launch_resolve(st, d_a, d_o, (uint32_t)n, (float)sample_count)) != cudaSuccess) break;
+        if ((e = cudaMemcpyAsync(rgba8, d_o, n * 4, cudaMemcpyDefault, st)) != cudaSuccess) break;
+        e = cudaStreamSynchronize(st);
+    } while (0);
+    cudaFree(d_a);
+    cudaFree(d_o);
+    if (e != cudaSuccess) return rt_set_error(ctx, RT_ERR_CUDA, "rt_resolve", cudaGetErrorString(e));
+    return RT_OK;
+}
+
+} /* extern "C" */

@@ -1,0 +1,445 @@
+/*
+ * rt_build.h — per-item logic of the GPU BVH build (the rtcCommitScene replacement,
+ * src/scene.cpp:101-107,406-439,483-507):
+ *
+ *   flatten      instance transform applied to the geometry (one world-space triangle soup;
+ *                Embree instead transforms the ray per instance, t/u/v are invariant)
+ *   morton       63-bit Morton code of the triangle-AABB centroid
+ *   (sort)       cub::DeviceRadixSort in bvh_build.cu
+ *   karras       binary radix tree over the sorted codes (Karras, HPG 2012)
+ *   fit          bottom-up AABB fit, one atomic flag per inner node
+ *   wide_select  greedy surface-area collapse of the binary tree into <= 8 children
+ *   wide_emit    quantise child boxes, assign octant-ordered slots, write the 80-byte node,
+ *                leaf-ordered triangles and the pre-gathered shading records
+ *
+ * Each function handles ONE item and is wrapped by a thin kernel in bvh_build.cu.
+ */
+#ifndef RT_BUILD_H
+#define RT_BUILD_H
+
+#include "rt_shade.h"
+
+#define RT_LEAF_MAX 3 /* triangles per leaf child (unary count in 3 meta bits) */
+
+struct RtInstanceGeom {
+    float transform[16]; /* column-major */
+    uint32_t first_vertex, first_index, first_tri, tri_count;
+};
+
+struct RtBuild {
+    uint32_t n_tris, n_inst;
+    /* concatenated instance geometry (object space) */
+    const float *positions, *normals, *uvs;
+    const uint32_t *indices;
+    const RtInstanceGeom *geom;
+    /* flatten */
+    rt_float4 *wtris;       /* 3 per triangle in global-id order; .w of the third = gid bits */
+    int32_t *cen_bounds;    /* 6 ordered-int floats: min xyz, max xyz of AABB centroids */
+    /* morton + sort */
+    uint64_t *keys;
+    uint32_t *vals;         /* sorted: vals[k] = global id of the k-th triangle in Morton order */
+    /* binary radix tree; unified node ids: inner i in [0, n-2], leaf j = (n-1) + j */
+    uint32_t *left, *right; /* n-1 */
+    uint32_t *parent;       /* 2n-1 */
+    uint32_t *range_first, *range_last; /* n-1 */
+    rt_float4 *box_lo, *box_hi;         /* 2n-1 */
+    uint32_t *flags;                    /* n-1 */
+    /* wide collapse (per level) */
+    const uint32_t *items;  /* binary node id of every wide node of this level */
+    uint32_t *next_items;
+    uint32_t *sel;          /* 8 per item: unified ids of the chosen children, RT_MISS = none */
+    uint64_t *counts;       /* per item: inner children << 32 | leaf triangles */
+    const uint64_t *offsets;/* exclusive scan of counts */
+    uint32_t level_first_node, next_level_first_node, tri_cursor;
+    /* outputs */
+    rt_uint4 *nodes;        /* 5 per wide node */
+    rt_float4 *tris;        /* 3 per triangle, leaf order */
+    rt_float4 *shade;       /* 4 per triangle, leaf order */
+};
+
+/* order-preserving float <-> int map for atomicMin/Max */
+RT_HD int32_t rt_float_to_ordered(float f) {
+    int32_t i = (int32_t)rt_f2u(f);
+    return i >= 0 ? i : i ^ 0x7fffffff;
+}
+RT_HD float rt_ordered_to_float(int32_t i) { return rt_u2f((uint32_t)(i >= 0 ? i : i ^ 0x7fffffff)); }
+
+RT_HD uint32_t rt_find_instance(const RtBuild &b, uint32_t gid) {
+    uint32_t lo = 0, hi = b.n_inst; /* last instance with first_tri <= gid and tri_count > 0 */
+    while (hi - lo > 1) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (b.geom[mid].first_tri <= gid) lo = mid;
+        else hi = mid;
+    }
+    return lo;
+}
+
+/* ---- flatten: world-space vertices of global triangle gid ------------------------------- */
+RT_HD void rt_flatten_tri(const RtBuild &b, uint32_t gid, f3 &lo, f3 &hi) {
+    const uint32_t inst = rt_find_instance(b, gid);
+    const RtInstanceGeom &g = b.geom[inst];
+    const uint32_t prim = gid - g.first_tri;
+    const float *T = g.transform;
+    f3 w[3];
+    for (int k = 0; k < 3; k++) {
+        const uint32_t vi = b.indices[(size_t)g.first_index + (size_t)prim * 3 + k] + g.first_vertex;
+        const float x = b.positions[(size_t)vi * 3], y = b.positions[(size_t)vi * 3 + 1],
+                    z = b.positions[(size_t)vi * 3 + 2];
+        /* glm mat4 * vec4(v, 1) = m[0]*x + m[1]*y + m[2]*z + m[3] */
+        w[k] = mk3(((T[0] * x + T[4] * y) + T[8] * z) + T[12], ((T[1] * x + T[5] * y) + T[9] * z) + T[13],
+                   ((T[2] * x + T[6] * y) + T[10] * z) + T[14]);
+    }
+    rt_float4 a, c, d;
+    a.x = w[0].x; a.y = w[0].y; a.z = w[0].z; a.w = 0.0f;
+    c.x = w[1].x; c.y = w[1].y; c.z = w[1].z; c.w = 0.0f;
+    d.x = w[2].x; d.y = w[2].y; d.z = w[2].z; d.w = rt_u2f(gid);
+    b.wtris[(size_t)gid * 3] = a;
+    b.wtris[(size_t)gid * 3 + 1] = c;
+    b.wtris[(size_t)gid * 3 + 2] = d;
+    lo = mk3(rt_min3(w[0].x, w[1].x, w[2].x), rt_min3(w[0].y, w[1].y, w[2].y), rt_min3(w[0].z, w[1].z, w[2].z));
+    hi = mk3(rt_max3(w[0].x, w[1].x, w[2].x), rt_max3(w[0].y, w[1].y, w[2].y), rt_max3(w[0].z, w[1].z, w[2].z));
+}
+
+RT_HD void rt_tri_box(const RtBuild &b, uint32_t gid, f3 &lo, f3 &hi) {
+    const rt_float4 a = b.wtris[(size_t)gid * 3], c = b.wtris[(size_t)gid * 3 + 1], d = b.wtris[(size_t)gid * 3 + 2];
+    lo = mk3(rt_min3(a.x, c.x, d.x), rt_min3(a.y, c.y, d.y), rt_min3(a.z, c.z, d.z));
+    hi = mk3(rt_max3(a.x, c.x, d.x), rt_max3(a.y, c.y, d.y), rt_max3(a.z, c.z, d.z));
+}
+
+/* ---- morton ------------------------------------------------------------------------------ */
+RT_HD uint64_t rt_expand_bits21(uint64_t v) {
+    v &= 0x1fffffull;
+    v = (v | v << 32) & 0x1f00000000ffffull;
+    v = (v | v << 16) & 0x1f0000ff0000ffull;
+    v = (v | v << 8) & 0x100f00f00f00f00full;
+    v = (v | v << 4) & 0x10c30c30c30c30c3ull;
+    v = (v | v << 2) & 0x1249249249249249ull;
+    return v;
+}
+
+RT_HD void rt_morton_tri(const RtBuild &b, uint32_t gid) {
+    f3 lo, hi;
+    rt_tri_box(b, gid, lo, hi);
+    const f3 c = mk3(0.5f * (lo.x + hi.x), 0.5f * (lo.y + hi.y), 0.5f * (lo.z + hi.z));
+    const f3 mn = mk3(rt_ordered_to_float(b.cen_bounds[0]), rt_ordered_to_float(b.cen_bounds[1]),
+                      rt_ordered_to_float(b.cen_bounds[2]));
+    const f3 mx = mk3(rt_ordered_to_float(b.cen_bounds[3]), rt_ordered_to_float(b.cen_bounds[4]),
+                      rt_ordered_to_float(b.cen_bounds[5]));
+    const float S = 2097152.0f; /* 2^21 */
+    const float ex = mx.x - mn.x, ey = mx.y - mn.y, ez = mx.z - mn.z;
+    float fx = ex > 0.0f ? (c.x - mn.x) / ex * S : 0.0f;
+    float fy = ey > 0.0f ? (c.y - mn.y) / ey * S : 0.0f;
+    float fz = ez > 0.0f ? (c.z - mn.z) / ez * S : 0.0f;
+    fx = rt_min(rt_max(fx, 0.0f), S - 1.0f);
+    fy = rt_min(rt_max(fy, 0.0f), S - 1.0f);
+    fz = rt_min(rt_max(fz, 0.0f), S - 1.0f);
+    b.keys[gid] = (rt_expand_bits21((uint64_t)fx) << 2) | (rt_expand_bits21((uint64_t)fy) << 1) |
+                  rt_expand_bits21((uint64_t)fz);
+    b.vals[gid] = gid;
+}
+
+/* ---- Karras 2012 radix tree ---------------------------------------------------------------- */
+RT_HD int rt_delta(const uint64_t *keys, int n, int i, int j) {
+    if (j < 0 || j >= n) return -1;
+    const uint64_t a = keys[i], c = keys[j];
+    if (a == c) return 64 + rt_clz32((uint32_t)i ^ (uint32_t)j);
+    return rt_clz64(a ^ c);
+}
+
+RT_HD void rt_karras_node(const RtBuild &b, uint32_t iu) {
+    const int n = (int)b.n_tris, i = (int)iu;
+    const uint64_t *keys = b.keys;
+    const int d = (rt_delta(keys, n, i, i + 1) - rt_delta(keys, n, i, i - 1)) >= 0 ? 1 : -1;
+    const int dmin = rt_delta(keys, n, i, i - d);
+    int lmax = 2;
+    while (rt_delta(keys, n, i, i + lmax * d) > dmin) lmax *= 2;
+    int l = 0;
+    for (int t = lmax / 2; t >= 1; t /= 2)
+        if (rt_delta(keys, n, i, i + (l + t) * d) > dmin) l += t;
+    const int j = i + l * d;
+    const int dnode = rt_delta(keys, n, i, j);
+    int s = 0;
+    int t = l;
+    do {
+        t = (t + 1) >> 1;
+        if (rt_delta(keys, n, i, i + (s + t) * d) > dnode) s += t;
+    } while (t > 1);
+    const int gamma = i + s * d + (d < 0 ? d : 0);
+    const int first = i < j ? i : j, last = i < j ? j : i;
+    const uint32_t leaf0 = (uint32_t)(n - 1);
+    const uint32_t lc = (first == gamma) ? leaf0 + (uint32_t)gamma : (uint32_t)gamma;
+    const uint32_t rc = (last == gamma + 1) ? leaf0 + (uint32_t)(gamma + 1) : (uint32_t)(gamma + 1);
+    b.left[i] = lc;
+    b.right[i] = rc;
+    b.parent[lc] = (uint32_t)i;
+    b.parent[rc] = (uint32_t)i;
+    b.range_first[i] = (uint32_t)first;
+    b.range_last[i] = (uint32_t)last;
+    if (i == 0) b.parent[0] = RT_MISS;
+}
+
+/* The fit reads boxes written by other SMs during the same launch: go through L2 (.cg), the
+ * per-SM L1 is not coherent and may hold a stale line that a neighbouring box pulled in. */
+RT_HD rt_float4 rt_ld_cg(const rt_float4 *p) {
+#if RT_DEVICE_CODE
+    return __ldcg(p);
+#else
+    return *p;
+#endif
+}
+RT_HD void rt_st_cg(rt_float4 *p, rt_float4 v) {
+#if RT_DEVICE_CODE
+    __stcg(p, v);
+#else
+    *p = v;
+#endif
+}
+
+/* ---- bottom-up fit: called once per leaf; `arrive` returns the previous flag value --------- */
+template <class Arrive>
+RT_HD void rt_fit_leaf(const RtBuild &b, uint32_t j, Arrive arrive) {
+    const uint32_t leaf0 = b.n_tris - 1;
+    f3 lo, hi;
+    rt_tri_box(b, b.vals[j], lo, hi);
+    rt_float4 l4, h4;
+    l4.x = lo.x; l4.y = lo.y; l4.z = lo.z; l4.w = 0.0f;
+    h4.x = hi.x; h4.y = hi.y; h4.z = hi.z; h4.w = 0.0f;
+    rt_st_cg(&b.box_lo[leaf0 + j], l4);
+    rt_st_cg(&b.box_hi[leaf0 + j], h4);
+    if (b.n_tris == 1) return;
+    uint32_t node = b.parent[leaf0 + j];
+    while (node != RT_MISS) {
+        if (arrive(&b.flags[node]) == 0) return; /* first child to arrive: the sibling finishes */
+        const uint32_t lc = b.left[node], rc = b.right[node];
+        const rt_float4 la = rt_ld_cg(&b.box_lo[lc]), lb = rt_ld_cg(&b.box_lo[rc]);
+        const rt_float4 ha = rt_ld_cg(&b.box_hi[lc]), hb = rt_ld_cg(&b.box_hi[rc]);
+        l4.x = rt_min(la.x, lb.x); l4.y = rt_min(la.y, lb.y); l4.z = rt_min(la.z, lb.z);
+        h4.x = rt_max(ha.x, hb.x); h4.y = rt_max(ha.y, hb.y); h4.z = rt_max(ha.z, hb.z);
+        rt_st_cg(&b.box_lo[node], l4);
+        rt_st_cg(&b.box_hi[node], h4);
+        node = b.parent[node];
+    }
+}
+
+/* ---- wide collapse ------------------------------------------------------------------------- */
+RT_HD bool rt_is_leaf_id(const RtBuild &b, uint32_t id) { return id >= b.n_tris - 1; }
+RT_HD uint32_t rt_subtree_count(const RtBuild &b, uint32_t id) {
+    return rt_is_leaf_id(b, id) ? 1u : b.range_last[id] - b.range_first[id] + 1u;
+}
+RT_HD uint32_t rt_subtree_first(const RtBuild &b, uint32_t id) {
+    return rt_is_leaf_id(b, id) ? id - (b.n_tris - 1) : b.range_first[id];
+}
+RT_HD float rt_box_area(const RtBuild &b, uint32_t id) {
+    const rt_float4 lo = b.box_lo[id], hi = b.box_hi[id];
+    const float dx = hi.x - lo.x, dy = hi.y - lo.y, dz = hi.z - lo.z;
+    return dx * dy + dy * dz + dz * dx;
+}
+
+/* choose <= 8 children for the wide node rooted at binary node items[item] */
+RT_HD void rt_wide_select(const RtBuild &b, uint32_t item) {
+    const uint32_t root = b.items[item];
+    uint32_t c[8];
+    int n;
+    if (rt_subtree_count(b, root) <= RT_LEAF_MAX) {
+        c[0] = root;
+        n = 1;
+    } else {
+        c[0] = b.left[root];
+        c[1] = b.right[root];
+        n = 2;
+        while (n < 8) {
+            int best = -1;
+            float best_area = -1.0f;
+            for (int k = 0; k < n; k++) {
+                if (rt_subtree_count(b, c[k]) <= RT_LEAF_MAX) continue;
+                const float a = rt_box_area(b, c[k]);
+                if (a > best_area) {
+                    best_area = a;
+                    best = k;
+                }
+            }
+            if (best < 0) break;
+            const uint32_t id = c[best];
+            c[best] = b.left[id];
+            c[n++] = b.right[id];
+        }
+    }
+    uint32_t n_inner = 0, n_leaf_tris = 0;
+    for (int k = 0; k < 8; k++) {
+        uint32_t id = k < n ? c[k] : RT_MISS;
+        b.sel[(size_t)item * 8 + k] = id;
+        if (k < n) {
+            const uint32_t cnt = rt_subtree_count(b, id);
+            if (cnt <= RT_LEAF_MAX) n_leaf_tris += cnt;
+            else n_inner++;
+        }
+    }
+    b.counts[item] = ((uint64_t)n_inner << 32) | n_leaf_tris;
+}
+
+/* pre-gather the shading attributes of global triangle gid (src/trace_ray.hpp:29-41) */
+RT_HD void rt_write_shade_record(const RtBuild &b, uint32_t gid, uint32_t slot) {
+    const uint32_t inst = rt_find_instance(b, gid);
+    const RtInstanceGeom &g = b.geom[inst];
+    const uint32_t prim = gid - g.first_tri;
+    float nrm[9], uv[6];
+    for (int k = 0; k < 3; k++) {
+        const uint32_t vi = b.indices[(size_t)g.first_index + (size_t)prim * 3 + k] + g.first_vertex;
+        nrm[k * 3] = b.normals[(size_t)vi * 3];
+        nrm[k * 3 + 1] = b.normals[(size_t)vi * 3 + 1];
+        nrm[k * 3 + 2] = b.normals[(size_t)vi * 3 + 2];
+        uv[k * 2] = b.uvs[(size_t)vi * 2];
+        uv[k * 2 + 1] = b.uvs[(size_t)vi * 2 + 1];
+    }
+    rt_float4 s0, s1, s2, s3;
+    s0.x = nrm[0]; s0.y = nrm[1]; s0.z = nrm[2]; s0.w = nrm[3];
+    s1.x = nrm[4]; s1.y = nrm[5]; s1.z = nrm[6]; s1.w = nrm[7];
+    s2.x = nrm[8]; s2.y = uv[0]; s2.z = uv[1]; s2.w = uv[2];
+    s3.x = uv[3]; s3.y = uv[4]; s3.z = uv[5]; s3.w = rt_u2f(inst);
+    b.shade[(size_t)slot * 4] = s0;
+    b.shade[(size_t)slot * 4 + 1] = s1;
+    b.shade[(size_t)slot * 4 + 2] = s2;
+    b.shade[(size_t)slot * 4 + 3] = s3;
+}
+
+/* smallest biased exponent e with p + 255 * 2^(e-127) >= hi */
+RT_HD uint32_t rt_quant_exponent(float lo, float hi) {
+    const float ext = hi - lo;
+    uint32_t e = 1;
+    if (ext > 0.0f) {
+        const uint32_t bits = rt_f2u(ext / 255.0f);
+        e = (bits >> 23) & 0xffu;
+        if (bits & 0x7fffffu) e++;
+        if (e < 1) e = 1;
+    }
+    while (e < 254 && lo + 255.0f * rt_u2f(e << 23) < hi) e++;
+    return e;
+}
+RT_HD uint32_t rt_quant_lo(float p, float scale, float v) {
+    float q = floorf((v - p) / scale);
+    q = rt_min(rt_max(q, 0.0f), 255.0f);
+    while (q > 0.0f && p + q * scale > v) q -= 1.0f;
+    return (uint32_t)q;
+}
+RT_HD uint32_t rt_quant_hi(float p, float scale, float v) {
+    float q = ceilf((v - p) / scale);
+    q = rt_min(rt_max(q, 0.0f), 255.0f);
+    while (q < 255.0f && p + q * scale < v) q += 1.0f;
+    return (uint32_t)q;
+}
+
+/* write wide node `level_first_node + item` and everything it owns */
+RT_HD void rt_wide_emit(const RtBuild &b, uint32_t item) {
+    const uint32_t root = b.items[item];
+    const uint64_t off = b.offsets[item];
+    const uint32_t child_base = b.next_level_first_node + (uint32_t)(off >> 32);
+    const uint32_t tri_base = b.tri_cursor + (uint32_t)(off & 0xffffffffu);
+
+    uint32_t c[8];
+    int n = 0;
+    for (int k = 0; k < 8; k++) {
+        const uint32_t id = b.sel[(size_t)item * 8 + k];
+        if (id != RT_MISS) c[n++] = id;
+    }
+    const rt_float4 plo = b.box_lo[root], phi = b.box_hi[root];
+    const f3 pc = mk3(0.5f * (plo.x + phi.x), 0.5f * (plo.y + phi.y), 0.5f * (plo.z + phi.z));
+
+    /* octant-ordered slot assignment: slot s is visited first by rays whose direction signs are
+     * D_s = (s&4 ? - : +, s&2 ? - : +, s&1 ? - : +); give it the child that is nearest along D_s.
+     * Greedy minimum over the 8x8 cost table. */
+    float cost[8][8];
+    for (int k = 0; k < n; k++) {
+        const rt_float4 lo = b.box_lo[c[k]], hi = b.box_hi[c[k]];
+        const f3 cc = mk3(0.5f * (lo.x + hi.x) - pc.x, 0.5f * (lo.y + hi.y) - pc.y, 0.5f * (lo.z + hi.z) - pc.z);
+        for (int s = 0; s < 8; s++)
+            cost[k][s] = ((s & 4) ? -cc.x : cc.x) + ((s & 2) ? -cc.y : cc.y) + ((s & 1) ? -cc.z : cc.z);
+    }
+    int slot_child[8];
+    for (int s = 0; s < 8; s++) slot_child[s] = -1;
+    uint32_t child_done = 0, slot_done = 0;
+    for (int it = 0; it < n; it++) {
+        int bk = -1, bs = -1;
+        float bc = 3.0e38f;
+        for (int k = 0; k < n; k++) {
+            if (child_done & (1u << k)) continue;
+            for (int s = 0; s < 8; s++) {
+                if (slot_done & (1u << s)) continue;
+                if (cost[k][s] < bc) {
+                    bc = cost[k][s];
+                    bk = k;
+                    bs = s;
+                }
+            }
+        }
+        if (bk < 0) { /* NaN boxes: fall back to first free pair */
+            for (int k = 0; k < n && bk < 0; k++)
+                if (!(child_done & (1u << k))) bk = k;
+            for (int s = 0; s < 8 && bs < 0; s++)
+                if (!(slot_done & (1u << s))) bs = s;
+        }
+        slot_child[bs] = bk;
+        child_done |= 1u << bk;
+        slot_done |= 1u << bs;
+    }
+
+    const uint32_t ex = rt_quant_exponent(plo.x, phi.x), ey = rt_quant_exponent(plo.y, phi.y),
+                   ez = rt_quant_exponent(plo.z, phi.z);
+    const float sx = rt_u2f(ex << 23), sy = rt_u2f(ey << 23), sz = rt_u2f(ez << 23);
+
+    uint32_t imask = 0, meta[2] = {0, 0};
+    uint32_t q[6][2]; /* qlo x,y,z, qhi x,y,z ; two words of four bytes */
+    for (int a = 0; a < 6; a++) {
+        q[a][0] = 0;
+        q[a][1] = 0;
+    }
+    uint32_t inner_rank = 0, tri_off = 0;
+    for (int s = 0; s < 8; s++) {
+        const int w = s >> 2, sh = (s & 3) * 8;
+        const int k = slot_child[s];
+        if (k < 0) { /* empty slot: inverted box never hits */
+            q[0][w] |= 255u << sh;
+            q[1][w] |= 255u << sh;
+            q[2][w] |= 255u << sh;
+            continue;
+        }
+        const uint32_t id = c[k];
+        const rt_float4 lo = b.box_lo[id], hi = b.box_hi[id];
+        q[0][w] |= rt_quant_lo(plo.x, sx, lo.x) << sh;
+        q[1][w] |= rt_quant_lo(plo.y, sy, lo.y) << sh;
+        q[2][w] |= rt_quant_lo(plo.z, sz, lo.z) << sh;
+        q[3][w] |= rt_quant_hi(plo.x, sx, hi.x) << sh;
+        q[4][w] |= rt_quant_hi(plo.y, sy, hi.y) << sh;
+        q[5][w] |= rt_quant_hi(plo.z, sz, hi.z) << sh;
+        const uint32_t cnt = rt_subtree_count(b, id);
+        if (cnt > RT_LEAF_MAX) {
+            imask |= 1u << s;
+            meta[w] |= (0x20u | (24u + (uint32_t)s)) << sh;
+            b.next_items[(child_base - b.next_level_first_node) + inner_rank] = id;
+            inner_rank++;
+        } else {
+            const uint32_t unary = (1u << cnt) - 1u;
+            meta[w] |= ((unary << 5) | tri_off) << sh;
+            const uint32_t first = rt_subtree_first(b, id);
+            for (uint32_t t = 0; t < cnt; t++) {
+                const uint32_t gid = b.vals[first + t];
+                const uint32_t slot = tri_base + tri_off + t;
+                b.tris[(size_t)slot * 3] = b.wtris[(size_t)gid * 3];
+                b.tris[(size_t)slot * 3 + 1] = b.wtris[(size_t)gid * 3 + 1];
+                b.tris[(size_t)slot * 3 + 2] = b.wtris[(size_t)gid * 3 + 2];
+                rt_write_shade_record(b, gid, slot);
+            }
+            tri_off += cnt;
+        }
+    }
+    rt_uint4 n0, n1, n2, n3, n4;
+    n0.x = rt_f2u(plo.x); n0.y = rt_f2u(plo.y); n0.z = rt_f2u(plo.z);
+    n0.w = ex | (ey << 8) | (ez << 16) | (imask << 24);
+    n1.x = child_base; n1.y = tri_base; n1.z = meta[0]; n1.w = meta[1];
+    n2.x = q[0][0]; n2.y = q[0][1]; n2.z = q[1][0]; n2.w = q[1][1];
+    n3.x = q[2][0]; n3.y = q[2][1]; n3.z = q[3][0]; n3.w = q[3][1];
+    n4.x = q[4][0]; n4.y = q[4][1]; n4.z = q[5][0]; n4.w = q[5][1];
+    rt_uint4 *np = b.nodes + (size_t)(b.level_first_node + item) * 5;
+    np[0] = n0; np[1] = n1; np[2] = n2; np[3] = n3; np[4] = n4;
+}
+
+#endif /* RT_BUILD_H */

@@ -1,0 +1,61 @@
+/*
+ * rt_internal.h — host-side objects behind the opaque handles of include/rt_api.h.
+ */
+#ifndef RT_INTERNAL_H
+#define RT_INTERNAL_H
+
+#include <cuda_runtime.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/rt_api.h"
+#include "rt_build.h"
+
+/* App (src/app.hpp:31-58): device + in-order stream owner */
+struct rt_context {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    int sm_count = 0;
+    std::string name;
+    std::string err;
+};
+
+/* Scene's device side (src/scene.hpp:64-91) */
+struct rt_scene {
+    rt_context *ctx = nullptr;
+    bool committed = false;
+    uint32_t n_inst = 0, n_tris = 0, n_verts = 0, n_indices = 0;
+    /* object-space geometry as uploaded (inputs of the build) */
+    float *d_positions = nullptr, *d_normals = nullptr, *d_uvs = nullptr;
+    uint32_t *d_indices = nullptr;
+    RtInstanceGeom *d_geom = nullptr;
+    std::vector<RtInstanceGeom> h_geom;
+    /* shading tables */
+    RtInstance *d_inst = nullptr;
+    std::vector<RtInstance> h_inst;
+    /* textures: layered CUDA array bound as a texture object (ImageManager, F13) */
+    cudaArray_t tex_array = nullptr;
+    cudaTextureObject_t tex = 0;
+    uint32_t n_layers = 0;
+    float sky[3] = {0.5f, 0.7f, 1.0f};
+    /* committed acceleration structure */
+    rt_uint4 *d_nodes = nullptr;
+    rt_float4 *d_tris = nullptr;
+    rt_float4 *d_shade = nullptr;
+    rt_scene_stats stats = {};
+    RtScene view = {};
+};
+
+rt_status rt_set_error(rt_context *ctx, rt_status st, const char *what, const char *detail);
+rt_status rt_build_bvh(rt_scene *s); /* bvh_build.cu */
+
+#define RT_CUDA_TRY(ctx, expr)                                                     \
+    do {                                                                           \
+        cudaError_t rt_e_ = (expr);                                                \
+        if (rt_e_ != cudaSuccess)                                                  \
+            return rt_set_error((ctx), RT_ERR_CUDA, #expr, cudaGetErrorString(rt_e_)); \
+    } while (0)
+
+#endif

@@ -1,0 +1,29 @@
+/*
+ * rt_render.h — kernel argument blocks and launchers shared by render.cu and rt_api.cu.
+ */
+#ifndef RT_RENDER_H
+#define RT_RENDER_H
+
+#include <cuda_runtime.h>
+
+#include "rt_wavefront.h"
+
+cudaError_t rt_launch_intersect(cudaStream_t st, const RtScene &scene, const RtInstance *inst, uint64_t n,
+                                const float *org, const float *dir, float tnear, float tfar, int32_t *o_inst,
+                                int32_t *o_prim, float *o_u, float *o_v, float *o_t);
+cudaError_t rt_megakernel_grid(int sm_count, int *grid);
+cudaError_t rt_launch_megakernel(cudaStream_t st, int grid, const RtScene &scene, const RtFrameParams &p,
+                                 const RtFrameOut &out, uint32_t *work_counter, unsigned long long *ray_counter);
+cudaError_t rt_wavefront_grid(int sm_count, int *grid_extend, int *grid_shade);
+cudaError_t rt_launch_wf_generate(cudaStream_t st, int grid, const RtFrameParams &p, const RtWavefrontState &w,
+                                  const RtFrameOut &out);
+cudaError_t rt_launch_wf_extend(cudaStream_t st, int grid, const RtScene &scene, const RtWavefrontState &w, int cur,
+                                unsigned long long *ray_counter);
+cudaError_t rt_launch_wf_shade(cudaStream_t st, int grid, const RtScene &scene, const RtFrameParams &p,
+                               const RtWavefrontState &w, const RtFrameOut &out, int cur);
+cudaError_t rt_launch_resolve(cudaStream_t st, const float *accum, uint32_t *rgba8, uint32_t n_pix, float spp);
+cudaError_t rt_launch_resolve_owned(cudaStream_t st, const RtFrameParams &p, const float *accum,
+                                    const uint32_t *rng_state, const RtFrameOut &out);
+cudaError_t rt_launch_selftest(cudaStream_t st, float a, float b, float c, float *o);
+
+#endif

@@ -1,0 +1,326 @@
+/*
+ * rt_traverse.h — closest-hit traversal of the 8-wide compressed BVH + watertight triangle test.
+ *
+ * Replaces Embree's rtcIntersect1 as called at src/trace_ray.hpp:18-22 (Embree 4 is a
+ * third-party dependency that is not under /root/reference; there is no source to follow, so
+ * the algorithm is our own and the oracle states the same contract):
+ *   - closest hit with tnear < t <= tfar, double sided, no filters;
+ *   - u, v = barycentric weights of vertex 1 and 2 (Embree convention, F11);
+ *   - ray/triangle test: Woop, Benthin, Wald, "Watertight Ray/Triangle Intersection"
+ *     (JCGT 2013), unfused fp32 with the double-precision fallback on zero edge functions;
+ *   - ties in t resolve to the lowest global triangle id, so the result does not depend on the
+ *     traversal order or on the tree.
+ *
+ * Node format (80 bytes = 5 x 16-byte vector loads, after Ylitie, Karras, Laine, "Efficient
+ * Incoherent Ray Traversal on GPUs Through Compressed Wide BVHs", HPG 2017):
+ *   n0 = { p.x, p.y, p.z, ex | ey<<8 | ez<<16 | imask<<24 }
+ *   n1 = { child_base, tri_base, meta[0..3], meta[4..7] }
+ *   n2 = { qlo_x[0..3], qlo_x[4..7], qlo_y[0..3], qlo_y[4..7] }
+ *   n3 = { qlo_z[0..3], qlo_z[4..7], qhi_x[0..3], qhi_x[4..7] }
+ *   n4 = { qhi_y[0..3], qhi_y[4..7], qhi_z[0..3], qhi_z[4..7] }
+ * child box k = p + q * 2^(e-127)  (e = biased fp32 exponent byte).
+ * meta: 0 = empty slot; inner child = 0x20 | (24 + slot); leaf = unary(count) << 5 | offset.
+ * Triangles: 3 x float4 in leaf order: {v0, 0}, {v1, 0}, {v2, global_id_bits}.
+ */
+#ifndef RT_TRAVERSE_H
+#define RT_TRAVERSE_H
+
+#include "rt_hd.h"
+
+#define RT_STACK_SIZE 40 /* node groups; rt_scene_commit refuses trees deeper than this */
+#define RT_MISS 0xffffffffu
+#define RT_BOX_PAD 1.00000048f /* 1 + 2^-21: far planes / tmax are padded by ~4 ulp */
+
+#if !defined(__CUDACC__)
+struct rt_u4 {
+    uint32_t x, y, z, w;
+};
+struct rt_f4 {
+    float x, y, z, w;
+};
+struct rt_u2 {
+    uint32_t x, y;
+};
+typedef rt_u4 rt_uint4;
+typedef rt_f4 rt_float4;
+typedef rt_u2 rt_uint2;
+#else
+typedef uint4 rt_uint4;
+typedef float4 rt_float4;
+typedef uint2 rt_uint2;
+#endif
+RT_HD rt_float4 rt_mk_float4(float x, float y, float z, float w) {
+    rt_float4 r;
+    r.x = x; r.y = y; r.z = z; r.w = w;
+    return r;
+}
+RT_HD rt_uint2 rt_mk_uint2(uint32_t x, uint32_t y) {
+    rt_uint2 r;
+    r.x = x; r.y = y;
+    return r;
+}
+
+struct RtHit {
+    float t, u, v;
+    uint32_t tri; /* slot in the leaf-ordered triangle array, RT_MISS when nothing was hit */
+    uint32_t gid; /* global triangle id = first_tri[inst] + primID (tie-break key) */
+};
+
+struct RtBvh {
+    const rt_uint4 *nodes;  /* 5 per node */
+    const rt_float4 *tris;  /* 3 per triangle */
+};
+
+/* read-only 16-byte loads (LDG.E.128.CONSTANT on device) */
+RT_HD rt_uint4 rt_ldg(const rt_uint4 *p) {
+#if RT_DEVICE_CODE
+    return __ldg(p);
+#else
+    return *p;
+#endif
+}
+RT_HD rt_float4 rt_ldg(const rt_float4 *p) {
+#if RT_DEVICE_CODE
+    return __ldg(p);
+#else
+    return *p;
+#endif
+}
+
+/* replicate the msb of every byte over the byte (PRMT with sign-replicate selectors) */
+RT_HD uint32_t rt_sign_extend_s8x4(uint32_t x) {
+#if RT_DEVICE_CODE
+    return __byte_perm(x, 0, 0xba98);
+#else
+    uint32_t r = 0;
+    for (int i = 0; i < 4; i++)
+        if (x & (0x80u << (8 * i))) r |= 0xffu << (8 * i);
+    return r;
+#endif
+}
+RT_HD float rt_byte_to_float(uint32_t w, int j) {
+    return (float)((w >> (8 * j)) & 0xffu); /* I2F.U8 with byte select on device */
+}
+
+/* ---- watertight ray/triangle -------------------------------------------------------- */
+struct RtRayTri {
+    f3 org;
+    int kx, ky, kz;
+    float Sx, Sy, Sz;
+};
+
+RT_HD RtRayTri rt_ray_tri_setup(f3 org, f3 dir) {
+    RtRayTri r;
+    r.org = org;
+    float ax = fabsf(dir.x), ay = fabsf(dir.y), az = fabsf(dir.z);
+    int kz = 0;
+    float am = ax;
+    if (ay > am) {
+        kz = 1;
+        am = ay;
+    }
+    if (az > am) kz = 2;
+    int kx = kz + 1;
+    if (kx == 3) kx = 0;
+    int ky = kx + 1;
+    if (ky == 3) ky = 0;
+    float dz = sel3(dir, kz);
+    if (dz < 0.0f) {
+        int tmp = kx;
+        kx = ky;
+        ky = tmp;
+    }
+    r.kx = kx;
+    r.ky = ky;
+    r.kz = kz;
+    r.Sx = rt_div(sel3(dir, kx), dz);
+    r.Sy = rt_div(sel3(dir, ky), dz);
+    r.Sz = rt_div(1.0f, dz);
+    return r;
+}
+
+/* Updates `best` when triangle (v0, v1, v2) is a closer hit (or an equal-t hit with a lower
+ * id). Exactly the oracle's operation order. */
+RT_HD void rt_tri_test(const RtRayTri &r, f3 v0, f3 v1, f3 v2, uint32_t slot, uint32_t gid,
+                       float tnear, RtHit &best) {
+    f3 A = v0 - r.org, B = v1 - r.org, C = v2 - r.org;
+    float Akz = sel3(A, r.kz), Bkz = sel3(B, r.kz), Ckz = sel3(C, r.kz);
+    float Ax = sel3(A, r.kx) - r.Sx * Akz;
+    float Ay = sel3(A, r.ky) - r.Sy * Akz;
+    float Bx = sel3(B, r.kx) - r.Sx * Bkz;
+    float By = sel3(B, r.ky) - r.Sy * Bkz;
+    float Cx = sel3(C, r.kx) - r.Sx * Ckz;
+    float Cy = sel3(C, r.ky) - r.Sy * Ckz;
+    float U = Cx * By - Cy * Bx;
+    float V = Ax * Cy - Ay * Cx;
+    float W = Bx * Ay - By * Ax;
+    if (U == 0.0f || V == 0.0f || W == 0.0f) {
+        double CxBy = (double)Cx * (double)By, CyBx = (double)Cy * (double)Bx;
+        U = (float)(CxBy - CyBx);
+        double AxCy = (double)Ax * (double)Cy, AyCx = (double)Ay * (double)Cx;
+        V = (float)(AxCy - AyCx);
+        double BxAy = (double)Bx * (double)Ay, ByAx = (double)By * (double)Ax;
+        W = (float)(BxAy - ByAx);
+    }
+    if ((U < 0.0f || V < 0.0f || W < 0.0f) && (U > 0.0f || V > 0.0f || W > 0.0f)) return;
+    float det = (U + V) + W;
+    if (det == 0.0f) return;
+    float Az = r.Sz * Akz, Bz = r.Sz * Bkz, Cz = r.Sz * Ckz;
+    float T = (U * Az + V * Bz) + W * Cz;
+    float rcp = rt_div(1.0f, det);
+    float t = T * rcp;
+    if (!(t > tnear)) return;
+    if (t < best.t || (t == best.t && gid < best.gid)) {
+        best.t = t;
+        best.u = V * rcp;
+        best.v = W * rcp;
+        best.tri = slot;
+        best.gid = gid;
+    }
+}
+
+/* ---- wide-node test ------------------------------------------------------------------ */
+struct RtRayBox {
+    f3 org;
+    f3 rcp;          /* 1 / dir with |dir| clamped away from 0 */
+    uint32_t neg;    /* bit0: dir.x < 0, bit1: dir.y < 0, bit2: dir.z < 0 */
+    uint32_t oct_inv4;
+};
+
+RT_HD RtRayBox rt_ray_box_setup(f3 org, f3 dir) {
+    RtRayBox r;
+    r.org = org;
+    const float tiny = 1e-20f;
+    float dx = fabsf(dir.x) > tiny ? dir.x : copysignf(tiny, dir.x);
+    float dy = fabsf(dir.y) > tiny ? dir.y : copysignf(tiny, dir.y);
+    float dz = fabsf(dir.z) > tiny ? dir.z : copysignf(tiny, dir.z);
+    r.rcp = mk3(rt_div(1.0f, dx), rt_div(1.0f, dy), rt_div(1.0f, dz));
+    r.neg = (dx < 0.0f ? 1u : 0u) | (dy < 0.0f ? 2u : 0u) | (dz < 0.0f ? 4u : 0u);
+    /* slot s is visited in order of increasing (s ^ octant), octant = x<<2 | y<<1 | z sign bits */
+    uint32_t octant = (dx < 0.0f ? 4u : 0u) | (dy < 0.0f ? 2u : 0u) | (dz < 0.0f ? 1u : 0u);
+    r.oct_inv4 = (7u - octant) * 0x01010101u;
+    return r;
+}
+
+/* returns the hit mask of one wide node: bits 24..31 inner children in visiting priority,
+ * bits 0..23 leaf triangles (offsets from tri_base) */
+RT_HD uint32_t rt_node_test(const RtRayBox &rb, rt_uint4 n0, rt_uint4 n1, rt_uint4 n2,
+                            rt_uint4 n3, rt_uint4 n4, float tmin, float tmax_pad) {
+    float sx = rt_u2f((n0.w & 0xffu) << 23), sy = rt_u2f(((n0.w >> 8) & 0xffu) << 23),
+          sz = rt_u2f(((n0.w >> 16) & 0xffu) << 23);
+    float idx = sx * rb.rcp.x, idy = sy * rb.rcp.y, idz = sz * rb.rcp.z;
+    float ox = (rt_u2f(n0.x) - rb.org.x) * rb.rcp.x, oy = (rt_u2f(n0.y) - rb.org.y) * rb.rcp.y,
+          oz = (rt_u2f(n0.z) - rb.org.z) * rb.rcp.z;
+    /* far planes padded (only positive far values matter, so scaling is monotone) */
+    float idxp = idx * RT_BOX_PAD, idyp = idy * RT_BOX_PAD, idzp = idz * RT_BOX_PAD;
+    float oxp = ox * RT_BOX_PAD, oyp = oy * RT_BOX_PAD, ozp = oz * RT_BOX_PAD;
+    uint32_t hitmask = 0;
+#if RT_DEVICE_CODE
+#pragma unroll
+#endif
+    for (int h = 0; h < 2; h++) {
+        uint32_t meta4 = h ? n1.w : n1.z;
+        uint32_t is_inner4 = (meta4 & (meta4 << 1)) & 0x10101010u;
+        uint32_t inner_mask4 = rt_sign_extend_s8x4(is_inner4 << 3);
+        uint32_t bit_index4 = (meta4 ^ (rb.oct_inv4 & inner_mask4)) & 0x1f1f1f1fu;
+        uint32_t child_bits4 = (meta4 >> 5) & 0x07070707u;
+        uint32_t qlox = h ? n2.y : n2.x, qloy = h ? n2.w : n2.z, qloz = h ? n3.y : n3.x;
+        uint32_t qhix = h ? n3.w : n3.z, qhiy = h ? n4.y : n4.x, qhiz = h ? n4.w : n4.z;
+        uint32_t nx = (rb.neg & 1u) ? qhix : qlox, fx = (rb.neg & 1u) ? qlox : qhix;
+        uint32_t ny = (rb.neg & 2u) ? qhiy : qloy, fy = (rb.neg & 2u) ? qloy : qhiy;
+        uint32_t nz = (rb.neg & 4u) ? qhiz : qloz, fz = (rb.neg & 4u) ? qloz : qhiz;
+#if RT_DEVICE_CODE
+#pragma unroll
+#endif
+        for (int j = 0; j < 4; j++) {
+            float tnx = rt_fma(rt_byte_to_float(nx, j), idx, ox);
+            float tny = rt_fma(rt_byte_to_float(ny, j), idy, oy);
+            float tnz = rt_fma(rt_byte_to_float(nz, j), idz, oz);
+            float tfx = rt_fma(rt_byte_to_float(fx, j), idxp, oxp);
+            float tfy = rt_fma(rt_byte_to_float(fy, j), idyp, oyp);
+            float tfz = rt_fma(rt_byte_to_float(fz, j), idzp, ozp);
+            float cmin = rt_max(rt_max3(tnx, tny, tnz), tmin);
+            float cmax = rt_min(rt_min3(tfx, tfy, tfz), tmax_pad);
+            if (cmin <= cmax) {
+                uint32_t bits = (child_bits4 >> (8 * j)) & 0xffu;
+                uint32_t idxb = (bit_index4 >> (8 * j)) & 0xffu;
+                hitmask |= bits << idxb;
+            }
+        }
+    }
+    return hitmask;
+}
+
+/* ---- traversal ------------------------------------------------------------------------ */
+#ifndef RT_COUNTERS
+#define RT_COUNT_NODE()
+#define RT_COUNT_TRI()
+#endif
+
+RT_HD RtHit rt_traverse(const RtBvh &bvh, f3 org, f3 dir, float tnear, float tfar) {
+    RtHit best;
+    best.t = tfar;
+    best.u = 0.0f;
+    best.v = 0.0f;
+    best.tri = RT_MISS;
+    best.gid = RT_MISS;
+    const RtRayTri rt = rt_ray_tri_setup(org, dir);
+    const RtRayBox rb = rt_ray_box_setup(org, dir);
+    const uint32_t oct_inv = rb.oct_inv4 & 7u;
+    float tmax_pad = tfar * RT_BOX_PAD;
+
+    uint32_t stack_x[RT_STACK_SIZE], stack_y[RT_STACK_SIZE];
+    int sp = 0;
+    uint32_t ng_x = 0, ng_y = 0x80000000u; /* node group: (child base, hits<<24 | imask) */
+    uint32_t tg_x = 0, tg_y = 0;           /* triangle group: (tri base, hit bits) */
+
+    for (;;) {
+        if (ng_y > 0x00ffffffu) {
+            const uint32_t imask = ng_y & 0xffu;
+            const int bit = rt_bfind(ng_y);
+            ng_y &= ~(1u << bit);
+            if (ng_y > 0x00ffffffu) {
+                stack_x[sp] = ng_x;
+                stack_y[sp] = ng_y;
+                sp++;
+            }
+            const uint32_t slot = ((uint32_t)bit - 24u) ^ oct_inv;
+            const uint32_t rel = (uint32_t)rt_popc(imask & ~(0xffffffffu << slot));
+            const rt_uint4 *np = bvh.nodes + (size_t)(ng_x + rel) * 5;
+            const rt_uint4 n0 = rt_ldg(np), n1 = rt_ldg(np + 1), n2 = rt_ldg(np + 2),
+                           n3 = rt_ldg(np + 3), n4 = rt_ldg(np + 4);
+            RT_COUNT_NODE();
+            const uint32_t hm = rt_node_test(rb, n0, n1, n2, n3, n4, tnear, tmax_pad);
+            ng_x = n1.x;
+            ng_y = (hm & 0xff000000u) | (n0.w >> 24);
+            tg_x = n1.y;
+            tg_y = hm & 0x00ffffffu;
+        } else {
+            tg_x = ng_x;
+            tg_y = ng_y;
+            ng_x = 0;
+            ng_y = 0;
+        }
+        while (tg_y) {
+            const int i = rt_ctz(tg_y);
+            tg_y &= tg_y - 1;
+            const uint32_t slot = tg_x + (uint32_t)i;
+            const rt_float4 *tp = bvh.tris + (size_t)slot * 3;
+            const rt_float4 a = rt_ldg(tp), b = rt_ldg(tp + 1), c = rt_ldg(tp + 2);
+            RT_COUNT_TRI();
+            const float before = best.t;
+            rt_tri_test(rt, mk3(a.x, a.y, a.z), mk3(b.x, b.y, b.z), mk3(c.x, c.y, c.z), slot,
+                        rt_f2u(c.w), tnear, best);
+            if (best.t != before) tmax_pad = best.t * RT_BOX_PAD;
+        }
+        if (ng_y <= 0x00ffffffu) {
+            if (sp == 0) break;
+            sp--;
+            ng_x = stack_x[sp];
+            ng_y = stack_y[sp];
+        }
+    }
+    return best;
+}
+
+#endif /* RT_TRAVERSE_H */

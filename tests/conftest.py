@@ -1,0 +1,49 @@
+import importlib
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+    config.addinivalue_line("markers", "slow: long-running CPU test")
+
+
+def load_package():
+    return importlib.import_module("sycl-ray-tracer_b200")
+
+
+@pytest.fixture(scope="session")
+def pkg():
+    return load_package()
+
+
+@pytest.fixture(scope="session")
+def scenes(pkg):
+    return importlib.import_module("sycl-ray-tracer_b200.scenes")
+
+
+@pytest.fixture(scope="session")
+def oracle():
+    import _oracle
+    return _oracle
+
+
+@pytest.fixture(scope="session")
+def hostemu():
+    import _hostemu
+    return _hostemu
+
+
+@pytest.fixture(scope="session")
+def app(pkg):
+    """one rt_context for the whole GPU session"""
+    a = pkg.App(0)
+    yield a
+    a.close()

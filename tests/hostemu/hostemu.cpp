@@ -1,0 +1,380 @@
+/*
+ * hostemu.cpp — TEST-ONLY host emulation of the CUDA kernels' per-item source.
+ *
+ * NOT a CPU fallback and not part of the product: librt_b200.so never loads or links this, and
+ * the package fails loudly without a GPU. The container that builds this repo has no GPU, so this
+ * harness compiles the SAME headers the kernels are made of (csrc/rt_build.h, rt_traverse.h,
+ * rt_shade.h, rt_wavefront.h) with plain g++ and drives them with sequential loops in place of
+ * the launch grid (std::stable_sort for the radix sort, a running sum for the scan). It lets the
+ * `-m "not gpu"` suite check the kernel logic (tree build, compressed-node traversal, shading,
+ * wavefront queueing) against the oracle before any GPU time is spent.
+ */
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <numeric>
+#include <vector>
+
+#include "../../include/rt_api.h"
+#include "../../sycl-ray-tracer_b200/csrc/rt_build.h"
+#include "../../sycl-ray-tracer_b200/csrc/rt_wavefront.h"
+
+namespace {
+
+void normal_matrix(const float T[16], float out[9]) {
+    float m[3][3];
+    for (int c = 0; c < 3; c++)
+        for (int r = 0; r < 3; r++) m[c][r] = T[c * 4 + r];
+    const float ood = 1.0f / (+m[0][0] * (m[1][1] * m[2][2] - m[2][1] * m[1][2]) -
+                              m[1][0] * (m[0][1] * m[2][2] - m[2][1] * m[0][2]) +
+                              m[2][0] * (m[0][1] * m[1][2] - m[1][1] * m[0][2]));
+    float inv[3][3];
+    inv[0][0] = +(m[1][1] * m[2][2] - m[2][1] * m[1][2]) * ood;
+    inv[1][0] = -(m[1][0] * m[2][2] - m[2][0] * m[1][2]) * ood;
+    inv[2][0] = +(m[1][0] * m[2][1] - m[2][0] * m[1][1]) * ood;
+    inv[0][1] = -(m[0][1] * m[2][2] - m[2][1] * m[0][2]) * ood;
+    inv[1][1] = +(m[0][0] * m[2][2] - m[2][0] * m[0][2]) * ood;
+    inv[2][1] = -(m[0][0] * m[2][1] - m[2][0] * m[0][1]) * ood;
+    inv[0][2] = +(m[0][1] * m[1][2] - m[1][1] * m[0][2]) * ood;
+    inv[1][2] = -(m[0][0] * m[1][2] - m[1][0] * m[0][2]) * ood;
+    inv[2][2] = +(m[0][0] * m[1][1] - m[1][0] * m[0][1]) * ood;
+    for (int c = 0; c < 3; c++)
+        for (int r = 0; r < 3; r++) out[c * 3 + r] = inv[r][c];
+}
+
+struct HostArrive {
+    uint32_t operator()(uint32_t *flag) const { return (*flag)++; }
+};
+
+} // namespace
+
+struct emu_scene {
+    std::vector<RtInstance> inst;
+    std::vector<uint8_t> tex;
+    std::vector<rt_uint4> nodes;
+    std::vector<rt_float4> tris, shade;
+    uint32_t n_tris = 0, n_nodes = 0, depth = 0;
+    RtScene view;
+};
+
+extern "C" {
+
+emu_scene *emu_scene_create(const rt_scene_desc *desc) {
+    emu_scene *s = new emu_scene();
+    std::vector<float> pos, nrm, uv;
+    std::vector<uint32_t> idx;
+    std::vector<RtInstanceGeom> geom(desc->instance_count ? desc->instance_count : 1);
+    s->inst.resize(desc->instance_count ? desc->instance_count : 1);
+    uint32_t v0 = 0, i0 = 0;
+    for (uint32_t i = 0; i < desc->instance_count; i++) {
+        const rt_instance &in = desc->instances[i];
+        pos.insert(pos.end(), in.positions, in.positions + (size_t)in.vertex_count * 3);
+        nrm.insert(nrm.end(), in.normals, in.normals + (size_t)in.vertex_count * 3);
+        uv.insert(uv.end(), in.uvs, in.uvs + (size_t)in.vertex_count * 2);
+        idx.insert(idx.end(), in.indices, in.indices + in.index_count);
+        RtInstanceGeom &g = geom[i];
+        memcpy(g.transform, in.transform, sizeof(g.transform));
+        g.first_vertex = v0;
+        g.first_index = i0;
+        g.first_tri = i0 / 3;
+        g.tri_count = in.index_count / 3;
+        RtInstance &m = s->inst[i];
+        normal_matrix(in.transform, m.nmat);
+        m.type = in.material.type;
+        m.albedo_image = in.material.albedo_image;
+        memcpy(m.albedo, in.material.albedo_color, sizeof(m.albedo));
+        m.roughness = in.material.roughness;
+        m.ior = in.material.ior;
+        memcpy(m.emissive, in.material.emissive, sizeof(m.emissive));
+        m.first_tri = g.first_tri;
+        v0 += in.vertex_count;
+        i0 += in.index_count;
+    }
+    const uint32_t n = i0 / 3;
+    s->n_tris = n;
+    if (desc->texture_layer_count)
+        s->tex.assign(desc->texture_layers,
+                      desc->texture_layers + (size_t)desc->texture_layer_count * RT_TEX_SIZE * RT_TEX_SIZE * 4);
+
+    if (n == 0) {
+        const uint32_t ff = 0xffffffffu;
+        s->nodes = {{0, 0, 0, 1u | (1u << 8) | (1u << 16)}, {0, 0, 0, 0}, {ff, ff, ff, ff}, {ff, ff, 0, 0}, {0, 0, 0, 0}};
+        s->tris.resize(3);
+        s->shade.resize(4);
+        s->n_nodes = 1;
+        s->depth = 1;
+    } else {
+        RtBuild b = {};
+        b.n_tris = n;
+        b.n_inst = desc->instance_count;
+        b.positions = pos.data();
+        b.normals = nrm.data();
+        b.uvs = uv.data();
+        b.indices = idx.data();
+        b.geom = geom.data();
+        std::vector<rt_float4> wtris((size_t)n * 3), box_lo((size_t)2 * n), box_hi((size_t)2 * n);
+        std::vector<int32_t> cb(8);
+        std::vector<uint64_t> keys(n), keys_s(n);
+        std::vector<uint32_t> vals(n), vals_s(n), left(n), right(n), parent((size_t)2 * n), rf(n), rl(n), flags(n, 0);
+        b.wtris = wtris.data();
+        b.cen_bounds = cb.data();
+        for (int k = 0; k < 3; k++) {
+            cb[k] = rt_float_to_ordered(INFINITY);
+            cb[3 + k] = rt_float_to_ordered(-INFINITY);
+        }
+        for (uint32_t g = 0; g < n; g++) {
+            f3 lo, hi;
+            rt_flatten_tri(b, g, lo, hi);
+            const float c[3] = {0.5f * (lo.x + hi.x), 0.5f * (lo.y + hi.y), 0.5f * (lo.z + hi.z)};
+            for (int k = 0; k < 3; k++) {
+                cb[k] = std::min(cb[k], rt_float_to_ordered(c[k]));
+                cb[3 + k] = std::max(cb[3 + k], rt_float_to_ordered(c[k]));
+            }
+        }
+        b.keys = keys.data();
+        b.vals = vals.data();
+        for (uint32_t g = 0; g < n; g++) rt_morton_tri(b, g);
+        std::vector<uint32_t> order(n);
+        std::iota(order.begin(), order.end(), 0u);
+        std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t c) { return keys[a] < keys[c]; });
+        for (uint32_t k = 0; k < n; k++) {
+            keys_s[k] = keys[order[k]];
+            vals_s[k] = vals[order[k]];
+        }
+        b.keys = keys_s.data();
+        b.vals = vals_s.data();
+        b.left = left.data();
+        b.right = right.data();
+        b.parent = parent.data();
+        b.range_first = rf.data();
+        b.range_last = rl.data();
+        b.box_lo = box_lo.data();
+        b.box_hi = box_hi.data();
+        b.flags = flags.data();
+        for (uint32_t i = 0; i + 1 < n; i++) rt_karras_node(b, i);
+        for (uint32_t j = 0; j < n; j++) rt_fit_leaf(b, j, HostArrive());
+
+        const size_t max_items = (size_t)n / (RT_LEAF_MAX + 1) + 8;
+        std::vector<uint32_t> items_a(max_items), items_b(max_items), sel(max_items * 8);
+        std::vector<uint64_t> counts(max_items), offsets(max_items);
+        s->nodes.resize((size_t)n * 5);
+        s->tris.resize((size_t)n * 3);
+        s->shade.resize((size_t)n * 4);
+        b.sel = sel.data();
+        b.counts = counts.data();
+        b.offsets = offsets.data();
+        b.nodes = s->nodes.data();
+        b.tris = s->tris.data();
+        b.shade = s->shade.data();
+        items_a[0] = 0;
+        uint32_t level_items = 1, level_first = 0, tri_cursor = 0, depth = 0;
+        uint32_t *cur = items_a.data(), *nxt = items_b.data();
+        while (level_items > 0) {
+            b.items = cur;
+            b.next_items = nxt;
+            b.level_first_node = level_first;
+            b.next_level_first_node = level_first + level_items;
+            b.tri_cursor = tri_cursor;
+            for (uint32_t i = 0; i < level_items; i++) rt_wide_select(b, i);
+            uint64_t run = 0;
+            for (uint32_t i = 0; i < level_items; i++) {
+                offsets[i] = run;
+                run += counts[i];
+            }
+            for (uint32_t i = 0; i < level_items; i++) rt_wide_emit(b, i);
+            level_first += level_items;
+            level_items = (uint32_t)(run >> 32);
+            tri_cursor += (uint32_t)(run & 0xffffffffu);
+            depth++;
+            std::swap(cur, nxt);
+        }
+        s->n_nodes = level_first;
+        s->depth = depth;
+        s->nodes.resize((size_t)s->n_nodes * 5);
+        if (tri_cursor != n) fprintf(stderr, "hostemu: triangle count mismatch %u != %u\n", tri_cursor, n);
+    }
+    s->view.bvh.nodes = s->nodes.data();
+    s->view.bvh.tris = s->tris.data();
+    s->view.shade = s->shade.data();
+    s->view.inst = s->inst.data();
+    s->view.tex_raw = s->tex.empty() ? nullptr : s->tex.data();
+    s->view.tex = 0;
+    s->view.n_layers = desc->texture_layer_count;
+    s->view.sky = mk3(desc->sky_color[0], desc->sky_color[1], desc->sky_color[2]);
+    return s;
+}
+
+void emu_scene_destroy(emu_scene *s) { delete s; }
+uint32_t emu_scene_node_count(const emu_scene *s) { return s->n_nodes; }
+uint32_t emu_scene_depth(const emu_scene *s) { return s->depth; }
+
+/* structural check of the emitted tree. 0 = ok */
+int emu_scene_validate(const emu_scene *s) {
+    const uint32_t n = s->n_tris;
+    if (n == 0) return 0;
+    std::vector<uint8_t> seen_tri(n, 0), seen_gid(n, 0), seen_node(s->n_nodes, 0);
+    std::vector<uint32_t> stack = {0};
+    seen_node[0] = 1;
+    while (!stack.empty()) {
+        const uint32_t ni = stack.back();
+        stack.pop_back();
+        const rt_uint4 *np = &s->nodes[(size_t)ni * 5];
+        const float p[3] = {rt_u2f(np[0].x), rt_u2f(np[0].y), rt_u2f(np[0].z)};
+        const float sc[3] = {rt_u2f((np[0].w & 0xffu) << 23), rt_u2f(((np[0].w >> 8) & 0xffu) << 23),
+                             rt_u2f(((np[0].w >> 16) & 0xffu) << 23)};
+        const uint32_t imask = np[0].w >> 24;
+        const uint32_t q[6][2] = {{np[2].x, np[2].y}, {np[2].z, np[2].w}, {np[3].x, np[3].y},
+                                  {np[3].z, np[3].w}, {np[4].x, np[4].y}, {np[4].z, np[4].w}};
+        uint32_t rank = 0;
+        for (int slot = 0; slot < 8; slot++) {
+            const uint32_t meta = ((slot < 4 ? np[1].z : np[1].w) >> ((slot & 3) * 8)) & 0xffu;
+            const bool inner = (imask >> slot) & 1u;
+            if (meta == 0) {
+                if (inner) return 1;
+                continue;
+            }
+            float lo[3], hi[3];
+            for (int a = 0; a < 3; a++) {
+                lo[a] = p[a] + (float)((q[a][slot >> 2] >> ((slot & 3) * 8)) & 0xffu) * sc[a];
+                hi[a] = p[a] + (float)((q[3 + a][slot >> 2] >> ((slot & 3) * 8)) & 0xffu) * sc[a];
+            }
+            if (inner) {
+                if (meta != (0x20u | (24u + (uint32_t)slot))) return 2;
+                const uint32_t child = np[1].x + rank++;
+                if (child >= s->n_nodes || seen_node[child]) return 3;
+                seen_node[child] = 1;
+                /* the child's own origin must lie inside the decoded box */
+                const rt_uint4 *cp = &s->nodes[(size_t)child * 5];
+                const float cpv[3] = {rt_u2f(cp[0].x), rt_u2f(cp[0].y), rt_u2f(cp[0].z)};
+                for (int a = 0; a < 3; a++)
+                    if (cpv[a] < lo[a] || cpv[a] > hi[a]) return 4;
+                stack.push_back(child);
+            } else {
+                const uint32_t cnt = rt_popc(meta >> 5), off = meta & 31u;
+                if (cnt < 1 || cnt > 3 || (meta >> 5) != (1u << cnt) - 1u) return 5;
+                for (uint32_t t = 0; t < cnt; t++) {
+                    const uint32_t tri = np[1].y + off + t;
+                    if (tri >= n || seen_tri[tri]) return 6;
+                    seen_tri[tri] = 1;
+                    const rt_float4 *tp = &s->tris[(size_t)tri * 3];
+                    const uint32_t gid = rt_f2u(tp[2].w);
+                    if (gid >= n || seen_gid[gid]) return 7;
+                    seen_gid[gid] = 1;
+                    for (int k = 0; k < 3; k++) {
+                        const float v[3] = {tp[k].x, tp[k].y, tp[k].z};
+                        for (int a = 0; a < 3; a++)
+                            if (v[a] < lo[a] || v[a] > hi[a]) return 8;
+                    }
+                }
+            }
+        }
+    }
+    for (uint32_t i = 0; i < n; i++)
+        if (!seen_tri[i] || !seen_gid[i]) return 9;
+    for (uint32_t i = 0; i < s->n_nodes; i++)
+        if (!seen_node[i]) return 10;
+    return 0;
+}
+
+void emu_intersect(const emu_scene *s, uint64_t n, const float *org, const float *dir, float tnear, float tfar,
+                   int32_t *inst, int32_t *prim, float *u, float *v, float *t) {
+    for (uint64_t i = 0; i < n; i++) {
+        const RtHit h = rt_traverse(s->view.bvh, mk3(org[i * 3], org[i * 3 + 1], org[i * 3 + 2]),
+                                    mk3(dir[i * 3], dir[i * 3 + 1], dir[i * 3 + 2]), tnear, tfar);
+        if (h.tri == RT_MISS) {
+            inst[i] = -1;
+            prim[i] = -1;
+            u[i] = 0;
+            v[i] = 0;
+            t[i] = tfar;
+        } else {
+            const uint32_t ii = rt_f2u(s->shade[(size_t)h.tri * 4 + 3].w);
+            inst[i] = (int32_t)ii;
+            prim[i] = (int32_t)(h.gid - s->inst[ii].first_tri);
+            u[i] = h.u;
+            v[i] = h.v;
+            t[i] = h.t;
+        }
+    }
+}
+
+/* emulates rt_render_frame: kind 0 = k_megakernel, 1 = generate / extend / shade loop */
+uint64_t emu_render(const emu_scene *s, int kind, const rt_camera *camera, const rt_render_params *params,
+                    float *accum, uint8_t *rgba8, uint32_t *rng_out) {
+    RtFrameParams p;
+    p.cam.center = mk3(camera->center[0], camera->center[1], camera->center[2]);
+    p.cam.pixel00 = mk3(camera->pixel00_loc[0], camera->pixel00_loc[1], camera->pixel00_loc[2]);
+    p.cam.du = mk3(camera->pixel_delta_u[0], camera->pixel_delta_u[1], camera->pixel_delta_u[2]);
+    p.cam.dv = mk3(camera->pixel_delta_v[0], camera->pixel_delta_v[1], camera->pixel_delta_v[2]);
+    p.cam.w = camera->img_size[0];
+    p.cam.h = camera->img_size[1];
+    p.max_depth = params->max_depth;
+    p.spp = params->sample_count;
+    p.seed_salt = params->shard.seed_salt;
+    p.rank = params->shard.rank;
+    p.world = params->shard.world;
+    p.tile_size = params->shard.tile_size;
+    p.wavefront_seed = kind == 1;
+    p.clamp_samples = kind == 1;
+    const uint32_t n_pix = (uint32_t)p.cam.w * (uint32_t)p.cam.h;
+    std::vector<rt_float4> acc(n_pix, rt_mk_float4(0, 0, 0, 0));
+    std::vector<uint32_t> bytes(n_pix, 0), rng_final(n_pix, 0);
+    unsigned long long rays = 0;
+    if (kind == 0) {
+        for (int y = 0; y < p.cam.h; y++)
+            for (int x = 0; x < p.cam.w; x++) {
+                if (!rt_owns_pixel(p, x, y)) continue;
+                XorShift32 rng;
+                const f3 sum = rt_megakernel_pixel(s->view, p, x, y, rng, rays);
+                const size_t pix = (size_t)y * p.cam.w + x;
+                acc[pix] = rt_mk_float4(sum.x, sum.y, sum.z, (float)p.spp);
+                bytes[pix] = rt_resolve_pixel(sum.x, sum.y, sum.z, (float)p.spp);
+                rng_final[pix] = rng.a;
+            }
+    } else {
+        std::vector<rt_float4> org(n_pix), hit(n_pix);
+        std::vector<rt_uint2> dir(n_pix), att(n_pix), rad(n_pix), prog(n_pix);
+        std::vector<uint32_t> rng(n_pix), q0(n_pix), q1(n_pix);
+        uint32_t counts[2] = {0, 0};
+        RtWavefrontState w;
+        w.org = org.data();
+        w.dir = dir.data();
+        w.att = att.data();
+        w.rad = rad.data();
+        w.hit = hit.data();
+        w.prog = prog.data();
+        w.rng = rng.data();
+        w.queue[0] = q0.data();
+        w.queue[1] = q1.data();
+        w.count[0] = &counts[0];
+        w.count[1] = &counts[1];
+        RtFrameOut out;
+        out.accum = acc.data();
+        out.rgba8 = bytes.data();
+        out.rng = rng_final.data();
+        for (uint32_t pix = 0; pix < n_pix; pix++)
+            if (rt_wf_generate_pixel(p, w, out, pix)) w.queue[0][counts[0]++] = pix;
+        int cur = 0;
+        while (counts[cur]) {
+            counts[cur ^ 1] = 0;
+            rays += counts[cur];
+            for (uint32_t i = 0; i < counts[cur]; i++) rt_wf_extend_pixel(s->view, w, w.queue[cur][i]);
+            for (uint32_t i = 0; i < counts[cur]; i++) {
+                const uint32_t pix = w.queue[cur][i];
+                if (rt_wf_shade_pixel(s->view, p, w, out, pix)) w.queue[cur ^ 1][counts[cur ^ 1]++] = pix;
+            }
+            cur ^= 1;
+        }
+        for (uint32_t pix = 0; pix < n_pix; pix++) {
+            const int x = (int)(pix % (uint32_t)p.cam.w), y = (int)(pix / (uint32_t)p.cam.w);
+            if (rt_owns_pixel(p, x, y)) bytes[pix] = rt_resolve_pixel(acc[pix].x, acc[pix].y, acc[pix].z, (float)p.spp);
+            rng_final[pix] = rng[pix];
+        }
+    }
+    if (accum) memcpy(accum, acc.data(), (size_t)n_pix * 16);
+    if (rgba8) memcpy(rgba8, bytes.data(), (size_t)n_pix * 4);
+    if (rng_out) memcpy(rng_out, rng_final.data(), (size_t)n_pix * 4);
+    return rays;
+}
+
+} /* extern "C" */
