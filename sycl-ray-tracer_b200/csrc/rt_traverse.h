@@ -90,7 +90,9 @@ RT_HD rt_float4 rt_ldg(const rt_float4 *p) {
 /* replicate the msb of every byte over the byte (PRMT with sign-replicate selectors) */
 RT_HD uint32_t rt_sign_extend_s8x4(uint32_t x) {
 #if RT_DEVICE_CODE
-    return __byte_perm(x, 0, 0xba98);
+    uint32_t r; /* __byte_perm() masks the selector to 3 bits; the replicate bit needs raw prmt */
+    asm("prmt.b32 %0, %1, %1, 0xba98;" : "=r"(r) : "r"(x));
+    return r;
 #else
     uint32_t r = 0;
     for (int i = 0; i < 4; i++)
