@@ -1,0 +1,381 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the path-tracing hot path on B200.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --steps K --warmup W     # the reference's algorithm on host cores
+
+Workload (BASELINE.json configs[2], the scene the north-star target is quoted on): Sponza-scale
+synthetic scene (~261 k triangles, textured, sky), 1920x1080, 256 spp, max depth 10, megakernel and
+wavefront. One "step" = one render_frame of that configuration.
+
+  value      Mrays/s, whole job, scene resident in HBM, device-timed (CUDA events on the launch
+             stream; per-step event pairs; L2 flushed between steps; max over ranks)
+  e2e        the same metric through the public API with HOST buffers: every step uploads the
+             scene from host memory (rt_scene_create), builds the BVH (rt_scene_commit), renders
+             and reads the RGBA8 image back to the host
+  roofline   memory-bound traversal roofline of the dominant kernel: algorithmic bytes
+             = rays * B(N) + samples * 16, B(N) = ceil(log8(N/4))*80 + 4*48 + 128 (+96 wavefront)
+  cpu_baseline  the oracle (CPU restatement of the reference, own SAH BVH instead of Embree)
+             timed on the box's host cores on a bounded sample of the same workload
+
+N > 1 (torchrun): spp sharding, weak scaling — every rank renders the full frame with its own
+256 spp (distinct seed salt), the fp32 accumulation buffers are combined with an NCCL all-reduce
+over NVLink inside the timed region and rank 0 resolves the image.
+"""
+import argparse
+import importlib
+import json
+import math
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+PKG = "sycl-ray-tracer_b200"
+
+WORKLOADS = {
+    # name: (scene factory name, kwargs, width, height, spp, depth)
+    "c1_cube": ("cube_scene", {}, 256, 256, 1, 8),
+    "c2_cornell": ("cornell_scene", {}, 1920, 1080, 64, 10),
+    "c3_sponza_scale": ("sponza_scale_scene", {}, 1920, 1080, 256, 10),
+    "c4_heightfield_10m": ("big_mesh_scene", {}, 3840, 2160, 16, 10),
+}
+
+
+def algorithmic_bytes_per_ray(n_tris, wavefront):
+    """one root-to-leaf descent of a balanced 8-wide tree with 4-triangle leaves + one
+    hit's shading gather (+ the reference's queue record for the wavefront)."""
+    levels = max(1, math.ceil(math.log(max(n_tris / 4.0, 1.0001), 8)))
+    return levels * 80 + 4 * 48 + 128 + (96 if wavefront else 0)
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.path = index, None, None
+
+    def start(self):
+        try:
+            f = tempfile.NamedTemporaryFile("w", suffix=".csv", delete=False)
+            self.path = f.name
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if not self.proc:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        try:
+            for line in open(self.path):
+                c = [x.strip() for x in line.split(",")]
+                if len(c) < 7:
+                    continue
+                try:
+                    sm.append(float(c[0]))
+                    mx.append(float(c[1]))
+                except ValueError:
+                    continue
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            # median under load = median of the upper half of the samples (idle samples before/after)
+            s = sorted(sm)
+            out.update(sm_mhz=s[len(s) // 2], sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+def build_scene_data(workload):
+    scenes = importlib.import_module(PKG + ".scenes")
+    fac, kw, w, h, spp, depth = WORKLOADS[workload]
+    return getattr(scenes, fac)(**kw), w, h, spp, depth
+
+
+def cpu_reference_run(data, w, h, depth, mode, target_s, threads=0):
+    """Time the oracle (CPU restatement of the reference's trace_ray/material code, own SAH BVH in
+    place of Embree's rtcIntersect1) on a bounded sample of the workload: a centred crop of the full
+    frame at reduced spp (Mrays/s is spp-independent, benchmark_avg.csv:12-19)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import _oracle
+    osc = _oracle.Scene(data)
+    ocam = _oracle.camera_for(data, w, h)
+    cw, ch = min(w, 480), min(h, 270)
+    crop = ((w - cw) // 2, (h - ch) // 2, (w - cw) // 2 + cw, (h - ch) // 2 + ch)
+    probe = osc.render(ocam, mode, depth, 1, use_bvh=True, crop=crop, threads=threads)  # also builds the BVH
+    probe = osc.render(ocam, mode, depth, 1, use_bvh=True, crop=crop, threads=threads)
+    rate = probe["ray_count"] / max(probe["seconds"], 1e-9)
+    spp = int(max(1, min(64, round(target_s * rate / max(probe["ray_count"], 1)))))
+    cores = _oracle.lib().orc_max_threads() if threads <= 0 else threads
+    sample = f"{cw}x{ch} centre crop of the {w}x{h} frame, {spp} spp, depth {depth}, {'wavefront' if mode else 'megakernel'} seeding"
+
+    def step():
+        r = osc.render(ocam, mode, depth, spp, use_bvh=True, crop=crop, threads=threads)
+        return r["ray_count"], r["seconds"], cw * ch * spp
+    return step, cores, sample
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    data, w, h, spp, depth = build_scene_data(args.workload)
+    step, cores, sample = cpu_reference_run(data, w, h, depth, 0, args.cpu_seconds)
+    for _ in range(args.warmup):
+        step()
+    rays = secs = samples = 0
+    for _ in range(args.steps):
+        r, s, n = step()
+        rays, secs, samples = rays + r, secs + s, samples + n
+    val = rays / secs / 1e6
+    line = {
+        "impl": "reference", "metric": "Mrays/s", "value": val, "unit": "Mrays/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": secs / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "msamples_per_s": samples / secs / 1e6,
+        "config": {"workload": args.workload, "triangles": data.triangle_count, "width": w, "height": h,
+                   "spp": spp, "max_depth": depth, "renderer": "megakernel",
+                   "note": "reference algorithm on host cores: oracle C++ restatement + own SAH BVH (Embree/SYCL absent, reference unbuildable here)"},
+        "cpu_baseline": {"value": val, "unit": "Mrays/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c3_sponza_scale", choices=sorted(WORKLOADS))
+    ap.add_argument("--renderer", default="both", choices=["both", "megakernel", "wavefront"])
+    ap.add_argument("--spp", type=int, default=0, help="override the workload's samples per pixel")
+    ap.add_argument("--cpu-seconds", type=float, default=6.0, help="target seconds per CPU-baseline step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import numpy as np
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.gpus > 1 and world == 1:
+        print("bench.py --gpus N>1 must be launched with torch.distributed.run (one rank per GPU)", file=sys.stderr)
+        return 2
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    pkg = importlib.import_module(PKG)
+    data, w, h, spp, depth = build_scene_data(args.workload)
+    if args.spp:
+        spp = args.spp
+    app = pkg.App(local_rank)
+    stream = torch.cuda.current_stream()
+    app.set_stream(stream.cuda_stream)  # kernels, NCCL and the timing events share one stream
+    scene = pkg.Scene(app, data)
+    stats = scene.stats
+    cam = pkg.Camera((w, h), data.camera_position, data.camera_direction, data.camera_focal_length)
+    shard = {"rank": rank, "world": world, "tile_size": 0, "seed_salt": (rank * 0x9E3779B9) & 0xFFFFFFFF} if world > 1 else None
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+
+    class DevAccum:  # zero-copy view of the renderer's device accumulation buffer
+        def __init__(self, ptr):
+            self.__cuda_array_interface__ = {"shape": (h, w, 4), "typestr": "<f4", "data": (int(ptr), False), "version": 3}
+
+    def barrier():
+        if dist:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def bench_renderer(cls, name):
+        r = cls(app, (w, h), None, depth, spp)
+        accum_t = torch.as_tensor(DevAccum(r.device_accum_ptr), device="cuda") if dist else None
+        out_rgba = torch.empty((h, w, 4), dtype=torch.uint8, device="cuda")
+
+        def step():
+            f = r.render_frame(cam, scene, want=(), shard=shard)
+            if dist:  # combine the accumulation buffers over NVLink, then resolve the image
+                dist.all_reduce(accum_t)
+                if rank == 0:
+                    pkg.resolve(app, accum_t, spp * world, w, h, out_rgba)
+            return f
+        for _ in range(args.warmup):
+            step()
+        ms, kms, rays, launches = 0.0, 0.0, 0, 0
+        sampler = ClockSampler(local_rank)
+        barrier()
+        if rank == 0:
+            sampler.start()
+        for _ in range(args.steps):
+            flush.fill_(1)  # L2 flush between timed iterations (outside the event pair)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            barrier()
+            e0.record(stream)
+            f = step()
+            e1.record(stream)
+            torch.cuda.synchronize()
+            ms += e0.elapsed_time(e1)
+            kms += f.device_ms
+            rays += f.ray_count
+            launches += f.kernel_launches + (1 if (dist and rank == 0) else 0)
+        clocks = sampler.stop() if rank == 0 else None
+        barrier()
+        t = torch.tensor([ms, kms, float(rays), float(launches)], dtype=torch.float64, device="cuda")
+        if dist:
+            mx = t.clone()
+            dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+            sm = t.clone()
+            dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+            ms, kms, rays, launches = float(mx[0]), float(mx[1]), int(sm[2]), int(sm[3])
+        r.close()
+        return {"name": name, "ms": ms, "kernel_ms": kms, "rays": rays, "launches": launches, "clocks": clocks,
+                "last_launches": f.kernel_launches}
+
+    results = []
+    if args.renderer in ("both", "megakernel"):
+        results.append(bench_renderer(pkg.MegakernelRenderer, "megakernel"))
+    if args.renderer in ("both", "wavefront"):
+        results.append(bench_renderer(pkg.WavefrontRenderer, "wavefront"))
+    best = max(results, key=lambda x: x["rays"] / x["ms"])
+    samples_total = w * h * spp * world * args.steps
+
+    # ---- end to end through the public API with host buffers -----------------------------------
+    e2e = None
+    if not args.no_e2e:
+        cls = pkg.MegakernelRenderer if best["name"] == "megakernel" else pkg.WavefrontRenderer
+        r = cls(app, (w, h), None, depth, spp)
+        accum_t = torch.as_tensor(DevAccum(r.device_accum_ptr), device="cuda") if dist else None
+        host_img = torch.empty((h, w, 4), dtype=torch.uint8).pin_memory()
+        h2d = sum(i.positions.nbytes + i.normals.nbytes + i.uvs.nbytes + i.indices.nbytes + 64 + 40 for i in data.instances)
+        h2d += (data.textures.nbytes if data.textures is not None else 0) + 56 + 24
+        d2h = w * h * 4 + 8
+
+        def e2e_step():
+            sc = pkg.Scene(app, data)  # H2D of the scene from host memory + GPU BVH build
+            if dist:
+                f = r.render_frame(cam, sc, want=(), shard=shard)
+                dist.all_reduce(accum_t)
+                pkg.resolve(app, accum_t, spp * world, w, h, host_img)  # D2H of the image
+            else:
+                f = r.render_frame(cam, sc, want=("rgba8",), outputs={"rgba8": host_img})  # D2H inside
+            sc.close()
+            return f
+        e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        e_rays = 0
+        for _ in range(args.steps):
+            e_rays += e2e_step().ray_count
+        barrier()
+        dt = time.perf_counter() - t0
+        t = torch.tensor([dt, float(e_rays)], dtype=torch.float64, device="cuda")
+        if dist:
+            mx = t.clone()
+            dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+            sm = t.clone()
+            dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+            dt, e_rays = float(mx[0]), int(sm[1])
+        e2e = {"value": e_rays / dt / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+               "ms_per_step": dt / args.steps * 1e3,
+               "includes": "scene upload from host + BVH build + render" + (" + NCCL all-reduce" if dist else "") + " + image read-back, every step"}
+        r.close()
+
+    if rank != 0:
+        if dist:
+            dist.destroy_process_group()
+        return 0
+
+    # ---- roofline of the dominant kernel ---------------------------------------------------------
+    peak, peak_src = measured_peak()
+    mega = next((x for x in results if x["name"] == best["name"]), best)
+    wave = best["name"] == "wavefront"
+    bpr = algorithmic_bytes_per_ray(stats["triangle_count"], wave)
+    # per launch: megakernel = 1 launch per step; wavefront = the extend+shade pair averaged over the step's launches
+    n_launch = args.steps * world if not wave else max(1, (mega["launches"] - 2 * args.steps * world))
+    alg_bytes_total = mega["rays"] * bpr + samples_total * 16
+    # per GPU: bytes of one rank's steps / that rank's render-kernel device time (max over ranks)
+    kernel_s = mega["kernel_ms"] * 1e-3
+    achieved = alg_bytes_total / world / kernel_s / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get(best["name"], {}).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "kernel": "k_megakernel" if not wave else "k_wf_extend+k_wf_shade",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                "peak_source": peak_src, "algorithmic_bytes_per_ray": bpr,
+                "algorithmic_bytes_per_launch": alg_bytes_total / max(1, n_launch),
+                "launch_ms": mega["kernel_ms"] / max(1, n_launch / world),
+                "note": "scene (BVH+shading = %.1f MB) is L2-resident; HBM is the stated (conservative) roofline, the physical limit is L1/L2 latency x occupancy" % ((stats["bvh_bytes"] + stats["shading_bytes"]) / 1e6)}
+
+    cpu = None
+    if not args.no_cpu_baseline and world == 1:
+        step, cores, sample = cpu_reference_run(data, w, h, depth, 1 if wave else 0, args.cpu_seconds)
+        rr, ss, _ = step()
+        rr2, ss2, _ = step()
+        cpu = {"value": (rr + rr2) / (ss + ss2) / 1e6, "unit": "Mrays/s", "cores": cores, "kind": "port", "sample": sample}
+
+    value = best["rays"] / (best["ms"] * 1e-3) / 1e6
+    line = {
+        "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": best["ms"] / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "msamples_per_s": samples_total / (best["ms"] * 1e-3) / 1e6,
+        "config": {"workload": args.workload, "triangles": int(stats["triangle_count"]), "width": w, "height": h, "spp": spp,
+                   "max_depth": depth, "renderer": best["name"], "l2": "flushed between timed steps (256 MB write)",
+                   "sharding": "none" if world == 1 else f"spp slices: {spp} spp per GPU, distinct seed salts, NCCL all-reduce of the fp32 accumulation buffer",
+                   "bvh": {"nodes": int(stats["node_count"]), "depth": int(stats["wide_depth"]), "build_ms": float(stats["build_ms"])}},
+        "renderers": {x["name"]: {"mrays_per_s": x["rays"] / (x["ms"] * 1e-3) / 1e6, "ms_per_step": x["ms"] / args.steps,
+                                  "msamples_per_s": samples_total / (x["ms"] * 1e-3) / 1e6,
+                                  "kernel_launches_per_step": x["last_launches"]} for x in results},
+        "clocks": best["clocks"], "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+        "gpu_launches": int(best["launches"]),
+    }
+    print(json.dumps(line))
+    if dist:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

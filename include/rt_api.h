@@ -145,6 +145,9 @@ rt_status rt_context_create(int device, rt_context **out);
 void rt_context_destroy(rt_context *ctx);
 /* the cudaStream_t all work is enqueued on (replaces App::queue, src/app.hpp:33) */
 void *rt_context_stream(rt_context *ctx);
+/* run on a caller-owned cudaStream_t instead (e.g. the stream an NCCL collective is issued on,
+ * so that render + all-reduce are ordered and timed on one stream). The stream is borrowed. */
+rt_status rt_context_set_stream(rt_context *ctx, void *cuda_stream);
 const char *rt_context_device_name(rt_context *ctx);
 /* last error message of this context (ctx may be NULL for creation failures) */
 const char *rt_last_error(rt_context *ctx);

@@ -143,6 +143,10 @@ class App:
     def stream(self):
         return self._lib.rt_context_stream(self.handle)
 
+    def set_stream(self, cuda_stream):
+        """borrow a caller-owned cudaStream_t (int), e.g. torch.cuda.current_stream().cuda_stream"""
+        self.check(self._lib.rt_context_set_stream(self.handle, C.c_void_p(int(cuda_stream))), "rt_context_set_stream")
+
     def check(self, st, what):
         if st != _capi.RT_OK:
             raise RtError(f"{what} failed ({st}): {self._lib.rt_last_error(self.handle).decode()}")

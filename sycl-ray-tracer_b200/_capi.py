@@ -70,6 +70,7 @@ SYMBOLS = {
     "rt_context_create": (C.c_int, [C.c_int, C.POINTER(C.c_void_p)]),
     "rt_context_destroy": (None, [C.c_void_p]),
     "rt_context_stream": (C.c_void_p, [C.c_void_p]),
+    "rt_context_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
     "rt_context_device_name": (C.c_char_p, [C.c_void_p]),
     "rt_scene_create": (C.c_int, [C.c_void_p, C.POINTER(rt_scene_desc), C.POINTER(C.c_void_p)]),
     "rt_scene_commit": (C.c_int, [C.c_void_p]),

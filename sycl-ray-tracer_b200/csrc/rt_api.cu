@@ -97,12 +97,13 @@ rt_status rt_context_create(int device, rt_context **out) {
     ctx->device = device;
     cudaDeviceProp prop;
     if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess ||
-        (e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking)) != cudaSuccess ||
         (e = cudaEventCreate(&ctx->ev0)) != cudaSuccess || (e = cudaEventCreate(&ctx->ev1)) != cudaSuccess) {
         rt_set_error(nullptr, RT_ERR_CUDA, "rt_context_create", cudaGetErrorString(e));
         delete ctx;
         return RT_ERR_CUDA;
     }
+    ctx->stream = ctx->own_stream;
     ctx->sm_count = prop.multiProcessorCount;
     ctx->name = prop.name;
     /* arithmetic-contract self test: a*b+c must not be contracted into an FMA */
@@ -133,11 +134,18 @@ void rt_context_destroy(rt_context *ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
-    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
 }
 
 void *rt_context_stream(rt_context *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+rt_status rt_context_set_stream(rt_context *ctx, void *cuda_stream) {
+    if (!ctx) return RT_ERR_INVALID;
+    RT_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    RT_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->stream = (cudaStream_t)cuda_stream;
+    return RT_OK;
+}
 const char *rt_context_device_name(rt_context *ctx) { return ctx ? ctx->name.c_str() : ""; }
 
 void rt_camera_init(rt_camera *cam, int32_t width, int32_t height, const float position[3], const float direction[3],

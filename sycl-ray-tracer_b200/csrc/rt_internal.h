@@ -16,6 +16,7 @@
 struct rt_context {
     int device = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t own_stream = nullptr; /* created by rt_context_create; `stream` may be borrowed */
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int sm_count = 0;
     std::string name;

@@ -1,0 +1,109 @@
+"""CPU-side check of the CUDA kernels' own source: tests/hostemu compiles the per-item headers
+the kernels are made of (csrc/rt_build.h, rt_traverse.h, rt_shade.h, rt_wavefront.h) with g++ and
+must agree bit for bit with the oracle. (Host emulation is test-only; the product has no CPU path.)"""
+import numpy as np
+import pytest
+
+
+def _rays(n, seed, extent):
+    rs = np.random.RandomState(seed)
+    org = ((rs.rand(n, 3) - 0.5) * 2 * extent).astype(np.float32)
+    d = (rs.rand(n, 3) - 0.5).astype(np.float32)
+    d[::89, 2] = 0.0
+    d[::103, :2] = 0.0
+    return org, d
+
+
+def _scene(scenes, which):
+    return {"cube": lambda: scenes.cube_scene(), "soup": lambda: scenes.random_soup(900, 7, 1.0, 4),
+            "cornell": lambda: scenes.cornell_scene(3), "field": lambda: scenes.big_mesh_scene(40),
+            "sponza_small": lambda: scenes.sponza_scale_scene(32, 2, 9)}[which]()
+
+
+EXT = {"cube": 4.0, "soup": 2.0, "cornell": 1.4, "field": 55.0, "sponza_small": 8.0}
+
+
+@pytest.mark.parametrize("which", ["cube", "soup", "cornell", "field", "sponza_small"])
+def test_tree_is_valid_and_traversal_matches_brute_force(oracle, hostemu, scenes, which):
+    data = _scene(scenes, which)
+    emu, orc = hostemu.Scene(data), oracle.Scene(data)
+    assert emu.validate() == 0
+    org, d = _rays(15000, 21, EXT[which])
+    a, b = orc.intersect(org, d, use_bvh=False), emu.intersect(org, d)
+    assert (a["inst"] >= 0).sum() > 50
+    for k in ("inst", "prim"):
+        assert np.array_equal(a[k], b[k]), k
+    for k in ("t", "u", "v"):
+        assert np.array_equal(a[k].view(np.uint32), b[k].view(np.uint32)), k
+
+
+@pytest.mark.parametrize("which", ["cube", "soup", "cornell", "sponza_small"])
+@pytest.mark.parametrize("kind", [0, 1])
+def test_render_matches_oracle(pkg, oracle, hostemu, scenes, which, kind):
+    data = _scene(scenes, which)
+    emu, orc = hostemu.Scene(data), oracle.Scene(data)
+    w, h = 40, 24
+    cam = pkg.Camera((w, h), data.camera_position, data.camera_direction, data.camera_focal_length)
+    ocam = oracle.camera_for(data, w, h)
+    for f in ("center", "pixel00_loc", "pixel_delta_u", "pixel_delta_v"):  # rt_camera_init == oracle
+        assert list(getattr(cam.c, f)) == list(getattr(ocam, f))
+    e = emu.render(cam, kind, 7, 3)
+    o = orc.render(ocam, kind, 7, 3, use_bvh=True)
+    assert e["ray_count"] == o["ray_count"]
+    assert np.array_equal(e["rng_state"], o["rng_state"])
+    assert np.array_equal(e["accum"].view(np.uint32), o["accum"].view(np.uint32))
+    assert np.array_equal(e["rgba8"], o["rgba8"])
+
+
+def test_edge_scenes(pkg, oracle, hostemu, scenes):
+    """empty scene, 1..4 triangles, degenerate and duplicated triangles"""
+    rs = np.random.RandomState(5)
+    for n in (0, 1, 2, 3, 4, 9):
+        pos = rs.rand(n * 3, 3).astype(np.float32)
+        if n >= 2:
+            pos[3:6] = pos[0:3]            # exact duplicate of triangle 0: tie -> lowest id
+        if n >= 3:
+            pos[8] = pos[7]                # degenerate (zero area)
+        inst = pkg.InstanceData(pos, np.tile(np.float32([0, 0, 1]), (n * 3, 1)), np.zeros((n * 3, 2), np.float32),
+                                np.arange(n * 3, dtype=np.uint32))
+        data = pkg.SceneData([inst], None, (0.5, 0.7, 1.0), (0.5, 0.5, 3), (0, 0, -1), 1.0)
+        emu, orc = hostemu.Scene(data), oracle.Scene(data)
+        assert emu.validate() == 0
+        org = np.tile(np.float32([0.5, 0.5, 3]), (4000, 1)) + (rs.rand(4000, 3).astype(np.float32) - 0.5)
+        d = np.float32([0, 0, -1]) + (rs.rand(4000, 3).astype(np.float32) - 0.5) * 0.6
+        a, b = orc.intersect(org, d), emu.intersect(org, d)
+        for k in ("inst", "prim"):
+            assert np.array_equal(a[k], b[k]), (n, k)
+        assert np.array_equal(a["t"].view(np.uint32), b["t"].view(np.uint32)), n
+        if n == 0:
+            assert (b["inst"] == -1).all()
+
+
+def test_depth_zero_and_salt(pkg, oracle, hostemu, scenes):
+    data = scenes.cube_scene()
+    emu, orc = hostemu.Scene(data), oracle.Scene(data)
+    cam = pkg.Camera((24, 16), data.camera_position, data.camera_direction, data.camera_focal_length)
+    ocam = oracle.camera_for(data, 24, 16)
+    for kind in (0, 1):
+        e, o = emu.render(cam, kind, 0, 3), orc.render(ocam, kind, 0, 3)   # max_depth 0: black, 2 draws per sample
+        assert e["ray_count"] == 0 == o["ray_count"]
+        assert np.array_equal(e["rng_state"], o["rng_state"]) and not e["rgba8"][..., :3].any()
+        e = emu.render(cam, kind, 5, 2, shard={"rank": 0, "world": 1, "seed_salt": 0xABCDEF01})
+        o = orc.render(ocam, kind, 5, 2, seed_salt=0xABCDEF01)
+        assert np.array_equal(e["rng_state"], o["rng_state"])
+        assert np.array_equal(e["accum"].view(np.uint32), o["accum"].view(np.uint32))
+
+
+def test_tile_shards_sum_to_the_full_image(pkg, hostemu, scenes):
+    data = scenes.cornell_scene(2)
+    emu = hostemu.Scene(data)
+    cam = pkg.Camera((48, 40), data.camera_position, data.camera_direction, data.camera_focal_length)
+    for kind in (0, 1):
+        full = emu.render(cam, kind, 6, 2)
+        parts = [emu.render(cam, kind, 6, 2, shard={"rank": r, "world": 3, "tile_size": 16}) for r in range(3)]
+        acc = sum(p["accum"] for p in parts)
+        assert np.array_equal(acc.view(np.uint32), full["accum"].view(np.uint32))   # x + 0 is exact
+        assert np.array_equal(sum(p["rgba8"].astype(np.uint32) for p in parts), full["rgba8"].astype(np.uint32))
+        assert sum(p["ray_count"] for p in parts) == full["ray_count"]
+        owned = [(p["accum"][..., 3] > 0) for p in parts]
+        assert (sum(o.astype(int) for o in owned) == 1).all()                      # a partition of the pixels
