@@ -213,9 +213,18 @@ RT_HD uint32_t rt_node_test(const RtRayBox &rb, rt_uint4 n0, rt_uint4 n1, rt_uin
     float idx = sx * rb.rcp.x, idy = sy * rb.rcp.y, idz = sz * rb.rcp.z;
     float ox = (rt_u2f(n0.x) - rb.org.x) * rb.rcp.x, oy = (rt_u2f(n0.y) - rb.org.y) * rb.rcp.y,
           oz = (rt_u2f(n0.z) - rb.org.z) * rb.rcp.z;
-    /* far planes padded (only positive far values matter, so scaling is monotone) */
-    float idxp = idx * RT_BOX_PAD, idyp = idy * RT_BOX_PAD, idzp = idz * RT_BOX_PAD;
-    float oxp = ox * RT_BOX_PAD, oyp = oy * RT_BOX_PAD, ozp = oz * RT_BOX_PAD;
+    /* Conservative slabs. t = q*id + o cancels when the ray starts next to a plane that lies far
+     * from the node origin p (|q*id|, |o| >> |t|), e.g. a bounce ray leaving an axis-aligned wall:
+     * the absolute error of the three roundings is <= 3 * 2^-24 * (|q*id| + |o|). Near planes are
+     * moved back and far planes forward by 2^-21 * (255*|id| + |o|), so rounding can never cull a
+     * box whose triangle the (exact-difference) triangle test would accept. */
+    const float kErr = 4.76837158e-7f; /* 2^-21 */
+    float ex = rt_fma(255.0f, fabsf(idx), fabsf(ox)) * kErr, ey = rt_fma(255.0f, fabsf(idy), fabsf(oy)) * kErr,
+          ez = rt_fma(255.0f, fabsf(idz), fabsf(oz)) * kErr;
+    float oxp = ox + ex, oyp = oy + ey, ozp = oz + ez;
+    ox -= ex;
+    oy -= ey;
+    oz -= ez;
     uint32_t hitmask = 0;
 #if RT_DEVICE_CODE
 #pragma unroll
@@ -238,9 +247,9 @@ RT_HD uint32_t rt_node_test(const RtRayBox &rb, rt_uint4 n0, rt_uint4 n1, rt_uin
             float tnx = rt_fma(rt_byte_to_float(nx, j), idx, ox);
             float tny = rt_fma(rt_byte_to_float(ny, j), idy, oy);
             float tnz = rt_fma(rt_byte_to_float(nz, j), idz, oz);
-            float tfx = rt_fma(rt_byte_to_float(fx, j), idxp, oxp);
-            float tfy = rt_fma(rt_byte_to_float(fy, j), idyp, oyp);
-            float tfz = rt_fma(rt_byte_to_float(fz, j), idzp, ozp);
+            float tfx = rt_fma(rt_byte_to_float(fx, j), idx, oxp);
+            float tfy = rt_fma(rt_byte_to_float(fy, j), idy, oyp);
+            float tfz = rt_fma(rt_byte_to_float(fz, j), idz, ozp);
             float cmin = rt_max(rt_max3(tnx, tny, tnz), tmin);
             float cmax = rt_min(rt_min3(tfx, tfy, tfz), tmax_pad);
             if (cmin <= cmax) {

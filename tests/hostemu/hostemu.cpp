@@ -378,3 +378,37 @@ uint64_t emu_render(const emu_scene *s, int kind, const rt_camera *camera, const
 }
 
 } /* extern "C" */
+
+/* debugging aid: record the (org, dir) of every segment of pixel (x, y) (megakernel formulation) */
+extern "C" uint32_t emu_trace_pixel(const emu_scene *s, int wavefront_seed, const rt_camera *camera,
+                                    const rt_render_params *params, int x, int y, float *rays6, uint32_t max_rays) {
+    RtCamera cam;
+    cam.center = mk3(camera->center[0], camera->center[1], camera->center[2]);
+    cam.pixel00 = mk3(camera->pixel00_loc[0], camera->pixel00_loc[1], camera->pixel00_loc[2]);
+    cam.du = mk3(camera->pixel_delta_u[0], camera->pixel_delta_u[1], camera->pixel_delta_u[2]);
+    cam.dv = mk3(camera->pixel_delta_v[0], camera->pixel_delta_v[1], camera->pixel_delta_v[2]);
+    cam.w = camera->img_size[0];
+    cam.h = camera->img_size[1];
+    XorShift32 rng;
+    rng.a = rt_pixel_seed(wavefront_seed, x, y, cam.w, cam.h) ^ params->shard.seed_salt;
+    uint32_t n = 0;
+    for (uint32_t sidx = 0; sidx < params->sample_count; sidx++) {
+        RtRayState r = rt_camera_ray(cam, x, y, rng);
+        for (uint32_t depth = 0; depth < params->max_depth; depth++) {
+            if (n < max_rays) {
+                float *o = rays6 + (size_t)n * 6;
+                o[0] = r.org.x; o[1] = r.org.y; o[2] = r.org.z; o[3] = r.dir.x; o[4] = r.dir.y; o[5] = r.dir.z;
+            }
+            n++;
+            const RtHit h = rt_traverse(s->view.bvh, r.org, r.dir, 0.0001f, INFINITY);
+            f3 org = r.org, dir = r.dir, att = r.att, rad = r.rad, res;
+            const bool done = rt_shade_segment(s->view, h, rng, org, dir, att, rad, res);
+            r.org = org;
+            r.dir = round_half3(dir);
+            r.att = round_half3(att);
+            r.rad = round_half3(rad);
+            if (done) break;
+        }
+    }
+    return n;
+}

@@ -107,3 +107,34 @@ def test_tile_shards_sum_to_the_full_image(pkg, hostemu, scenes):
         assert sum(p["ray_count"] for p in parts) == full["ray_count"]
         owned = [(p["accum"][..., 3] > 0) for p in parts]
         assert (sum(o.astype(int) for o in owned) == 1).all()                      # a partition of the pixels
+
+
+def test_rays_leaving_axis_aligned_walls(oracle, hostemu, scenes):
+    """Regression: a bounce ray that starts one ulp off an axis-aligned wall and grazes back into it
+    (t ~ 1.3e-4 > tnear). The quantised slab arithmetic cancels there (|q*id|, |o| >> t), so the
+    node test must be conservative by its own rounding error or the hit is culled."""
+    data = scenes.cornell_scene(2)
+    emu, orc = hostemu.Scene(data), oracle.Scene(data)
+    rs = np.random.RandomState(9)
+    n = 30000
+    org = (rs.rand(n, 3).astype(np.float32) - 0.5) * 2
+    d = (rs.rand(n, 3).astype(np.float32) - 0.5)
+    axis, side = rs.randint(0, 3, n), rs.randint(0, 2, n) * 2 - 1
+    for i in range(n):   # put the origin 0..2 ulp outside / inside a wall, direction barely toward it
+        w = np.float32(side[i])
+        org[i, axis[i]] = np.nextafter(w, np.float32(w * 2)) if i % 3 == 0 else (w if i % 3 == 1 else np.nextafter(w, np.float32(0)))
+        d[i, axis[i]] = np.float32(-side[i] * rs.rand() * 2e-3)
+    a, b = orc.intersect(org, d, use_bvh=False), emu.intersect(org, d)
+    assert ((a["t"] < 1e-3) & (a["inst"] >= 0)).sum() > 100   # the case is actually exercised
+    for k in ("inst", "prim"):
+        assert np.array_equal(a[k], b[k]), k
+    assert np.array_equal(a["t"].view(np.uint32), b["t"].view(np.uint32))
+
+
+def test_cornell_paths_regression(pkg, oracle, hostemu, scenes):
+    data = scenes.cornell_scene(4)
+    emu, orc = hostemu.Scene(data), oracle.Scene(data)
+    cam = pkg.Camera((160, 90), data.camera_position, data.camera_direction, data.camera_focal_length)
+    e = emu.render(cam, 0, 10, 8)
+    o = orc.render(oracle.camera_for(data, 160, 90), 0, 10, 8, use_bvh=True)
+    assert e["ray_count"] == o["ray_count"] and np.array_equal(e["rng_state"], o["rng_state"])
