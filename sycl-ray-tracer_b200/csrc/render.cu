@@ -54,31 +54,121 @@ __global__ void k_intersect(RtScene scene, const RtInstance *inst, uint64_t n, c
 }
 
 /* ------------------------------------------------------------------------------ megakernel */
+/* Persistent lanes. Every lane owns one pixel at a time and walks that pixel's samples back to
+ * back on the pixel's own xorshift stream (F4). The warp alternates between two phases:
+ *   regenerate : lanes whose traversal finished shade their hit (rt_shade_segment), start the next
+ *                bounce / the pixel's next sample, or write the finished pixel and fetch a new one
+ *                (one warp-aggregated atomicAdd on the global pixel counter);
+ *   traverse   : all lanes with a live ray advance one wide node per iteration; the warp leaves the
+ *                loop as soon as kRefill lanes have finished, so finished lanes never idle for long
+ *                (terminated-ray replacement, after Aila & Laine, HPG 2009).
+ * The per-pixel arithmetic is the same as rt_megakernel_pixel (rt_shade.h), which the host
+ * emulation and the oracle comparison exercise; only the scheduling differs. */
+enum { kNeedPixel = 0, kNeedRay = 1, kStart = 2, kTraversing = 3, kHitPending = 4, kExhausted = 5 };
+constexpr int kRefill = 8; /* leave the traversal loop once this many lanes have finished */
+
 __global__ void __launch_bounds__(kMegaBlock) k_megakernel(RtScene scene, RtFrameParams p, RtFrameOut out,
                                                            uint32_t *work_counter, unsigned long long *ray_counter) {
+    const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const uint32_t tiles_x = ((uint32_t)p.cam.w + 7u) / 8u, tiles_y = ((uint32_t)p.cam.h + 3u) / 4u;
-    const uint32_t n_work = tiles_x * tiles_y;
+    const uint32_t n_work = tiles_x * tiles_y * 32u; /* pixel slots in 8x4-tile-major order */
     unsigned long long rays = 0;
-    for (;;) { /* persistent warps: fetch the next 8x4 pixel tile */
-        uint32_t work = 0;
-        if (lane == 0) work = atomicAdd(work_counter, 1u);
-        work = __shfl_sync(0xffffffffu, work, 0);
-        if (work >= n_work) break;
-        const int x = (int)((work % tiles_x) * 8u) + (lane & 7);
-        const int y = (int)((work / tiles_x) * 4u) + (lane >> 3);
-        if (x < p.cam.w && y < p.cam.h && rt_owns_pixel(p, x, y)) {
-            XorShift32 rng;
-            const f3 sum = rt_megakernel_pixel(scene, p, x, y, rng, rays);
-            const size_t pix = (size_t)y * (size_t)p.cam.w + (size_t)x;
-            out.accum[pix] = make_float4(sum.x, sum.y, sum.z, (float)p.spp);
-            out.rgba8[pix] = rt_resolve_pixel(sum.x, sum.y, sum.z, (float)p.spp);
-            out.rng[pix] = rng.a;
+    int mode = kNeedPixel;
+    int x = 0, y = 0;
+    uint32_t s = 0, depth = 0;
+    XorShift32 rng;
+    rng.a = 0;
+    f3 sum = mk3(0.0f, 0.0f, 0.0f);
+    RtRayState r;
+    r.org = r.dir = r.att = r.rad = sum;
+    RtTravState tv;
+    tv.sp = 0;
+
+    for (;;) {
+        /* ---------------- regenerate ---------------- */
+        if (mode == kHitPending) {
+            f3 org = r.org, dir = r.dir, att = r.att, rad = r.rad, res = mk3(0.0f, 0.0f, 0.0f);
+            bool done = rt_shade_segment(scene, tv.best, rng, org, dir, att, rad, res);
+            r.org = org; /* src/render_megakernel.cpp:41-55: re-quantise the ray state (F6) */
+            r.dir = round_half3(dir);
+            r.att = round_half3(att);
+            r.rad = round_half3(rad);
+            depth++;
+            if (!done && depth == p.max_depth) { /* :62, survivors are black (F7) */
+                done = true;
+                res = mk3(0.0f, 0.0f, 0.0f);
+            }
+            if (done) {
+                if (p.clamp_samples) res = mk3(rt_clamp01(res.x), rt_clamp01(res.y), rt_clamp01(res.z));
+                sum = sum + res;
+                s++;
+                mode = kNeedRay;
+            } else {
+                mode = kStart;
+            }
         }
-        __syncwarp();
+        for (;;) { /* warp-uniform: runs until no lane is waiting for a pixel */
+            if (mode == kNeedRay) {
+                while (p.max_depth == 0 && s < p.spp) { /* the bounce loop never runs: black sample */
+                    rng.next();
+                    rng.next();
+                    s++;
+                }
+                if (s == p.spp) { /* pixel finished: :154-158 mean, gamma, image write */
+                    const size_t pix = (size_t)y * (size_t)p.cam.w + (size_t)x;
+                    out.accum[pix] = make_float4(sum.x, sum.y, sum.z, (float)p.spp);
+                    out.rgba8[pix] = rt_resolve_pixel(sum.x, sum.y, sum.z, (float)p.spp);
+                    out.rng[pix] = rng.a;
+                    mode = kNeedPixel;
+                } else {
+                    r = rt_camera_ray(p.cam, x, y, rng); /* 2 draws (F5) */
+                    depth = 0;
+                    mode = kStart;
+                }
+            }
+            const unsigned need = __ballot_sync(full, mode == kNeedPixel);
+            if (!need) break;
+            uint32_t base = 0;
+            const int leader = __ffs(need) - 1;
+            if (lane == leader) base = atomicAdd(work_counter, (uint32_t)__popc(need));
+            base = __shfl_sync(full, base, leader);
+            if (mode == kNeedPixel) {
+                const uint32_t idx = base + (uint32_t)__popc(need & ((1u << lane) - 1u));
+                if (idx >= n_work) {
+                    mode = kExhausted;
+                } else {
+                    const uint32_t tile = idx >> 5, in = idx & 31u;
+                    x = (int)((tile % tiles_x) * 8u + (in & 7u));
+                    y = (int)((tile / tiles_x) * 4u + (in >> 3));
+                    if (x < p.cam.w && y < p.cam.h && rt_owns_pixel(p, x, y)) {
+                        rng.a = rt_pixel_seed(p.wavefront_seed, x, y, p.cam.w, p.cam.h) ^ p.seed_salt;
+                        sum = mk3(0.0f, 0.0f, 0.0f);
+                        s = 0;
+                        mode = kNeedRay;
+                    } /* else: padding / another rank's pixel, fetch again */
+                }
+            }
+        }
+        if (mode == kStart) {
+            rt_trav_init(tv, r.org, r.dir, 0.0001f, INFINITY);
+            rays++;
+            mode = kTraversing;
+        }
+        /* ---------------- traverse ---------------- */
+        const unsigned act0 = __ballot_sync(full, mode == kTraversing);
+        if (!act0) break; /* every lane is exhausted */
+        const int target = __popc(act0) - kRefill;
+        for (;;) {
+            if (mode == kTraversing) {
+                if (!rt_trav_step(scene.bvh, tv)) mode = kHitPending;
+            }
+            const int active = __popc(__ballot_sync(full, mode == kTraversing));
+            if (active == 0 || active <= target) break;
+        }
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) rays += __shfl_xor_sync(0xffffffffu, rays, o);
+    for (int o = 16; o > 0; o >>= 1) rays += __shfl_xor_sync(full, rays, o);
     if (lane == 0 && rays) atomicAdd(ray_counter, rays);
 }
 
@@ -123,16 +213,55 @@ __global__ void __launch_bounds__(kWfBlock) k_wf_generate(RtFrameParams p, RtWav
     }
 }
 
+/* extend: traversal only. Persistent warps pull rays from the id queue through a device-side head
+ * counter and replace finished rays inside the traversal loop (same scheme as the megakernel). */
 __global__ void __launch_bounds__(kWfBlock) k_wf_extend(RtScene scene, RtWavefrontState w, int cur,
                                                          unsigned long long *ray_counter) {
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
     const uint32_t count = *w.count[cur];
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         *w.count[cur ^ 1] = 0u; /* the shade kernel of this bounce appends here */
         atomicAdd(ray_counter, (unsigned long long)count); /* src/render_wavefront.cpp:407 */
     }
     const uint32_t *queue = w.queue[cur];
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
-        rt_wf_extend_pixel(scene, w, queue[i]);
+    int mode = kNeedPixel; /* kNeedPixel = idle, kTraversing, kHitPending, kExhausted */
+    uint32_t pix = 0;
+    RtTravState tv;
+    tv.sp = 0;
+    for (;;) {
+        if (mode == kHitPending) {
+            w.hit[pix] = make_float4(tv.best.t, tv.best.u, tv.best.v, __uint_as_float(tv.best.tri));
+            mode = kNeedPixel;
+        }
+        const unsigned need = __ballot_sync(full, mode == kNeedPixel);
+        if (need) {
+            uint32_t base = 0;
+            const int leader = __ffs(need) - 1;
+            if (lane == leader) base = atomicAdd(w.head, (uint32_t)__popc(need));
+            base = __shfl_sync(full, base, leader);
+            if (mode == kNeedPixel) {
+                const uint32_t idx = base + (uint32_t)__popc(need & ((1u << lane) - 1u));
+                if (idx >= count) {
+                    mode = kExhausted;
+                } else {
+                    pix = queue[idx];
+                    const float4 o = w.org[pix];
+                    rt_trav_init(tv, mk3(o.x, o.y, o.z), rt_unpack_half3(w.dir[pix]), 0.0001f, INFINITY);
+                    mode = kTraversing;
+                }
+            }
+        }
+        const unsigned act0 = __ballot_sync(full, mode == kTraversing);
+        if (!act0) break;
+        const int target = __popc(act0) - kRefill;
+        for (;;) {
+            if (mode == kTraversing) {
+                if (!rt_trav_step(scene.bvh, tv)) mode = kHitPending;
+            }
+            const int active = __popc(__ballot_sync(full, mode == kTraversing));
+            if (active == 0 || active <= target) break;
+        }
     }
 }
 
@@ -141,6 +270,7 @@ __global__ void __launch_bounds__(kWfBlock) k_wf_shade(RtScene scene, RtFramePar
     __shared__ uint32_t s_warp[kWfBlock / 32];
     __shared__ uint32_t s_base;
     const uint32_t count = *w.count[cur];
+    if (blockIdx.x == 0 && threadIdx.x == 0) *w.head = 0u; /* next bounce's extend starts at slot 0 */
     const uint32_t *queue = w.queue[cur];
     uint32_t *next_queue = w.queue[cur ^ 1];
     const uint32_t stride = gridDim.x * blockDim.x;

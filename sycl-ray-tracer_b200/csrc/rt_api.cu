@@ -418,7 +418,7 @@ rt_status rt_renderer_create(rt_context *ctx, rt_renderer_kind kind, int32_t wid
         if ((e = dev_alloc(&r->d_rng, n)) != cudaSuccess) break;
         if ((e = dev_alloc(&r->d_work, 1)) != cudaSuccess) break;
         if ((e = dev_alloc(&r->d_rays, 1)) != cudaSuccess) break;
-        if ((e = dev_alloc(&r->d_counts, 2)) != cudaSuccess) break;
+        if ((e = dev_alloc(&r->d_counts, 4)) != cudaSuccess) break;
         if ((e = cudaMallocHost((void **)&r->h_counts, 2 * sizeof(uint32_t))) != cudaSuccess) break;
         if ((e = cudaMallocHost((void **)&r->h_rays, sizeof(unsigned long long))) != cudaSuccess) break;
         if (kind == RT_MEGAKERNEL) {
@@ -436,6 +436,7 @@ rt_status rt_renderer_create(rt_context *ctx, rt_renderer_kind kind, int32_t wid
             if ((e = dev_alloc(&r->wf.queue[1], n)) != cudaSuccess) break;
             r->wf.count[0] = r->d_counts;
             r->wf.count[1] = r->d_counts + 1;
+            r->wf.head = r->d_counts + 2;
             if ((e = rt_wavefront_grid(ctx->sm_count, &r->grid_extend, &r->grid_shade)) != cudaSuccess) break;
         }
     } while (0);
@@ -518,7 +519,7 @@ rt_status rt_render_frame(rt_renderer *r, const rt_scene *scene, const rt_camera
         RT_CUDA_TRY(ctx, rt_launch_megakernel(st, r->grid_mega, scene->view, p, out, r->d_work, r->d_rays));
         launches++;
     } else {
-        RT_CUDA_TRY(ctx, cudaMemsetAsync(r->d_counts, 0, 2 * sizeof(uint32_t), st));
+        RT_CUDA_TRY(ctx, cudaMemsetAsync(r->d_counts, 0, 4 * sizeof(uint32_t), st));
         RT_CUDA_TRY(ctx, rt_launch_wf_generate(st, r->grid_shade, p, r->wf, out));
         launches++;
         /* every pixel traces at most spp * max_depth segments, one per bounce iteration */

@@ -268,70 +268,82 @@ RT_HD uint32_t rt_node_test(const RtRayBox &rb, rt_uint4 n0, rt_uint4 n1, rt_uin
 #define RT_COUNT_TRI()
 #endif
 
-RT_HD RtHit rt_traverse(const RtBvh &bvh, f3 org, f3 dir, float tnear, float tfar) {
+/* Resumable traversal state: the persistent kernels advance it one wide node at a time so that a
+ * warp can leave the loop, replace its finished rays and come back (rt_trav_step). */
+struct RtTravState {
+    RtRayTri rt;
+    RtRayBox rb;
+    float tnear, tmax_pad;
     RtHit best;
-    best.t = tfar;
-    best.u = 0.0f;
-    best.v = 0.0f;
-    best.tri = RT_MISS;
-    best.gid = RT_MISS;
-    const RtRayTri rt = rt_ray_tri_setup(org, dir);
-    const RtRayBox rb = rt_ray_box_setup(org, dir);
-    const uint32_t oct_inv = rb.oct_inv4 & 7u;
-    float tmax_pad = tfar * RT_BOX_PAD;
-
+    uint32_t ng_x, ng_y; /* current node group: (child base, child hit bits << 24 | imask) */
+    int sp;
     uint32_t stack_x[RT_STACK_SIZE], stack_y[RT_STACK_SIZE];
-    int sp = 0;
-    uint32_t ng_x = 0, ng_y = 0x80000000u; /* node group: (child base, hits<<24 | imask) */
-    uint32_t tg_x = 0, tg_y = 0;           /* triangle group: (tri base, hit bits) */
+};
 
-    for (;;) {
-        if (ng_y > 0x00ffffffu) {
-            const uint32_t imask = ng_y & 0xffu;
-            const int bit = rt_bfind(ng_y);
-            ng_y &= ~(1u << bit);
-            if (ng_y > 0x00ffffffu) {
-                stack_x[sp] = ng_x;
-                stack_y[sp] = ng_y;
-                sp++;
-            }
-            const uint32_t slot = ((uint32_t)bit - 24u) ^ oct_inv;
-            const uint32_t rel = (uint32_t)rt_popc(imask & ~(0xffffffffu << slot));
-            const rt_uint4 *np = bvh.nodes + (size_t)(ng_x + rel) * 5;
-            const rt_uint4 n0 = rt_ldg(np), n1 = rt_ldg(np + 1), n2 = rt_ldg(np + 2),
-                           n3 = rt_ldg(np + 3), n4 = rt_ldg(np + 4);
-            RT_COUNT_NODE();
-            const uint32_t hm = rt_node_test(rb, n0, n1, n2, n3, n4, tnear, tmax_pad);
-            ng_x = n1.x;
-            ng_y = (hm & 0xff000000u) | (n0.w >> 24);
-            tg_x = n1.y;
-            tg_y = hm & 0x00ffffffu;
-        } else {
-            tg_x = ng_x;
-            tg_y = ng_y;
-            ng_x = 0;
-            ng_y = 0;
-        }
-        while (tg_y) {
-            const int i = rt_ctz(tg_y);
-            tg_y &= tg_y - 1;
-            const uint32_t slot = tg_x + (uint32_t)i;
-            const rt_float4 *tp = bvh.tris + (size_t)slot * 3;
-            const rt_float4 a = rt_ldg(tp), b = rt_ldg(tp + 1), c = rt_ldg(tp + 2);
-            RT_COUNT_TRI();
-            const float before = best.t;
-            rt_tri_test(rt, mk3(a.x, a.y, a.z), mk3(b.x, b.y, b.z), mk3(c.x, c.y, c.z), slot,
-                        rt_f2u(c.w), tnear, best);
-            if (best.t != before) tmax_pad = best.t * RT_BOX_PAD;
-        }
-        if (ng_y <= 0x00ffffffu) {
-            if (sp == 0) break;
-            sp--;
-            ng_x = stack_x[sp];
-            ng_y = stack_y[sp];
-        }
+RT_HD void rt_trav_init(RtTravState &s, f3 org, f3 dir, float tnear, float tfar) {
+    s.best.t = tfar;
+    s.best.u = 0.0f;
+    s.best.v = 0.0f;
+    s.best.tri = RT_MISS;
+    s.best.gid = RT_MISS;
+    s.rt = rt_ray_tri_setup(org, dir);
+    s.rb = rt_ray_box_setup(org, dir);
+    s.tnear = tnear;
+    s.tmax_pad = tfar * RT_BOX_PAD;
+    s.sp = 0;
+    s.ng_x = 0;
+    s.ng_y = 0x80000000u; /* the root, as the only child of a virtual group */
+}
+
+/* Visit the nearest pending wide node and intersect its leaf triangles.
+ * Returns false when the traversal is complete (s.best is final). */
+RT_HD bool rt_trav_step(const RtBvh &bvh, RtTravState &s) {
+    const uint32_t oct_inv = s.rb.oct_inv4 & 7u;
+    const uint32_t imask = s.ng_y & 0xffu;
+    const int bit = rt_bfind(s.ng_y);
+    s.ng_y &= ~(1u << bit);
+    if (s.ng_y > 0x00ffffffu) { /* siblings still pending: keep the group for later */
+        s.stack_x[s.sp] = s.ng_x;
+        s.stack_y[s.sp] = s.ng_y;
+        s.sp++;
     }
-    return best;
+    const uint32_t slot = ((uint32_t)bit - 24u) ^ oct_inv;
+    const uint32_t rel = (uint32_t)rt_popc(imask & ~(0xffffffffu << slot));
+    const rt_uint4 *np = bvh.nodes + (size_t)(s.ng_x + rel) * 5;
+    const rt_uint4 n0 = rt_ldg(np), n1 = rt_ldg(np + 1), n2 = rt_ldg(np + 2), n3 = rt_ldg(np + 3),
+                   n4 = rt_ldg(np + 4);
+    RT_COUNT_NODE();
+    const uint32_t hm = rt_node_test(s.rb, n0, n1, n2, n3, n4, s.tnear, s.tmax_pad);
+    s.ng_x = n1.x;
+    s.ng_y = (hm & 0xff000000u) | (n0.w >> 24);
+    uint32_t tg_y = hm & 0x00ffffffu;
+    while (tg_y) {
+        const int i = rt_ctz(tg_y);
+        tg_y &= tg_y - 1;
+        const uint32_t tslot = n1.y + (uint32_t)i;
+        const rt_float4 *tp = bvh.tris + (size_t)tslot * 3;
+        const rt_float4 a = rt_ldg(tp), b = rt_ldg(tp + 1), c = rt_ldg(tp + 2);
+        RT_COUNT_TRI();
+        const float before = s.best.t;
+        rt_tri_test(s.rt, mk3(a.x, a.y, a.z), mk3(b.x, b.y, b.z), mk3(c.x, c.y, c.z), tslot, rt_f2u(c.w),
+                    s.tnear, s.best);
+        if (s.best.t != before) s.tmax_pad = s.best.t * RT_BOX_PAD;
+    }
+    if (s.ng_y <= 0x00ffffffu) {
+        if (s.sp == 0) return false;
+        s.sp--;
+        s.ng_x = s.stack_x[s.sp];
+        s.ng_y = s.stack_y[s.sp];
+    }
+    return true;
+}
+
+RT_HD RtHit rt_traverse(const RtBvh &bvh, f3 org, f3 dir, float tnear, float tfar) {
+    RtTravState s;
+    rt_trav_init(s, org, dir, tnear, tfar);
+    while (rt_trav_step(bvh, s)) {
+    }
+    return s.best;
 }
 
 #endif /* RT_TRAVERSE_H */

@@ -24,6 +24,7 @@ struct RtWavefrontState {
     uint32_t *rng;      /* XorShift32State per pixel (src/render_wavefront.hpp:52) */
     uint32_t *queue[2]; /* live pixel ids, double buffered */
     uint32_t *count[2];
+    uint32_t *head;     /* extend kernel's fetch cursor into queue[cur] */
 };
 
 RT_HD rt_uint2 rt_pack_half3(f3 v) {

@@ -197,7 +197,10 @@ def cornell_scene(sphere_subdiv=5):
     I.append(InstanceData(*quad((-1, -1, 1), (-1, -1, -1), (-1, 1, -1), (-1, 1, 1), (1, 0, 0)), None, Material.diffuse(red)))
     I.append(InstanceData(*quad((1, -1, -1), (1, -1, 1), (1, 1, 1), (1, 1, -1), (-1, 0, 0)), None, Material.diffuse(green)))
     I.append(InstanceData(*quad((-0.25, 0.998, -0.25), (0.25, 0.998, -0.25), (0.25, 0.998, 0.25), (-0.25, 0.998, 0.25),
-                                (0, -1, 0)), None, Material.diffuse((0, 0, 0), emissive=(15, 15, 15))))
+                                (0, -1, 0)), None, Material.diffuse((0.78, 0.78, 0.78), emissive=(15, 15, 15))))
+    # (the light keeps a non-black albedo on purpose: under the reference's radiance rule (F7) the
+    # emitted term is scaled by the WHOLE path attenuation, emitter included, so a black-albedo
+    # emitter would contribute nothing and the box would render black)
     sp = icosphere(sphere_subdiv)
     I.append(InstanceData(*sp, trs((0.4, -0.65, 0.3), (0.35,) * 3), Material.dielectric(1.5)))
     I.append(InstanceData(*sp, trs((-0.4, -0.65, -0.3), (0.35,) * 3), Material.metallic((0.9, 0.9, 0.9), 0.1)))

@@ -108,7 +108,7 @@ def test_c2_cornell_materials(pkg, oracle, app, scenes, kind):
     assert np.array_equal(f.rng_state, o["rng_state"])
     assert np.array_equal(f.accum.view(np.uint32), o["accum"].view(np.uint32))
     assert np.array_equal(f.rgba8, o["rgba8"])
-    assert f.accum[..., :3].max() > 1.0 if kind == 0 else True   # emissive light is visible
+    assert f.accum[..., :3].max() > 0.5   # the emissive ceiling quad lights the box (not an all-black frame)
 
 
 @pytest.mark.parametrize("kind", [0, 1])
