@@ -65,7 +65,29 @@ __global__ void k_intersect(RtScene scene, const RtInstance *inst, uint64_t n, c
  * The per-pixel arithmetic is the same as rt_megakernel_pixel (rt_shade.h), which the host
  * emulation and the oracle comparison exercise; only the scheduling differs. */
 enum { kNeedPixel = 0, kNeedRay = 1, kStart = 2, kTraversing = 3, kHitPending = 4, kExhausted = 5 };
-constexpr int kRefill = 8; /* leave the traversal loop once this many lanes have finished */
+
+/* Traverse phase shared by the megakernel and the wavefront extend kernel (warp-uniform control
+ * flow): node steps for every lane with node work until `refill` lanes have run out of nodes, or
+ * `tri_lanes` lanes have triangles pending, or a lane's triangle stack is full; then all pending
+ * triangles are tested together. Lanes left with neither nodes nor triangles become kHitPending. */
+__device__ __forceinline__ void traverse_phase(const RtBvh &bvh, RtTravState &tv, int &mode, int refill, int tri_lanes) {
+    const unsigned full = 0xffffffffu;
+    for (;;) {
+        const bool trav = mode == kTraversing;
+        if (trav && rt_trav_has_node(tv)) rt_trav_node_step(bvh, tv);
+        const unsigned m_node = __ballot_sync(full, trav && rt_trav_has_node(tv));
+        const unsigned m_idle = __ballot_sync(full, trav && !rt_trav_has_node(tv));
+        const unsigned m_tri = __ballot_sync(full, trav && rt_trav_has_tri(tv));
+        const unsigned m_full = __ballot_sync(full, trav && rt_trav_tri_full(tv));
+        if (!m_node || m_full || __popc(m_idle) >= refill || __popc(m_tri) >= tri_lanes) break;
+    }
+    for (;;) { /* drain */
+        const bool tri = mode == kTraversing && rt_trav_has_tri(tv);
+        if (!__any_sync(full, tri)) break;
+        if (tri) rt_trav_tri_step(bvh, tv);
+    }
+    if (mode == kTraversing && !rt_trav_has_node(tv)) mode = kHitPending;
+}
 
 __global__ void __launch_bounds__(kMegaBlock) k_megakernel(RtScene scene, RtFrameParams p, RtFrameOut out,
                                                            uint32_t *work_counter, unsigned long long *ray_counter) {
@@ -158,14 +180,7 @@ __global__ void __launch_bounds__(kMegaBlock) k_megakernel(RtScene scene, RtFram
         /* ---------------- traverse ---------------- */
         const unsigned act0 = __ballot_sync(full, mode == kTraversing);
         if (!act0) break; /* every lane is exhausted */
-        const int target = __popc(act0) - kRefill;
-        for (;;) {
-            if (mode == kTraversing) {
-                if (!rt_trav_step(scene.bvh, tv)) mode = kHitPending;
-            }
-            const int active = __popc(__ballot_sync(full, mode == kTraversing));
-            if (active == 0 || active <= target) break;
-        }
+        traverse_phase(scene.bvh, tv, mode, p.tune_refill, p.tune_tridiv);
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) rays += __shfl_xor_sync(full, rays, o);
@@ -216,7 +231,8 @@ __global__ void __launch_bounds__(kWfBlock) k_wf_generate(RtFrameParams p, RtWav
 /* extend: traversal only. Persistent warps pull rays from the id queue through a device-side head
  * counter and replace finished rays inside the traversal loop (same scheme as the megakernel). */
 __global__ void __launch_bounds__(kWfBlock) k_wf_extend(RtScene scene, RtWavefrontState w, int cur,
-                                                         unsigned long long *ray_counter) {
+                                                         unsigned long long *ray_counter, int tune_refill,
+                                                         int tune_tridiv) {
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const uint32_t count = *w.count[cur];
@@ -254,14 +270,7 @@ __global__ void __launch_bounds__(kWfBlock) k_wf_extend(RtScene scene, RtWavefro
         }
         const unsigned act0 = __ballot_sync(full, mode == kTraversing);
         if (!act0) break;
-        const int target = __popc(act0) - kRefill;
-        for (;;) {
-            if (mode == kTraversing) {
-                if (!rt_trav_step(scene.bvh, tv)) mode = kHitPending;
-            }
-            const int active = __popc(__ballot_sync(full, mode == kTraversing));
-            if (active == 0 || active <= target) break;
-        }
+        traverse_phase(scene.bvh, tv, mode, tune_refill, tune_tridiv);
     }
 }
 
@@ -362,8 +371,8 @@ cudaError_t rt_launch_wf_generate(cudaStream_t st, int grid, const RtFrameParams
 }
 
 cudaError_t rt_launch_wf_extend(cudaStream_t st, int grid, const RtScene &scene, const RtWavefrontState &w, int cur,
-                                unsigned long long *ray_counter) {
-    k_wf_extend<<<grid, kWfBlock, 0, st>>>(scene, w, cur, ray_counter);
+                                unsigned long long *ray_counter, const RtFrameParams &p) {
+    k_wf_extend<<<grid, kWfBlock, 0, st>>>(scene, w, cur, ray_counter, p.tune_refill, p.tune_tridiv);
     return cudaGetLastError();
 }
 

@@ -4,6 +4,7 @@
  * the context's stream.
  */
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -33,6 +34,7 @@ struct rt_renderer {
     uint32_t *h_counts = nullptr;           /* pinned mirror */
     unsigned long long *h_rays = nullptr;   /* pinned */
     int grid_mega = 0, grid_extend = 0, grid_shade = 0;
+    int tune_refill = 8, tune_tridiv = 10; /* RT_TUNE_REFILL / RT_TUNE_TRIDIV override (development) */
 };
 
 namespace {
@@ -410,6 +412,8 @@ rt_status rt_renderer_create(rt_context *ctx, rt_renderer_kind kind, int32_t wid
     r->kind = kind;
     r->w = width;
     r->h = height;
+    if (const char *e = getenv("RT_TUNE_REFILL")) r->tune_refill = atoi(e) > 0 ? atoi(e) : r->tune_refill;
+    if (const char *e = getenv("RT_TUNE_TRIDIV")) r->tune_tridiv = atoi(e) > 0 ? atoi(e) : r->tune_tridiv;
     const size_t n = (size_t)width * (size_t)height;
     cudaError_t e = cudaSuccess;
     do {
@@ -500,6 +504,8 @@ rt_status rt_render_frame(rt_renderer *r, const rt_scene *scene, const rt_camera
     p.tile_size = sh.tile_size;
     p.wavefront_seed = r->kind == RT_WAVEFRONT ? 1 : 0;
     p.clamp_samples = r->kind == RT_WAVEFRONT ? 1 : 0;
+    p.tune_refill = r->tune_refill;
+    p.tune_tridiv = r->tune_tridiv;
     RtFrameOut out;
     out.accum = r->d_accum;
     out.rgba8 = r->d_rgba8;
@@ -529,7 +535,7 @@ rt_status rt_render_frame(rt_renderer *r, const rt_scene *scene, const rt_camera
         while (it < max_iters) {
             const uint64_t batch = (max_iters - it) < 8 ? (max_iters - it) : 8;
             for (uint64_t k = 0; k < batch; k++) {
-                RT_CUDA_TRY(ctx, rt_launch_wf_extend(st, r->grid_extend, scene->view, r->wf, cur, r->d_rays));
+                RT_CUDA_TRY(ctx, rt_launch_wf_extend(st, r->grid_extend, scene->view, r->wf, cur, r->d_rays, p));
                 RT_CUDA_TRY(ctx, rt_launch_wf_shade(st, r->grid_shade, scene->view, p, r->wf, out, cur));
                 launches += 2;
                 cur ^= 1;

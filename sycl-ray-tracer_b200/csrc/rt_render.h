@@ -18,7 +18,7 @@ cudaError_t rt_wavefront_grid(int sm_count, int *grid_extend, int *grid_shade);
 cudaError_t rt_launch_wf_generate(cudaStream_t st, int grid, const RtFrameParams &p, const RtWavefrontState &w,
                                   const RtFrameOut &out);
 cudaError_t rt_launch_wf_extend(cudaStream_t st, int grid, const RtScene &scene, const RtWavefrontState &w, int cur,
-                                unsigned long long *ray_counter);
+                                unsigned long long *ray_counter, const RtFrameParams &p);
 cudaError_t rt_launch_wf_shade(cudaStream_t st, int grid, const RtScene &scene, const RtFrameParams &p,
                                const RtWavefrontState &w, const RtFrameOut &out, int cur);
 cudaError_t rt_launch_resolve(cudaStream_t st, const float *accum, uint32_t *rgba8, uint32_t n_pix, float spp);

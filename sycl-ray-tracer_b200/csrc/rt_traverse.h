@@ -27,7 +27,7 @@
 
 #include "rt_hd.h"
 
-#define RT_STACK_SIZE 40 /* node groups; rt_scene_commit refuses trees deeper than this */
+#define RT_STACK_SIZE 40 /* pending node groups (<= 1 per level); rt_scene_commit refuses deeper trees */
 #define RT_MISS 0xffffffffu
 #define RT_BOX_PAD 1.00000048f /* 1 + 2^-21: far planes / tmax are padded by ~4 ulp */
 
@@ -268,16 +268,24 @@ RT_HD uint32_t rt_node_test(const RtRayBox &rb, rt_uint4 n0, rt_uint4 n1, rt_uin
 #define RT_COUNT_TRI()
 #endif
 
-/* Resumable traversal state: the persistent kernels advance it one wide node at a time so that a
- * warp can leave the loop, replace its finished rays and come back (rt_trav_step). */
+/* Resumable traversal state. The traversal is split into two kinds of unit work so that the
+ * persistent kernels can run each kind with the warp converged:
+ *   rt_trav_node_step : visit one wide node; leaf hits are only RECORDED (a small per-lane stack of
+ *                       triangle groups), not tested;
+ *   rt_trav_tri_step  : test one recorded triangle.
+ * The kernels run node steps for all lanes until enough lanes have triangles pending (or have run out
+ * of nodes), then drain the pending triangles together. Deferring the triangle tests only delays the
+ * shrinking of tmax; the closest hit (min t, then min id) does not depend on the test order. */
+#define RT_TSTACK_SIZE 8
 struct RtTravState {
     RtRayTri rt;
     RtRayBox rb;
     float tnear, tmax_pad;
     RtHit best;
     uint32_t ng_x, ng_y; /* current node group: (child base, child hit bits << 24 | imask) */
-    int sp;
-    uint32_t stack_x[RT_STACK_SIZE], stack_y[RT_STACK_SIZE];
+    int sp, tsp;
+    uint32_t stack_x[RT_STACK_SIZE], stack_y[RT_STACK_SIZE];    /* pending node groups */
+    uint32_t tstack_x[RT_TSTACK_SIZE], tstack_y[RT_TSTACK_SIZE]; /* pending triangle groups */
 };
 
 RT_HD void rt_trav_init(RtTravState &s, f3 org, f3 dir, float tnear, float tfar) {
@@ -291,13 +299,17 @@ RT_HD void rt_trav_init(RtTravState &s, f3 org, f3 dir, float tnear, float tfar)
     s.tnear = tnear;
     s.tmax_pad = tfar * RT_BOX_PAD;
     s.sp = 0;
+    s.tsp = 0;
     s.ng_x = 0;
     s.ng_y = 0x80000000u; /* the root, as the only child of a virtual group */
 }
 
-/* Visit the nearest pending wide node and intersect its leaf triangles.
- * Returns false when the traversal is complete (s.best is final). */
-RT_HD bool rt_trav_step(const RtBvh &bvh, RtTravState &s) {
+RT_HD bool rt_trav_has_node(const RtTravState &s) { return s.ng_y > 0x00ffffffu; }
+RT_HD bool rt_trav_has_tri(const RtTravState &s) { return s.tsp > 0; }
+RT_HD bool rt_trav_tri_full(const RtTravState &s) { return s.tsp >= RT_TSTACK_SIZE; }
+
+/* precondition: rt_trav_has_node(s) && !rt_trav_tri_full(s) */
+RT_HD void rt_trav_node_step(const RtBvh &bvh, RtTravState &s) {
     const uint32_t oct_inv = s.rb.oct_inv4 & 7u;
     const uint32_t imask = s.ng_y & 0xffu;
     const int bit = rt_bfind(s.ng_y);
@@ -316,32 +328,43 @@ RT_HD bool rt_trav_step(const RtBvh &bvh, RtTravState &s) {
     const uint32_t hm = rt_node_test(s.rb, n0, n1, n2, n3, n4, s.tnear, s.tmax_pad);
     s.ng_x = n1.x;
     s.ng_y = (hm & 0xff000000u) | (n0.w >> 24);
-    uint32_t tg_y = hm & 0x00ffffffu;
-    while (tg_y) {
-        const int i = rt_ctz(tg_y);
-        tg_y &= tg_y - 1;
-        const uint32_t tslot = n1.y + (uint32_t)i;
-        const rt_float4 *tp = bvh.tris + (size_t)tslot * 3;
-        const rt_float4 a = rt_ldg(tp), b = rt_ldg(tp + 1), c = rt_ldg(tp + 2);
-        RT_COUNT_TRI();
-        const float before = s.best.t;
-        rt_tri_test(s.rt, mk3(a.x, a.y, a.z), mk3(b.x, b.y, b.z), mk3(c.x, c.y, c.z), tslot, rt_f2u(c.w),
-                    s.tnear, s.best);
-        if (s.best.t != before) s.tmax_pad = s.best.t * RT_BOX_PAD;
+    if (hm & 0x00ffffffu) {
+        s.tstack_x[s.tsp] = n1.y;
+        s.tstack_y[s.tsp] = hm & 0x00ffffffu;
+        s.tsp++;
     }
-    if (s.ng_y <= 0x00ffffffu) {
-        if (s.sp == 0) return false;
+    if (s.ng_y <= 0x00ffffffu && s.sp > 0) { /* no child hit: next pending group */
         s.sp--;
         s.ng_x = s.stack_x[s.sp];
         s.ng_y = s.stack_y[s.sp];
     }
-    return true;
 }
 
+/* precondition: rt_trav_has_tri(s) */
+RT_HD void rt_trav_tri_step(const RtBvh &bvh, RtTravState &s) {
+    const uint32_t base = s.tstack_x[s.tsp - 1];
+    uint32_t bits = s.tstack_y[s.tsp - 1];
+    const int i = rt_ctz(bits);
+    bits &= bits - 1;
+    if (bits) s.tstack_y[s.tsp - 1] = bits;
+    else s.tsp--;
+    const uint32_t tslot = base + (uint32_t)i;
+    const rt_float4 *tp = bvh.tris + (size_t)tslot * 3;
+    const rt_float4 a = rt_ldg(tp), b = rt_ldg(tp + 1), c = rt_ldg(tp + 2);
+    RT_COUNT_TRI();
+    const float before = s.best.t;
+    rt_tri_test(s.rt, mk3(a.x, a.y, a.z), mk3(b.x, b.y, b.z), mk3(c.x, c.y, c.z), tslot, rt_f2u(c.w), s.tnear,
+                s.best);
+    if (s.best.t != before) s.tmax_pad = s.best.t * RT_BOX_PAD;
+}
+
+/* simple front-to-back traversal: triangles are tested right after the node that produced them */
 RT_HD RtHit rt_traverse(const RtBvh &bvh, f3 org, f3 dir, float tnear, float tfar) {
     RtTravState s;
     rt_trav_init(s, org, dir, tnear, tfar);
-    while (rt_trav_step(bvh, s)) {
+    while (rt_trav_has_node(s)) {
+        rt_trav_node_step(bvh, s);
+        while (rt_trav_has_tri(s)) rt_trav_tri_step(bvh, s);
     }
     return s.best;
 }
