@@ -70,11 +70,12 @@ enum { kNeedPixel = 0, kNeedRay = 1, kStart = 2, kTraversing = 3, kHitPending = 
  * flow): node steps for every lane with node work until `refill` lanes have run out of nodes, or
  * `tri_lanes` lanes have triangles pending, or a lane's triangle stack is full; then all pending
  * triangles are tested together. Lanes left with neither nodes nor triangles become kHitPending. */
-__device__ __forceinline__ void traverse_phase(const RtBvh &bvh, RtTravState &tv, int &mode, int refill, int tri_lanes) {
+__device__ __forceinline__ void traverse_phase(const RtBvh &bvh, RtTravState &tv, RtTravStacks &ks, int &mode, int refill,
+                                               int tri_lanes) {
     const unsigned full = 0xffffffffu;
     for (;;) {
         const bool trav = mode == kTraversing;
-        if (trav && rt_trav_has_node(tv)) rt_trav_node_step(bvh, tv);
+        if (trav && rt_trav_has_node(tv)) rt_trav_node_step(bvh, tv, ks);
         const unsigned m_node = __ballot_sync(full, trav && rt_trav_has_node(tv));
         const unsigned m_idle = __ballot_sync(full, trav && !rt_trav_has_node(tv));
         const unsigned m_tri = __ballot_sync(full, trav && rt_trav_has_tri(tv));
@@ -84,7 +85,7 @@ __device__ __forceinline__ void traverse_phase(const RtBvh &bvh, RtTravState &tv
     for (;;) { /* drain */
         const bool tri = mode == kTraversing && rt_trav_has_tri(tv);
         if (!__any_sync(full, tri)) break;
-        if (tri) rt_trav_tri_step(bvh, tv);
+        if (tri) rt_trav_tri_step(bvh, tv, ks);
     }
     if (mode == kTraversing && !rt_trav_has_node(tv)) mode = kHitPending;
 }
@@ -105,7 +106,10 @@ __global__ void __launch_bounds__(kMegaBlock) k_megakernel(RtScene scene, RtFram
     RtRayState r;
     r.org = r.dir = r.att = r.rad = sum;
     RtTravState tv;
+    RtTravStacks ks;
     tv.sp = 0;
+    tv.tsp = 0;
+    tv.ng_y = 0;
 
     for (;;) {
         /* ---------------- regenerate ---------------- */
@@ -180,7 +184,7 @@ __global__ void __launch_bounds__(kMegaBlock) k_megakernel(RtScene scene, RtFram
         /* ---------------- traverse ---------------- */
         const unsigned act0 = __ballot_sync(full, mode == kTraversing);
         if (!act0) break; /* every lane is exhausted */
-        traverse_phase(scene.bvh, tv, mode, p.tune_refill, p.tune_tridiv);
+        traverse_phase(scene.bvh, tv, ks, mode, p.tune_refill, p.tune_tridiv);
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) rays += __shfl_xor_sync(full, rays, o);
@@ -244,7 +248,10 @@ __global__ void __launch_bounds__(kWfBlock) k_wf_extend(RtScene scene, RtWavefro
     int mode = kNeedPixel; /* kNeedPixel = idle, kTraversing, kHitPending, kExhausted */
     uint32_t pix = 0;
     RtTravState tv;
+    RtTravStacks ks;
     tv.sp = 0;
+    tv.tsp = 0;
+    tv.ng_y = 0;
     for (;;) {
         if (mode == kHitPending) {
             w.hit[pix] = make_float4(tv.best.t, tv.best.u, tv.best.v, __uint_as_float(tv.best.tri));
@@ -270,7 +277,7 @@ __global__ void __launch_bounds__(kWfBlock) k_wf_extend(RtScene scene, RtWavefro
         }
         const unsigned act0 = __ballot_sync(full, mode == kTraversing);
         if (!act0) break;
-        traverse_phase(scene.bvh, tv, mode, tune_refill, tune_tridiv);
+        traverse_phase(scene.bvh, tv, ks, mode, tune_refill, tune_tridiv);
     }
 }
 

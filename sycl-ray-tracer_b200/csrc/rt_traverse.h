@@ -284,9 +284,15 @@ struct RtTravState {
     RtHit best;
     uint32_t ng_x, ng_y; /* current node group: (child base, child hit bits << 24 | imask) */
     int sp, tsp;
-    uint32_t stack_x[RT_STACK_SIZE], stack_y[RT_STACK_SIZE];    /* pending node groups */
-    uint32_t tstack_x[RT_TSTACK_SIZE], tstack_y[RT_TSTACK_SIZE]; /* pending triangle groups */
 };
+
+/* The dynamically indexed storage is kept apart from RtTravState so that the scalar state is
+ * promoted to registers; entries are (base, bits) pairs packed in 64 bits (one access each). */
+struct RtTravStacks {
+    uint64_t node[RT_STACK_SIZE];  /* pending node groups */
+    uint64_t tri[RT_TSTACK_SIZE];  /* pending triangle groups */
+};
+RT_HD uint64_t rt_pack2(uint32_t x, uint32_t y) { return (uint64_t)x | ((uint64_t)y << 32); }
 
 RT_HD void rt_trav_init(RtTravState &s, f3 org, f3 dir, float tnear, float tfar) {
     s.best.t = tfar;
@@ -309,14 +315,13 @@ RT_HD bool rt_trav_has_tri(const RtTravState &s) { return s.tsp > 0; }
 RT_HD bool rt_trav_tri_full(const RtTravState &s) { return s.tsp >= RT_TSTACK_SIZE; }
 
 /* precondition: rt_trav_has_node(s) && !rt_trav_tri_full(s) */
-RT_HD void rt_trav_node_step(const RtBvh &bvh, RtTravState &s) {
+RT_HD void rt_trav_node_step(const RtBvh &bvh, RtTravState &s, RtTravStacks &k) {
     const uint32_t oct_inv = s.rb.oct_inv4 & 7u;
     const uint32_t imask = s.ng_y & 0xffu;
     const int bit = rt_bfind(s.ng_y);
     s.ng_y &= ~(1u << bit);
     if (s.ng_y > 0x00ffffffu) { /* siblings still pending: keep the group for later */
-        s.stack_x[s.sp] = s.ng_x;
-        s.stack_y[s.sp] = s.ng_y;
+        k.node[s.sp] = rt_pack2(s.ng_x, s.ng_y);
         s.sp++;
     }
     const uint32_t slot = ((uint32_t)bit - 24u) ^ oct_inv;
@@ -329,24 +334,25 @@ RT_HD void rt_trav_node_step(const RtBvh &bvh, RtTravState &s) {
     s.ng_x = n1.x;
     s.ng_y = (hm & 0xff000000u) | (n0.w >> 24);
     if (hm & 0x00ffffffu) {
-        s.tstack_x[s.tsp] = n1.y;
-        s.tstack_y[s.tsp] = hm & 0x00ffffffu;
+        k.tri[s.tsp] = rt_pack2(n1.y, hm & 0x00ffffffu);
         s.tsp++;
     }
     if (s.ng_y <= 0x00ffffffu && s.sp > 0) { /* no child hit: next pending group */
         s.sp--;
-        s.ng_x = s.stack_x[s.sp];
-        s.ng_y = s.stack_y[s.sp];
+        const uint64_t e = k.node[s.sp];
+        s.ng_x = (uint32_t)e;
+        s.ng_y = (uint32_t)(e >> 32);
     }
 }
 
 /* precondition: rt_trav_has_tri(s) */
-RT_HD void rt_trav_tri_step(const RtBvh &bvh, RtTravState &s) {
-    const uint32_t base = s.tstack_x[s.tsp - 1];
-    uint32_t bits = s.tstack_y[s.tsp - 1];
+RT_HD void rt_trav_tri_step(const RtBvh &bvh, RtTravState &s, RtTravStacks &k) {
+    const uint64_t e = k.tri[s.tsp - 1];
+    const uint32_t base = (uint32_t)e;
+    uint32_t bits = (uint32_t)(e >> 32);
     const int i = rt_ctz(bits);
     bits &= bits - 1;
-    if (bits) s.tstack_y[s.tsp - 1] = bits;
+    if (bits) k.tri[s.tsp - 1] = rt_pack2(base, bits);
     else s.tsp--;
     const uint32_t tslot = base + (uint32_t)i;
     const rt_float4 *tp = bvh.tris + (size_t)tslot * 3;
@@ -361,10 +367,11 @@ RT_HD void rt_trav_tri_step(const RtBvh &bvh, RtTravState &s) {
 /* simple front-to-back traversal: triangles are tested right after the node that produced them */
 RT_HD RtHit rt_traverse(const RtBvh &bvh, f3 org, f3 dir, float tnear, float tfar) {
     RtTravState s;
+    RtTravStacks k;
     rt_trav_init(s, org, dir, tnear, tfar);
     while (rt_trav_has_node(s)) {
-        rt_trav_node_step(bvh, s);
-        while (rt_trav_has_tri(s)) rt_trav_tri_step(bvh, s);
+        rt_trav_node_step(bvh, s, k);
+        while (rt_trav_has_tri(s)) rt_trav_tri_step(bvh, s, k);
     }
     return s.best;
 }

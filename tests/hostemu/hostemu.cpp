@@ -15,6 +15,12 @@
 #include <numeric>
 #include <vector>
 
+/* traversal statistics (nodes visited / triangles tested), host emulation only */
+static unsigned long long g_count_node = 0, g_count_tri = 0;
+#define RT_COUNTERS 1
+#define RT_COUNT_NODE() (g_count_node++)
+#define RT_COUNT_TRI() (g_count_tri++)
+
 #include "../../include/rt_api.h"
 #include "../../sycl-ray-tracer_b200/csrc/rt_build.h"
 #include "../../sycl-ray-tracer_b200/csrc/rt_wavefront.h"
@@ -413,4 +419,10 @@ extern "C" uint32_t emu_trace_pixel(const emu_scene *s, int wavefront_seed, cons
         }
     }
     return n;
+}
+
+extern "C" void emu_counters(unsigned long long *nodes, unsigned long long *tris, int reset) {
+    *nodes = g_count_node;
+    *tris = g_count_tri;
+    if (reset) g_count_node = g_count_tri = 0;
 }
