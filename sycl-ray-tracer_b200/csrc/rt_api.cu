@@ -34,7 +34,7 @@ struct rt_renderer {
     uint32_t *h_counts = nullptr;           /* pinned mirror */
     unsigned long long *h_rays = nullptr;   /* pinned */
     int grid_mega = 0, grid_extend = 0, grid_shade = 0;
-    int tune_refill = 8, tune_tridiv = 10; /* RT_TUNE_REFILL / RT_TUNE_TRIDIV override (development) */
+    int tune_refill = 12, tune_tridiv = 33; /* RT_TUNE_REFILL / RT_TUNE_TRIDIV override (development) */
 };
 
 namespace {
