@@ -184,11 +184,16 @@ struct Hit {
 
 struct RayPre {
     V3 org;
-    int kx, ky, kz;
-    float Sx, Sy, Sz;
+    V3 mx, my, mz;
 };
 
-/* Woop, Benthin, Wald, "Watertight Ray/Triangle Intersection", JCGT 2013, section 3 */
+/* Woop, Benthin, Wald, "Watertight Ray/Triangle Intersection", JCGT 2013, section 3. The axis
+ * permutation (kx, ky, kz) is folded into three vectors: sheared coordinate of P = P.m with
+ * mx[kx] = 1, mx[kz] = -Sx, my[ky] = 1, my[kz] = -Sy, mz[kz] = Sz, other components 0; products
+ * with 0 and 1 are exact, so P.mx is the paper's P[kx] - Sx*P[kz]. The dot is pinned as
+ * fma(P.x, m.x, fma(P.y, m.y, P.z*m.z)) (std::fmaf = one IEEE rounding per fma). */
+inline float shear(V3 p, V3 m) { return std::fmaf(p.x, m.x, std::fmaf(p.y, m.y, p.z * m.z)); }
+
 inline RayPre ray_precompute(V3 org, V3 dir) {
     RayPre r;
     r.org = org;
@@ -205,24 +210,27 @@ inline RayPre ray_precompute(V3 org, V3 dir) {
     int ky = kx + 1;
     if (ky == 3) ky = 0;
     if (at(dir, kz) < 0.0f) std::swap(kx, ky);
-    r.kx = kx;
-    r.ky = ky;
-    r.kz = kz;
-    r.Sx = at(dir, kx) / at(dir, kz);
-    r.Sy = at(dir, ky) / at(dir, kz);
-    r.Sz = 1.0f / at(dir, kz);
+    const float nSx = -(at(dir, kx) / at(dir, kz));
+    const float nSy = -(at(dir, ky) / at(dir, kz));
+    const float Sz = 1.0f / at(dir, kz);
+    float mx[3] = {0, 0, 0}, my[3] = {0, 0, 0}, mz[3] = {0, 0, 0};
+    mx[kx] = 1.0f;
+    mx[kz] = nSx;
+    my[ky] = 1.0f;
+    my[kz] = nSy;
+    mz[kz] = Sz;
+    r.mx = v3(mx[0], mx[1], mx[2]);
+    r.my = v3(my[0], my[1], my[2]);
+    r.mz = v3(mz[0], mz[1], mz[2]);
     return r;
 }
 
 /* closest-hit update with the deterministic tie-break (min t, then min triangle id) */
 inline void tri_test(const RayPre &r, const float *tv, uint32_t tri_id, float tnear, Hit &best) {
     V3 A = ld3(tv) - r.org, B = ld3(tv + 3) - r.org, C = ld3(tv + 6) - r.org;
-    float Ax = at(A, r.kx) - r.Sx * at(A, r.kz);
-    float Ay = at(A, r.ky) - r.Sy * at(A, r.kz);
-    float Bx = at(B, r.kx) - r.Sx * at(B, r.kz);
-    float By = at(B, r.ky) - r.Sy * at(B, r.kz);
-    float Cx = at(C, r.kx) - r.Sx * at(C, r.kz);
-    float Cy = at(C, r.ky) - r.Sy * at(C, r.kz);
+    float Ax = shear(A, r.mx), Ay = shear(A, r.my);
+    float Bx = shear(B, r.mx), By = shear(B, r.my);
+    float Cx = shear(C, r.mx), Cy = shear(C, r.my);
     float U = Cx * By - Cy * Bx;
     float V = Ax * Cy - Ay * Cx;
     float W = Bx * Ay - By * Ax;
@@ -237,7 +245,7 @@ inline void tri_test(const RayPre &r, const float *tv, uint32_t tri_id, float tn
     if ((U < 0.0f || V < 0.0f || W < 0.0f) && (U > 0.0f || V > 0.0f || W > 0.0f)) return;
     float det = (U + V) + W;
     if (det == 0.0f) return;
-    float Az = r.Sz * at(A, r.kz), Bz = r.Sz * at(B, r.kz), Cz = r.Sz * at(C, r.kz);
+    float Az = shear(A, r.mz), Bz = shear(B, r.mz), Cz = shear(C, r.mz);
     float T = (U * Az + V * Bz) + W * Cz;
     float rcp = 1.0f / det;
     float t = T * rcp;

@@ -82,9 +82,12 @@ __device__ __forceinline__ void traverse_phase(const RtBvh &bvh, RtTravState &tv
         const unsigned m_full = __ballot_sync(full, trav && rt_trav_tri_full(tv));
         if (!m_node || m_full || __popc(m_idle) >= refill || __popc(m_tri) >= tri_lanes) break;
     }
-    for (;;) { /* drain */
+    for (;;) { /* drain: lanes that are out of nodes (or nearly out of triangle-stack room) must
+                  finish their triangles; every other lane with triangles pending joins in, and
+                  carries what is left to the next drain */
         const bool tri = mode == kTraversing && rt_trav_has_tri(tv);
-        if (!__any_sync(full, tri)) break;
+        const bool must = tri && (!rt_trav_has_node(tv) || tv.tsp >= RT_TSTACK_SIZE - 2);
+        if (!__any_sync(full, must)) break;
         if (tri) rt_trav_tri_step(bvh, tv, ks);
     }
     if (mode == kTraversing && !rt_trav_has_node(tv)) mode = kHitPending;

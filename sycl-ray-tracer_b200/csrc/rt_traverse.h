@@ -105,11 +105,21 @@ RT_HD float rt_byte_to_float(uint32_t w, int j) {
 }
 
 /* ---- watertight ray/triangle -------------------------------------------------------- */
+/* Woop/Benthin/Wald shear, with the axis permutation folded into three per-ray vectors so that the
+ * per-triangle work has no selects: for kz = dominant axis of dir, (kx, ky) the other two (swapped
+ * when dir[kz] < 0),
+ *     mx[kx] = 1, mx[kz] = -dir[kx]/dir[kz];  my[ky] = 1, my[kz] = -dir[ky]/dir[kz];  mz[kz] = 1/dir[kz]
+ * (all other components 0) and the sheared coordinates of a vertex P are P.mx, P.my, P.mz. Products
+ * with 0 and 1 are exact, so this IS the paper's  P[kx] - Sx*P[kz]  etc. The dot is evaluated as
+ * fma(P.x, m.x, fma(P.y, m.y, P.z*m.z)) in both the CUDA path and the oracle. A vertex shared by two
+ * triangles gets identical sheared coordinates, and the edge functions below stay unfused, so edge
+ * functions of a shared edge are exact negatives of each other (watertightness). */
 struct RtRayTri {
     f3 org;
-    int kx, ky, kz;
-    float Sx, Sy, Sz;
+    f3 mx, my, mz;
 };
+
+RT_HD float rt_shear(f3 p, f3 m) { return rt_fma(p.x, m.x, rt_fma(p.y, m.y, p.z * m.z)); }
 
 RT_HD RtRayTri rt_ray_tri_setup(f3 org, f3 dir) {
     RtRayTri r;
@@ -126,18 +136,18 @@ RT_HD RtRayTri rt_ray_tri_setup(f3 org, f3 dir) {
     if (kx == 3) kx = 0;
     int ky = kx + 1;
     if (ky == 3) ky = 0;
-    float dz = sel3(dir, kz);
+    const float dz = sel3(dir, kz);
     if (dz < 0.0f) {
         int tmp = kx;
         kx = ky;
         ky = tmp;
     }
-    r.kx = kx;
-    r.ky = ky;
-    r.kz = kz;
-    r.Sx = rt_div(sel3(dir, kx), dz);
-    r.Sy = rt_div(sel3(dir, ky), dz);
-    r.Sz = rt_div(1.0f, dz);
+    const float nSx = -rt_div(sel3(dir, kx), dz), nSy = -rt_div(sel3(dir, ky), dz), Sz = rt_div(1.0f, dz);
+    r.mx = mk3(kx == 0 ? 1.0f : (kz == 0 ? nSx : 0.0f), kx == 1 ? 1.0f : (kz == 1 ? nSx : 0.0f),
+               kx == 2 ? 1.0f : (kz == 2 ? nSx : 0.0f));
+    r.my = mk3(ky == 0 ? 1.0f : (kz == 0 ? nSy : 0.0f), ky == 1 ? 1.0f : (kz == 1 ? nSy : 0.0f),
+               ky == 2 ? 1.0f : (kz == 2 ? nSy : 0.0f));
+    r.mz = mk3(kz == 0 ? Sz : 0.0f, kz == 1 ? Sz : 0.0f, kz == 2 ? Sz : 0.0f);
     return r;
 }
 
@@ -145,14 +155,10 @@ RT_HD RtRayTri rt_ray_tri_setup(f3 org, f3 dir) {
  * id). Exactly the oracle's operation order. */
 RT_HD void rt_tri_test(const RtRayTri &r, f3 v0, f3 v1, f3 v2, uint32_t slot, uint32_t gid,
                        float tnear, RtHit &best) {
-    f3 A = v0 - r.org, B = v1 - r.org, C = v2 - r.org;
-    float Akz = sel3(A, r.kz), Bkz = sel3(B, r.kz), Ckz = sel3(C, r.kz);
-    float Ax = sel3(A, r.kx) - r.Sx * Akz;
-    float Ay = sel3(A, r.ky) - r.Sy * Akz;
-    float Bx = sel3(B, r.kx) - r.Sx * Bkz;
-    float By = sel3(B, r.ky) - r.Sy * Bkz;
-    float Cx = sel3(C, r.kx) - r.Sx * Ckz;
-    float Cy = sel3(C, r.ky) - r.Sy * Ckz;
+    const f3 A = v0 - r.org, B = v1 - r.org, C = v2 - r.org;
+    const float Ax = rt_shear(A, r.mx), Ay = rt_shear(A, r.my);
+    const float Bx = rt_shear(B, r.mx), By = rt_shear(B, r.my);
+    const float Cx = rt_shear(C, r.mx), Cy = rt_shear(C, r.my);
     float U = Cx * By - Cy * Bx;
     float V = Ax * Cy - Ay * Cx;
     float W = Bx * Ay - By * Ax;
@@ -165,12 +171,12 @@ RT_HD void rt_tri_test(const RtRayTri &r, f3 v0, f3 v1, f3 v2, uint32_t slot, ui
         W = (float)(BxAy - ByAx);
     }
     if ((U < 0.0f || V < 0.0f || W < 0.0f) && (U > 0.0f || V > 0.0f || W > 0.0f)) return;
-    float det = (U + V) + W;
+    const float det = (U + V) + W;
     if (det == 0.0f) return;
-    float Az = r.Sz * Akz, Bz = r.Sz * Bkz, Cz = r.Sz * Ckz;
-    float T = (U * Az + V * Bz) + W * Cz;
-    float rcp = rt_div(1.0f, det);
-    float t = T * rcp;
+    const float Az = rt_shear(A, r.mz), Bz = rt_shear(B, r.mz), Cz = rt_shear(C, r.mz);
+    const float T = (U * Az + V * Bz) + W * Cz;
+    const float rcp = rt_div(1.0f, det);
+    const float t = T * rcp;
     if (!(t > tnear)) return;
     if (t < best.t || (t == best.t && gid < best.gid)) {
         best.t = t;
