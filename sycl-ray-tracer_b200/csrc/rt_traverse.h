@@ -100,8 +100,18 @@ RT_HD uint32_t rt_sign_extend_s8x4(uint32_t x) {
     return r;
 #endif
 }
-RT_HD float rt_byte_to_float(uint32_t w, int j) {
-    return (float)((w >> (8 * j)) & 0xffu); /* I2F.U8 with byte select on device */
+/* byte j of w -> the float 1 + b * 2^-15, built with ONE byte permute (no I2F: the conversion
+ * pipe is the narrowest one on sm_100a and 48 conversions per node visit made it the busiest):
+ * 0x3F800000 | b << 8. The node test folds the "1 +" and the 2^-15 into its per-node constants. */
+template <int J>
+RT_HD float rt_byte_to_unit(uint32_t w) {
+#if RT_DEVICE_CODE
+    uint32_t r;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(w), "r"(0x3F800000u), "n"(0x7604 | (J << 4)));
+    return __uint_as_float(r);
+#else
+    return rt_u2f(0x3F800000u | (((w >> (8 * J)) & 0xffu) << 8));
+#endif
 }
 
 /* ---- watertight ray/triangle -------------------------------------------------------- */
@@ -212,58 +222,64 @@ RT_HD RtRayBox rt_ray_box_setup(f3 org, f3 dir) {
 
 /* returns the hit mask of one wide node: bits 24..31 inner children in visiting priority,
  * bits 0..23 leaf triangles (offsets from tri_base) */
+template <int J>
+RT_HD void rt_child_test(uint32_t nx, uint32_t ny, uint32_t nz, uint32_t fx, uint32_t fy, uint32_t fz, float Sx,
+                         float Sy, float Sz, float onx, float ony, float onz, float ofx, float ofy, float ofz,
+                         float tmin, float tmax_pad, uint32_t child_bits4, uint32_t bit_index4, uint32_t &hitmask) {
+    const float tnx = rt_fma(rt_byte_to_unit<J>(nx), Sx, onx);
+    const float tny = rt_fma(rt_byte_to_unit<J>(ny), Sy, ony);
+    const float tnz = rt_fma(rt_byte_to_unit<J>(nz), Sz, onz);
+    const float tfx = rt_fma(rt_byte_to_unit<J>(fx), Sx, ofx);
+    const float tfy = rt_fma(rt_byte_to_unit<J>(fy), Sy, ofy);
+    const float tfz = rt_fma(rt_byte_to_unit<J>(fz), Sz, ofz);
+    const float cmin = rt_max(rt_max3(tnx, tny, tnz), tmin);
+    const float cmax = rt_min(rt_min3(tfx, tfy, tfz), tmax_pad);
+    const uint32_t bits = (child_bits4 >> (8 * J)) & 0xffu;
+    const uint32_t idxb = (bit_index4 >> (8 * J)) & 0xffu;
+    hitmask |= (cmin <= cmax) ? (bits << idxb) : 0u;
+}
+
 RT_HD uint32_t rt_node_test(const RtRayBox &rb, rt_uint4 n0, rt_uint4 n1, rt_uint4 n2,
                             rt_uint4 n3, rt_uint4 n4, float tmin, float tmax_pad) {
-    float sx = rt_u2f((n0.w & 0xffu) << 23), sy = rt_u2f(((n0.w >> 8) & 0xffu) << 23),
-          sz = rt_u2f(((n0.w >> 16) & 0xffu) << 23);
-    float idx = sx * rb.rcp.x, idy = sy * rb.rcp.y, idz = sz * rb.rcp.z;
-    float ox = (rt_u2f(n0.x) - rb.org.x) * rb.rcp.x, oy = (rt_u2f(n0.y) - rb.org.y) * rb.rcp.y,
-          oz = (rt_u2f(n0.z) - rb.org.z) * rb.rcp.z;
-    /* Conservative slabs. t = q*id + o cancels when the ray starts next to a plane that lies far
-     * from the node origin p (|q*id|, |o| >> |t|), e.g. a bounce ray leaving an axis-aligned wall:
-     * the absolute error of the three roundings is <= 3 * 2^-24 * (|q*id| + |o|). Near planes are
-     * moved back and far planes forward by 2^-21 * (255*|id| + |o|), so rounding can never cull a
-     * box whose triangle the (exact-difference) triangle test would accept. */
-    const float kErr = 4.76837158e-7f; /* 2^-21 */
-    float ex = rt_fma(255.0f, fabsf(idx), fabsf(ox)) * kErr, ey = rt_fma(255.0f, fabsf(idy), fabsf(oy)) * kErr,
-          ez = rt_fma(255.0f, fabsf(idz), fabsf(oz)) * kErr;
-    float oxp = ox + ex, oyp = oy + ey, ozp = oz + ez;
-    ox -= ex;
-    oy -= ey;
-    oz -= ez;
+    const float sx = rt_u2f((n0.w & 0xffu) << 23), sy = rt_u2f(((n0.w >> 8) & 0xffu) << 23),
+                sz = rt_u2f(((n0.w >> 16) & 0xffu) << 23);
+    /* plane t = q*id + o with id = 2^e/d, o = (p - org)/d */
+    const float idx = sx * rb.rcp.x, idy = sy * rb.rcp.y, idz = sz * rb.rcp.z;
+    const float ox = (rt_u2f(n0.x) - rb.org.x) * rb.rcp.x, oy = (rt_u2f(n0.y) - rb.org.y) * rb.rcp.y,
+                oz = (rt_u2f(n0.z) - rb.org.z) * rb.rcp.z;
+    /* q enters as u = 1 + q*2^-15 (rt_byte_to_unit): t = u*S + (o - S), S = id * 2^15 (exact). */
+    const float Sx = idx * 32768.0f, Sy = idy * 32768.0f, Sz = idz * 32768.0f;
+    /* Conservative slabs. The sum cancels when the ray starts next to a plane that lies far from
+     * the node origin p (|q*id|, |o| >> |t|), e.g. a bounce ray leaving an axis-aligned wall. The
+     * roundings of o, of o - S and of the fma are bounded by 2^-24 * (3|o| + 2|S|) plus the three
+     * roundings of the plain formula, 3 * 2^-24 * (255|id| + |o|); near planes are moved back and
+     * far planes forward by e = 2^-21 |o| + 2^-8 |id| (> the bound, ~0.4 % of a quantisation
+     * step), so rounding can never cull a box whose triangle the exact-difference triangle test
+     * would accept. */
+    const float ex = rt_fma(fabsf(idx), 0.00390625f, fabsf(ox) * 4.76837158e-7f),
+                ey = rt_fma(fabsf(idy), 0.00390625f, fabsf(oy) * 4.76837158e-7f),
+                ez = rt_fma(fabsf(idz), 0.00390625f, fabsf(oz) * 4.76837158e-7f);
+    const float onx = (ox - ex) - Sx, ony = (oy - ey) - Sy, onz = (oz - ez) - Sz;
+    const float ofx = (ox + ex) - Sx, ofy = (oy + ey) - Sy, ofz = (oz + ez) - Sz;
     uint32_t hitmask = 0;
 #if RT_DEVICE_CODE
 #pragma unroll
 #endif
     for (int h = 0; h < 2; h++) {
-        uint32_t meta4 = h ? n1.w : n1.z;
-        uint32_t is_inner4 = (meta4 & (meta4 << 1)) & 0x10101010u;
-        uint32_t inner_mask4 = rt_sign_extend_s8x4(is_inner4 << 3);
-        uint32_t bit_index4 = (meta4 ^ (rb.oct_inv4 & inner_mask4)) & 0x1f1f1f1fu;
-        uint32_t child_bits4 = (meta4 >> 5) & 0x07070707u;
-        uint32_t qlox = h ? n2.y : n2.x, qloy = h ? n2.w : n2.z, qloz = h ? n3.y : n3.x;
-        uint32_t qhix = h ? n3.w : n3.z, qhiy = h ? n4.y : n4.x, qhiz = h ? n4.w : n4.z;
-        uint32_t nx = (rb.neg & 1u) ? qhix : qlox, fx = (rb.neg & 1u) ? qlox : qhix;
-        uint32_t ny = (rb.neg & 2u) ? qhiy : qloy, fy = (rb.neg & 2u) ? qloy : qhiy;
-        uint32_t nz = (rb.neg & 4u) ? qhiz : qloz, fz = (rb.neg & 4u) ? qloz : qhiz;
-#if RT_DEVICE_CODE
-#pragma unroll
-#endif
-        for (int j = 0; j < 4; j++) {
-            float tnx = rt_fma(rt_byte_to_float(nx, j), idx, ox);
-            float tny = rt_fma(rt_byte_to_float(ny, j), idy, oy);
-            float tnz = rt_fma(rt_byte_to_float(nz, j), idz, oz);
-            float tfx = rt_fma(rt_byte_to_float(fx, j), idx, oxp);
-            float tfy = rt_fma(rt_byte_to_float(fy, j), idy, oyp);
-            float tfz = rt_fma(rt_byte_to_float(fz, j), idz, ozp);
-            float cmin = rt_max(rt_max3(tnx, tny, tnz), tmin);
-            float cmax = rt_min(rt_min3(tfx, tfy, tfz), tmax_pad);
-            if (cmin <= cmax) {
-                uint32_t bits = (child_bits4 >> (8 * j)) & 0xffu;
-                uint32_t idxb = (bit_index4 >> (8 * j)) & 0xffu;
-                hitmask |= bits << idxb;
-            }
-        }
+        const uint32_t meta4 = h ? n1.w : n1.z;
+        const uint32_t is_inner4 = (meta4 & (meta4 << 1)) & 0x10101010u;
+        const uint32_t inner_mask4 = rt_sign_extend_s8x4(is_inner4 << 3);
+        const uint32_t bit_index4 = (meta4 ^ (rb.oct_inv4 & inner_mask4)) & 0x1f1f1f1fu;
+        const uint32_t child_bits4 = (meta4 >> 5) & 0x07070707u;
+        const uint32_t qlox = h ? n2.y : n2.x, qloy = h ? n2.w : n2.z, qloz = h ? n3.y : n3.x;
+        const uint32_t qhix = h ? n3.w : n3.z, qhiy = h ? n4.y : n4.x, qhiz = h ? n4.w : n4.z;
+        const uint32_t nx = (rb.neg & 1u) ? qhix : qlox, fx = (rb.neg & 1u) ? qlox : qhix;
+        const uint32_t ny = (rb.neg & 2u) ? qhiy : qloy, fy = (rb.neg & 2u) ? qloy : qhiy;
+        const uint32_t nz = (rb.neg & 4u) ? qhiz : qloz, fz = (rb.neg & 4u) ? qloz : qhiz;
+        rt_child_test<0>(nx, ny, nz, fx, fy, fz, Sx, Sy, Sz, onx, ony, onz, ofx, ofy, ofz, tmin, tmax_pad, child_bits4, bit_index4, hitmask);
+        rt_child_test<1>(nx, ny, nz, fx, fy, fz, Sx, Sy, Sz, onx, ony, onz, ofx, ofy, ofz, tmin, tmax_pad, child_bits4, bit_index4, hitmask);
+        rt_child_test<2>(nx, ny, nz, fx, fy, fz, Sx, Sy, Sz, onx, ony, onz, ofx, ofy, ofz, tmin, tmax_pad, child_bits4, bit_index4, hitmask);
+        rt_child_test<3>(nx, ny, nz, fx, fy, fz, Sx, Sy, Sz, onx, ony, onz, ofx, ofy, ofz, tmin, tmax_pad, child_bits4, bit_index4, hitmask);
     }
     return hitmask;
 }
