@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "librt_b200.so")
+LIB_PATH = os.environ.get("RT_LIB_PATH") or os.path.join(_HERE, "librt_b200.so")  # RT_LIB_PATH: development builds
 
 RT_OK = 0
 RT_MEGAKERNEL, RT_WAVEFRONT = 0, 1

@@ -93,7 +93,10 @@ __device__ __forceinline__ void traverse_phase(const RtBvh &bvh, RtTravState &tv
     if (mode == kTraversing && !rt_trav_has_node(tv)) mode = kHitPending;
 }
 
-__global__ void __launch_bounds__(kMegaBlock) k_megakernel(RtScene scene, RtFrameParams p, RtFrameOut out,
+#ifndef RT_MEGA_MIN_BLOCKS
+#define RT_MEGA_MIN_BLOCKS 8
+#endif
+__global__ void __launch_bounds__(kMegaBlock, RT_MEGA_MIN_BLOCKS) k_megakernel(RtScene scene, RtFrameParams p, RtFrameOut out,
                                                            uint32_t *work_counter, unsigned long long *ray_counter) {
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
@@ -237,7 +240,10 @@ __global__ void __launch_bounds__(kWfBlock) k_wf_generate(RtFrameParams p, RtWav
 
 /* extend: traversal only. Persistent warps pull rays from the id queue through a device-side head
  * counter and replace finished rays inside the traversal loop (same scheme as the megakernel). */
-__global__ void __launch_bounds__(kWfBlock) k_wf_extend(RtScene scene, RtWavefrontState w, int cur,
+#ifndef RT_EXT_MIN_BLOCKS
+#define RT_EXT_MIN_BLOCKS 4
+#endif
+__global__ void __launch_bounds__(kWfBlock, RT_EXT_MIN_BLOCKS) k_wf_extend(RtScene scene, RtWavefrontState w, int cur,
                                                          unsigned long long *ray_counter, int tune_refill,
                                                          int tune_tridiv) {
     const unsigned full = 0xffffffffu;
