@@ -148,7 +148,9 @@ def run_reference(args):
     if rank != 0:
         return 0
     data, w, h, spp, depth = build_scene_data(args.workload)
-    step, cores, sample = cpu_reference_run(data, w, h, depth, 0, args.cpu_seconds)
+    # all host cores, also under torchrun (which exports OMP_NUM_THREADS=1)
+    ncores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    step, cores, sample = cpu_reference_run(data, w, h, depth, 0, args.cpu_seconds, threads=ncores)
     for _ in range(args.warmup):
         step()
     rays = secs = samples = 0
@@ -208,8 +210,9 @@ def main():
     if args.spp:
         spp = args.spp
     app = pkg.App(local_rank)
-    stream = torch.cuda.current_stream()
-    app.set_stream(stream.cuda_stream)  # kernels, NCCL and the timing events share one stream
+    stream = torch.cuda.Stream()  # a non-default stream: kernels, NCCL and the timing events share it
+    torch.cuda.set_stream(stream)
+    app.set_stream(stream.cuda_stream)
     scene = pkg.Scene(app, data)
     stats = scene.stats
     cam = pkg.Camera((w, h), data.camera_position, data.camera_direction, data.camera_focal_length)
@@ -350,7 +353,8 @@ def main():
 
     cpu = None
     if not args.no_cpu_baseline and world == 1:
-        step, cores, sample = cpu_reference_run(data, w, h, depth, 1 if wave else 0, args.cpu_seconds)
+        ncores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+        step, cores, sample = cpu_reference_run(data, w, h, depth, 1 if wave else 0, args.cpu_seconds, threads=ncores)
         rr, ss, _ = step()
         rr2, ss2, _ = step()
         cpu = {"value": (rr + rr2) / (ss + ss2) / 1e6, "unit": "Mrays/s", "cores": cores, "kind": "port", "sample": sample}

@@ -34,6 +34,7 @@ struct rt_renderer {
     uint32_t *h_counts = nullptr;           /* pinned mirror */
     unsigned long long *h_rays = nullptr;   /* pinned */
     int grid_mega = 0, grid_extend = 0, grid_shade = 0;
+    cudaEvent_t ev_batch[2] = {nullptr, nullptr}; /* wavefront: per-batch queue-length read-back */
     int tune_refill = 12, tune_tridiv = 33; /* RT_TUNE_REFILL / RT_TUNE_TRIDIV override (development) */
 };
 
@@ -425,6 +426,8 @@ rt_status rt_renderer_create(rt_context *ctx, rt_renderer_kind kind, int32_t wid
         if ((e = dev_alloc(&r->d_counts, 4)) != cudaSuccess) break;
         if ((e = cudaMallocHost((void **)&r->h_counts, 2 * sizeof(uint32_t))) != cudaSuccess) break;
         if ((e = cudaMallocHost((void **)&r->h_rays, sizeof(unsigned long long))) != cudaSuccess) break;
+        if ((e = cudaEventCreateWithFlags(&r->ev_batch[0], cudaEventDisableTiming)) != cudaSuccess) break;
+        if ((e = cudaEventCreateWithFlags(&r->ev_batch[1], cudaEventDisableTiming)) != cudaSuccess) break;
         if (kind == RT_MEGAKERNEL) {
             if ((e = rt_megakernel_grid(ctx->sm_count, &r->grid_mega)) != cudaSuccess) break;
         } else {
@@ -464,6 +467,8 @@ void rt_renderer_destroy(rt_renderer *r) {
     cudaFree(r->d_counts);
     if (r->h_counts) cudaFreeHost(r->h_counts);
     if (r->h_rays) cudaFreeHost(r->h_rays);
+    if (r->ev_batch[0]) cudaEventDestroy(r->ev_batch[0]);
+    if (r->ev_batch[1]) cudaEventDestroy(r->ev_batch[1]);
     cudaFree(r->wf.org);
     cudaFree(r->wf.dir);
     cudaFree(r->wf.att);
@@ -530,21 +535,51 @@ rt_status rt_render_frame(rt_renderer *r, const rt_scene *scene, const rt_camera
         launches++;
         /* every pixel traces at most spp * max_depth segments, one per bounce iteration */
         const uint64_t max_iters = (uint64_t)p.spp * (uint64_t)p.max_depth;
-        int cur = 0;
-        uint64_t it = 0;
-        while (it < max_iters) {
-            const uint64_t batch = (max_iters - it) < 8 ? (max_iters - it) : 8;
-            for (uint64_t k = 0; k < batch; k++) {
-                RT_CUDA_TRY(ctx, rt_launch_wf_extend(st, r->grid_extend, scene->view, r->wf, cur, r->d_rays, p));
-                RT_CUDA_TRY(ctx, rt_launch_wf_shade(st, r->grid_shade, scene->view, p, r->wf, out, cur));
-                launches += 2;
+        /* One batch = kBatch (even) bounce iterations = 2*kBatch kernels, captured once per frame in
+         * a CUDA graph and replayed (the queues ping-pong, so every batch starts at queue 0). The
+         * queue length is copied back after every batch, but the host only looks at the PREVIOUS
+         * batch's value after enqueueing the next one, so the GPU never waits for the host. Batches
+         * issued after the queue ran empty are no-ops (count 0). */
+        const int kBatch = 8;
+        cudaGraph_t graph = nullptr;
+        cudaGraphExec_t exec = nullptr;
+        auto issue_batch = [&]() -> cudaError_t {
+            int cur = 0;
+            for (int k = 0; k < kBatch; k++) {
+                cudaError_t e = rt_launch_wf_extend(st, r->grid_extend, scene->view, r->wf, cur, r->d_rays, p);
+                if (e != cudaSuccess) return e;
+                e = rt_launch_wf_shade(st, r->grid_shade, scene->view, p, r->wf, out, cur);
+                if (e != cudaSuccess) return e;
                 cur ^= 1;
             }
-            it += batch;
-            RT_CUDA_TRY(ctx, cudaMemcpyAsync(r->h_counts, r->d_counts, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-            RT_CUDA_TRY(ctx, cudaStreamSynchronize(st));
-            if (r->h_counts[cur] == 0) break; /* every pixel has finished its samples */
+            return cudaSuccess;
+        };
+        if (max_iters > (uint64_t)kBatch && cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed) == cudaSuccess) {
+            cudaError_t e1 = issue_batch();
+            cudaError_t e2 = cudaStreamEndCapture(st, &graph);
+            if (e1 != cudaSuccess || e2 != cudaSuccess || cudaGraphInstantiate(&exec, graph, 0) != cudaSuccess) {
+                if (graph) cudaGraphDestroy(graph);
+                graph = nullptr;
+                exec = nullptr;
+            }
         }
+        (void)cudaGetLastError(); /* capture is unsupported on the legacy default stream: plain launches */
+        cudaError_t werr = cudaSuccess;
+        bool finished = false;
+        uint64_t b = 0;
+        for (uint64_t it = 0; it < max_iters && !finished && werr == cudaSuccess; it += kBatch, b++) {
+            werr = exec ? cudaGraphLaunch(exec, st) : issue_batch();
+            launches += 2 * kBatch;
+            if (werr == cudaSuccess) werr = cudaMemcpyAsync(&r->h_counts[b & 1], r->d_counts, sizeof(uint32_t), cudaMemcpyDeviceToHost, st);
+            if (werr == cudaSuccess) werr = cudaEventRecord(r->ev_batch[b & 1], st);
+            if (werr == cudaSuccess && b >= 1) {
+                werr = cudaEventSynchronize(r->ev_batch[(b - 1) & 1]);
+                if (r->h_counts[(b - 1) & 1] == 0) finished = true; /* every pixel has finished its samples */
+            }
+        }
+        if (exec) cudaGraphExecDestroy(exec);
+        if (graph) cudaGraphDestroy(graph);
+        if (werr != cudaSuccess) return rt_set_error(ctx, RT_ERR_CUDA, "rt_render_frame(wavefront)", cudaGetErrorString(werr));
         RT_CUDA_TRY(ctx, rt_launch_resolve_owned(st, p, (const float *)r->d_accum, r->wf.rng, out));
         launches++;
     }
