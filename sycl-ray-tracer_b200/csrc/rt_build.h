@@ -251,7 +251,10 @@ RT_HD void rt_wide_select(const RtBuild &b, uint32_t item) {
             int best = -1;
             float best_area = -1.0f;
             for (int k = 0; k < n; k++) {
-                if (rt_subtree_count(b, c[k]) <= RT_LEAF_MAX) continue;
+                /* any binary inner node may be opened, also one small enough to be a leaf: the node
+                 * test evaluates all eight slots anyway, so filling them with tighter (1-2 triangle)
+                 * leaf boxes is free and saves triangle tests and whole tree levels */
+                if (rt_is_leaf_id(b, c[k])) continue;
                 const float a = rt_box_area(b, c[k]);
                 if (a > best_area) {
                     best_area = a;

@@ -11,6 +11,7 @@
  */
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <numeric>
 #include <vector>
@@ -157,6 +158,65 @@ emu_scene *emu_scene_create(const rt_scene_desc *desc) {
         b.box_lo = box_lo.data();
         b.box_hi = box_hi.data();
         b.flags = flags.data();
+        if (getenv("EMU_SAH") && n > 1) {
+            /* EXPERIMENT ONLY: quality headroom of a SAH binary tree under the same wide collapse */
+            std::vector<float> clo((size_t)n * 3), chi((size_t)n * 3);
+            for (uint32_t g = 0; g < n; g++) {
+                f3 lo, hi;
+                rt_tri_box(b, g, lo, hi);
+                clo[g * 3] = lo.x; clo[g * 3 + 1] = lo.y; clo[g * 3 + 2] = lo.z;
+                chi[g * 3] = hi.x; chi[g * 3 + 1] = hi.y; chi[g * 3 + 2] = hi.z;
+            }
+            std::iota(vals_s.begin(), vals_s.end(), 0u);
+            uint32_t next_inner = 0;
+            struct Job { uint32_t first, count, parent; int side; };
+            std::vector<Job> jobs = {{0, n, RT_MISS, 0}};
+            while (!jobs.empty()) {
+                Job j = jobs.back();
+                jobs.pop_back();
+                uint32_t id;
+                if (j.count == 1) id = (n - 1) + j.first;
+                else id = next_inner++;
+                if (j.parent != RT_MISS) { (j.side ? right : left)[j.parent] = id; }
+                parent[id] = j.parent;
+                if (j.count == 1) continue;
+                rf[id] = j.first; rl[id] = j.first + j.count - 1;
+                float cl[3] = {1e30f, 1e30f, 1e30f}, ch[3] = {-1e30f, -1e30f, -1e30f};
+                for (uint32_t i = j.first; i < j.first + j.count; i++)
+                    for (int a = 0; a < 3; a++) {
+                        float c = 0.5f * (clo[vals_s[i] * 3 + a] + chi[vals_s[i] * 3 + a]);
+                        cl[a] = std::min(cl[a], c); ch[a] = std::max(ch[a], c);
+                    }
+                int bax = -1, bsp = -1; float bcost = 1e30f; const int NB = 16;
+                for (int a = 0; a < 3; a++) {
+                    if (!(ch[a] > cl[a])) continue;
+                    float bl[NB][3], bh[NB][3]; uint32_t bc[NB];
+                    for (int q = 0; q < NB; q++) { bc[q] = 0; for (int k = 0; k < 3; k++) { bl[q][k] = 1e30f; bh[q][k] = -1e30f; } }
+                    float sc = NB / (ch[a] - cl[a]);
+                    for (uint32_t i = j.first; i < j.first + j.count; i++) {
+                        uint32_t g = vals_s[i];
+                        int q = std::min(NB - 1, (int)((0.5f * (clo[g * 3 + a] + chi[g * 3 + a]) - cl[a]) * sc));
+                        bc[q]++;
+                        for (int k = 0; k < 3; k++) { bl[q][k] = std::min(bl[q][k], clo[g * 3 + k]); bh[q][k] = std::max(bh[q][k], chi[g * 3 + k]); }
+                    }
+                    float ra[NB]; uint32_t rc[NB]; float tl[3] = {1e30f, 1e30f, 1e30f}, th[3] = {-1e30f, -1e30f, -1e30f}; uint32_t cnt = 0;
+                    auto area = [](float *l, float *h) { float dx = h[0] - l[0], dy = h[1] - l[1], dz = h[2] - l[2]; return dx * dy + dy * dz + dz * dx; };
+                    for (int q = NB - 1; q > 0; q--) { for (int k = 0; k < 3; k++) { tl[k] = std::min(tl[k], bl[q][k]); th[k] = std::max(th[k], bh[q][k]); } cnt += bc[q]; ra[q] = cnt ? area(tl, th) : 0; rc[q] = cnt; }
+                    for (int k = 0; k < 3; k++) { tl[k] = 1e30f; th[k] = -1e30f; } cnt = 0;
+                    for (int q = 0; q < NB - 1; q++) { for (int k = 0; k < 3; k++) { tl[k] = std::min(tl[k], bl[q][k]); th[k] = std::max(th[k], bh[q][k]); } cnt += bc[q]; if (!cnt || !rc[q + 1]) continue; float c = area(tl, th) * cnt + ra[q + 1] * rc[q + 1]; if (c < bcost) { bcost = c; bax = a; bsp = q; } }
+                }
+                uint32_t mid = j.first + j.count / 2;
+                if (bax >= 0) {
+                    float sc = NB / (ch[bax] - cl[bax]);
+                    auto m = std::partition(vals_s.begin() + j.first, vals_s.begin() + j.first + j.count, [&](uint32_t g) {
+                        return std::min(NB - 1, (int)((0.5f * (clo[g * 3 + bax] + chi[g * 3 + bax]) - cl[bax]) * sc)) <= bsp; });
+                    uint32_t mm = (uint32_t)(m - vals_s.begin());
+                    if (mm > j.first && mm < j.first + j.count) mid = mm;
+                }
+                jobs.push_back({mid, j.first + j.count - mid, id, 1});
+                jobs.push_back({j.first, mid - j.first, id, 0});
+            }
+        } else
         for (uint32_t i = 0; i + 1 < n; i++) rt_karras_node(b, i);
         for (uint32_t j = 0; j < n; j++) rt_fit_leaf(b, j, HostArrive());
 
@@ -425,4 +485,25 @@ extern "C" void emu_counters(unsigned long long *nodes, unsigned long long *tris
     *nodes = g_count_node;
     *tris = g_count_tri;
     if (reset) g_count_node = g_count_tri = 0;
+}
+
+/* tree statistics: out[0..8] = histogram of children per node, out[9] = leaf children, out[10] = inner children,
+ * out[11..13] = leaves holding 1/2/3 triangles */
+extern "C" void emu_scene_tree_stats(const emu_scene *s, uint64_t *out) {
+    for (int i = 0; i < 14; i++) out[i] = 0;
+    for (uint32_t ni = 0; ni < s->n_nodes; ni++) {
+        const rt_uint4 *np = &s->nodes[(size_t)ni * 5];
+        int n = 0;
+        for (int slot = 0; slot < 8; slot++) {
+            const uint32_t meta = ((slot < 4 ? np[1].z : np[1].w) >> ((slot & 3) * 8)) & 0xffu;
+            if (!meta) continue;
+            n++;
+            if ((np[0].w >> 24) & (1u << slot)) out[10]++;
+            else {
+                out[9]++;
+                out[10 + rt_popc(meta >> 5)]++;
+            }
+        }
+        out[n]++;
+    }
 }
