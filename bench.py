@@ -349,7 +349,9 @@ def main():
                 "peak_source": peak_src, "algorithmic_bytes_per_ray": bpr,
                 "algorithmic_bytes_per_launch": alg_bytes_total / max(1, n_launch),
                 "launch_ms": mega["kernel_ms"] / max(1, n_launch / world),
-                "note": "scene (BVH+shading = %.1f MB) is L2-resident; HBM is the stated (conservative) roofline, the physical limit is L1/L2 latency x occupancy" % ((stats["bvh_bytes"] + stats["shading_bytes"]) / 1e6)}
+                "note": ("scene (BVH+shading = %.1f MB) %s" % ((stats["bvh_bytes"] + stats["shading_bytes"]) / 1e6,
+                         "is L2-resident (126 MB L2): HBM is the stated, conservative roofline; the physical limits are issue slots and the L1TEX wavefront rate (profiles/)"
+                         if stats["bvh_bytes"] + stats["shading_bytes"] < 100e6 else "exceeds the 126 MB L2: node/triangle fetches are HBM traffic"))}
 
     cpu = None
     if not args.no_cpu_baseline and world == 1:
