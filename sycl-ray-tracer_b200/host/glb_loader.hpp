@@ -1,0 +1,537 @@
+/*
+ * glb_loader.hpp — binary glTF (.glb) -> rt_scene_desc, following the reference loader's rules
+ * (src/scene.cpp:54-129 Scene::Scene, :148-162 load_images, :164-442 load_primitives,
+ * :444-510 load_node). The reference uses tinygltf + stb; this is a from-scratch reader (own JSON
+ * parser, zlib for embedded PNGs) that reproduces what reaches the kernels:
+ *
+ *   - one instance per glTF node x mesh primitive, in node-index order then primitive order
+ *     (= Embree attach order = instID, F11); POSITION / NORMAL / TEXCOORD_0 and indices required
+ *     (:256-276), indices u8/u16/u32 widened to u32 (:359-401), byteStride honoured (:289-292);
+ *   - node transform local = T * R * S * matrix (:18-21), global = parents... * (local * scale(gs))
+ *     (:137-146); a node without rotation keeps glm::quat{} = (0,0,0,0) whose mat4 cast is the
+ *     identity (src/scene.hpp:48);
+ *   - material classification (:188-254): KHR_materials_ior && KHR_materials_transmission ->
+ *     dielectric(ior); else metallicFactor > 0.01 -> metallic(albedo tex|colour, roughness, emissive);
+ *     else diffuse(albedo tex|colour, emissive); emissive = emissiveFactor * emissiveStrength, and the
+ *     strength is 0 when KHR_materials_emissive_strength is absent (:203-211);
+ *   - scene extras sky_color (3 numbers) and sky_strength (:80-94), default sky (0.5,0.7,1.0);
+ *   - camera node: position = global[3], direction = normalize(rotation * (0,0,-1)),
+ *     focal = 1 / tan(yfov / 2) (:109-128);
+ *   - images: every image is resized to 512x512 RGBA8 and baked into the layer array
+ *     (src/image_manager.hpp:39-100). Embedded PNG (8-bit, non-interlaced) is decoded here; the resize
+ *     is an sRGB-aware box / bilinear filter, NOT stb_image_resize2's default kernel, so textures
+ *     that are not already 512x512 differ from the reference in the filtered texels (documented gap).
+ *
+ * Explicit fallbacks where the reference relies on undefined behaviour (F15): a primitive without a
+ * material -> diffuse 0.8 grey; no camera node -> position (0,0,0), direction (0,0,-1), focal 1.
+ */
+#pragma once
+
+#include <zlib.h>
+
+#include <array>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <map>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/rt_api.h"
+
+namespace raytracer {
+namespace glb {
+
+/* ------------------------------------------------------------------ minimal JSON */
+struct Json {
+    enum Type { Null, Bool, Num, Str, Arr, Obj } type = Null;
+    double num = 0;
+    bool b = false;
+    std::string str;
+    std::vector<Json> arr;
+    std::map<std::string, Json> obj;
+    bool has(const std::string &k) const { return type == Obj && obj.count(k); }
+    const Json &operator[](const std::string &k) const {
+        static const Json null_json;
+        auto it = obj.find(k);
+        return it == obj.end() ? null_json : it->second;
+    }
+    const Json &operator[](size_t i) const { return arr[i]; }
+    size_t size() const { return type == Arr ? arr.size() : 0; }
+    double number(double dflt) const { return type == Num ? num : dflt; }
+    int integer(int dflt) const { return type == Num ? (int)num : dflt; }
+};
+
+class JsonParser {
+    const char *p, *end;
+    void ws() {
+        while (p < end && (*p == ' ' || *p == '\n' || *p == '\t' || *p == '\r')) p++;
+    }
+    [[noreturn]] void fail(const char *m) { throw std::runtime_error(std::string("Failed to load .glTF : JSON ") + m); }
+    Json value() {
+        ws();
+        if (p >= end) fail("truncated");
+        Json j;
+        if (*p == '{') {
+            j.type = Json::Obj;
+            p++;
+            ws();
+            if (p < end && *p == '}') { p++; return j; }
+            for (;;) {
+                ws();
+                Json k = string();
+                ws();
+                if (p >= end || *p != ':') fail("expected ':'");
+                p++;
+                j.obj[k.str] = value();
+                ws();
+                if (p < end && *p == ',') { p++; continue; }
+                if (p < end && *p == '}') { p++; break; }
+                fail("expected ',' or '}'");
+            }
+        } else if (*p == '[') {
+            j.type = Json::Arr;
+            p++;
+            ws();
+            if (p < end && *p == ']') { p++; return j; }
+            for (;;) {
+                j.arr.push_back(value());
+                ws();
+                if (p < end && *p == ',') { p++; continue; }
+                if (p < end && *p == ']') { p++; break; }
+                fail("expected ',' or ']'");
+            }
+        } else if (*p == '"') {
+            j = string();
+        } else if (!strncmp(p, "true", 4)) {
+            j.type = Json::Bool; j.b = true; p += 4;
+        } else if (!strncmp(p, "false", 5)) {
+            j.type = Json::Bool; p += 5;
+        } else if (!strncmp(p, "null", 4)) {
+            p += 4;
+        } else {
+            char *e = nullptr;
+            j.type = Json::Num;
+            j.num = strtod(p, &e);
+            if (e == p) fail("bad token");
+            p = e;
+        }
+        return j;
+    }
+    Json string() {
+        if (p >= end || *p != '"') fail("expected string");
+        p++;
+        Json j;
+        j.type = Json::Str;
+        while (p < end && *p != '"') {
+            if (*p == '\\' && p + 1 < end) {
+                p++;
+                switch (*p) {
+                case 'n': j.str += '\n'; break;
+                case 't': j.str += '\t'; break;
+                case 'u': j.str += '?'; p += 4; break;
+                default: j.str += *p;
+                }
+                p++;
+            } else j.str += *p++;
+        }
+        if (p >= end) fail("unterminated string");
+        p++;
+        return j;
+    }
+
+  public:
+    static Json parse(const char *s, size_t n) {
+        JsonParser q;
+        q.p = s;
+        q.end = s + n;
+        return q.value();
+    }
+};
+
+/* ------------------------------------------------------------------ small column-major mat4 */
+struct Mat4 {
+    float m[16]; /* m[col * 4 + row], like glm */
+    static Mat4 identity() {
+        Mat4 r{};
+        r.m[0] = r.m[5] = r.m[10] = r.m[15] = 1.0f;
+        return r;
+    }
+};
+inline Mat4 mul(const Mat4 &a, const Mat4 &b) { /* glm order: (a * b)[c] = sum_k a[k] * b[c][k] */
+    Mat4 r{};
+    for (int c = 0; c < 4; c++)
+        for (int row = 0; row < 4; row++)
+            r.m[c * 4 + row] = a.m[0 * 4 + row] * b.m[c * 4 + 0] + a.m[1 * 4 + row] * b.m[c * 4 + 1] +
+                               a.m[2 * 4 + row] * b.m[c * 4 + 2] + a.m[3 * 4 + row] * b.m[c * 4 + 3];
+    return r;
+}
+inline Mat4 translate(const float t[3]) {
+    Mat4 r = Mat4::identity();
+    r.m[12] = t[0]; r.m[13] = t[1]; r.m[14] = t[2];
+    return r;
+}
+inline Mat4 scale(const float s[3]) {
+    Mat4 r = Mat4::identity();
+    r.m[0] = s[0]; r.m[5] = s[1]; r.m[10] = s[2];
+    return r;
+}
+/* glm::mat4_cast(quat(w,x,y,z)); the all-zero default quaternion gives the identity */
+inline Mat4 from_quat(const float q[4] /* x y z w */) {
+    const float x = q[0], y = q[1], z = q[2], w = q[3];
+    Mat4 r = Mat4::identity();
+    r.m[0] = 1 - 2 * (y * y + z * z); r.m[1] = 2 * (x * y + w * z);     r.m[2] = 2 * (x * z - w * y);
+    r.m[4] = 2 * (x * y - w * z);     r.m[5] = 1 - 2 * (x * x + z * z); r.m[6] = 2 * (y * z + w * x);
+    r.m[8] = 2 * (x * z + w * y);     r.m[9] = 2 * (y * z - w * x);     r.m[10] = 1 - 2 * (x * x + y * y);
+    return r;
+}
+
+/* ------------------------------------------------------------------ PNG (zlib) */
+inline uint32_t be32(const uint8_t *p) { return (uint32_t)p[0] << 24 | p[1] << 16 | p[2] << 8 | p[3]; }
+
+/* decode an 8-bit, non-interlaced grey / grey+alpha / RGB / RGBA PNG to RGBA8 */
+inline std::vector<uint8_t> png_decode(const uint8_t *d, size_t n, uint32_t &w, uint32_t &h) {
+    static const uint8_t sig[8] = {0x89, 'P', 'N', 'G', 0x0d, 0x0a, 0x1a, 0x0a};
+    if (n < 8 || memcmp(d, sig, 8)) throw std::runtime_error("unsupported image (only embedded PNG is decoded)");
+    std::vector<uint8_t> idat;
+    int depth = 0, ctype = 0, interlace = 0;
+    for (size_t o = 8; o + 12 <= n;) {
+        const uint32_t len = be32(d + o);
+        const char *ty = (const char *)d + o + 4;
+        if (!strncmp(ty, "IHDR", 4)) {
+            w = be32(d + o + 8); h = be32(d + o + 12);
+            depth = d[o + 16]; ctype = d[o + 17]; interlace = d[o + 20];
+        } else if (!strncmp(ty, "IDAT", 4)) idat.insert(idat.end(), d + o + 8, d + o + 8 + len);
+        else if (!strncmp(ty, "IEND", 4)) break;
+        o += 12 + len;
+    }
+    const int ch = ctype == 0 ? 1 : ctype == 2 ? 3 : ctype == 4 ? 2 : ctype == 6 ? 4 : 0;
+    if (depth != 8 || !ch || interlace) throw std::runtime_error("unsupported PNG variant (need 8-bit, non-interlaced, non-palette)");
+    const size_t stride = (size_t)w * ch;
+    std::vector<uint8_t> raw((stride + 1) * h);
+    uLongf out_len = raw.size();
+    if (uncompress(raw.data(), &out_len, idat.data(), idat.size()) != Z_OK || out_len != raw.size())
+        throw std::runtime_error("PNG inflate failed");
+    std::vector<uint8_t> px(stride * h), out((size_t)w * h * 4);
+    for (uint32_t y = 0; y < h; y++) {
+        const uint8_t ft = raw[(stride + 1) * y], *src = &raw[(stride + 1) * y + 1];
+        uint8_t *cur = &px[stride * y];
+        const uint8_t *up = y ? &px[stride * (y - 1)] : nullptr;
+        for (size_t x = 0; x < stride; x++) {
+            const int a = x >= (size_t)ch ? cur[x - ch] : 0, b = up ? up[x] : 0, c = (up && x >= (size_t)ch) ? up[x - ch] : 0;
+            int pred = 0;
+            if (ft == 1) pred = a;
+            else if (ft == 2) pred = b;
+            else if (ft == 3) pred = (a + b) / 2;
+            else if (ft == 4) {
+                const int p = a + b - c, pa = std::abs(p - a), pb = std::abs(p - b), pc = std::abs(p - c);
+                pred = (pa <= pb && pa <= pc) ? a : (pb <= pc ? b : c);
+            }
+            cur[x] = (uint8_t)(src[x] + pred);
+        }
+    }
+    for (size_t i = 0; i < (size_t)w * h; i++) {
+        const uint8_t *s = &px[i * ch];
+        uint8_t *o = &out[i * 4];
+        if (ch == 1) { o[0] = o[1] = o[2] = s[0]; o[3] = 255; }
+        else if (ch == 2) { o[0] = o[1] = o[2] = s[0]; o[3] = s[1]; }
+        else if (ch == 3) { o[0] = s[0]; o[1] = s[1]; o[2] = s[2]; o[3] = 255; }
+        else memcpy(o, s, 4);
+    }
+    return out;
+}
+
+/* RGBA8 PNG writer (filter 0, one zlib stream) — what stbi_write_png does for out.png (src/util.hpp:27) */
+inline bool png_write(const std::string &path, const uint8_t *rgba, uint32_t w, uint32_t h) {
+    std::vector<uint8_t> raw((size_t)(w * 4 + 1) * h);
+    for (uint32_t y = 0; y < h; y++) {
+        raw[(size_t)(w * 4 + 1) * y] = 0;
+        memcpy(&raw[(size_t)(w * 4 + 1) * y + 1], rgba + (size_t)y * w * 4, (size_t)w * 4);
+    }
+    uLongf clen = compressBound(raw.size());
+    std::vector<uint8_t> comp(clen);
+    if (compress2(comp.data(), &clen, raw.data(), raw.size(), 6) != Z_OK) return false;
+    std::ofstream f(path, std::ios::binary);
+    if (!f) return false;
+    auto chunk = [&](const char *type, const uint8_t *data, uint32_t len) {
+        uint8_t hdr[8] = {(uint8_t)(len >> 24), (uint8_t)(len >> 16), (uint8_t)(len >> 8), (uint8_t)len,
+                          (uint8_t)type[0], (uint8_t)type[1], (uint8_t)type[2], (uint8_t)type[3]};
+        f.write((const char *)hdr, 8);
+        if (len) f.write((const char *)data, len);
+        uLong crc = crc32(0L, hdr + 4, 4);
+        if (len) crc = crc32(crc, data, len);
+        const uint8_t c[4] = {(uint8_t)(crc >> 24), (uint8_t)(crc >> 16), (uint8_t)(crc >> 8), (uint8_t)crc};
+        f.write((const char *)c, 4);
+    };
+    static const uint8_t sig[8] = {0x89, 'P', 'N', 'G', 0x0d, 0x0a, 0x1a, 0x0a};
+    f.write((const char *)sig, 8);
+    const uint8_t ihdr[13] = {(uint8_t)(w >> 24), (uint8_t)(w >> 16), (uint8_t)(w >> 8), (uint8_t)w, (uint8_t)(h >> 24),
+                              (uint8_t)(h >> 16), (uint8_t)(h >> 8), (uint8_t)h, 8, 6, 0, 0, 0};
+    chunk("IHDR", ihdr, 13);
+    chunk("IDAT", comp.data(), (uint32_t)clen);
+    chunk("IEND", nullptr, 0);
+    return (bool)f;
+}
+
+/* resize to 512x512 in linear light (sRGB decode -> box/bilinear -> sRGB encode); see header note */
+inline std::vector<uint8_t> resize_to_layer(const std::vector<uint8_t> &src, uint32_t w, uint32_t h) {
+    const uint32_t N = RT_TEX_SIZE;
+    if (w == N && h == N) return src;
+    auto to_lin = [](uint8_t v) { float c = v / 255.0f; return c <= 0.04045f ? c / 12.92f : std::pow((c + 0.055f) / 1.055f, 2.4f); };
+    auto to_srgb = [](float l) {
+        float c = l <= 0.0031308f ? l * 12.92f : 1.055f * std::pow(l, 1.0f / 2.4f) - 0.055f;
+        return (uint8_t)std::lround(std::fmin(std::fmax(c, 0.0f), 1.0f) * 255.0f);
+    };
+    std::vector<uint8_t> out((size_t)N * N * 4);
+    for (uint32_t y = 0; y < N; y++)
+        for (uint32_t x = 0; x < N; x++) {
+            const double x0 = (double)x * w / N, x1 = (double)(x + 1) * w / N, y0 = (double)y * h / N, y1 = (double)(y + 1) * h / N;
+            double acc[4] = {0, 0, 0, 0}, wsum = 0;
+            for (uint32_t sy = (uint32_t)y0; sy < h && sy < (uint32_t)std::ceil(y1); sy++)
+                for (uint32_t sx = (uint32_t)x0; sx < w && sx < (uint32_t)std::ceil(x1); sx++) {
+                    const double wx = std::fmin(x1, sx + 1.0) - std::fmax(x0, (double)sx), wy = std::fmin(y1, sy + 1.0) - std::fmax(y0, (double)sy);
+                    const double wt = std::fmax(wx, 1e-9) * std::fmax(wy, 1e-9);
+                    const uint8_t *p = &src[((size_t)sy * w + sx) * 4];
+                    for (int c = 0; c < 3; c++) acc[c] += wt * to_lin(p[c]);
+                    acc[3] += wt * p[3] / 255.0;
+                    wsum += wt;
+                }
+            uint8_t *o = &out[((size_t)y * N + x) * 4];
+            for (int c = 0; c < 3; c++) o[c] = to_srgb((float)(acc[c] / wsum));
+            o[3] = (uint8_t)std::lround(acc[3] / wsum * 255.0);
+        }
+    return out;
+}
+
+/* ------------------------------------------------------------------ the loaded scene */
+struct LoadedScene {
+    struct Inst {
+        std::vector<float> positions, normals, uvs;
+        std::vector<uint32_t> indices;
+        Mat4 transform;
+        rt_material material;
+        int node, mesh, primitive;
+    };
+    std::vector<Inst> instances;
+    std::vector<uint8_t> texture_layers; /* n * 512 * 512 * 4 */
+    uint32_t texture_layer_count = 0;
+    float sky_color[3] = {0.5f, 0.7f, 1.0f};
+    float camera_position[3] = {0, 0, 0}, camera_direction[3] = {0, 0, -1};
+    float camera_focal_length = 1.0f;
+    bool has_camera = false;
+    std::vector<rt_instance> rt_instances;
+
+    rt_scene_desc desc() {
+        rt_instances.clear();
+        for (auto &i : instances) {
+            rt_instance r{};
+            r.positions = i.positions.data();
+            r.normals = i.normals.data();
+            r.uvs = i.uvs.data();
+            r.indices = i.indices.data();
+            r.vertex_count = (uint32_t)(i.positions.size() / 3);
+            r.index_count = (uint32_t)i.indices.size();
+            memcpy(r.transform, i.transform.m, sizeof(r.transform));
+            r.material = i.material;
+            rt_instances.push_back(r);
+        }
+        rt_scene_desc d{};
+        d.instances = rt_instances.data();
+        d.instance_count = (uint32_t)rt_instances.size();
+        d.texture_layers = texture_layer_count ? texture_layers.data() : nullptr;
+        d.texture_layer_count = texture_layer_count;
+        memcpy(d.sky_color, sky_color, sizeof(sky_color));
+        return d;
+    }
+};
+
+namespace detail {
+struct Reader {
+    Json j;
+    std::vector<uint8_t> bin;
+    const uint8_t *view_ptr(int view, size_t extra, size_t &stride_out) const {
+        const Json &v = j["bufferViews"][(size_t)view];
+        stride_out = (size_t)v["byteStride"].integer(0);
+        const size_t off = (size_t)v["byteOffset"].integer(0) + extra;
+        if (off > bin.size()) throw std::runtime_error("Failed to load .glTF : buffer view out of range");
+        return bin.data() + off;
+    }
+    std::vector<float> floats(int accessor, int comps) const {
+        const Json &a = j["accessors"][(size_t)accessor];
+        if (a["componentType"].integer(0) != 5126) throw std::runtime_error("Failed to load .glTF : float accessor expected");
+        size_t stride = 0;
+        const uint8_t *p = view_ptr(a["bufferView"].integer(0), (size_t)a["byteOffset"].integer(0), stride);
+        if (!stride) stride = (size_t)comps * 4;
+        const size_t n = (size_t)a["count"].integer(0);
+        std::vector<float> out(n * comps);
+        for (size_t i = 0; i < n; i++) memcpy(&out[i * comps], p + i * stride, (size_t)comps * 4);
+        return out;
+    }
+    std::vector<uint32_t> indices(int accessor) const {
+        const Json &a = j["accessors"][(size_t)accessor];
+        size_t stride = 0;
+        const uint8_t *p = view_ptr(a["bufferView"].integer(0), (size_t)a["byteOffset"].integer(0), stride);
+        const size_t n = (size_t)a["count"].integer(0);
+        const int ct = a["componentType"].integer(0);
+        std::vector<uint32_t> out(n);
+        for (size_t i = 0; i < n; i++) {
+            if (ct == 5125) { uint32_t v; memcpy(&v, p + i * 4, 4); out[i] = v; }
+            else if (ct == 5123) { uint16_t v; memcpy(&v, p + i * 2, 2); out[i] = v; }
+            else if (ct == 5121) out[i] = p[i];
+            else throw std::runtime_error("Index component type not supported!"); /* src/scene.cpp:394-400 */
+        }
+        return out;
+    }
+};
+} // namespace detail
+
+inline LoadedScene load(const std::string &path, const float global_scale[3] = nullptr) {
+    std::ifstream f(path, std::ios::binary);
+    if (!f) throw std::runtime_error("Failed to load .glTF : cannot open " + path); /* src/scene.cpp:68-70 */
+    std::vector<uint8_t> file((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+    if (file.size() < 20 || memcmp(file.data(), "glTF", 4)) throw std::runtime_error("Failed to load .glTF : not a binary glTF");
+    auto le32 = [&](size_t o) { uint32_t v; memcpy(&v, &file[o], 4); return v; };
+    detail::Reader rd;
+    for (size_t o = 12; o + 8 <= file.size();) {
+        const uint32_t len = le32(o), type = le32(o + 4);
+        if (o + 8 + len > file.size()) throw std::runtime_error("Failed to load .glTF : truncated chunk");
+        if (type == 0x4E4F534A) rd.j = JsonParser::parse((const char *)&file[o + 8], len);
+        else if (type == 0x004E4942) rd.bin.assign(file.begin() + o + 8, file.begin() + o + 8 + len);
+        o += 8 + ((len + 3) & ~3u);
+    }
+    const Json &j = rd.j;
+    LoadedScene out;
+    const float gs_default[3] = {1, 1, 1};
+    const float *gs = global_scale ? global_scale : gs_default;
+
+    /* images -> 512x512 layers (src/scene.cpp:148-162) */
+    const size_t n_images = j["images"].size();
+    if (n_images > RT_MAX_IMAGES) throw std::runtime_error("Too many images uploaded"); /* src/image_manager.hpp:41-44 */
+    for (size_t i = 0; i < n_images; i++) {
+        const Json &im = j["images"][i];
+        if (!im.has("bufferView")) throw std::runtime_error("Failed to load .glTF : external image URIs are not supported");
+        size_t stride;
+        const Json &v = j["bufferViews"][(size_t)im["bufferView"].integer(0)];
+        const uint8_t *p = rd.view_ptr(im["bufferView"].integer(0), 0, stride);
+        uint32_t w = 0, h = 0;
+        std::vector<uint8_t> px = png_decode(p, (size_t)v["byteLength"].integer(0), w, h);
+        std::vector<uint8_t> layer = resize_to_layer(px, w, h);
+        out.texture_layers.insert(out.texture_layers.end(), layer.begin(), layer.end());
+        out.texture_layer_count++;
+    }
+
+    /* node hierarchy: parent links by traversal from the default scene (src/scene.cpp:96-99,444-480) */
+    const size_t n_nodes = j["nodes"].size();
+    std::vector<int> parent(n_nodes, -1);
+    std::vector<char> reached(n_nodes, 0);
+    std::vector<Mat4> local(n_nodes);
+    for (size_t n = 0; n < n_nodes; n++) {
+        const Json &nd = j["nodes"][n];
+        float t[3] = {0, 0, 0}, s[3] = {1, 1, 1}, q[4] = {0, 0, 0, 0};
+        Mat4 m = Mat4::identity();
+        if (nd["translation"].size() == 3) for (int k = 0; k < 3; k++) t[k] = (float)nd["translation"][k].num;
+        if (nd["rotation"].size() == 4) for (int k = 0; k < 4; k++) q[k] = (float)nd["rotation"][k].num;
+        if (nd["scale"].size() == 3) for (int k = 0; k < 3; k++) s[k] = (float)nd["scale"][k].num;
+        if (nd["matrix"].size() == 16) for (int k = 0; k < 16; k++) m.m[k] = (float)nd["matrix"][k].num;
+        local[n] = mul(mul(mul(translate(t), from_quat(q)), scale(s)), m); /* T * R * S * matrix */
+    }
+    const Json &scene = j["scenes"][(size_t)std::max(0, j["scene"].integer(0))];
+    int camera_node = -1;
+    std::vector<int> stack;
+    for (size_t k = 0; k < scene["nodes"].size(); k++) stack.push_back(scene["nodes"][k].integer(0));
+    while (!stack.empty()) {
+        const int n = stack.back();
+        stack.pop_back();
+        reached[(size_t)n] = 1;
+        const Json &nd = j["nodes"][(size_t)n];
+        if (nd.has("camera")) camera_node = n;
+        for (size_t k = 0; k < nd["children"].size(); k++) {
+            const int c = nd["children"][k].integer(0);
+            parent[(size_t)c] = n;
+            stack.push_back(c);
+        }
+    }
+    auto global_matrix = [&](int n) { /* src/scene.cpp:137-146 */
+        Mat4 m = mul(local[(size_t)n], scale(gs));
+        for (int p = parent[(size_t)n]; p >= 0; p = parent[(size_t)p]) m = mul(local[(size_t)p], m);
+        return m;
+    };
+
+    /* scene extras (src/scene.cpp:80-94) */
+    const Json &extras = scene["extras"];
+    if (extras["sky_color"].size() == 3) for (int k = 0; k < 3; k++) out.sky_color[k] = (float)extras["sky_color"][k].num;
+    if (extras["sky_strength"].type == Json::Num) for (int k = 0; k < 3; k++) out.sky_color[k] *= (float)extras["sky_strength"].num;
+
+    /* instances in node-index order (src/scene.cpp:101-106), primitives in order */
+    for (size_t n = 0; n < n_nodes; n++) {
+        const Json &nd = j["nodes"][n];
+        if (!reached[n] || !nd.has("mesh")) continue;
+        const int mesh = nd["mesh"].integer(0);
+        const Json &prims = j["meshes"][(size_t)mesh]["primitives"];
+        for (size_t pi = 0; pi < prims.size(); pi++) {
+            const Json &pr = prims[pi];
+            const Json &at = pr["attributes"];
+            if (!pr.has("indices") || !at.has("POSITION") || !at.has("NORMAL") || !at.has("TEXCOORD_0"))
+                throw std::runtime_error("Failed to load .glTF : primitives need indices, POSITION, NORMAL and TEXCOORD_0"); /* :256-276 */
+            LoadedScene::Inst in;
+            in.node = (int)n; in.mesh = mesh; in.primitive = (int)pi;
+            in.positions = rd.floats(at["POSITION"].integer(0), 3);
+            in.normals = rd.floats(at["NORMAL"].integer(0), 3);
+            in.uvs = rd.floats(at["TEXCOORD_0"].integer(0), 2);
+            in.indices = rd.indices(pr["indices"].integer(0));
+            in.transform = global_matrix((int)n);
+            rt_material m{};
+            m.albedo_image = -1;
+            m.ior = 1.5f;
+            if (!pr.has("material")) { /* F15 fallback: the reference indexes materials[-1] */
+                m.type = RT_MAT_DIFFUSE;
+                m.albedo_color[0] = m.albedo_color[1] = m.albedo_color[2] = 0.8f;
+            } else {
+                const Json &mat = j["materials"][(size_t)pr["material"].integer(0)];
+                const Json &pbr = mat["pbrMetallicRoughness"];
+                for (int k = 0; k < 3; k++) m.albedo_color[k] = pbr["baseColorFactor"].size() >= 3 ? (float)pbr["baseColorFactor"][k].num : 1.0f;
+                const Json &ext = mat["extensions"];
+                float strength = 0.0f; /* 0 when the extension is absent (src/scene.cpp:203-211) */
+                if (ext.has("KHR_materials_emissive_strength")) strength = (float)ext["KHR_materials_emissive_strength"]["emissiveStrength"].number(1.0);
+                for (int k = 0; k < 3; k++) m.emissive[k] = (mat["emissiveFactor"].size() == 3 ? (float)mat["emissiveFactor"][k].num : 0.0f) * strength;
+                const int tex = pbr["baseColorTexture"]["index"].integer(-1);
+                const int image = tex >= 0 ? j["textures"][(size_t)tex]["source"].integer(-1) : -1;
+                if (ext.has("KHR_materials_ior") && ext.has("KHR_materials_transmission")) {
+                    m.type = RT_MAT_DIELECTRIC;
+                    m.ior = (float)ext["KHR_materials_ior"]["ior"].number(1.5);
+                } else if ((float)pbr["metallicFactor"].number(1.0) > 0.01f) { /* glTF default metallicFactor = 1 */
+                    m.type = RT_MAT_METALLIC;
+                    m.roughness = (float)pbr["roughnessFactor"].number(1.0);
+                    m.albedo_image = image;
+                } else {
+                    m.type = RT_MAT_DIFFUSE;
+                    m.albedo_image = image;
+                }
+            }
+            in.material = m;
+            out.instances.push_back(std::move(in));
+        }
+    }
+
+    /* camera (src/scene.cpp:109-128) */
+    if (camera_node >= 0) {
+        const Mat4 m = global_matrix(camera_node);
+        for (int k = 0; k < 3; k++) out.camera_position[k] = m.m[12 + k];
+        /* rotation * (0,0,-1) with the rotation part normalised (glm::quat_cast of the 3x3) */
+        float c2[3] = {m.m[8], m.m[9], m.m[10]};
+        const float len = std::sqrt(c2[0] * c2[0] + c2[1] * c2[1] + c2[2] * c2[2]);
+        for (int k = 0; k < 3; k++) out.camera_direction[k] = len > 0 ? -c2[k] / len : (k == 2 ? -1.0f : 0.0f);
+        const Json &cam = j["cameras"][(size_t)j["nodes"][(size_t)camera_node]["camera"].integer(0)];
+        const float yfov = (float)cam["perspective"]["yfov"].number(1.0);
+        out.camera_focal_length = 1.0f / std::tan(yfov / 2.0f);
+        out.has_camera = true;
+    }
+    return out;
+}
+
+} // namespace glb
+} // namespace raytracer

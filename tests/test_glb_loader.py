@@ -1,0 +1,219 @@
+"""GLB loader + PNG writer of the C++ host (host/glb_loader.hpp), i.e. the "next" rows of the scope
+table. A synthetic .glb is written here with every feature the reference loader
+(src/scene.cpp) interprets; the loader's output is compared with what that file must produce."""
+import ctypes as C
+import json
+import os
+import struct
+import subprocess
+import zlib
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HOST = os.path.join(ROOT, "sycl-ray-tracer_b200", "host")
+
+
+@pytest.fixture(scope="module")
+def glb(pkg):
+    subprocess.run(["make", "-s", "-C", HOST], check=True)
+    L = C.CDLL(os.path.join(HOST, "libglb_loader.so"))
+    L.glb_load.restype = C.c_void_p
+    L.glb_load.argtypes = [C.c_char_p]
+    L.glb_last_error.restype = C.c_char_p
+    L.glb_free.argtypes = [C.c_void_p]
+    L.glb_instance_count.argtypes = [C.c_void_p]
+    L.glb_layer_count.argtypes = [C.c_void_p]
+    L.glb_layers.restype = C.POINTER(C.c_uint8)
+    L.glb_layers.argtypes = [C.c_void_p]
+    L.glb_globals.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
+    L.glb_png_write.argtypes = [C.c_char_p, C.c_void_p, C.c_uint32, C.c_uint32]
+    L.glb_png_read.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
+    fp, up = C.POINTER(C.c_float), C.POINTER(C.c_uint32)
+    L.glb_instance.argtypes = [C.c_void_p, C.c_uint32, up, up, C.POINTER(fp), C.POINTER(fp), C.POINTER(fp), C.POINTER(up),
+                               fp, C.POINTER(pkg._capi.rt_material), C.POINTER(C.c_int32)]
+    return L
+
+
+def _png(rgba):
+    h, w, _ = rgba.shape
+    raw = b"".join(b"\x00" + rgba[y].tobytes() for y in range(h))
+
+    def chunk(t, d):
+        return struct.pack(">I", len(d)) + t + d + struct.pack(">I", zlib.crc32(t + d) & 0xFFFFFFFF)
+    return b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", w, h, 8, 6, 0, 0, 0)) + chunk(b"IDAT", zlib.compress(raw)) + chunk(b"IEND", b"")
+
+
+def _write_glb(path, tex):
+    """two meshes under a parent/child hierarchy, u8/u16/u32 indices, an interleaved (strided) vertex
+    buffer, diffuse-textured / metallic / dielectric / emissive materials, sky extras, a camera node"""
+    rs = np.random.RandomState(4)
+    blobs, views, accessors = [], [], []
+
+    def add_view(data, stride=None):
+        off = sum(len(b) for b in blobs)
+        pad = (-len(data)) % 4
+        blobs.append(data + b"\x00" * pad)
+        v = {"buffer": 0, "byteOffset": off, "byteLength": len(data)}
+        if stride:
+            v["byteStride"] = stride
+        views.append(v)
+        return len(views) - 1
+
+    def add_acc(view, ctype, count, typ, offset=0):
+        accessors.append({"bufferView": view, "componentType": ctype, "count": count, "type": typ, "byteOffset": offset})
+        return len(accessors) - 1
+    prims, expect = [], []
+    for k, (nv, ntri, ict, itype) in enumerate([(12, 7, 5121, np.uint8), (40, 30, 5123, np.uint16), (9, 3, 5125, np.uint32)]):
+        pos, nrm, uv = rs.randn(nv, 3).astype(np.float32), rs.randn(nv, 3).astype(np.float32), rs.rand(nv, 2).astype(np.float32)
+        idx = rs.randint(0, nv, ntri * 3).astype(itype)
+        if k == 1:   # interleaved pos|nrm|uv, stride 32
+            inter = np.concatenate([pos, nrm, uv], 1).astype(np.float32)
+            v = add_view(inter.tobytes(), 32)
+            a = (add_acc(v, 5126, nv, "VEC3", 0), add_acc(v, 5126, nv, "VEC3", 12), add_acc(v, 5126, nv, "VEC2", 24))
+        else:
+            a = (add_acc(add_view(pos.tobytes()), 5126, nv, "VEC3"), add_acc(add_view(nrm.tobytes()), 5126, nv, "VEC3"),
+                 add_acc(add_view(uv.tobytes()), 5126, nv, "VEC2"))
+        ia = add_acc(add_view(idx.tobytes()), ict, ntri * 3, "SCALAR")
+        prims.append({"attributes": {"POSITION": a[0], "NORMAL": a[1], "TEXCOORD_0": a[2]}, "indices": ia, "material": k})
+        expect.append((pos, nrm, uv, idx.astype(np.uint32)))
+    img_view = add_view(_png(tex))
+    prims.append({"attributes": prims[0]["attributes"], "indices": prims[0]["indices"]})   # no material: F15 fallback
+    expect.append(expect[0])
+    q = np.array([0.0, np.sin(0.35), 0.0, np.cos(0.35)])          # rotation about Y
+    qc = np.array([np.sin(0.2), 0.0, 0.0, np.cos(0.2)])           # camera pitch
+    child_m = np.eye(4)
+    child_m[:3, 3] = (0.5, -1.0, 2.0)
+    child_m[0, 0] = 2.0
+    j = {"asset": {"version": "2.0"}, "scene": 0,
+         "scenes": [{"nodes": [0, 3], "extras": {"sky_color": [0.2, 0.4, 0.8], "sky_strength": 2.0}}],
+         "nodes": [{"translation": [1.0, 2.0, -3.0], "rotation": q.tolist(), "scale": [1.5, 1.0, 0.5], "children": [1, 2], "mesh": 0},
+                   {"matrix": child_m.T.reshape(-1).tolist(), "mesh": 1},
+                   {"translation": [0.0, 1.0, 0.0], "mesh": 0},
+                   {"translation": [0.0, 1.0, 5.0], "rotation": qc.tolist(), "camera": 0},
+                   {"mesh": 1}],                                   # node 4 is not in the scene: ignored
+         "cameras": [{"type": "perspective", "perspective": {"yfov": 0.8, "aspectRatio": 1.5, "znear": 0.1}}],
+         "meshes": [{"primitives": prims[:2] + [prims[3]]}, {"primitives": [prims[2]]}],
+         "materials": [{"pbrMetallicRoughness": {"baseColorFactor": [0.9, 0.8, 0.7, 1], "metallicFactor": 0.0, "baseColorTexture": {"index": 0}},
+                        "emissiveFactor": [1.0, 0.5, 0.25], "extensions": {"KHR_materials_emissive_strength": {"emissiveStrength": 4.0}}},
+                       {"pbrMetallicRoughness": {"baseColorFactor": [0.5, 0.5, 0.5, 1], "metallicFactor": 0.7, "roughnessFactor": 0.25},
+                        "emissiveFactor": [1.0, 1.0, 1.0]},       # no emissive_strength extension -> emissive 0
+                       {"pbrMetallicRoughness": {"metallicFactor": 0.9},
+                        "extensions": {"KHR_materials_ior": {"ior": 1.33}, "KHR_materials_transmission": {"transmissionFactor": 1}}}],
+         "textures": [{"source": 0}], "images": [{"bufferView": img_view, "mimeType": "image/png"}],
+         "accessors": accessors, "bufferViews": views, "buffers": [{"byteLength": sum(len(b) for b in blobs)}]}
+    js = json.dumps(j).encode()
+    js += b" " * ((-len(js)) % 4)
+    binc = b"".join(blobs)
+    total = 12 + 8 + len(js) + 8 + len(binc)
+    with open(path, "wb") as f:
+        f.write(struct.pack("<4sII", b"glTF", 2, total) + struct.pack("<II", len(js), 0x4E4F534A) + js + struct.pack("<II", len(binc), 0x004E4942) + binc)
+
+    def trs(t, qq, s):
+        x, y, z, w = qq
+        R = np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - w * z), 2 * (x * z + w * y)],
+                      [2 * (x * y + w * z), 1 - 2 * (x * x + z * z), 2 * (y * z - w * x)],
+                      [2 * (x * z - w * y), 2 * (y * z + w * x), 1 - 2 * (x * x + y * y)]])
+        M = np.eye(4)
+        M[:3, :3] = R @ np.diag(s)
+        M[:3, 3] = t
+        return M
+    M0 = trs((1, 2, -3), q, (1.5, 1.0, 0.5))
+    M2 = trs((0, 1, 0), (0, 0, 0, 1), (1, 1, 1))
+    globals_ = {0: M0, 1: M0 @ child_m, 2: M0 @ M2}
+    cam = trs((0, 1, 5), qc, (1, 1, 1))
+    return expect, globals_, cam
+
+
+def test_loader_follows_the_reference_rules(glb, pkg, tmp_path):
+    tex = (np.random.RandomState(1).rand(512, 512, 4) * 255).astype(np.uint8)   # already 512x512: baked verbatim
+    path = str(tmp_path / "synthetic.glb")
+    expect, M, cam = _write_glb(path, tex)
+    h = glb.glb_load(path.encode())
+    assert h, glb.glb_last_error()
+    # node order 0,1,2 (node 3 = camera, node 4 unreachable); node 0 and 2 carry mesh 0 (3 primitives), node 1 mesh 1
+    want = [(0, 0, 0), (0, 0, 1), (0, 0, 2), (1, 1, 0), (2, 0, 0), (2, 0, 1), (2, 0, 2)]
+    assert glb.glb_instance_count(h) == len(want)
+    prim_data = {(0, 0): expect[0], (0, 1): expect[1], (0, 2): expect[3], (1, 0): expect[2]}
+    mats = []
+    for i, (node, mesh, prim) in enumerate(want):
+        nv, ni = C.c_uint32(), C.c_uint32()
+        fp, up = C.POINTER(C.c_float), C.POINTER(C.c_uint32)
+        pos, nrm, uv, idx = fp(), fp(), fp(), up()
+        T = (C.c_float * 16)()
+        mat = pkg._capi.rt_material()
+        nmp = (C.c_int32 * 3)()
+        glb.glb_instance(h, i, C.byref(nv), C.byref(ni), C.byref(pos), C.byref(nrm), C.byref(uv), C.byref(idx), T, C.byref(mat), nmp)
+        assert list(nmp) == [node, mesh, prim]
+        e = prim_data[(mesh, prim)]
+        assert np.array_equal(np.ctypeslib.as_array(pos, (nv.value, 3)), e[0])
+        assert np.array_equal(np.ctypeslib.as_array(nrm, (nv.value, 3)), e[1])
+        assert np.array_equal(np.ctypeslib.as_array(uv, (nv.value, 2)), e[2])
+        assert np.array_equal(np.ctypeslib.as_array(idx, (ni.value,)), e[3])     # u8 / u16 / u32 widened
+        assert np.allclose(np.array(list(T)).reshape(4, 4).T, M[node], atol=1e-5)  # T*R*S*matrix, parents applied
+        mats.append((mat.type, mat.albedo_image, list(mat.albedo_color), mat.roughness, mat.ior, list(mat.emissive)))
+    D, Mt, Di = pkg._capi.RT_MAT_DIFFUSE, pkg._capi.RT_MAT_METALLIC, pkg._capi.RT_MAT_DIELECTRIC
+    t, img, col, rough, ior, em = mats[0]
+    assert (t, img) == (D, 0) and np.allclose(col, [0.9, 0.8, 0.7]) and np.allclose(em, [4.0, 2.0, 1.0])   # factor * strength
+    t, img, col, rough, ior, em = mats[1]
+    assert (t, img) == (Mt, -1) and np.isclose(rough, 0.25) and em == [0, 0, 0]      # strength extension absent -> 0
+    assert mats[2][0] == D and np.allclose(mats[2][2], [0.8, 0.8, 0.8])              # F15 fallback
+    assert mats[3][0] == Di and np.isclose(mats[3][4], 1.33)                         # ior + transmission beat metallic
+    g = (C.c_float * 16)()
+    glb.glb_globals(h, g)
+    assert np.allclose(list(g)[:3], [0.4, 0.8, 1.6])                                # sky_color * sky_strength
+    assert np.allclose(list(g)[3:6], cam[:3, 3]) and np.allclose(list(g)[6:9], -cam[:3, 2], atol=1e-6)
+    assert np.isclose(g[9], 1.0 / np.tan(0.4)) and g[10] == 1.0
+    assert glb.glb_layer_count(h) == 1
+    assert np.array_equal(np.ctypeslib.as_array(glb.glb_layers(h), (512, 512, 4)), tex)
+    glb.glb_free(h)
+
+
+def test_errors_and_png_round_trip(glb, tmp_path):
+    assert not glb.glb_load(str(tmp_path / "missing.glb").encode())
+    assert b"Failed to load .glTF" in glb.glb_last_error()
+    bad = tmp_path / "bad.glb"
+    bad.write_bytes(b"not a gltf file at all.....")
+    assert not glb.glb_load(str(bad).encode())
+    img = (np.random.RandomState(2).rand(37, 53, 4) * 255).astype(np.uint8)
+    out = str(tmp_path / "o.png")
+    assert glb.glb_png_write(out.encode(), img.ctypes.data, 53, 37) == 1
+    data = open(out, "rb").read()
+    from PIL import Image
+    assert np.array_equal(np.array(Image.open(out).convert("RGBA")), img)           # an independent decoder agrees
+    back = np.zeros_like(img)
+    w, h = C.c_uint32(), C.c_uint32()
+    assert glb.glb_png_read(data, len(data), back.ctypes.data, back.nbytes, C.byref(w), C.byref(h)) == 1
+    assert (w.value, h.value) == (53, 37) and np.array_equal(back, img)
+
+
+def test_reference_assets_when_present(glb):
+    """assets/cube.glb (config 1) and assets/triangle.glb load with the documented fallbacks"""
+    cube = "/root/reference/assets/cube.glb"
+    if not os.path.exists(cube):
+        pytest.skip("reference assets not present on this machine")
+    h = glb.glb_load(cube.encode())
+    assert h and glb.glb_instance_count(h) == 1
+    g = (C.c_float * 16)()
+    glb.glb_globals(h, g)
+    assert list(g)[:3] == [0.5, np.float32(0.7), 1.0] and g[10] == 0.0 and list(g)[6:9] == [0, 0, -1] and g[9] == 1.0
+    glb.glb_free(h)
+    h = glb.glb_load(b"/root/reference/assets/triangle.glb")
+    assert h and glb.glb_instance_count(h) == 1
+    glb.glb_free(h)
+
+
+@pytest.mark.gpu
+def test_cli_renders_a_glb_to_png(glb, oracle, scenes, tmp_path):
+    """raytracer scene.glb -> out.png: the whole reference CLI flow on the GPU"""
+    from PIL import Image
+    tex = (np.random.RandomState(1).rand(512, 512, 4) * 255).astype(np.uint8)
+    path = str(tmp_path / "synthetic.glb")
+    _write_glb(path, tex)
+    png = str(tmp_path / "out.png")
+    r = subprocess.run([os.path.join(HOST, "raytracer"), "-m", "-d", "6", "-s", "2", "--size", "96x64", "--png", png, path],
+                       capture_output=True, text=True, check=True)
+    assert "Total rays:" in r.stdout and "Writing image to disk" in r.stdout
+    img = np.array(Image.open(png))
+    assert img.shape == (64, 96, 4) and (img[..., 3] == 255).all() and img[..., :3].std() > 1.0
