@@ -92,6 +92,9 @@ __global__ void k_empty_root(rt_uint4 *nodes) {
     nodes[2] = make_uint4(ff, ff, ff, ff); /* qlo x, y = 255 */
     nodes[3] = make_uint4(ff, ff, 0, 0);   /* qlo z = 255, qhi x = 0 */
     nodes[4] = make_uint4(0, 0, 0, 0);
+#if RT_NODE_VEC4 > 5
+    nodes[5] = make_uint4(0, 0, 0, 0);
+#endif
 }
 
 inline uint32_t grid_for(uint64_t n) { return (uint32_t)((n + kBlock - 1) / kBlock); }
@@ -121,8 +124,8 @@ rt_status rt_build_bvh(rt_scene *s) {
     RT_CUDA_TRY(ctx, cudaEventRecord(ctx->ev0, st));
 
     if (n == 0) { /* empty scene: a root with no children, every ray misses */
-        RT_CUDA_TRY(ctx, cudaMalloc(&s->d_nodes, 5 * sizeof(rt_uint4)));
-        RT_CUDA_TRY(ctx, cudaMalloc(&s->d_tris, 3 * sizeof(rt_float4)));
+        RT_CUDA_TRY(ctx, cudaMalloc(&s->d_nodes, RT_NODE_VEC4 * sizeof(rt_uint4)));
+        RT_CUDA_TRY(ctx, cudaMalloc(&s->d_tris, RT_TRI_VEC4 * sizeof(rt_float4)));
         RT_CUDA_TRY(ctx, cudaMalloc(&s->d_shade, 4 * sizeof(rt_float4)));
         k_empty_root<<<1, 1, 0, st>>>(s->d_nodes);
         RT_CUDA_TRY(ctx, cudaGetLastError());
@@ -168,8 +171,8 @@ rt_status rt_build_bvh(rt_scene *s) {
     RT_CUDA_TRY(ctx, scratch.alloc(&b.sel, max_level_items * 8));
     RT_CUDA_TRY(ctx, scratch.alloc(&counts, max_level_items));
     RT_CUDA_TRY(ctx, scratch.alloc(&offsets, max_level_items));
-    RT_CUDA_TRY(ctx, scratch.alloc(&nodes_tmp, (size_t)n * 5));
-    RT_CUDA_TRY(ctx, cudaMalloc(&s->d_tris, (size_t)n * 3 * sizeof(rt_float4)));
+    RT_CUDA_TRY(ctx, scratch.alloc(&nodes_tmp, (size_t)n * RT_NODE_VEC4));
+    RT_CUDA_TRY(ctx, cudaMalloc(&s->d_tris, (size_t)n * RT_TRI_VEC4 * sizeof(rt_float4)));
     RT_CUDA_TRY(ctx, cudaMalloc(&s->d_shade, (size_t)n * 4 * sizeof(rt_float4)));
     b.tris = s->d_tris;
     b.shade = s->d_shade;
@@ -246,8 +249,8 @@ rt_status rt_build_bvh(rt_scene *s) {
         return rt_set_error(ctx, RT_ERR_STATE, "rt_build_bvh", "wide tree deeper than the traversal stack");
 
     const uint32_t node_count = level_first;
-    RT_CUDA_TRY(ctx, cudaMalloc(&s->d_nodes, (size_t)node_count * 5 * sizeof(rt_uint4)));
-    RT_CUDA_TRY(ctx, cudaMemcpyAsync(s->d_nodes, nodes_tmp, (size_t)node_count * 5 * sizeof(rt_uint4),
+    RT_CUDA_TRY(ctx, cudaMalloc(&s->d_nodes, (size_t)node_count * RT_NODE_VEC4 * sizeof(rt_uint4)));
+    RT_CUDA_TRY(ctx, cudaMemcpyAsync(s->d_nodes, nodes_tmp, (size_t)node_count * RT_NODE_VEC4 * sizeof(rt_uint4),
                                      cudaMemcpyDeviceToDevice, st));
     RT_CUDA_TRY(ctx, cudaEventRecord(ctx->ev1, st));
     RT_CUDA_TRY(ctx, cudaStreamSynchronize(st));

@@ -71,16 +71,18 @@ enum { kNeedPixel = 0, kNeedRay = 1, kStart = 2, kTraversing = 3, kHitPending = 
  * `tri_lanes` lanes have triangles pending, or a lane's triangle stack is full; then all pending
  * triangles are tested together. Lanes left with neither nodes nor triangles become kHitPending. */
 __device__ __forceinline__ void traverse_phase(const RtBvh &bvh, RtTravState &tv, RtTravStacks &ks, int &mode, int refill,
-                                               int tri_lanes) {
+                                               int /*tri_lanes: unused*/) {
     const unsigned full = 0xffffffffu;
+    const bool trav = mode == kTraversing;
+    const unsigned m_trav = __ballot_sync(full, trav); /* does not change inside the node loop */
     for (;;) {
-        const bool trav = mode == kTraversing;
         if (trav && rt_trav_has_node(tv)) rt_trav_node_step(bvh, tv, ks);
-        const unsigned m_node = __ballot_sync(full, trav && rt_trav_has_node(tv));
-        const unsigned m_idle = __ballot_sync(full, trav && !rt_trav_has_node(tv));
-        const unsigned m_tri = __ballot_sync(full, trav && rt_trav_has_tri(tv));
-        const unsigned m_full = __ballot_sync(full, trav && rt_trav_tri_full(tv));
-        if (!m_node || m_full || __popc(m_idle) >= refill || __popc(m_tri) >= tri_lanes) break;
+        const bool node = trav && rt_trav_has_node(tv);
+        const unsigned m_node = __ballot_sync(full, node);
+        /* leave when no lane has nodes left, `refill` lanes have run dry, or a lane's triangle stack
+         * is full (draining on a pending-triangle count instead was measured and never paid off) */
+        const bool out = trav && rt_trav_tri_full(tv);
+        if (!m_node || __popc(m_trav & ~m_node) >= refill || __any_sync(full, out)) break;
     }
     for (;;) { /* drain: lanes that are out of nodes (or nearly out of triangle-stack room) must
                   finish their triangles; every other lane with triangles pending joins in, and

@@ -52,8 +52,8 @@ struct RtBuild {
     const uint64_t *offsets;/* exclusive scan of counts */
     uint32_t level_first_node, next_level_first_node, tri_cursor;
     /* outputs */
-    rt_uint4 *nodes;        /* 5 per wide node */
-    rt_float4 *tris;        /* 3 per triangle, leaf order */
+    rt_uint4 *nodes;        /* RT_NODE_VEC4 per wide node */
+    rt_float4 *tris;        /* RT_TRI_VEC4 per triangle, leaf order */
     rt_float4 *shade;       /* 4 per triangle, leaf order */
 };
 
@@ -426,9 +426,12 @@ RT_HD void rt_wide_emit(const RtBuild &b, uint32_t item) {
             for (uint32_t t = 0; t < cnt; t++) {
                 const uint32_t gid = b.vals[first + t];
                 const uint32_t slot = tri_base + tri_off + t;
-                b.tris[(size_t)slot * 3] = b.wtris[(size_t)gid * 3];
-                b.tris[(size_t)slot * 3 + 1] = b.wtris[(size_t)gid * 3 + 1];
-                b.tris[(size_t)slot * 3 + 2] = b.wtris[(size_t)gid * 3 + 2];
+                b.tris[(size_t)slot * RT_TRI_VEC4] = b.wtris[(size_t)gid * 3];
+                b.tris[(size_t)slot * RT_TRI_VEC4 + 1] = b.wtris[(size_t)gid * 3 + 1];
+                b.tris[(size_t)slot * RT_TRI_VEC4 + 2] = b.wtris[(size_t)gid * 3 + 2];
+#if RT_TRI_VEC4 > 3
+                b.tris[(size_t)slot * RT_TRI_VEC4 + 3] = rt_mk_float4(0.0f, 0.0f, 0.0f, 0.0f);
+#endif
                 rt_write_shade_record(b, gid, slot);
             }
             tri_off += cnt;
@@ -441,8 +444,11 @@ RT_HD void rt_wide_emit(const RtBuild &b, uint32_t item) {
     n2.x = q[0][0]; n2.y = q[0][1]; n2.z = q[1][0]; n2.w = q[1][1];
     n3.x = q[2][0]; n3.y = q[2][1]; n3.z = q[3][0]; n3.w = q[3][1];
     n4.x = q[4][0]; n4.y = q[4][1]; n4.z = q[5][0]; n4.w = q[5][1];
-    rt_uint4 *np = b.nodes + (size_t)(b.level_first_node + item) * 5;
+    rt_uint4 *np = b.nodes + (size_t)(b.level_first_node + item) * RT_NODE_VEC4;
     np[0] = n0; np[1] = n1; np[2] = n2; np[3] = n3; np[4] = n4;
+#if RT_NODE_VEC4 > 5
+    np[5] = n0; /* spare */
+#endif
 }
 
 #endif /* RT_BUILD_H */

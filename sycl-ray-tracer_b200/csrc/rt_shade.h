@@ -140,7 +140,9 @@ RT_HD bool rt_shade_segment(const RtScene &s, const RtHit &h, XorShift32 &rng, f
         return true;
     }
     const rt_float4 *sp = s.shade + (size_t)h.tri * 4;
-    const rt_float4 s0 = rt_ldg(sp), s1 = rt_ldg(sp + 1), s2 = rt_ldg(sp + 2), s3 = rt_ldg(sp + 3);
+    rt_float4 s0, s1, s2, s3;
+    rt_ldg2(sp, s0, s1);
+    rt_ldg2(sp + 2, s2, s3);
     const RtInstance &g = s.inst[rt_f2u(s3.w)];
     const float bx = h.u, by = h.v;
     const float bw = (1.0f - bx) - by;

@@ -67,9 +67,24 @@ struct RtHit {
 };
 
 struct RtBvh {
-    const rt_uint4 *nodes;  /* 5 per node */
-    const rt_float4 *tris;  /* 3 per triangle */
+    const rt_uint4 *nodes;  /* RT_NODE_VEC4 per node, 32-byte aligned */
+    const rt_float4 *tris;  /* RT_TRI_VEC4 per triangle, 32-byte aligned */
 };
+
+/* Record strides in 16-byte units. Records are padded to multiples of 32 bytes so that they can be
+ * fetched with 256-bit loads (LDG.E.ENL2.256 on sm_100a): every lane of an incoherent warp touches
+ * its own cache line, and the L1TEX data stage spends one wavefront per (instruction, line), so a
+ * 96-byte node costs 3 wavefronts per lane instead of 5 with 128-bit loads (profiles/README.md). */
+#ifndef RT_USE_LDG256
+#define RT_USE_LDG256 0 /* measured on B200 (C3/C4): no gain over 128-bit loads, 20-33 % more memory */
+#endif
+#if RT_USE_LDG256
+#define RT_NODE_VEC4 6 /* 80 bytes of node + 16 spare */
+#define RT_TRI_VEC4 4  /* 48 bytes of vertices/id + 16 spare */
+#else
+#define RT_NODE_VEC4 5
+#define RT_TRI_VEC4 3
+#endif
 
 /* read-only 16-byte loads (LDG.E.128.CONSTANT on device) */
 RT_HD rt_uint4 rt_ldg(const rt_uint4 *p) {
@@ -84,6 +99,28 @@ RT_HD rt_float4 rt_ldg(const rt_float4 *p) {
     return __ldg(p);
 #else
     return *p;
+#endif
+}
+
+/* read-only 32-byte load of two consecutive 16-byte records (p must be 32-byte aligned) */
+RT_HD void rt_ldg2(const rt_uint4 *p, rt_uint4 &a, rt_uint4 &b) {
+#if RT_DEVICE_CODE && RT_USE_LDG256
+    asm("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)
+        : "l"(p));
+#else
+    a = rt_ldg(p);
+    b = rt_ldg(p + 1);
+#endif
+}
+RT_HD void rt_ldg2(const rt_float4 *p, rt_float4 &a, rt_float4 &b) {
+#if RT_DEVICE_CODE && RT_USE_LDG256
+    asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
+        : "l"(p));
+#else
+    a = rt_ldg(p);
+    b = rt_ldg(p + 1);
 #endif
 }
 
@@ -348,9 +385,17 @@ RT_HD void rt_trav_node_step(const RtBvh &bvh, RtTravState &s, RtTravStacks &k) 
     }
     const uint32_t slot = ((uint32_t)bit - 24u) ^ oct_inv;
     const uint32_t rel = (uint32_t)rt_popc(imask & ~(0xffffffffu << slot));
-    const rt_uint4 *np = bvh.nodes + (size_t)(s.ng_x + rel) * 5;
-    const rt_uint4 n0 = rt_ldg(np), n1 = rt_ldg(np + 1), n2 = rt_ldg(np + 2), n3 = rt_ldg(np + 3),
-                   n4 = rt_ldg(np + 4);
+    const rt_uint4 *np = bvh.nodes + (size_t)(s.ng_x + rel) * RT_NODE_VEC4;
+    rt_uint4 n0, n1, n2, n3, n4;
+    rt_ldg2(np, n0, n1);
+    rt_ldg2(np + 2, n2, n3);
+#if RT_USE_LDG256
+    rt_uint4 n5;
+    rt_ldg2(np + 4, n4, n5);
+    (void)n5;
+#else
+    n4 = rt_ldg(np + 4);
+#endif
     RT_COUNT_NODE();
     const uint32_t hm = rt_node_test(s.rb, n0, n1, n2, n3, n4, s.tnear, s.tmax_pad);
     s.ng_x = n1.x;
@@ -377,8 +422,16 @@ RT_HD void rt_trav_tri_step(const RtBvh &bvh, RtTravState &s, RtTravStacks &k) {
     if (bits) k.tri[s.tsp - 1] = rt_pack2(base, bits);
     else s.tsp--;
     const uint32_t tslot = base + (uint32_t)i;
-    const rt_float4 *tp = bvh.tris + (size_t)tslot * 3;
-    const rt_float4 a = rt_ldg(tp), b = rt_ldg(tp + 1), c = rt_ldg(tp + 2);
+    const rt_float4 *tp = bvh.tris + (size_t)tslot * RT_TRI_VEC4;
+    rt_float4 a, b, c;
+    rt_ldg2(tp, a, b);
+#if RT_USE_LDG256
+    rt_float4 d;
+    rt_ldg2(tp + 2, c, d);
+    (void)d;
+#else
+    c = rt_ldg(tp + 2);
+#endif
     RT_COUNT_TRI();
     const float before = s.best.t;
     rt_tri_test(s.rt, mk3(a.x, a.y, a.z), mk3(b.x, b.y, b.z), mk3(c.x, c.y, c.z), tslot, rt_f2u(c.w), s.tnear,

@@ -106,7 +106,8 @@ emu_scene *emu_scene_create(const rt_scene_desc *desc) {
     if (n == 0) {
         const uint32_t ff = 0xffffffffu;
         s->nodes = {{0, 0, 0, 1u | (1u << 8) | (1u << 16)}, {0, 0, 0, 0}, {ff, ff, ff, ff}, {ff, ff, 0, 0}, {0, 0, 0, 0}};
-        s->tris.resize(3);
+        s->nodes.resize(RT_NODE_VEC4);
+        s->tris.resize(RT_TRI_VEC4);
         s->shade.resize(4);
         s->n_nodes = 1;
         s->depth = 1;
@@ -223,8 +224,8 @@ emu_scene *emu_scene_create(const rt_scene_desc *desc) {
         const size_t max_items = (size_t)n / (RT_LEAF_MAX + 1) + 8;
         std::vector<uint32_t> items_a(max_items), items_b(max_items), sel(max_items * 8);
         std::vector<uint64_t> counts(max_items), offsets(max_items);
-        s->nodes.resize((size_t)n * 5);
-        s->tris.resize((size_t)n * 3);
+        s->nodes.resize((size_t)n * RT_NODE_VEC4);
+        s->tris.resize((size_t)n * RT_TRI_VEC4);
         s->shade.resize((size_t)n * 4);
         b.sel = sel.data();
         b.counts = counts.data();
@@ -256,7 +257,7 @@ emu_scene *emu_scene_create(const rt_scene_desc *desc) {
         }
         s->n_nodes = level_first;
         s->depth = depth;
-        s->nodes.resize((size_t)s->n_nodes * 5);
+        s->nodes.resize((size_t)s->n_nodes * RT_NODE_VEC4);
         if (tri_cursor != n) fprintf(stderr, "hostemu: triangle count mismatch %u != %u\n", tri_cursor, n);
     }
     s->view.bvh.nodes = s->nodes.data();
@@ -284,7 +285,7 @@ int emu_scene_validate(const emu_scene *s) {
     while (!stack.empty()) {
         const uint32_t ni = stack.back();
         stack.pop_back();
-        const rt_uint4 *np = &s->nodes[(size_t)ni * 5];
+        const rt_uint4 *np = &s->nodes[(size_t)ni * RT_NODE_VEC4];
         const float p[3] = {rt_u2f(np[0].x), rt_u2f(np[0].y), rt_u2f(np[0].z)};
         const float sc[3] = {rt_u2f((np[0].w & 0xffu) << 23), rt_u2f(((np[0].w >> 8) & 0xffu) << 23),
                              rt_u2f(((np[0].w >> 16) & 0xffu) << 23)};
@@ -310,7 +311,7 @@ int emu_scene_validate(const emu_scene *s) {
                 if (child >= s->n_nodes || seen_node[child]) return 3;
                 seen_node[child] = 1;
                 /* the child's own origin must lie inside the decoded box */
-                const rt_uint4 *cp = &s->nodes[(size_t)child * 5];
+                const rt_uint4 *cp = &s->nodes[(size_t)child * RT_NODE_VEC4];
                 const float cpv[3] = {rt_u2f(cp[0].x), rt_u2f(cp[0].y), rt_u2f(cp[0].z)};
                 for (int a = 0; a < 3; a++)
                     if (cpv[a] < lo[a] || cpv[a] > hi[a]) return 4;
@@ -322,7 +323,7 @@ int emu_scene_validate(const emu_scene *s) {
                     const uint32_t tri = np[1].y + off + t;
                     if (tri >= n || seen_tri[tri]) return 6;
                     seen_tri[tri] = 1;
-                    const rt_float4 *tp = &s->tris[(size_t)tri * 3];
+                    const rt_float4 *tp = &s->tris[(size_t)tri * RT_TRI_VEC4];
                     const uint32_t gid = rt_f2u(tp[2].w);
                     if (gid >= n || seen_gid[gid]) return 7;
                     seen_gid[gid] = 1;
@@ -492,7 +493,7 @@ extern "C" void emu_counters(unsigned long long *nodes, unsigned long long *tris
 extern "C" void emu_scene_tree_stats(const emu_scene *s, uint64_t *out) {
     for (int i = 0; i < 14; i++) out[i] = 0;
     for (uint32_t ni = 0; ni < s->n_nodes; ni++) {
-        const rt_uint4 *np = &s->nodes[(size_t)ni * 5];
+        const rt_uint4 *np = &s->nodes[(size_t)ni * RT_NODE_VEC4];
         int n = 0;
         for (int slot = 0; slot < 8; slot++) {
             const uint32_t meta = ((slot < 4 ? np[1].z : np[1].w) >> ((slot & 3) * 8)) & 0xffu;
