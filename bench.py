@@ -46,6 +46,18 @@ WORKLOADS = {
 }
 
 
+_JSON_FD = None
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def algorithmic_bytes_per_ray(n_tris, wavefront):
     """one root-to-leaf descent of a balanced 8-wide tree with 4-triangle leaves + one
     hit's shading gather (+ the reference's queue record for the wavefront)."""
@@ -64,53 +76,87 @@ def measured_peak():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """SM clock / throttle reasons DURING the timed region, sampled every 50 ms through NVML
+    (nvidia_ml_py) on a background thread; falls back to polling nvidia-smi."""
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
-    def __init__(self, index):
-        self.index, self.proc, self.path = index, None, None
+    def __init__(self, index, uuid=None):
+        self.index, self.uuid = index, uuid
+        self.sm, self.mx, self.reasons, self.stop_flag, self.thread, self.proc, self.path = [], [], set(), False, None, None, None
+
+    def _nvml_loop(self, nv, h):
+        while not self.stop_flag:
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                self.mx.append(float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)))
+                mask = nv.nvmlDeviceGetCurrentClocksEventReasons(h) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+                    else nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for bit, name in self.REASONS.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.05)
 
     def start(self):
         try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = None
+            if self.uuid:
+                try:
+                    h = nv.nvmlDeviceGetHandleByUUID(("GPU-" + str(self.uuid)).encode() if not str(self.uuid).startswith("GPU-") else str(self.uuid).encode())
+                except Exception:
+                    h = None
+            if h is None:
+                h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.thread = threading.Thread(target=self._nvml_loop, args=(nv, h), daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.thread = None
+        try:
             f = tempfile.NamedTemporaryFile("w", suffix=".csv", delete=False)
             self.path = f.name
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=f, stderr=subprocess.DEVNULL)
+            q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+                 "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=f, stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
 
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        if not self.proc:
-            return out
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        try:
-            for line in open(self.path):
-                c = [x.strip() for x in line.split(",")]
-                if len(c) < 7:
-                    continue
-                try:
-                    sm.append(float(c[0]))
-                    mx.append(float(c[1]))
-                except ValueError:
-                    continue
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[3:7]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
-            os.unlink(self.path)
-        except Exception:
-            pass
-        if sm:
-            # median under load = median of the upper half of the samples (idle samples before/after)
-            s = sorted(sm)
-            out.update(sm_mhz=s[len(s) // 2], sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+        if self.thread:
+            if not self.sm:
+                time.sleep(0.06)  # a very short timed region: make sure one sample exists
+            self.stop_flag = True
+            self.thread.join(timeout=2)
+        elif self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
+            try:
+                for line in open(self.path):
+                    c = [x.strip() for x in line.split(",")]
+                    if len(c) < 6:
+                        continue
+                    try:
+                        self.sm.append(float(c[0]))
+                        self.mx.append(float(c[1]))
+                    except ValueError:
+                        continue
+                    for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[2:6]):
+                        if v.lower().startswith("active"):
+                            self.reasons.add(name)
+                os.unlink(self.path)
+            except Exception:
+                pass
+        if self.sm:
+            s = sorted(self.sm)
+            out.update(sm_mhz=s[len(s) // 2], sm_max_mhz=max(self.mx), reasons=sorted(self.reasons), samples=len(s))
         return out
 
 
@@ -170,11 +216,16 @@ def run_reference(args):
         "e2e": {"value": val, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
 def main():
+    # libraries (NCCL's version banner) write to stdout: keep fd 1 for the ONE JSON line only
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -184,6 +235,9 @@ def main():
     ap.add_argument("--renderer", default="both", choices=["both", "megakernel", "wavefront"])
     ap.add_argument("--spp", type=int, default=0, help="override the workload's samples per pixel")
     ap.add_argument("--cpu-seconds", type=float, default=6.0, help="target seconds per CPU-baseline step")
+    ap.add_argument("--sharding", default="spp", choices=["spp", "tiles"],
+                    help="N>1: spp = every rank renders the full frame with its own spp (weak scaling, default); "
+                         "tiles = 64x64 image tiles dealt round robin, total work fixed (strong scaling, config 4's mode)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -216,7 +270,14 @@ def main():
     scene = pkg.Scene(app, data)
     stats = scene.stats
     cam = pkg.Camera((w, h), data.camera_position, data.camera_direction, data.camera_focal_length)
-    shard = {"rank": rank, "world": world, "tile_size": 0, "seed_salt": (rank * 0x9E3779B9) & 0xFFFFFFFF} if world > 1 else None
+    tiles = args.sharding == "tiles" and world > 1
+    if world == 1:
+        shard = None
+    elif tiles:
+        shard = {"rank": rank, "world": world, "tile_size": 64, "seed_salt": 0}
+    else:
+        shard = {"rank": rank, "world": world, "tile_size": 0, "seed_salt": (rank * 0x9E3779B9) & 0xFFFFFFFF}
+    spp_total = spp if (tiles or world == 1) else spp * world
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
 
     class DevAccum:  # zero-copy view of the renderer's device accumulation buffer
@@ -238,12 +299,16 @@ def main():
             if dist:  # combine the accumulation buffers over NVLink, then resolve the image
                 dist.all_reduce(accum_t)
                 if rank == 0:
-                    pkg.resolve(app, accum_t, spp * world, w, h, out_rgba)
+                    pkg.resolve(app, accum_t, spp_total, w, h, out_rgba)
             return f
         for _ in range(args.warmup):
             step()
         ms, kms, rays, launches = 0.0, 0.0, 0, 0
-        sampler = ClockSampler(local_rank)
+        try:
+            uuid = str(torch.cuda.get_device_properties(local_rank).uuid)
+        except Exception:
+            uuid = None
+        sampler = ClockSampler(local_rank, uuid)
         barrier()
         if rank == 0:
             sampler.start()
@@ -278,7 +343,7 @@ def main():
     if args.renderer in ("both", "wavefront"):
         results.append(bench_renderer(pkg.WavefrontRenderer, "wavefront"))
     best = max(results, key=lambda x: x["rays"] / x["ms"])
-    samples_total = w * h * spp * world * args.steps
+    samples_total = w * h * spp_total * args.steps
 
     # ---- end to end through the public API with host buffers -----------------------------------
     e2e = None
@@ -296,7 +361,7 @@ def main():
             if dist:
                 f = r.render_frame(cam, sc, want=(), shard=shard)
                 dist.all_reduce(accum_t)
-                pkg.resolve(app, accum_t, spp * world, w, h, host_img)  # D2H of the image
+                pkg.resolve(app, accum_t, spp_total, w, h, host_img)  # D2H of the image
             else:
                 f = r.render_frame(cam, sc, want=("rgba8",), outputs={"rgba8": host_img})  # D2H inside
             sc.close()
@@ -341,7 +406,7 @@ def main():
     tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.exists(tp):
         try:
-            traffic = json.load(open(tp)).get(best["name"], {}).get("dram_bytes_per_launch")
+            traffic = json.load(open(tp)).get(args.workload, {}).get(best["name"], {}).get("dram_bytes_per_launch")
         except Exception:
             traffic = None
     roofline = {"bound": "hbm", "kernel": "k_megakernel" if not wave else "k_wf_extend+k_wf_shade",
@@ -364,12 +429,12 @@ def main():
     value = best["rays"] / (best["ms"] * 1e-3) / 1e6
     line = {
         "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": best["ms"] / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": best["ms"] / args.steps, "higher_is_better": True, "scaling": "strong" if tiles else "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "msamples_per_s": samples_total / (best["ms"] * 1e-3) / 1e6,
         "config": {"workload": args.workload, "triangles": int(stats["triangle_count"]), "width": w, "height": h, "spp": spp,
                    "max_depth": depth, "renderer": best["name"], "l2": "flushed between timed steps (256 MB write)",
-                   "sharding": "none" if world == 1 else f"spp slices: {spp} spp per GPU, distinct seed salts, NCCL all-reduce of the fp32 accumulation buffer",
+                   "sharding": "none" if world == 1 else ("image tiles: 64x64 tiles round robin over ranks, bit-identical to 1 GPU, NCCL all-reduce (sum) of the fp32 accumulation buffer" if tiles else f"spp slices: {spp} spp per GPU, distinct seed salts, NCCL all-reduce of the fp32 accumulation buffer"),
                    "bvh": {"nodes": int(stats["node_count"]), "depth": int(stats["wide_depth"]), "build_ms": float(stats["build_ms"])}},
         "renderers": {x["name"]: {"mrays_per_s": x["rays"] / (x["ms"] * 1e-3) / 1e6, "ms_per_step": x["ms"] / args.steps,
                                   "msamples_per_s": samples_total / (x["ms"] * 1e-3) / 1e6,
@@ -377,7 +442,7 @@ def main():
         "clocks": best["clocks"], "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
         "gpu_launches": int(best["launches"]),
     }
-    print(json.dumps(line))
+    emit(line)
     if dist:
         dist.destroy_process_group()
     return 0
