@@ -224,3 +224,31 @@ def test_spp_shards_match_salted_oracle_and_resolve(pkg, oracle, app, scenes):
     assert np.array_equal(img[..., :3], want) and (img[..., 3] == 255).all()
     r.close()
     scene.close()
+
+
+@pytest.mark.parametrize("kind", [0, 1])
+def test_c4_style_half_million_triangles(pkg, oracle, app, scenes, kind):
+    """config 4's kind of scene (one displaced height field, grazing camera) at 500 k triangles so
+    the oracle's BVH finishes in seconds: random rays + a crop of a 4K frame"""
+    data = scenes.big_mesh_scene(500)
+    assert data.triangle_count == 500000
+    scene = pkg.Scene(app, data)
+    st = scene.stats
+    assert st["triangle_count"] == 500000 and st["wide_depth"] <= 16
+    osc = oracle.Scene(data)
+    if kind == 0:
+        org, d = _rays(40000, 77, 50.0)
+        org[:, 1] = np.abs(org[:, 1]) * 0.2 + 1.0
+        g, o = pkg.intersect(app, scene, org, d), osc.intersect(org, d, use_bvh=True)
+        assert _check_hits(o, g) == 1.0 and np.array_equal(o["t"].view(np.uint32), g["t"].view(np.uint32))
+    w, h, crop = 3840, 2160, (1900, 1300, 1964, 1332)
+    cam = pkg.Camera((w, h), data.camera_position, data.camera_direction, data.camera_focal_length)
+    cls = pkg.MegakernelRenderer if kind == 0 else pkg.WavefrontRenderer
+    r = cls(app, (w, h), None, 10, 2)
+    f = r.render_frame(cam, scene)
+    o = osc.render(oracle.camera_for(data, w, h), kind, 10, 2, use_bvh=True, crop=crop)
+    x0, y0, x1, y1 = crop
+    assert np.array_equal(f.rng_state[y0:y1, x0:x1], o["rng_state"])
+    assert np.array_equal(f.accum[y0:y1, x0:x1].view(np.uint32), o["accum"].view(np.uint32))
+    r.close()
+    scene.close()
