@@ -150,7 +150,7 @@ rt_status rt_build_bvh(rt_scene *s) {
     uint32_t *items_a = nullptr, *items_b = nullptr;
     uint64_t *counts = nullptr, *offsets = nullptr;
     rt_uint4 *nodes_tmp = nullptr;
-    const size_t max_level_items = (size_t)n / (RT_LEAF_MAX + 1) + 8;
+    const size_t max_level_items = (size_t)n / 2 + 8; /* an inner wide node covers >= 2 triangles */
 
     RT_CUDA_TRY(ctx, scratch.alloc(&b.wtris, (size_t)n * 3));
     RT_CUDA_TRY(ctx, scratch.alloc(&b.cen_bounds, 8));
@@ -166,6 +166,8 @@ rt_status rt_build_bvh(rt_scene *s) {
     RT_CUDA_TRY(ctx, scratch.alloc(&b.box_lo, (size_t)2 * n));
     RT_CUDA_TRY(ctx, scratch.alloc(&b.box_hi, (size_t)2 * n));
     RT_CUDA_TRY(ctx, scratch.alloc(&b.flags, n));
+    RT_CUDA_TRY(ctx, scratch.alloc(&b.dp_cost, (size_t)4 * n));
+    RT_CUDA_TRY(ctx, scratch.alloc(&b.dp_dec, (size_t)4 * n));
     RT_CUDA_TRY(ctx, scratch.alloc(&items_a, max_level_items));
     RT_CUDA_TRY(ctx, scratch.alloc(&items_b, max_level_items));
     RT_CUDA_TRY(ctx, scratch.alloc(&b.sel, max_level_items * 8));

@@ -44,6 +44,9 @@ struct RtBuild {
     uint32_t *range_first, *range_last; /* n-1 */
     rt_float4 *box_lo, *box_hi;         /* 2n-1 */
     uint32_t *flags;                    /* n-1 */
+    /* SAH-optimal wide collapse (Ylitie et al. 2017, section 4.1), filled bottom-up by the fit pass */
+    rt_float4 *dp_cost;                 /* 2 per node: C(n,1..4), C(n,5..7) */
+    uint32_t *dp_dec;                   /* 2 per node: 8 decision bytes, see rt_dp_node */
     /* wide collapse (per level) */
     const uint32_t *items;  /* binary node id of every wide node of this level */
     uint32_t *next_items;
@@ -195,7 +198,83 @@ RT_HD void rt_st_cg(rt_float4 *p, rt_float4 v) {
 #endif
 }
 
-/* ---- bottom-up fit: called once per leaf; `arrive` returns the previous flag value --------- */
+/* ---- SAH-optimal collapse: dynamic program over the binary tree ---------------------------------
+ * C(n, i) = cheapest way to represent the subtree of binary node n by at most i wide-tree children:
+ *   C(n,1) = min( A_n * P_n * c_prim            if P_n <= RT_LEAF_MAX   (one leaf child),
+ *                 A_n * c_node + D(n,8) )                               (one inner wide node)
+ *   C(n,i) = min( D(n,i), C(n,i-1) ),  D(n,j) = min_{0<k<j} C(left,k) + C(right,j-k)
+ * Decision bytes per node: d[0] = 1 when C(n,1) is the leaf; d[1] = k of D(n,8);
+ * d[i] (i = 2..7) = k of D(n,i), or 0 when C(n,i) = C(n,i-1). */
+#ifndef RT_SAH_C_NODE
+#define RT_SAH_C_NODE 1.0f
+#endif
+#ifndef RT_SAH_C_PRIM
+#define RT_SAH_C_PRIM 0.6f
+#endif
+
+RT_HD float rt_half_area(rt_float4 lo, rt_float4 hi) {
+    const float dx = hi.x - lo.x, dy = hi.y - lo.y, dz = hi.z - lo.z;
+    return dx * dy + dy * dz + dz * dx;
+}
+RT_HD float rt_dp_get(rt_float4 a, rt_float4 c, int i) { /* i = 1..7 */
+    return i == 1 ? a.x : i == 2 ? a.y : i == 3 ? a.z : i == 4 ? a.w : i == 5 ? c.x : i == 6 ? c.y : c.z;
+}
+
+RT_HD void rt_dp_leaf(const RtBuild &b, uint32_t id, rt_float4 lo, rt_float4 hi) {
+    const float c = rt_half_area(lo, hi) * RT_SAH_C_PRIM;
+    rt_st_cg(&b.dp_cost[(size_t)id * 2], rt_mk_float4(c, c, c, c));
+    rt_st_cg(&b.dp_cost[(size_t)id * 2 + 1], rt_mk_float4(c, c, c, c));
+    b.dp_dec[(size_t)id * 2] = 1u; /* d[0] = leaf */
+    b.dp_dec[(size_t)id * 2 + 1] = 0u;
+}
+
+RT_HD void rt_dp_node(const RtBuild &b, uint32_t node, uint32_t lc, uint32_t rc, rt_float4 lo, rt_float4 hi) {
+    const rt_float4 l0 = rt_ld_cg(&b.dp_cost[(size_t)lc * 2]), l1 = rt_ld_cg(&b.dp_cost[(size_t)lc * 2 + 1]);
+    const rt_float4 r0 = rt_ld_cg(&b.dp_cost[(size_t)rc * 2]), r1 = rt_ld_cg(&b.dp_cost[(size_t)rc * 2 + 1]);
+    float D[9];
+    uint32_t K[9];
+    for (int j = 2; j <= 8; j++) {
+        float best = 3.0e38f;
+        uint32_t bk = 1;
+        for (int k = 1; k < j; k++) {
+            if (k > 7 || j - k > 7) continue;
+            const float c = rt_dp_get(l0, l1, k) + rt_dp_get(r0, r1, j - k);
+            if (c < best) {
+                best = c;
+                bk = (uint32_t)k;
+            }
+        }
+        D[j] = best;
+        K[j] = bk;
+    }
+    const float area = rt_half_area(lo, hi);
+    const uint32_t count = b.range_last[node] - b.range_first[node] + 1u;
+    const float c_inner = area * RT_SAH_C_NODE + D[8];
+    const float c_leaf = count <= RT_LEAF_MAX ? area * (float)count * RT_SAH_C_PRIM : 3.0e38f;
+    float C[8];
+    uint32_t d[8];
+    d[0] = c_leaf <= c_inner ? 1u : 0u;
+    d[1] = K[8];
+    C[1] = d[0] ? c_leaf : c_inner;
+    for (int i = 2; i <= 7; i++) {
+        if (D[i] < C[i - 1]) {
+            C[i] = D[i];
+            d[i] = K[i];
+        } else {
+            C[i] = C[i - 1];
+            d[i] = 0u;
+        }
+    }
+    rt_st_cg(&b.dp_cost[(size_t)node * 2], rt_mk_float4(C[1], C[2], C[3], C[4]));
+    rt_st_cg(&b.dp_cost[(size_t)node * 2 + 1], rt_mk_float4(C[5], C[6], C[7], 0.0f));
+    b.dp_dec[(size_t)node * 2] = d[0] | (d[1] << 8) | (d[2] << 16) | (d[3] << 24);
+    b.dp_dec[(size_t)node * 2 + 1] = d[4] | (d[5] << 8) | (d[6] << 16) | (d[7] << 24);
+}
+RT_HD uint32_t rt_dp_decision(const RtBuild &b, uint32_t id, int i) { /* byte i of the node's decisions */
+    return (b.dp_dec[(size_t)id * 2 + (i >> 2)] >> ((i & 3) * 8)) & 0xffu;
+}
+
+/* ---- bottom-up fit + DP: called once per leaf; `arrive` returns the previous flag value -------- */
 template <class Arrive>
 RT_HD void rt_fit_leaf(const RtBuild &b, uint32_t j, Arrive arrive) {
     const uint32_t leaf0 = b.n_tris - 1;
@@ -206,6 +285,7 @@ RT_HD void rt_fit_leaf(const RtBuild &b, uint32_t j, Arrive arrive) {
     h4.x = hi.x; h4.y = hi.y; h4.z = hi.z; h4.w = 0.0f;
     rt_st_cg(&b.box_lo[leaf0 + j], l4);
     rt_st_cg(&b.box_hi[leaf0 + j], h4);
+    rt_dp_leaf(b, leaf0 + j, l4, h4);
     if (b.n_tris == 1) return;
     uint32_t node = b.parent[leaf0 + j];
     while (node != RT_MISS) {
@@ -217,6 +297,7 @@ RT_HD void rt_fit_leaf(const RtBuild &b, uint32_t j, Arrive arrive) {
         h4.x = rt_max(ha.x, hb.x); h4.y = rt_max(ha.y, hb.y); h4.z = rt_max(ha.z, hb.z);
         rt_st_cg(&b.box_lo[node], l4);
         rt_st_cg(&b.box_hi[node], h4);
+        rt_dp_node(b, node, lc, rc, l4, h4);
         node = b.parent[node];
     }
 }
@@ -235,45 +316,50 @@ RT_HD float rt_box_area(const RtBuild &b, uint32_t id) {
     return dx * dy + dy * dz + dz * dx;
 }
 
-/* choose <= 8 children for the wide node rooted at binary node items[item] */
+/* a child of a wide node is a leaf when it is a single triangle or the DP chose "leaf" for it */
+RT_HD bool rt_child_is_leaf(const RtBuild &b, uint32_t id) {
+    return rt_is_leaf_id(b, id) || rt_dp_decision(b, id, 0) != 0u;
+}
+
+/* children of the wide node rooted at binary node items[item]: follow the DP decisions
+ * (roots(n, i) = the <= i subtrees that represent n) */
 RT_HD void rt_wide_select(const RtBuild &b, uint32_t item) {
     const uint32_t root = b.items[item];
     uint32_t c[8];
-    int n;
-    if (rt_subtree_count(b, root) <= RT_LEAF_MAX) {
-        c[0] = root;
-        n = 1;
+    int n = 0;
+    if (rt_is_leaf_id(b, root) || rt_subtree_count(b, root) <= 1u) {
+        c[n++] = root;
     } else {
-        c[0] = b.left[root];
-        c[1] = b.right[root];
-        n = 2;
-        while (n < 8) {
-            int best = -1;
-            float best_area = -1.0f;
-            for (int k = 0; k < n; k++) {
-                /* any binary inner node may be opened, also one small enough to be a leaf: the node
-                 * test evaluates all eight slots anyway, so filling them with tighter (1-2 triangle)
-                 * leaf boxes is free and saves triangle tests and whole tree levels */
-                if (rt_is_leaf_id(b, c[k])) continue;
-                const float a = rt_box_area(b, c[k]);
-                if (a > best_area) {
-                    best_area = a;
-                    best = k;
-                }
+        uint32_t st_id[16];
+        int st_i[16], sp = 0;
+        const int k8 = (int)rt_dp_decision(b, root, 1);
+        st_id[sp] = b.right[root]; st_i[sp++] = 8 - k8;
+        st_id[sp] = b.left[root]; st_i[sp++] = k8;
+        while (sp > 0) {
+            sp--;
+            const uint32_t m = st_id[sp];
+            int i = st_i[sp];
+            if (rt_is_leaf_id(b, m)) {
+                c[n++] = m;
+                continue;
             }
-            if (best < 0) break;
-            const uint32_t id = c[best];
-            c[best] = b.left[id];
-            c[n++] = b.right[id];
+            if (i > 7) i = 7;
+            while (i > 1 && rt_dp_decision(b, m, i) == 0u) i--; /* C(m,i) = C(m,i-1) */
+            if (i <= 1) {
+                c[n++] = m;
+                continue;
+            }
+            const int k = (int)rt_dp_decision(b, m, i);
+            st_id[sp] = b.right[m]; st_i[sp++] = i - k;
+            st_id[sp] = b.left[m]; st_i[sp++] = k;
         }
     }
     uint32_t n_inner = 0, n_leaf_tris = 0;
     for (int k = 0; k < 8; k++) {
-        uint32_t id = k < n ? c[k] : RT_MISS;
+        const uint32_t id = k < n ? c[k] : RT_MISS;
         b.sel[(size_t)item * 8 + k] = id;
         if (k < n) {
-            const uint32_t cnt = rt_subtree_count(b, id);
-            if (cnt <= RT_LEAF_MAX) n_leaf_tris += cnt;
+            if (rt_child_is_leaf(b, id)) n_leaf_tris += rt_subtree_count(b, id);
             else n_inner++;
         }
     }
@@ -414,7 +500,7 @@ RT_HD void rt_wide_emit(const RtBuild &b, uint32_t item) {
         q[4][w] |= rt_quant_hi(plo.y, sy, hi.y) << sh;
         q[5][w] |= rt_quant_hi(plo.z, sz, hi.z) << sh;
         const uint32_t cnt = rt_subtree_count(b, id);
-        if (cnt > RT_LEAF_MAX) {
+        if (!rt_child_is_leaf(b, id)) {
             imask |= 1u << s;
             meta[w] |= (0x20u | (24u + (uint32_t)s)) << sh;
             b.next_items[(child_base - b.next_level_first_node) + inner_rank] = id;

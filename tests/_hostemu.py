@@ -19,7 +19,7 @@ def lib():
         newest = max([os.path.getmtime(src)] + [os.path.getmtime(os.path.join(csrc, f)) for f in os.listdir(csrc) if f.endswith(".h")])
         if not os.path.exists(LIB) or os.path.getmtime(LIB) < newest:
             subprocess.run(["/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++", "-O2", "-std=c++17",
-                            "-ffp-contract=off", "-mfma", "-fPIC", "-shared", "-o", LIB, src], check=True)
+                            "-ffp-contract=off", "-mfma", "-fPIC", "-shared", "-o", LIB, src] + os.environ.get("EMU_CXXFLAGS", "").split(), check=True)
         L = C.CDLL(LIB)
         L.emu_scene_create.restype = C.c_void_p
         L.emu_scene_destroy.argtypes = [C.c_void_p]

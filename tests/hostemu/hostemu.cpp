@@ -159,6 +159,10 @@ emu_scene *emu_scene_create(const rt_scene_desc *desc) {
         b.box_lo = box_lo.data();
         b.box_hi = box_hi.data();
         b.flags = flags.data();
+        std::vector<rt_float4> dp_cost((size_t)4 * n);
+        std::vector<uint32_t> dp_dec((size_t)4 * n);
+        b.dp_cost = dp_cost.data();
+        b.dp_dec = dp_dec.data();
         if (getenv("EMU_SAH") && n > 1) {
             /* EXPERIMENT ONLY: quality headroom of a SAH binary tree under the same wide collapse */
             std::vector<float> clo((size_t)n * 3), chi((size_t)n * 3);
@@ -221,7 +225,7 @@ emu_scene *emu_scene_create(const rt_scene_desc *desc) {
         for (uint32_t i = 0; i + 1 < n; i++) rt_karras_node(b, i);
         for (uint32_t j = 0; j < n; j++) rt_fit_leaf(b, j, HostArrive());
 
-        const size_t max_items = (size_t)n / (RT_LEAF_MAX + 1) + 8;
+        const size_t max_items = (size_t)n / 2 + 8;
         std::vector<uint32_t> items_a(max_items), items_b(max_items), sel(max_items * 8);
         std::vector<uint64_t> counts(max_items), offsets(max_items);
         s->nodes.resize((size_t)n * RT_NODE_VEC4);
