@@ -367,13 +367,23 @@ def main():
             sc.close()
             return f
         e2e_step()
+        try:
+            uuid = str(torch.cuda.get_device_properties(local_rank).uuid)
+        except Exception:
+            uuid = None
+        e_sampler = ClockSampler(local_rank, uuid)
         barrier()
+        if rank == 0:
+            e_sampler.start()
         t0 = time.perf_counter()
-        e_rays = 0
+        e_rays, e_dev_ms = 0, 0.0
         for _ in range(args.steps):
-            e_rays += e2e_step().ray_count
+            ef = e2e_step()
+            e_rays += ef.ray_count
+            e_dev_ms += ef.device_ms
         barrier()
         dt = time.perf_counter() - t0
+        e_clocks = e_sampler.stop() if rank == 0 else None
         t = torch.tensor([dt, float(e_rays)], dtype=torch.float64, device="cuda")
         if dist:
             mx = t.clone()
@@ -382,7 +392,7 @@ def main():
             dist.all_reduce(sm, op=dist.ReduceOp.SUM)
             dt, e_rays = float(mx[0]), int(sm[1])
         e2e = {"value": e_rays / dt / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-               "ms_per_step": dt / args.steps * 1e3,
+               "ms_per_step": dt / args.steps * 1e3, "render_device_ms_per_step": e_dev_ms / args.steps, "clocks": e_clocks,
                "includes": "scene upload from host + BVH build + render" + (" + NCCL all-reduce" if dist else "") + " + image read-back, every step"}
         r.close()
 
@@ -438,7 +448,7 @@ def main():
                    "bvh": {"nodes": int(stats["node_count"]), "depth": int(stats["wide_depth"]), "build_ms": float(stats["build_ms"])}},
         "renderers": {x["name"]: {"mrays_per_s": x["rays"] / (x["ms"] * 1e-3) / 1e6, "ms_per_step": x["ms"] / args.steps,
                                   "msamples_per_s": samples_total / (x["ms"] * 1e-3) / 1e6,
-                                  "kernel_launches_per_step": x["last_launches"]} for x in results},
+                                  "kernel_launches_per_step": x["last_launches"], "clocks": x["clocks"]} for x in results},
         "clocks": best["clocks"], "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
         "gpu_launches": int(best["launches"]),
     }
