@@ -99,3 +99,23 @@ def test_error_behaviour(pkg, app, scenes):
     assert lib.rt_context_create(9999, C.byref(h)) != cap.RT_OK
     assert b"rt_context_create" in lib.rt_last_error(None)
     s.close()
+
+
+@pytest.mark.parametrize("which", ["awkward_transforms", "coincident_centroids"])
+def test_awkward_scenes(pkg, oracle, app, which):
+    """mirrored / huge / tiny / far-away instance transforms; all-equal Morton keys in a flat scene"""
+    import edge_scenes
+    data, org, d = getattr(edge_scenes, which)()
+    scene = pkg.Scene(app, data)
+    g, o = pkg.intersect(app, scene, org, d), oracle.Scene(data).intersect(org, d, use_bvh=False)
+    assert (o["inst"] >= 0).sum() > 500
+    for k in ("inst", "prim"):
+        assert np.array_equal(g[k], o[k])
+    for k in ("t", "u", "v"):
+        assert np.array_equal(g[k].view(np.uint32), o[k].view(np.uint32))
+    cam = pkg.Camera((64, 40), data.camera_position, data.camera_direction, data.camera_focal_length)
+    for cls, mode in ((pkg.MegakernelRenderer, 0), (pkg.WavefrontRenderer, 1)):
+        f = cls(app, (64, 40), None, 6, 2).render_frame(cam, scene)
+        oo = oracle.Scene(data).render(oracle.camera_for(data, 64, 40), mode, 6, 2, use_bvh=True)
+        assert f.ray_count == oo["ray_count"] and np.array_equal(f.accum.view(np.uint32), oo["accum"].view(np.uint32))
+    scene.close()

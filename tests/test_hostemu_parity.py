@@ -138,3 +138,29 @@ def test_cornell_paths_regression(pkg, oracle, hostemu, scenes):
     e = emu.render(cam, 0, 10, 8)
     o = orc.render(oracle.camera_for(data, 160, 90), 0, 10, 8, use_bvh=True)
     assert e["ray_count"] == o["ray_count"] and np.array_equal(e["rng_state"], o["rng_state"])
+
+
+def test_awkward_transforms_and_scales(pkg, oracle, hostemu):
+    import edge_scenes
+    data, org, d = edge_scenes.awkward_transforms()
+    emu, orc = hostemu.Scene(data), oracle.Scene(data)
+    assert emu.validate() == 0
+    a, b = orc.intersect(org, d, use_bvh=False), emu.intersect(org, d)
+    assert (a["inst"] >= 0).sum() > 500
+    for k in ("inst", "prim"):
+        assert np.array_equal(a[k], b[k])
+    assert np.array_equal(a["t"].view(np.uint32), b["t"].view(np.uint32))
+    cam = pkg.Camera((40, 30), data.camera_position, data.camera_direction, data.camera_focal_length)
+    e = emu.render(cam, 0, 6, 2)
+    o = orc.render(oracle.camera_for(data, 40, 30), 0, 6, 2, use_bvh=True)
+    assert e["ray_count"] == o["ray_count"] and np.array_equal(e["accum"].view(np.uint32), o["accum"].view(np.uint32))
+
+
+def test_coincident_centroids_and_flat_scene(oracle, hostemu):
+    import edge_scenes
+    data, org, d = edge_scenes.coincident_centroids()
+    emu, orc = hostemu.Scene(data), oracle.Scene(data)
+    assert emu.validate() == 0
+    a, b = orc.intersect(org, d), emu.intersect(org, d)
+    assert np.array_equal(a["prim"], b["prim"]) and np.array_equal(a["t"].view(np.uint32), b["t"].view(np.uint32))
+    assert (a["prim"] >= 0).mean() > 0.5
