@@ -140,15 +140,30 @@ RT_HD uint32_t rt_sign_extend_s8x4(uint32_t x) {
 /* byte j of w -> the float 1 + b * 2^-15, built with ONE byte permute (no I2F: the conversion
  * pipe is the narrowest one on sm_100a and 48 conversions per node visit made it the busiest):
  * 0x3F800000 | b << 8. The node test folds the "1 +" and the 2^-15 into its per-node constants. */
-template <int J>
-RT_HD float rt_byte_to_unit(uint32_t w) {
+template <int J, int UNIQ>
+RT_HD float rt_byte_to_unit(uint32_t w, uint32_t one_bits /* 0x3F800000, held in a register */) {
 #if RT_DEVICE_CODE
+    /* selector: byte0 <- one.b0, byte1 <- w.bJ, byte2 <- one.b2, byte3 <- one.b3. Only the low 16 bits
+     * of a PRMT selector are read; UNIQ makes every call site's constant different so that ptxas
+     * encodes it as an immediate instead of hoisting four shared selectors into registers and
+     * re-materialising them before each of the 48 permutes of a node test (measured: +48 moves). */
     uint32_t r;
-    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(w), "r"(0x3F800000u), "n"(0x7604 | (J << 4)));
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(w), "r"(one_bits), "n"(0x7604 | (J << 4) | (UNIQ << 16)));
     return __uint_as_float(r);
 #else
-    return rt_u2f(0x3F800000u | (((w >> (8 * J)) & 0xffu) << 8));
+    return rt_u2f(one_bits | (((w >> (8 * J)) & 0xffu) << 8));
 #endif
+}
+/* PRMT takes one immediate: if the compiler sees both 0x3F800000 and the selector as constants it keeps
+ * the SELECTOR in a register and re-materialises it before every one of the 48 permutes of a node
+ * test (measured: +48 moves per node visit). Hiding the constant behind an empty asm pins it in a
+ * register instead, so the selectors are encoded as immediates. */
+RT_HD uint32_t rt_unit_bits() {
+    uint32_t one_bits = 0x3F800000u;
+#if RT_DEVICE_CODE
+    asm volatile("" : "+r"(one_bits));
+#endif
+    return one_bits;
 }
 
 /* ---- watertight ray/triangle -------------------------------------------------------- */
@@ -259,21 +274,40 @@ RT_HD RtRayBox rt_ray_box_setup(f3 org, f3 dir) {
 
 /* returns the hit mask of one wide node: bits 24..31 inner children in visiting priority,
  * bits 0..23 leaf triangles (offsets from tri_base) */
-template <int J>
+template <int J, int H>
 RT_HD void rt_child_test(uint32_t nx, uint32_t ny, uint32_t nz, uint32_t fx, uint32_t fy, uint32_t fz, float Sx,
                          float Sy, float Sz, float onx, float ony, float onz, float ofx, float ofy, float ofz,
-                         float tmin, float tmax_pad, uint32_t child_bits4, uint32_t bit_index4, uint32_t &hitmask) {
-    const float tnx = rt_fma(rt_byte_to_unit<J>(nx), Sx, onx);
-    const float tny = rt_fma(rt_byte_to_unit<J>(ny), Sy, ony);
-    const float tnz = rt_fma(rt_byte_to_unit<J>(nz), Sz, onz);
-    const float tfx = rt_fma(rt_byte_to_unit<J>(fx), Sx, ofx);
-    const float tfy = rt_fma(rt_byte_to_unit<J>(fy), Sy, ofy);
-    const float tfz = rt_fma(rt_byte_to_unit<J>(fz), Sz, ofz);
+                         float tmin, float tmax_pad, uint32_t child_bits4, uint32_t bit_index4, uint32_t one,
+                         uint32_t &hitmask) {
+    const float tnx = rt_fma(rt_byte_to_unit<J, 1 + 0 + 6 * J + 24 * H>(nx, one), Sx, onx);
+    const float tny = rt_fma(rt_byte_to_unit<J, 1 + 1 + 6 * J + 24 * H>(ny, one), Sy, ony);
+    const float tnz = rt_fma(rt_byte_to_unit<J, 1 + 2 + 6 * J + 24 * H>(nz, one), Sz, onz);
+    const float tfx = rt_fma(rt_byte_to_unit<J, 1 + 3 + 6 * J + 24 * H>(fx, one), Sx, ofx);
+    const float tfy = rt_fma(rt_byte_to_unit<J, 1 + 4 + 6 * J + 24 * H>(fy, one), Sy, ofy);
+    const float tfz = rt_fma(rt_byte_to_unit<J, 1 + 5 + 6 * J + 24 * H>(fz, one), Sz, ofz);
     const float cmin = rt_max(rt_max3(tnx, tny, tnz), tmin);
     const float cmax = rt_min(rt_min3(tfx, tfy, tfz), tmax_pad);
     const uint32_t bits = (child_bits4 >> (8 * J)) & 0xffu;
     const uint32_t idxb = (bit_index4 >> (8 * J)) & 0xffu;
     hitmask |= (cmin <= cmax) ? (bits << idxb) : 0u;
+}
+
+/* four children (one 32-bit word of every quantised plane) */
+template <int H>
+RT_HD void rt_half_test(const RtRayBox &rb, uint32_t meta4, uint32_t qlox, uint32_t qloy, uint32_t qloz, uint32_t qhix,
+                        uint32_t qhiy, uint32_t qhiz, float Sx, float Sy, float Sz, float onx, float ony, float onz,
+                        float ofx, float ofy, float ofz, float tmin, float tmax_pad, uint32_t one, uint32_t &hitmask) {
+    const uint32_t is_inner4 = (meta4 & (meta4 << 1)) & 0x10101010u;
+    const uint32_t inner_mask4 = rt_sign_extend_s8x4(is_inner4 << 3);
+    const uint32_t bit_index4 = (meta4 ^ (rb.oct_inv4 & inner_mask4)) & 0x1f1f1f1fu;
+    const uint32_t child_bits4 = (meta4 >> 5) & 0x07070707u;
+    const uint32_t nx = (rb.neg & 1u) ? qhix : qlox, fx = (rb.neg & 1u) ? qlox : qhix;
+    const uint32_t ny = (rb.neg & 2u) ? qhiy : qloy, fy = (rb.neg & 2u) ? qloy : qhiy;
+    const uint32_t nz = (rb.neg & 4u) ? qhiz : qloz, fz = (rb.neg & 4u) ? qloz : qhiz;
+    rt_child_test<0, H>(nx, ny, nz, fx, fy, fz, Sx, Sy, Sz, onx, ony, onz, ofx, ofy, ofz, tmin, tmax_pad, child_bits4, bit_index4, one, hitmask);
+    rt_child_test<1, H>(nx, ny, nz, fx, fy, fz, Sx, Sy, Sz, onx, ony, onz, ofx, ofy, ofz, tmin, tmax_pad, child_bits4, bit_index4, one, hitmask);
+    rt_child_test<2, H>(nx, ny, nz, fx, fy, fz, Sx, Sy, Sz, onx, ony, onz, ofx, ofy, ofz, tmin, tmax_pad, child_bits4, bit_index4, one, hitmask);
+    rt_child_test<3, H>(nx, ny, nz, fx, fy, fz, Sx, Sy, Sz, onx, ony, onz, ofx, ofy, ofz, tmin, tmax_pad, child_bits4, bit_index4, one, hitmask);
 }
 
 RT_HD uint32_t rt_node_test(const RtRayBox &rb, rt_uint4 n0, rt_uint4 n1, rt_uint4 n2,
@@ -299,25 +333,9 @@ RT_HD uint32_t rt_node_test(const RtRayBox &rb, rt_uint4 n0, rt_uint4 n1, rt_uin
     const float onx = (ox - ex) - Sx, ony = (oy - ey) - Sy, onz = (oz - ez) - Sz;
     const float ofx = (ox + ex) - Sx, ofy = (oy + ey) - Sy, ofz = (oz + ez) - Sz;
     uint32_t hitmask = 0;
-#if RT_DEVICE_CODE
-#pragma unroll
-#endif
-    for (int h = 0; h < 2; h++) {
-        const uint32_t meta4 = h ? n1.w : n1.z;
-        const uint32_t is_inner4 = (meta4 & (meta4 << 1)) & 0x10101010u;
-        const uint32_t inner_mask4 = rt_sign_extend_s8x4(is_inner4 << 3);
-        const uint32_t bit_index4 = (meta4 ^ (rb.oct_inv4 & inner_mask4)) & 0x1f1f1f1fu;
-        const uint32_t child_bits4 = (meta4 >> 5) & 0x07070707u;
-        const uint32_t qlox = h ? n2.y : n2.x, qloy = h ? n2.w : n2.z, qloz = h ? n3.y : n3.x;
-        const uint32_t qhix = h ? n3.w : n3.z, qhiy = h ? n4.y : n4.x, qhiz = h ? n4.w : n4.z;
-        const uint32_t nx = (rb.neg & 1u) ? qhix : qlox, fx = (rb.neg & 1u) ? qlox : qhix;
-        const uint32_t ny = (rb.neg & 2u) ? qhiy : qloy, fy = (rb.neg & 2u) ? qloy : qhiy;
-        const uint32_t nz = (rb.neg & 4u) ? qhiz : qloz, fz = (rb.neg & 4u) ? qloz : qhiz;
-        rt_child_test<0>(nx, ny, nz, fx, fy, fz, Sx, Sy, Sz, onx, ony, onz, ofx, ofy, ofz, tmin, tmax_pad, child_bits4, bit_index4, hitmask);
-        rt_child_test<1>(nx, ny, nz, fx, fy, fz, Sx, Sy, Sz, onx, ony, onz, ofx, ofy, ofz, tmin, tmax_pad, child_bits4, bit_index4, hitmask);
-        rt_child_test<2>(nx, ny, nz, fx, fy, fz, Sx, Sy, Sz, onx, ony, onz, ofx, ofy, ofz, tmin, tmax_pad, child_bits4, bit_index4, hitmask);
-        rt_child_test<3>(nx, ny, nz, fx, fy, fz, Sx, Sy, Sz, onx, ony, onz, ofx, ofy, ofz, tmin, tmax_pad, child_bits4, bit_index4, hitmask);
-    }
+    const uint32_t one = rt_unit_bits();
+    rt_half_test<0>(rb, n1.z, n2.x, n2.z, n3.x, n3.z, n4.x, n4.z, Sx, Sy, Sz, onx, ony, onz, ofx, ofy, ofz, tmin, tmax_pad, one, hitmask);
+    rt_half_test<1>(rb, n1.w, n2.y, n2.w, n3.y, n3.w, n4.y, n4.w, Sx, Sy, Sz, onx, ony, onz, ofx, ofy, ofz, tmin, tmax_pad, one, hitmask);
     return hitmask;
 }
 
