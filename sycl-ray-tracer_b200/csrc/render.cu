@@ -68,10 +68,9 @@ enum { kNeedPixel = 0, kNeedRay = 1, kStart = 2, kTraversing = 3, kHitPending = 
 
 /* Traverse phase shared by the megakernel and the wavefront extend kernel (warp-uniform control
  * flow): node steps for every lane with node work until `refill` lanes have run out of nodes, or
- * `tri_lanes` lanes have triangles pending, or a lane's triangle stack is full; then all pending
+ * a lane's triangle stack is full; then all pending
  * triangles are tested together. Lanes left with neither nodes nor triangles become kHitPending. */
-__device__ __forceinline__ void traverse_phase(const RtBvh &bvh, RtTravState &tv, RtTravStacks &ks, int &mode, int refill,
-                                               int /*tri_lanes: unused*/) {
+__device__ __forceinline__ void traverse_phase(const RtBvh &bvh, RtTravState &tv, RtTravStacks &ks, int &mode, int refill) {
     const unsigned full = 0xffffffffu;
     const bool trav = mode == kTraversing;
     const unsigned m_trav = __ballot_sync(full, trav); /* does not change inside the node loop */
@@ -192,7 +191,7 @@ __global__ void __launch_bounds__(kMegaBlock, RT_MEGA_MIN_BLOCKS) k_megakernel(R
         /* ---------------- traverse ---------------- */
         const unsigned act0 = __ballot_sync(full, mode == kTraversing);
         if (!act0) break; /* every lane is exhausted */
-        traverse_phase(scene.bvh, tv, ks, mode, p.tune_refill, p.tune_tridiv);
+        traverse_phase(scene.bvh, tv, ks, mode, p.tune_refill);
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) rays += __shfl_xor_sync(full, rays, o);
@@ -246,8 +245,7 @@ __global__ void __launch_bounds__(kWfBlock) k_wf_generate(RtFrameParams p, RtWav
 #define RT_EXT_MIN_BLOCKS 4
 #endif
 __global__ void __launch_bounds__(kWfBlock, RT_EXT_MIN_BLOCKS) k_wf_extend(RtScene scene, RtWavefrontState w, int cur,
-                                                         unsigned long long *ray_counter, int tune_refill,
-                                                         int tune_tridiv) {
+                                                         unsigned long long *ray_counter, int tune_refill) {
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const uint32_t count = *w.count[cur];
@@ -288,7 +286,7 @@ __global__ void __launch_bounds__(kWfBlock, RT_EXT_MIN_BLOCKS) k_wf_extend(RtSce
         }
         const unsigned act0 = __ballot_sync(full, mode == kTraversing);
         if (!act0) break;
-        traverse_phase(scene.bvh, tv, ks, mode, tune_refill, tune_tridiv);
+        traverse_phase(scene.bvh, tv, ks, mode, tune_refill);
     }
 }
 
@@ -390,7 +388,7 @@ cudaError_t rt_launch_wf_generate(cudaStream_t st, int grid, const RtFrameParams
 
 cudaError_t rt_launch_wf_extend(cudaStream_t st, int grid, const RtScene &scene, const RtWavefrontState &w, int cur,
                                 unsigned long long *ray_counter, const RtFrameParams &p) {
-    k_wf_extend<<<grid, kWfBlock, 0, st>>>(scene, w, cur, ray_counter, p.tune_refill, p.tune_tridiv);
+    k_wf_extend<<<grid, kWfBlock, 0, st>>>(scene, w, cur, ray_counter, p.tune_refill);
     return cudaGetLastError();
 }
 

@@ -233,7 +233,6 @@ struct RtFrameParams {
     int32_t clamp_samples;  /* F9: wavefront clamps every sample to [0,1] */
     /* scheduling knobs of the persistent kernels (no effect on results) */
     int32_t tune_refill;    /* leave the traversal loop once this many lanes have finished */
-    int32_t tune_tridiv;    /* drain the pending triangle tests once this many lanes have some */
 };
 
 /* image-tile sharding: tile t (row major, tile_size^2 pixels) belongs to rank t % world */

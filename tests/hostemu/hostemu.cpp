@@ -388,7 +388,6 @@ uint64_t emu_render(const emu_scene *s, int kind, const rt_camera *camera, const
     p.wavefront_seed = kind == 1;
     p.clamp_samples = kind == 1;
     p.tune_refill = 8;
-    p.tune_tridiv = 5;
     const uint32_t n_pix = (uint32_t)p.cam.w * (uint32_t)p.cam.h;
     std::vector<rt_float4> acc(n_pix, rt_mk_float4(0, 0, 0, 0));
     std::vector<uint32_t> bytes(n_pix, 0), rng_final(n_pix, 0);
