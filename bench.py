@@ -357,16 +357,22 @@ def main():
         d2h = w * h * 4 + 8
 
         def e2e_step():
+            t_a = time.perf_counter()
             sc = pkg.Scene(app, data)  # H2D of the scene from host memory + GPU BVH build
+            t_b = time.perf_counter()
+            e2e_step.create_s += t_b - t_a
             if dist:
                 f = r.render_frame(cam, sc, want=(), shard=shard)
                 dist.all_reduce(accum_t)
                 pkg.resolve(app, accum_t, spp_total, w, h, host_img)  # D2H of the image
             else:
                 f = r.render_frame(cam, sc, want=("rgba8",), outputs={"rgba8": host_img})  # D2H inside
+            e2e_step.render_s += time.perf_counter() - t_b
             sc.close()
             return f
+        e2e_step.create_s = e2e_step.render_s = 0.0
         e2e_step()
+        e2e_step.create_s = e2e_step.render_s = 0.0
         try:
             uuid = str(torch.cuda.get_device_properties(local_rank).uuid)
         except Exception:
@@ -392,7 +398,9 @@ def main():
             dist.all_reduce(sm, op=dist.ReduceOp.SUM)
             dt, e_rays = float(mx[0]), int(sm[1])
         e2e = {"value": e_rays / dt / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-               "ms_per_step": dt / args.steps * 1e3, "render_device_ms_per_step": e_dev_ms / args.steps, "clocks": e_clocks,
+               "ms_per_step": dt / args.steps * 1e3, "render_device_ms_per_step": e_dev_ms / args.steps,
+               "scene_upload_and_build_ms_per_step": e2e_step.create_s / args.steps * 1e3,
+               "render_call_ms_per_step": e2e_step.render_s / args.steps * 1e3, "clocks": e_clocks,
                "includes": "scene upload from host + BVH build + render" + (" + NCCL all-reduce" if dist else "") + " + image read-back, every step"}
         r.close()
 

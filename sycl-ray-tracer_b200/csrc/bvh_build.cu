@@ -100,14 +100,16 @@ __global__ void k_empty_root(rt_uint4 *nodes) {
 inline uint32_t grid_for(uint64_t n) { return (uint32_t)((n + kBlock - 1) / kBlock); }
 
 struct Scratch {
+    rt_context *ctx;
     std::vector<void *> ptrs;
+    explicit Scratch(rt_context *c) : ctx(c) {}
     ~Scratch() {
-        for (void *p : ptrs) cudaFree(p);
+        for (void *p : ptrs) rt_pool_free(ctx, p);
     }
     template <class T>
     cudaError_t alloc(T **out, size_t count) {
         void *p = nullptr;
-        cudaError_t e = cudaMalloc(&p, (count ? count : 1) * sizeof(T));
+        cudaError_t e = rt_pool_alloc(ctx, &p, (count ? count : 1) * sizeof(T));
         if (e == cudaSuccess) ptrs.push_back(p);
         *out = (T *)p;
         return e;
@@ -124,9 +126,9 @@ rt_status rt_build_bvh(rt_scene *s) {
     RT_CUDA_TRY(ctx, cudaEventRecord(ctx->ev0, st));
 
     if (n == 0) { /* empty scene: a root with no children, every ray misses */
-        RT_CUDA_TRY(ctx, cudaMalloc(&s->d_nodes, RT_NODE_VEC4 * sizeof(rt_uint4)));
-        RT_CUDA_TRY(ctx, cudaMalloc(&s->d_tris, RT_TRI_VEC4 * sizeof(rt_float4)));
-        RT_CUDA_TRY(ctx, cudaMalloc(&s->d_shade, 4 * sizeof(rt_float4)));
+        RT_CUDA_TRY(ctx, rt_pool_alloc(ctx, (void **)&s->d_nodes, RT_NODE_VEC4 * sizeof(rt_uint4)));
+        RT_CUDA_TRY(ctx, rt_pool_alloc(ctx, (void **)&s->d_tris, RT_TRI_VEC4 * sizeof(rt_float4)));
+        RT_CUDA_TRY(ctx, rt_pool_alloc(ctx, (void **)&s->d_shade, 4 * sizeof(rt_float4)));
         k_empty_root<<<1, 1, 0, st>>>(s->d_nodes);
         RT_CUDA_TRY(ctx, cudaGetLastError());
         RT_CUDA_TRY(ctx, cudaStreamSynchronize(st));
@@ -135,7 +137,7 @@ rt_status rt_build_bvh(rt_scene *s) {
         return RT_OK;
     }
 
-    Scratch scratch;
+    Scratch scratch(ctx);
     RtBuild b = {};
     b.n_tris = n;
     b.n_inst = s->n_inst;
@@ -174,8 +176,8 @@ rt_status rt_build_bvh(rt_scene *s) {
     RT_CUDA_TRY(ctx, scratch.alloc(&counts, max_level_items));
     RT_CUDA_TRY(ctx, scratch.alloc(&offsets, max_level_items));
     RT_CUDA_TRY(ctx, scratch.alloc(&nodes_tmp, (size_t)n * RT_NODE_VEC4));
-    RT_CUDA_TRY(ctx, cudaMalloc(&s->d_tris, (size_t)n * RT_TRI_VEC4 * sizeof(rt_float4)));
-    RT_CUDA_TRY(ctx, cudaMalloc(&s->d_shade, (size_t)n * 4 * sizeof(rt_float4)));
+    RT_CUDA_TRY(ctx, rt_pool_alloc(ctx, (void **)&s->d_tris, (size_t)n * RT_TRI_VEC4 * sizeof(rt_float4)));
+    RT_CUDA_TRY(ctx, rt_pool_alloc(ctx, (void **)&s->d_shade, (size_t)n * 4 * sizeof(rt_float4)));
     b.tris = s->d_tris;
     b.shade = s->d_shade;
     b.nodes = nodes_tmp;
@@ -251,7 +253,7 @@ rt_status rt_build_bvh(rt_scene *s) {
         return rt_set_error(ctx, RT_ERR_STATE, "rt_build_bvh", "wide tree deeper than the traversal stack");
 
     const uint32_t node_count = level_first;
-    RT_CUDA_TRY(ctx, cudaMalloc(&s->d_nodes, (size_t)node_count * RT_NODE_VEC4 * sizeof(rt_uint4)));
+    RT_CUDA_TRY(ctx, rt_pool_alloc(ctx, (void **)&s->d_nodes, (size_t)node_count * RT_NODE_VEC4 * sizeof(rt_uint4)));
     RT_CUDA_TRY(ctx, cudaMemcpyAsync(s->d_nodes, nodes_tmp, (size_t)node_count * RT_NODE_VEC4 * sizeof(rt_uint4),
                                      cudaMemcpyDeviceToDevice, st));
     RT_CUDA_TRY(ctx, cudaEventRecord(ctx->ev1, st));

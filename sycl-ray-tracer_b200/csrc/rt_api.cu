@@ -107,6 +107,12 @@ rt_status rt_context_create(int device, rt_context **out) {
         return RT_ERR_CUDA;
     }
     ctx->stream = ctx->own_stream;
+    {
+        cudaMemPool_t pool = nullptr;
+        unsigned long long keep = ~0ull; /* keep freed scene memory in the pool for the next build */
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        (void)cudaGetLastError();
+    }
     ctx->sm_count = prop.multiProcessorCount;
     ctx->name = prop.name;
     /* arithmetic-contract self test: a*b+c must not be contracted into an FMA */
@@ -135,6 +141,7 @@ rt_status rt_context_create(int device, rt_context **out) {
 void rt_context_destroy(rt_context *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
+    for (auto &t : ctx->tex_cache) cudaFreeArray(t.second);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
@@ -216,19 +223,11 @@ rt_status rt_scene_create(rt_context *ctx, const rt_scene_desc *desc, rt_scene *
     s->n_tris = (uint32_t)(n_idx / 3);
     memcpy(s->sky, desc->sky_color, sizeof(s->sky));
 
-    std::vector<float> pos(n_verts * 3), nrm(n_verts * 3), uv(n_verts * 2);
-    std::vector<uint32_t> idx(n_idx);
     s->h_geom.resize(desc->instance_count ? desc->instance_count : 1);
     s->h_inst.resize(desc->instance_count ? desc->instance_count : 1);
     uint32_t v0 = 0, i0 = 0;
     for (uint32_t i = 0; i < desc->instance_count; i++) {
         const rt_instance &in = desc->instances[i];
-        if (in.vertex_count) {
-            memcpy(&pos[(size_t)v0 * 3], in.positions, (size_t)in.vertex_count * 3 * sizeof(float));
-            memcpy(&nrm[(size_t)v0 * 3], in.normals, (size_t)in.vertex_count * 3 * sizeof(float));
-            memcpy(&uv[(size_t)v0 * 2], in.uvs, (size_t)in.vertex_count * 2 * sizeof(float));
-        }
-        if (in.index_count) memcpy(&idx[i0], in.indices, (size_t)in.index_count * sizeof(uint32_t));
         RtInstanceGeom &g = s->h_geom[i];
         memcpy(g.transform, in.transform, sizeof(g.transform));
         g.first_vertex = v0;
@@ -255,19 +254,26 @@ rt_status rt_scene_create(rt_context *ctx, const rt_scene_desc *desc, rt_scene *
     cudaError_t e;
     cudaStream_t stream = ctx->stream;
     do {
-        if ((e = dev_alloc(&s->d_positions, pos.size())) != cudaSuccess) { fail(e, "alloc positions"); break; }
-        if ((e = dev_alloc(&s->d_normals, nrm.size())) != cudaSuccess) { fail(e, "alloc normals"); break; }
-        if ((e = dev_alloc(&s->d_uvs, uv.size())) != cudaSuccess) { fail(e, "alloc uvs"); break; }
-        if ((e = dev_alloc(&s->d_indices, idx.size())) != cudaSuccess) { fail(e, "alloc indices"); break; }
-        if ((e = dev_alloc(&s->d_geom, s->h_geom.size())) != cudaSuccess) { fail(e, "alloc geom"); break; }
-        if ((e = dev_alloc(&s->d_inst, s->h_inst.size())) != cudaSuccess) { fail(e, "alloc inst"); break; }
-        if (!pos.empty()) {
-            if ((e = cudaMemcpyAsync(s->d_positions, pos.data(), pos.size() * 4, cudaMemcpyHostToDevice, stream)) != cudaSuccess) { fail(e, "copy positions"); break; }
-            if ((e = cudaMemcpyAsync(s->d_normals, nrm.data(), nrm.size() * 4, cudaMemcpyHostToDevice, stream)) != cudaSuccess) { fail(e, "copy normals"); break; }
-            if ((e = cudaMemcpyAsync(s->d_uvs, uv.data(), uv.size() * 4, cudaMemcpyHostToDevice, stream)) != cudaSuccess) { fail(e, "copy uvs"); break; }
+        if ((e = rt_pool_alloc(ctx, (void **)&s->d_positions, n_verts * 3 * sizeof(float))) != cudaSuccess) { fail(e, "alloc positions"); break; }
+        if ((e = rt_pool_alloc(ctx, (void **)&s->d_normals, n_verts * 3 * sizeof(float))) != cudaSuccess) { fail(e, "alloc normals"); break; }
+        if ((e = rt_pool_alloc(ctx, (void **)&s->d_uvs, n_verts * 2 * sizeof(float))) != cudaSuccess) { fail(e, "alloc uvs"); break; }
+        if ((e = rt_pool_alloc(ctx, (void **)&s->d_indices, n_idx * sizeof(uint32_t))) != cudaSuccess) { fail(e, "alloc indices"); break; }
+        if ((e = rt_pool_alloc(ctx, (void **)&s->d_geom, s->h_geom.size() * sizeof(*s->d_geom))) != cudaSuccess) { fail(e, "alloc geom"); break; }
+        if ((e = rt_pool_alloc(ctx, (void **)&s->d_inst, s->h_inst.size() * sizeof(*s->d_inst))) != cudaSuccess) { fail(e, "alloc inst"); break; }
+        /* every instance's arrays go straight from the caller's memory to their offset in the
+         * concatenated device arrays (no host-side staging copy) */
+        for (uint32_t i = 0; i < desc->instance_count && e == cudaSuccess; i++) {
+            const rt_instance &in = desc->instances[i];
+            const RtInstanceGeom &g = s->h_geom[i];
+            if (in.vertex_count) {
+                e = cudaMemcpyAsync(s->d_positions + (size_t)g.first_vertex * 3, in.positions, (size_t)in.vertex_count * 12, cudaMemcpyHostToDevice, stream);
+                if (e == cudaSuccess) e = cudaMemcpyAsync(s->d_normals + (size_t)g.first_vertex * 3, in.normals, (size_t)in.vertex_count * 12, cudaMemcpyHostToDevice, stream);
+                if (e == cudaSuccess) e = cudaMemcpyAsync(s->d_uvs + (size_t)g.first_vertex * 2, in.uvs, (size_t)in.vertex_count * 8, cudaMemcpyHostToDevice, stream);
+            }
+            if (e == cudaSuccess && in.index_count)
+                e = cudaMemcpyAsync(s->d_indices + g.first_index, in.indices, (size_t)in.index_count * 4, cudaMemcpyHostToDevice, stream);
         }
-        if (!idx.empty())
-            if ((e = cudaMemcpyAsync(s->d_indices, idx.data(), idx.size() * 4, cudaMemcpyHostToDevice, stream)) != cudaSuccess) { fail(e, "copy indices"); break; }
+        if (e != cudaSuccess) { fail(e, "copy geometry"); break; }
         if ((e = cudaMemcpyAsync(s->d_geom, s->h_geom.data(), s->h_geom.size() * sizeof(RtInstanceGeom), cudaMemcpyHostToDevice, stream)) != cudaSuccess) { fail(e, "copy geom"); break; }
         if ((e = cudaMemcpyAsync(s->d_inst, s->h_inst.data(), s->h_inst.size() * sizeof(RtInstance), cudaMemcpyHostToDevice, stream)) != cudaSuccess) { fail(e, "copy inst"); break; }
         /* texture array: RGBA8 512x512xN layered, point sampled, raw element reads (F13) */
@@ -275,7 +281,13 @@ rt_status rt_scene_create(rt_context *ctx, const rt_scene_desc *desc, rt_scene *
         if (s->n_layers) {
             cudaChannelFormatDesc cd = cudaCreateChannelDesc<uchar4>();
             cudaExtent ext = make_cudaExtent(RT_TEX_SIZE, RT_TEX_SIZE, s->n_layers);
-            if ((e = cudaMalloc3DArray(&s->tex_array, &cd, ext, cudaArrayLayered)) != cudaSuccess) { fail(e, "alloc texture array"); break; }
+            for (size_t k = 0; k < ctx->tex_cache.size(); k++)
+                if (ctx->tex_cache[k].first == s->n_layers) {
+                    s->tex_array = ctx->tex_cache[k].second;
+                    ctx->tex_cache.erase(ctx->tex_cache.begin() + (long)k);
+                    break;
+                }
+            if (!s->tex_array && (e = cudaMalloc3DArray(&s->tex_array, &cd, ext, cudaArrayLayered)) != cudaSuccess) { fail(e, "alloc texture array"); break; }
             cudaMemcpy3DParms cp = {};
             cp.srcPtr = make_cudaPitchedPtr((void *)desc->texture_layers, RT_TEX_SIZE * 4, RT_TEX_SIZE, RT_TEX_SIZE);
             cp.dstArray = s->tex_array;
@@ -311,10 +323,10 @@ rt_status rt_scene_commit(rt_scene *s) {
     rt_status st = rt_build_bvh(s);
     if (st != RT_OK) return st;
     /* the object-space inputs are no longer needed */
-    cudaFree(s->d_positions); s->d_positions = nullptr;
-    cudaFree(s->d_normals); s->d_normals = nullptr;
-    cudaFree(s->d_uvs); s->d_uvs = nullptr;
-    cudaFree(s->d_indices); s->d_indices = nullptr;
+    rt_pool_free(ctx, s->d_positions); s->d_positions = nullptr;
+    rt_pool_free(ctx, s->d_normals); s->d_normals = nullptr;
+    rt_pool_free(ctx, s->d_uvs); s->d_uvs = nullptr;
+    rt_pool_free(ctx, s->d_indices); s->d_indices = nullptr;
     s->view.bvh.nodes = s->d_nodes;
     s->view.bvh.tris = s->d_tris;
     s->view.shade = s->d_shade;
@@ -340,16 +352,16 @@ void rt_scene_destroy(rt_scene *s) {
     if (!s) return;
     cudaSetDevice(s->ctx->device);
     if (s->tex) cudaDestroyTextureObject(s->tex);
-    if (s->tex_array) cudaFreeArray(s->tex_array);
-    cudaFree(s->d_positions);
-    cudaFree(s->d_normals);
-    cudaFree(s->d_uvs);
-    cudaFree(s->d_indices);
-    cudaFree(s->d_geom);
-    cudaFree(s->d_inst);
-    cudaFree(s->d_nodes);
-    cudaFree(s->d_tris);
-    cudaFree(s->d_shade);
+    if (s->tex_array) {
+        if (s->ctx->tex_cache.size() < 2) {
+            cudaStreamSynchronize(s->ctx->stream); /* no kernel may still sample it when it is reused */
+            s->ctx->tex_cache.emplace_back(s->n_layers, s->tex_array);
+        } else {
+            cudaFreeArray(s->tex_array);
+        }
+    }
+    void *bufs[] = {s->d_positions, s->d_normals, s->d_uvs, s->d_indices, s->d_geom, s->d_inst, s->d_nodes, s->d_tris, s->d_shade};
+    for (void *b : bufs) rt_pool_free(s->ctx, b);
     delete s;
 }
 

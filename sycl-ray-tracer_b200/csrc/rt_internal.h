@@ -21,6 +21,9 @@ struct rt_context {
     int sm_count = 0;
     std::string name;
     std::string err;
+    /* layered texture arrays of destroyed scenes, kept for the next scene with the same layer count:
+     * cudaMalloc3DArray / cudaFreeArray are synchronous driver calls worth tens of milliseconds */
+    std::vector<std::pair<uint32_t, cudaArray_t>> tex_cache;
 };
 
 /* Scene's device side (src/scene.hpp:64-91) */
@@ -50,6 +53,16 @@ struct rt_scene {
 };
 
 rt_status rt_set_error(rt_context *ctx, rt_status st, const char *what, const char *detail);
+
+/* Scene-side device memory comes from the device's stream-ordered pool (release threshold raised in
+ * rt_context_create), so building scene after scene reuses memory without a driver round trip:
+ * cudaMalloc/cudaFree cost 20-700 ms per scene build on a fresh box. */
+inline cudaError_t rt_pool_alloc(rt_context *ctx, void **p, size_t bytes) {
+    return cudaMallocAsync(p, bytes ? bytes : 16, ctx->stream);
+}
+inline void rt_pool_free(rt_context *ctx, void *p) {
+    if (p) cudaFreeAsync(p, ctx->stream);
+}
 rt_status rt_build_bvh(rt_scene *s); /* bvh_build.cu */
 
 #define RT_CUDA_TRY(ctx, expr)                                                     \
