@@ -29,8 +29,9 @@ for f in os.listdir(tmp):
             lines.append((int(m.group(1), 16), cur, m.group(2)))
 src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(src.splitlines()))
-hi = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
-hdr, data = rows[hi], [r for r in rows[hi + 1:] if len(r) == len(rows[hi])]
+his = [i for i, r in enumerate(rows) if r and r[0] == "Address"]
+hi, end = his[0], (his[1] - 2 if len(his) > 1 else len(rows))  # first kernel of the report
+hdr, data = rows[hi], [r for r in rows[hi + 1:end] if len(r) == len(rows[hi])]
 ix = {h: i for i, h in enumerate(hdr)}
 assert len(data) == len(lines), (len(data), len(lines))
 agg = collections.defaultdict(lambda: [0.0, 0.0, 0.0])

@@ -23,8 +23,9 @@ for r in rows[2:]:
             print(f"  {h:72s} {v:>18s} {u}")
 src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(src.splitlines()))
-hi = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
-hdr, data = rows[hi], [r for r in rows[hi + 1:] if len(r) == len(rows[hi])]
+his = [i for i, r in enumerate(rows) if r and r[0] == "Address"]
+hi, end = his[0], (his[1] - 2 if len(his) > 1 else len(rows))  # first kernel of the report
+hdr, data = rows[hi], [r for r in rows[hi + 1:end] if len(r) == len(rows[hi])]
 ix = {h: i for i, h in enumerate(hdr)}
 f = lambda r, k: float(r[ix[k]] or 0)
 tot = sum(f(r, "Instructions Executed") for r in data)
