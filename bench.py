@@ -240,6 +240,7 @@ def main():
                          "tiles = 64x64 image tiles dealt round robin, total work fixed (strong scaling, config 4's mode)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-also", action="store_true", help="skip the quick secondary measurement of configs[1] (Cornell)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
@@ -344,6 +345,27 @@ def main():
         results.append(bench_renderer(pkg.WavefrontRenderer, "wavefront"))
     best = max(results, key=lambda x: x["rays"] / x["ms"])
     samples_total = w * h * spp_total * args.steps
+
+    # ---- the other single-GPU configuration of BASELINE.json (configs[1], Cornell, wavefront), quick ----
+    also = None
+    if args.workload == "c3_sponza_scale" and world == 1 and not args.no_also:
+        data2, w2, h2, spp2, depth2 = build_scene_data("c2_cornell")
+        sc2 = pkg.Scene(app, data2)
+        cam2 = pkg.Camera((w2, h2), data2.camera_position, data2.camera_direction, data2.camera_focal_length)
+        also = {"workload": "c2_cornell", "triangles": int(sc2.stats["triangle_count"]), "width": w2, "height": h2, "spp": spp2,
+                "max_depth": depth2, "steps": 3}
+        for cls, name in ((pkg.WavefrontRenderer, "wavefront"), (pkg.MegakernelRenderer, "megakernel")):
+            r2 = cls(app, (w2, h2), None, depth2, spp2)
+            for _ in range(3):
+                r2.render_frame(cam2, sc2, want=())
+            ms2, rays2 = 0.0, 0
+            for _ in range(3):
+                flush.fill_(1)
+                f2 = r2.render_frame(cam2, sc2, want=())
+                ms2, rays2 = ms2 + f2.device_ms, rays2 + f2.ray_count
+            also[name] = {"mrays_per_s": rays2 / ms2 / 1e3, "msamples_per_s": 3 * w2 * h2 * spp2 / ms2 / 1e3, "ms_per_step": ms2 / 3}
+            r2.close()
+        sc2.close()
 
     # ---- end to end through the public API with host buffers -----------------------------------
     e2e = None
@@ -457,7 +479,7 @@ def main():
         "renderers": {x["name"]: {"mrays_per_s": x["rays"] / (x["ms"] * 1e-3) / 1e6, "ms_per_step": x["ms"] / args.steps,
                                   "msamples_per_s": samples_total / (x["ms"] * 1e-3) / 1e6,
                                   "kernel_launches_per_step": x["last_launches"], "clocks": x["clocks"]} for x in results},
-        "clocks": best["clocks"], "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+        "also": also, "clocks": best["clocks"], "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
         "gpu_launches": int(best["launches"]),
     }
     emit(line)
