@@ -43,7 +43,12 @@ WORKLOADS = {
     "c2_cornell": ("cornell_scene", {}, 1920, 1080, 64, 10),
     "c3_sponza_scale": ("sponza_scale_scene", {}, 1920, 1080, 256, 10),
     "c4_heightfield_10m": ("big_mesh_scene", {}, 3840, 2160, 16, 10),
+    # configs[4]: 4K, 4096 spp TOTAL, rendered progressively (frames of --batch-spp samples chained with
+    # RT_RENDER_RESUME) and split over the ranks by spp (4096 / N each): ~40 s per step on one GPU, so it is
+    # an explicit --workload, not the default
+    "c5_progressive_4k": ("sponza_scale_scene", {}, 3840, 2160, 4096, 10),
 }
+PROGRESSIVE = {"c5_progressive_4k": 256}  # default --batch-spp
 
 
 _JSON_FD = None
@@ -234,6 +239,8 @@ def main():
     ap.add_argument("--workload", default="c3_sponza_scale", choices=sorted(WORKLOADS))
     ap.add_argument("--renderer", default="both", choices=["both", "megakernel", "wavefront"])
     ap.add_argument("--spp", type=int, default=0, help="override the workload's samples per pixel")
+    ap.add_argument("--batch-spp", type=int, default=-1, help="progressive rendering: samples per frame, frames chained with "
+                    "RT_RENDER_RESUME (bit-identical to one frame); 0 = one frame, default: 256 for c5, else 0")
     ap.add_argument("--cpu-seconds", type=float, default=6.0, help="target seconds per CPU-baseline step")
     ap.add_argument("--sharding", default="spp", choices=["spp", "tiles"],
                     help="N>1: spp = every rank renders the full frame with its own spp (weak scaling, default); "
@@ -278,7 +285,27 @@ def main():
         shard = {"rank": rank, "world": world, "tile_size": 64, "seed_salt": 0}
     else:
         shard = {"rank": rank, "world": world, "tile_size": 0, "seed_salt": (rank * 0x9E3779B9) & 0xFFFFFFFF}
+    batch = PROGRESSIVE.get(args.workload, 0) if args.batch_spp < 0 else args.batch_spp
+    split_total = args.workload in PROGRESSIVE and world > 1 and not tiles  # c5: the total spp is divided over the ranks
+    if split_total:
+        spp = max(1, spp // world)
     spp_total = spp if (tiles or world == 1) else spp * world
+
+    def render(r, sc, **kw):
+        """one step's rendering: a single rt_render_frame, or a progressive chain of them"""
+        if not batch or batch >= spp:
+            return r.render_frame(cam, sc, **kw)
+        done, agg = 0, None
+        while done < spp:
+            r.sample_count = min(batch, spp - done)
+            f = r.render_frame(cam, sc, resume=done > 0, **kw)
+            done += r.sample_count
+            if agg is None:
+                agg = f
+            else:
+                agg.ray_count, agg.device_ms, agg.kernel_launches = agg.ray_count + f.ray_count, agg.device_ms + f.device_ms, agg.kernel_launches + f.kernel_launches
+        r.sample_count = spp
+        return agg
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
 
     class DevAccum:  # zero-copy view of the renderer's device accumulation buffer
@@ -296,7 +323,7 @@ def main():
         out_rgba = torch.empty((h, w, 4), dtype=torch.uint8, device="cuda")
 
         def step():
-            f = r.render_frame(cam, scene, want=(), shard=shard)
+            f = render(r, scene, want=(), shard=shard)
             if dist:  # combine the accumulation buffers over NVLink, then resolve the image
                 dist.all_reduce(accum_t)
                 if rank == 0:
@@ -384,11 +411,11 @@ def main():
             t_b = time.perf_counter()
             e2e_step.create_s += t_b - t_a
             if dist:
-                f = r.render_frame(cam, sc, want=(), shard=shard)
+                f = render(r, sc, want=(), shard=shard)
                 dist.all_reduce(accum_t)
                 pkg.resolve(app, accum_t, spp_total, w, h, host_img)  # D2H of the image
             else:
-                f = r.render_frame(cam, sc, want=("rgba8",), outputs={"rgba8": host_img})  # D2H inside
+                f = render(r, sc, want=("rgba8",), outputs={"rgba8": host_img})  # D2H inside (every progressive frame)
             e2e_step.render_s += time.perf_counter() - t_b
             sc.close()
             return f
@@ -469,11 +496,12 @@ def main():
     value = best["rays"] / (best["ms"] * 1e-3) / 1e6
     line = {
         "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": best["ms"] / args.steps, "higher_is_better": True, "scaling": "strong" if tiles else "weak", "vs_baseline": None,
+        "ms_per_step": best["ms"] / args.steps, "higher_is_better": True, "scaling": "strong" if (tiles or split_total) else "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "msamples_per_s": samples_total / (best["ms"] * 1e-3) / 1e6,
         "config": {"workload": args.workload, "triangles": int(stats["triangle_count"]), "width": w, "height": h, "spp": spp,
-                   "max_depth": depth, "renderer": best["name"], "l2": "flushed between timed steps (256 MB write)",
+                   "max_depth": depth, "renderer": best["name"],
+                   "progressive": (f"{-(-spp // batch)} frames of {batch} spp chained with RT_RENDER_RESUME" if batch and batch < spp else None), "l2": "flushed between timed steps (256 MB write)",
                    "sharding": "none" if world == 1 else ("image tiles: 64x64 tiles round robin over ranks, bit-identical to 1 GPU, NCCL all-reduce (sum) of the fp32 accumulation buffer" if tiles else f"spp slices: {spp} spp per GPU, distinct seed salts, NCCL all-reduce of the fp32 accumulation buffer"),
                    "bvh": {"nodes": int(stats["node_count"]), "depth": int(stats["wide_depth"]), "build_ms": float(stats["build_ms"])}},
         "renderers": {x["name"]: {"mrays_per_s": x["rays"] / (x["ms"] * 1e-3) / 1e6, "ms_per_step": x["ms"] / args.steps,

@@ -107,10 +107,17 @@ typedef struct rt_shard {
                             reproduces the reference stream). */
 } rt_shard;
 
+/* rt_render_params.flags */
+#define RT_RENDER_RESUME 1u /* progressive rendering: continue the previous rt_render_frame of this
+                              renderer (same scene, camera, shard) — per-pixel xorshift streams and the
+                              accumulation carry on, so k frames of n samples are bit-identical to one
+                              frame of k*n samples (BASELINE config 5: 4096 spp in batches) */
+
 typedef struct rt_render_params {
     uint32_t max_depth;    /* -d, src/main.cpp:11 */
-    uint32_t sample_count; /* -s, src/main.cpp:13 */
+    uint32_t sample_count; /* -s, src/main.cpp:13; with RT_RENDER_RESUME: samples ADDED by this call */
     rt_shard shard;
+    uint32_t flags;        /* 0 or RT_RENDER_RESUME */
 } rt_render_params;
 
 /* Result of one render_frame. Every pointer is optional (NULL = not wanted) and ANY-space. */

@@ -252,7 +252,7 @@ class IRenderer:
                                                C.byref(h)), "rt_renderer_create")
         self.handle = h
 
-    def render_frame(self, camera, scene, want=("rgba8", "accum", "rng_state"), shard=None, outputs=None):
+    def render_frame(self, camera, scene, want=("rgba8", "accum", "rng_state"), shard=None, outputs=None, resume=False):
         """IRenderer::render_frame. `want` selects which host copies to make; `outputs` may map
         names to caller buffers (numpy arrays or torch tensors, host or device)."""
         w, h = self.img_size
@@ -265,6 +265,7 @@ class IRenderer:
             outputs["rng_state"] = np.empty((h, w), np.uint32)
         p = _capi.rt_render_params()
         p.max_depth, p.sample_count = self.max_depth, self.sample_count
+        p.flags = _capi.RT_RENDER_RESUME if resume else 0  # progressive: continue the previous frame
         if shard:
             p.shard.rank, p.shard.world = int(shard.get("rank", 0)), int(shard.get("world", 1))
             p.shard.tile_size, p.shard.seed_salt = int(shard.get("tile_size", 0)), int(shard.get("seed_salt", 0))

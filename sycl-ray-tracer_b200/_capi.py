@@ -13,6 +13,7 @@ RT_OK = 0
 RT_MEGAKERNEL, RT_WAVEFRONT = 0, 1
 RT_MAT_NONE, RT_MAT_DIFFUSE, RT_MAT_METALLIC, RT_MAT_DIELECTRIC = 0, 1, 2, 3
 RT_TEX_SIZE, RT_MAX_IMAGES = 512, 128
+RT_RENDER_RESUME = 1
 
 f32p = C.POINTER(C.c_float)
 u32p = C.POINTER(C.c_uint32)
@@ -49,7 +50,7 @@ class rt_shard(C.Structure):
 
 
 class rt_render_params(C.Structure):
-    _fields_ = [("max_depth", C.c_uint32), ("sample_count", C.c_uint32), ("shard", rt_shard)]
+    _fields_ = [("max_depth", C.c_uint32), ("sample_count", C.c_uint32), ("shard", rt_shard), ("flags", C.c_uint32)]
 
 
 class rt_frame(C.Structure):

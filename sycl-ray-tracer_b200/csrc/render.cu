@@ -110,6 +110,7 @@ __global__ void __launch_bounds__(kMegaBlock, RT_MEGA_MIN_BLOCKS) k_megakernel(R
     XorShift32 rng;
     rng.a = 0;
     f3 sum = mk3(0.0f, 0.0f, 0.0f);
+    float base_count = 0.0f; /* samples accumulated by earlier frames (RT_RENDER_RESUME) */
     RtRayState r;
     r.org = r.dir = r.att = r.rad = sum;
     RtTravState tv;
@@ -150,8 +151,9 @@ __global__ void __launch_bounds__(kMegaBlock, RT_MEGA_MIN_BLOCKS) k_megakernel(R
                 }
                 if (s == p.spp) { /* pixel finished: :154-158 mean, gamma, image write */
                     const size_t pix = (size_t)y * (size_t)p.cam.w + (size_t)x;
-                    out.accum[pix] = make_float4(sum.x, sum.y, sum.z, (float)p.spp);
-                    out.rgba8[pix] = rt_resolve_pixel(sum.x, sum.y, sum.z, (float)p.spp);
+                    const float count = base_count + (float)p.spp;
+                    out.accum[pix] = make_float4(sum.x, sum.y, sum.z, count);
+                    out.rgba8[pix] = rt_resolve_pixel(sum.x, sum.y, sum.z, count);
                     out.rng[pix] = rng.a;
                     mode = kNeedPixel;
                 } else {
@@ -175,8 +177,17 @@ __global__ void __launch_bounds__(kMegaBlock, RT_MEGA_MIN_BLOCKS) k_megakernel(R
                     x = (int)((tile % tiles_x) * 8u + (in & 7u));
                     y = (int)((tile / tiles_x) * 4u + (in >> 3));
                     if (x < p.cam.w && y < p.cam.h && rt_owns_pixel(p, x, y)) {
-                        rng.a = rt_pixel_seed(p.wavefront_seed, x, y, p.cam.w, p.cam.h) ^ p.seed_salt;
-                        sum = mk3(0.0f, 0.0f, 0.0f);
+                        if (p.resume) { /* carry on where the previous frame stopped */
+                            const size_t pix = (size_t)y * (size_t)p.cam.w + (size_t)x;
+                            const float4 a = out.accum[pix];
+                            rng.a = out.rng[pix];
+                            sum = mk3(a.x, a.y, a.z);
+                            base_count = a.w;
+                        } else {
+                            rng.a = rt_pixel_seed(p.wavefront_seed, x, y, p.cam.w, p.cam.h) ^ p.seed_salt;
+                            sum = mk3(0.0f, 0.0f, 0.0f);
+                            base_count = 0.0f;
+                        }
                         s = 0;
                         mode = kNeedRay;
                     } /* else: padding / another rank's pixel, fetch again */
@@ -328,7 +339,7 @@ __global__ void k_resolve_owned(RtFrameParams p, const float4 *accum, const uint
     const int x = (int)(i % (uint32_t)p.cam.w), y = (int)(i / (uint32_t)p.cam.w);
     if (rt_owns_pixel(p, x, y)) {
         const float4 a = accum[i];
-        out.rgba8[i] = rt_resolve_pixel(a.x, a.y, a.z, (float)p.spp);
+        out.rgba8[i] = rt_resolve_pixel(a.x, a.y, a.z, a.w); /* a.w = samples accumulated (= spp, or more after resumes) */
     } else {
         out.rgba8[i] = 0u;
     }

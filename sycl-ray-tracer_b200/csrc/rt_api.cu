@@ -35,6 +35,7 @@ struct rt_renderer {
     unsigned long long *h_rays = nullptr;   /* pinned */
     int grid_mega = 0, grid_extend = 0, grid_shade = 0;
     cudaEvent_t ev_batch[2] = {nullptr, nullptr}; /* wavefront: per-batch queue-length read-back */
+    bool has_frame = false; /* a frame has been rendered: RT_RENDER_RESUME is allowed */
     int tune_refill = 12; /* lanes that must run dry before a warp refills (RT_TUNE_REFILL overrides; 12-14 measured best) */
 };
 
@@ -521,6 +522,8 @@ rt_status rt_render_frame(rt_renderer *r, const rt_scene *scene, const rt_camera
     p.wavefront_seed = r->kind == RT_WAVEFRONT ? 1 : 0;
     p.clamp_samples = r->kind == RT_WAVEFRONT ? 1 : 0;
     p.tune_refill = r->tune_refill;
+    p.resume = (params->flags & RT_RENDER_RESUME) ? 1 : 0;
+    if (p.resume && !r->has_frame) return rt_set_error(ctx, RT_ERR_STATE, "rt_render_frame", "RT_RENDER_RESUME without a previous frame");
     RtFrameOut out;
     out.accum = r->d_accum;
     out.rgba8 = r->d_rgba8;
@@ -532,7 +535,7 @@ rt_status rt_render_frame(rt_renderer *r, const rt_scene *scene, const rt_camera
     RT_CUDA_TRY(ctx, cudaMemsetAsync(r->d_rays, 0, sizeof(unsigned long long), st));
     if (r->kind == RT_MEGAKERNEL) {
         RT_CUDA_TRY(ctx, cudaMemsetAsync(r->d_work, 0, sizeof(uint32_t), st));
-        if (sh.world > 1 && sh.tile_size) { /* pixels of other ranks stay zero */
+        if (sh.world > 1 && sh.tile_size && !p.resume) { /* pixels of other ranks stay zero */
             RT_CUDA_TRY(ctx, cudaMemsetAsync(r->d_accum, 0, n * sizeof(float4), st));
             RT_CUDA_TRY(ctx, cudaMemsetAsync(r->d_rgba8, 0, n * 4, st));
             RT_CUDA_TRY(ctx, cudaMemsetAsync(r->d_rng, 0, n * 4, st));
@@ -604,6 +607,7 @@ rt_status rt_render_frame(rt_renderer *r, const rt_scene *scene, const rt_camera
     frame->device_ms = ms;
     frame->ray_count = *r->h_rays;
     frame->kernel_launches = launches;
+    r->has_frame = true;
     return RT_OK;
 }
 

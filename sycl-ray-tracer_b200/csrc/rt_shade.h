@@ -231,6 +231,7 @@ struct RtFrameParams {
     uint32_t rank, world, tile_size;
     int32_t wavefront_seed; /* F3: 0 = x*H_pad + y, 1 = x + y*W */
     int32_t clamp_samples;  /* F9: wavefront clamps every sample to [0,1] */
+    int32_t resume;         /* continue the streams / accumulation left by the previous frame */
     /* scheduling knobs of the persistent kernels (no effect on results) */
     int32_t tune_refill;    /* leave the traversal loop once this many lanes have finished */
 };
@@ -248,12 +249,11 @@ RT_HD bool rt_owns_pixel(const RtFrameParams &p, int x, int y) {
  * path regenerates the next sample inside the same loop, so a lane is never idle while its
  * pixel has samples left. Returns the linear sum; `rays` counts rtcIntersect1-equivalents. */
 RT_HD f3 rt_megakernel_pixel(const RtScene &scene, const RtFrameParams &p, int x, int y, XorShift32 &rng,
-                             unsigned long long &rays) {
-    rng.a = rt_pixel_seed(p.wavefront_seed, x, y, p.cam.w, p.cam.h) ^ p.seed_salt;
-    f3 sum = mk3(0.0f, 0.0f, 0.0f);
+                             unsigned long long &rays, f3 sum = mk3(0.0f, 0.0f, 0.0f), bool resume = false) {
+    if (!resume) rng.a = rt_pixel_seed(p.wavefront_seed, x, y, p.cam.w, p.cam.h) ^ p.seed_salt;
     uint32_t s = 0, depth = 0;
     RtRayState r;
-    r.org = r.dir = r.att = r.rad = sum;
+    r.org = r.dir = r.att = r.rad = mk3(0.0f, 0.0f, 0.0f);
     bool need_ray = true;
     for (;;) {
         if (need_ray) {

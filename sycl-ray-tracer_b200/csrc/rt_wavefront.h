@@ -48,13 +48,13 @@ RT_HD void rt_wf_store_ray(const RtWavefrontState &w, uint32_t pix, f3 org, f3 d
 RT_HD bool rt_wf_generate_pixel(const RtFrameParams &p, const RtWavefrontState &w, const RtFrameOut &out,
                                 uint32_t pix) {
     const int x = (int)(pix % (uint32_t)p.cam.w), y = (int)(pix / (uint32_t)p.cam.w);
-    out.accum[pix] = rt_mk_float4(0.0f, 0.0f, 0.0f, 0.0f); /* the reference forgets combined_image (:56-57) */
+    if (!p.resume) out.accum[pix] = rt_mk_float4(0.0f, 0.0f, 0.0f, 0.0f); /* the reference forgets combined_image (:56-57) */
     if (!rt_owns_pixel(p, x, y)) {
         w.rng[pix] = 0u;
         return false;
     }
     XorShift32 rng;
-    rng.a = rt_pixel_seed(p.wavefront_seed, x, y, p.cam.w, p.cam.h) ^ p.seed_salt;
+    rng.a = p.resume ? w.rng[pix] : (rt_pixel_seed(p.wavefront_seed, x, y, p.cam.w, p.cam.h) ^ p.seed_salt);
     bool live = false;
     if (p.spp > 0 && p.max_depth > 0) {
         const RtRayState r = rt_camera_ray(p.cam, x, y, rng);
@@ -66,7 +66,9 @@ RT_HD bool rt_wf_generate_pixel(const RtFrameParams &p, const RtWavefrontState &
             rng.next();
             rng.next();
         }
-        out.accum[pix] = rt_mk_float4(0.0f, 0.0f, 0.0f, (float)p.spp);
+        rt_float4 a = p.resume ? out.accum[pix] : rt_mk_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        a.w += (float)p.spp;
+        out.accum[pix] = a;
     }
     w.rng[pix] = rng.a;
     return live;

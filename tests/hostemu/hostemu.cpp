@@ -387,6 +387,7 @@ uint64_t emu_render(const emu_scene *s, int kind, const rt_camera *camera, const
     p.tile_size = params->shard.tile_size;
     p.wavefront_seed = kind == 1;
     p.clamp_samples = kind == 1;
+    p.resume = 0;
     p.tune_refill = 8;
     const uint32_t n_pix = (uint32_t)p.cam.w * (uint32_t)p.cam.h;
     std::vector<rt_float4> acc(n_pix, rt_mk_float4(0, 0, 0, 0));

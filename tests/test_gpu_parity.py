@@ -227,6 +227,39 @@ def test_spp_shards_match_salted_oracle_and_resolve(pkg, oracle, app, scenes):
 
 
 @pytest.mark.parametrize("kind", [0, 1])
+def test_progressive_resume_is_bit_identical_to_one_frame(pkg, oracle, app, scenes, kind):
+    """config 5 renders 4096 spp progressively: frames chained with RT_RENDER_RESUME continue the
+    per-pixel xorshift streams and the accumulation, so 2 + 3 + 1 samples equal one 6-sample frame
+    (itself equal to the oracle) in every output — also under tile and spp sharding"""
+    data = scenes.cornell_scene(3)
+    scene = pkg.Scene(app, data)
+    w, h = 160, 96
+    cam = pkg.Camera((w, h), data.camera_position, data.camera_direction, data.camera_focal_length)
+    cls = pkg.MegakernelRenderer if kind == 0 else pkg.WavefrontRenderer
+    o = oracle.Scene(data).render(oracle.camera_for(data, w, h), kind, 8, 6, use_bvh=True)
+    r = cls(app, (w, h), None, 8, 6)
+    with pytest.raises(pkg.RtError):
+        r.render_frame(cam, scene, resume=True)          # nothing to continue yet
+    for shard in (None, {"rank": 1, "world": 3, "tile_size": 32}, {"rank": 1, "world": 2, "tile_size": 0, "seed_salt": 0x9E3779B9}):
+        r.sample_count = 6
+        one = r.render_frame(cam, scene, shard=shard)
+        one = (one.accum.copy(), one.rgba8.copy(), one.rng_state.copy(), one.ray_count)
+        rays = 0
+        for i, n in enumerate((2, 3, 1)):
+            r.sample_count = n
+            f = r.render_frame(cam, scene, shard=shard, resume=i > 0)
+            rays += f.ray_count
+        assert rays == one[3]
+        assert np.array_equal(f.accum.view(np.uint32), one[0].view(np.uint32))
+        assert np.array_equal(f.rgba8, one[1]) and np.array_equal(f.rng_state, one[2])
+        if shard is None:
+            assert np.array_equal(f.accum.view(np.uint32), o["accum"].view(np.uint32))
+            assert np.array_equal(f.rgba8, o["rgba8"]) and rays == o["ray_count"]
+    r.close()
+    scene.close()
+
+
+@pytest.mark.parametrize("kind", [0, 1])
 def test_c4_style_half_million_triangles(pkg, oracle, app, scenes, kind):
     """config 4's kind of scene (one displaced height field, grazing camera) at 500 k triangles so
     the oracle's BVH finishes in seconds: random rays + a crop of a 4K frame"""
