@@ -88,14 +88,19 @@ class ClockSampler:
     def __init__(self, index, uuid=None):
         self.index, self.uuid = index, uuid
         self.sm, self.mx, self.reasons, self.stop_flag, self.thread, self.proc, self.path = [], [], set(), False, None, None, None
+        self.slowest_query_ms = 0.0
 
     def _nvml_loop(self, nv, h):
+        reasons = nv.nvmlDeviceGetCurrentClocksEventReasons if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+            else nv.nvmlDeviceGetCurrentClocksThrottleReasons
         while not self.stop_flag:
             try:
+                t0 = time.perf_counter()
                 self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
-                self.mx.append(float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)))
-                mask = nv.nvmlDeviceGetCurrentClocksEventReasons(h) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
-                    else nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                t1 = time.perf_counter()
+                mask = reasons(h)
+                t2 = time.perf_counter()
+                self.slowest_query_ms = max(self.slowest_query_ms, (t1 - t0) * 1e3, (t2 - t1) * 1e3)
                 for bit, name in self.REASONS.items():
                     if mask & bit:
                         self.reasons.add(name)
@@ -115,6 +120,7 @@ class ClockSampler:
                     h = None
             if h is None:
                 h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.mx.append(float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)))  # constant: asked once, outside the loop
             self.thread = threading.Thread(target=self._nvml_loop, args=(nv, h), daemon=True)
             self.thread.start()
             return
