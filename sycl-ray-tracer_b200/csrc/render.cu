@@ -70,7 +70,53 @@ enum { kNeedPixel = 0, kNeedRay = 1, kStart = 2, kTraversing = 3, kHitPending = 
  * flow): node steps for every lane with node work until `refill` lanes have run out of nodes, or
  * a lane's triangle stack is full; then all pending
  * triangles are tested together. Lanes left with neither nodes nor triangles become kHitPending. */
-__device__ __forceinline__ void traverse_phase(const RtBvh &bvh, RtTravState &tv, RtTravStacks &ks, int &mode, int refill) {
+/* Traversal stacks of the persistent kernels. The triangle-group stack and the first RT_SMEM_NODE entries
+ * of the node-group stack can live in shared memory ([entry][thread]: conflict-free when the lanes of a
+ * warp are at the same depth); deeper node entries stay in local memory. RT_SMEM_TRI / RT_SMEM_NODE = 0
+ * select plain local-memory stacks — the default: measured on B200, every shared-memory split (tri only,
+ * tri + 4, tri + 8, 8 node entries only) is 3-4 % SLOWER on C2/C3/C4 in both renderers, because the shared
+ * memory comes out of the L1 that caches the nodes and the (small, hot) local stacks. */
+#ifndef RT_SMEM_TRI
+#define RT_SMEM_TRI 0
+#endif
+#ifndef RT_SMEM_NODE
+#define RT_SMEM_NODE 0
+#endif
+#define RT_SMEM_ENTRIES ((RT_SMEM_TRI ? RT_TSTACK_SIZE : 0) + RT_SMEM_NODE)
+template <int BLOCK>
+struct SmemStacks {
+    uint64_t node[RT_STACK_SIZE - RT_SMEM_NODE];
+#if !RT_SMEM_TRI
+    uint64_t tri[RT_TSTACK_SIZE];
+#endif
+    uint64_t *sm; /* this thread's column of the CTA's shared array */
+    __device__ __forceinline__ uint64_t node_get(int i) const {
+#if RT_SMEM_NODE
+        if (i < RT_SMEM_NODE) return sm[((RT_SMEM_TRI ? RT_TSTACK_SIZE : 0) + i) * BLOCK];
+        return node[i - RT_SMEM_NODE];
+#else
+        return node[i];
+#endif
+    }
+    __device__ __forceinline__ void node_put(int i, uint64_t v) {
+#if RT_SMEM_NODE
+        if (i < RT_SMEM_NODE) sm[((RT_SMEM_TRI ? RT_TSTACK_SIZE : 0) + i) * BLOCK] = v;
+        else node[i - RT_SMEM_NODE] = v;
+#else
+        node[i] = v;
+#endif
+    }
+#if RT_SMEM_TRI
+    __device__ __forceinline__ uint64_t tri_get(int i) const { return sm[i * BLOCK]; }
+    __device__ __forceinline__ void tri_put(int i, uint64_t v) { sm[i * BLOCK] = v; }
+#else
+    __device__ __forceinline__ uint64_t tri_get(int i) const { return tri[i]; }
+    __device__ __forceinline__ void tri_put(int i, uint64_t v) { tri[i] = v; }
+#endif
+};
+
+template <class Stacks>
+__device__ __forceinline__ void traverse_phase(const RtBvh &bvh, RtTravState &tv, Stacks &ks, int &mode, int refill) {
     const unsigned full = 0xffffffffu;
     const bool trav = mode == kTraversing;
     const unsigned m_trav = __ballot_sync(full, trav); /* does not change inside the node loop */
@@ -114,7 +160,11 @@ __global__ void __launch_bounds__(kMegaBlock, RT_MEGA_MIN_BLOCKS) k_megakernel(R
     RtRayState r;
     r.org = r.dir = r.att = r.rad = sum;
     RtTravState tv;
-    RtTravStacks ks;
+    SmemStacks<kMegaBlock> ks;
+#if RT_SMEM_TRI || RT_SMEM_NODE
+    __shared__ uint64_t s_stacks[RT_SMEM_ENTRIES * kMegaBlock];
+    ks.sm = s_stacks + threadIdx.x;
+#endif
     tv.sp = 0;
     tv.tsp = 0;
     tv.ng_y = 0;
@@ -268,7 +318,11 @@ __global__ void __launch_bounds__(kWfBlock, RT_EXT_MIN_BLOCKS) k_wf_extend(RtSce
     int mode = kNeedPixel; /* kNeedPixel = idle, kTraversing, kHitPending, kExhausted */
     uint32_t pix = 0;
     RtTravState tv;
-    RtTravStacks ks;
+    SmemStacks<kWfBlock> ks;
+#if RT_SMEM_TRI || RT_SMEM_NODE
+    __shared__ uint64_t s_stacks[RT_SMEM_ENTRIES * kWfBlock];
+    ks.sm = s_stacks + threadIdx.x;
+#endif
     tv.sp = 0;
     tv.tsp = 0;
     tv.ng_y = 0;

@@ -90,6 +90,25 @@ RT_HD float rt_fma(float a, float b, float c) {
     return fmaf(a, b, c);
 #endif
 }
+/* two independent fused multiply-adds sharing the multiplier b: d0 = fma(a0, b, c0), d1 = fma(a1, b, c1).
+ * sm_100a has a packed FFMA2 (fma.rn.f32x2): one issue slot for both, each half rounded exactly like
+ * FFMA, so results stay bit-identical to the host emulation and the oracle. */
+#ifndef RT_USE_FFMA2
+#define RT_USE_FFMA2 0 /* measured neutral (C3 +0.7 %, C2/C4 -0.4 %): the node test is not issue-slot bound */
+#endif
+RT_HD void rt_fma2(float a0, float a1, float b, float c0, float c1, float &d0, float &d1) {
+#if RT_DEVICE_CODE && RT_USE_FFMA2
+    unsigned long long A, B, C, D;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(A) : "f"(a0), "f"(a1));
+    asm("mov.b64 %0, {%1, %1};" : "=l"(B) : "f"(b));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(C) : "f"(c0), "f"(c1));
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(D) : "l"(A), "l"(B), "l"(C));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(d0), "=f"(d1) : "l"(D));
+#else
+    d0 = rt_fma(a0, b, c0);
+    d1 = rt_fma(a1, b, c1);
+#endif
+}
 RT_HD float rt_min(float a, float b) { return fminf(a, b); }
 RT_HD float rt_max(float a, float b) { return fmaxf(a, b); }
 /* 3-input min/max: one FMNMX3 on sm_100a */

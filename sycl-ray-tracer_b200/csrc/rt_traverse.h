@@ -279,12 +279,10 @@ RT_HD void rt_child_test(uint32_t nx, uint32_t ny, uint32_t nz, uint32_t fx, uin
                          float Sy, float Sz, float onx, float ony, float onz, float ofx, float ofy, float ofz,
                          float tmin, float tmax_pad, uint32_t child_bits4, uint32_t bit_index4, uint32_t one,
                          uint32_t &hitmask) {
-    const float tnx = rt_fma(rt_byte_to_unit<J, 1 + 0 + 6 * J + 24 * H>(nx, one), Sx, onx);
-    const float tny = rt_fma(rt_byte_to_unit<J, 1 + 1 + 6 * J + 24 * H>(ny, one), Sy, ony);
-    const float tnz = rt_fma(rt_byte_to_unit<J, 1 + 2 + 6 * J + 24 * H>(nz, one), Sz, onz);
-    const float tfx = rt_fma(rt_byte_to_unit<J, 1 + 3 + 6 * J + 24 * H>(fx, one), Sx, ofx);
-    const float tfy = rt_fma(rt_byte_to_unit<J, 1 + 4 + 6 * J + 24 * H>(fy, one), Sy, ofy);
-    const float tfz = rt_fma(rt_byte_to_unit<J, 1 + 5 + 6 * J + 24 * H>(fz, one), Sz, ofz);
+    float tnx, tny, tnz, tfx, tfy, tfz; /* near and far plane of one axis share the multiplier: one FFMA2 */
+    rt_fma2(rt_byte_to_unit<J, 1 + 0 + 6 * J + 24 * H>(nx, one), rt_byte_to_unit<J, 1 + 3 + 6 * J + 24 * H>(fx, one), Sx, onx, ofx, tnx, tfx);
+    rt_fma2(rt_byte_to_unit<J, 1 + 1 + 6 * J + 24 * H>(ny, one), rt_byte_to_unit<J, 1 + 4 + 6 * J + 24 * H>(fy, one), Sy, ony, ofy, tny, tfy);
+    rt_fma2(rt_byte_to_unit<J, 1 + 2 + 6 * J + 24 * H>(nz, one), rt_byte_to_unit<J, 1 + 5 + 6 * J + 24 * H>(fz, one), Sz, onz, ofz, tnz, tfz);
     const float cmin = rt_max(rt_max3(tnx, tny, tnz), tmin);
     const float cmax = rt_min(rt_min3(tfx, tfy, tfz), tmax_pad);
     const uint32_t bits = (child_bits4 >> (8 * J)) & 0xffu;
@@ -368,6 +366,10 @@ struct RtTravState {
 struct RtTravStacks {
     uint64_t node[RT_STACK_SIZE];  /* pending node groups */
     uint64_t tri[RT_TSTACK_SIZE];  /* pending triangle groups */
+    RT_HD uint64_t node_get(int i) const { return node[i]; }
+    RT_HD void node_put(int i, uint64_t v) { node[i] = v; }
+    RT_HD uint64_t tri_get(int i) const { return tri[i]; }
+    RT_HD void tri_put(int i, uint64_t v) { tri[i] = v; }
 };
 RT_HD uint64_t rt_pack2(uint32_t x, uint32_t y) { return (uint64_t)x | ((uint64_t)y << 32); }
 
@@ -392,13 +394,14 @@ RT_HD bool rt_trav_has_tri(const RtTravState &s) { return s.tsp > 0; }
 RT_HD bool rt_trav_tri_full(const RtTravState &s) { return s.tsp >= RT_TSTACK_SIZE; }
 
 /* precondition: rt_trav_has_node(s) && !rt_trav_tri_full(s) */
-RT_HD void rt_trav_node_step(const RtBvh &bvh, RtTravState &s, RtTravStacks &k) {
+template <class Stacks>
+RT_HD void rt_trav_node_step(const RtBvh &bvh, RtTravState &s, Stacks &k) {
     const uint32_t oct_inv = s.rb.oct_inv4 & 7u;
     const uint32_t imask = s.ng_y & 0xffu;
     const int bit = rt_bfind(s.ng_y);
     s.ng_y &= ~(1u << bit);
     if (s.ng_y > 0x00ffffffu) { /* siblings still pending: keep the group for later */
-        k.node[s.sp] = rt_pack2(s.ng_x, s.ng_y);
+        k.node_put(s.sp, rt_pack2(s.ng_x, s.ng_y));
         s.sp++;
     }
     const uint32_t slot = ((uint32_t)bit - 24u) ^ oct_inv;
@@ -419,25 +422,26 @@ RT_HD void rt_trav_node_step(const RtBvh &bvh, RtTravState &s, RtTravStacks &k) 
     s.ng_x = n1.x;
     s.ng_y = (hm & 0xff000000u) | (n0.w >> 24);
     if (hm & 0x00ffffffu) {
-        k.tri[s.tsp] = rt_pack2(n1.y, hm & 0x00ffffffu);
+        k.tri_put(s.tsp, rt_pack2(n1.y, hm & 0x00ffffffu));
         s.tsp++;
     }
     if (s.ng_y <= 0x00ffffffu && s.sp > 0) { /* no child hit: next pending group */
         s.sp--;
-        const uint64_t e = k.node[s.sp];
+        const uint64_t e = k.node_get(s.sp);
         s.ng_x = (uint32_t)e;
         s.ng_y = (uint32_t)(e >> 32);
     }
 }
 
 /* precondition: rt_trav_has_tri(s) */
-RT_HD void rt_trav_tri_step(const RtBvh &bvh, RtTravState &s, RtTravStacks &k) {
-    const uint64_t e = k.tri[s.tsp - 1];
+template <class Stacks>
+RT_HD void rt_trav_tri_step(const RtBvh &bvh, RtTravState &s, Stacks &k) {
+    const uint64_t e = k.tri_get(s.tsp - 1);
     const uint32_t base = (uint32_t)e;
     uint32_t bits = (uint32_t)(e >> 32);
     const int i = rt_ctz(bits);
     bits &= bits - 1;
-    if (bits) k.tri[s.tsp - 1] = rt_pack2(base, bits);
+    if (bits) k.tri_put(s.tsp - 1, rt_pack2(base, bits));
     else s.tsp--;
     const uint32_t tslot = base + (uint32_t)i;
     const rt_float4 *tp = bvh.tris + (size_t)tslot * RT_TRI_VEC4;
