@@ -251,6 +251,10 @@ def main():
     ap.add_argument("--sharding", default="spp", choices=["spp", "tiles"],
                     help="N>1: spp = every rank renders the full frame with its own spp (weak scaling, default); "
                          "tiles = 64x64 image tiles dealt round robin, total work fixed (strong scaling, config 4's mode)")
+    ap.add_argument("--gather", default="peer", choices=["peer", "allreduce"],
+                    help="tile sharding: peer = every rank's kernel stores its finished RGBA8 pixels straight into rank 0's image "
+                         "over NVLink peer memory (CUDA IPC), a 4-byte all-reduce orders the frame; allreduce = NCCL all-reduce of the "
+                         "fp32 accumulation buffers + resolve on rank 0")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-also", action="store_true", help="skip the quick secondary measurement of configs[1] (Cornell)")
@@ -323,14 +327,39 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    gather_peer = tiles and args.gather == "peer"
+    token = torch.zeros(1, dtype=torch.int32, device="cuda") if gather_peer else None
+
+    class DevImage:  # zero-copy view of a renderer's device RGBA8 image
+        def __init__(self, ptr):
+            self.__cuda_array_interface__ = {"shape": (h, w, 4), "typestr": "|u1", "data": (int(ptr), False), "version": 3}
+
+    def attach_gather(r):
+        """rank 0 exports its renderer's image, the others open it (CUDA IPC) as their gather target"""
+        box = [r.export_image() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        if rank != 0:
+            r.set_gather(handle=box[0])
+        barrier()
+
+    def detach_gather(r):
+        barrier()
+        if rank != 0:
+            r.set_gather()
+        barrier()
+
     def bench_renderer(cls, name):
         r = cls(app, (w, h), None, depth, spp)
-        accum_t = torch.as_tensor(DevAccum(r.device_accum_ptr), device="cuda") if dist else None
+        accum_t = torch.as_tensor(DevAccum(r.device_accum_ptr), device="cuda") if dist and not gather_peer else None
         out_rgba = torch.empty((h, w, 4), dtype=torch.uint8, device="cuda")
+        if gather_peer:
+            attach_gather(r)
 
         def step():
             f = render(r, scene, want=(), shard=shard)
-            if dist:  # combine the accumulation buffers over NVLink, then resolve the image
+            if gather_peer:  # the pixels are already in rank 0's image; order the frame across ranks on the stream
+                dist.all_reduce(token)
+            elif dist:  # combine the accumulation buffers over NVLink, then resolve the image
                 dist.all_reduce(accum_t)
                 if rank == 0:
                     pkg.resolve(app, accum_t, spp_total, w, h, out_rgba)
@@ -357,7 +386,7 @@ def main():
             ms += e0.elapsed_time(e1)
             kms += f.device_ms
             rays += f.ray_count
-            launches += f.kernel_launches + (1 if (dist and rank == 0) else 0)
+            launches += f.kernel_launches + (1 if (dist and rank == 0 and not gather_peer) else 0)
         clocks = sampler.stop() if rank == 0 else None
         barrier()
         t = torch.tensor([ms, kms, float(rays), float(launches)], dtype=torch.float64, device="cuda")
@@ -367,8 +396,14 @@ def main():
             sm = t.clone()
             dist.all_reduce(sm, op=dist.ReduceOp.SUM)
             ms, kms, rays, launches = float(mx[0]), float(mx[1]), int(sm[2]), int(sm[3])
+        gathered = None
+        if gather_peer:
+            barrier()
+            if rank == 0:  # untimed check: every pixel of rank 0's image was stored by its owner (alpha = 255 everywhere)
+                gathered = bool((torch.as_tensor(DevImage(r.device_rgba8_ptr), device="cuda")[..., 3] == 255).all().item())
+            detach_gather(r)
         r.close()
-        return {"name": name, "ms": ms, "kernel_ms": kms, "rays": rays, "launches": launches, "clocks": clocks,
+        return {"name": name, "gather_complete": gathered, "ms": ms, "kernel_ms": kms, "rays": rays, "launches": launches, "clocks": clocks,
                 "last_launches": f.kernel_launches}
 
     results = []
@@ -405,8 +440,11 @@ def main():
     if not args.no_e2e:
         cls = pkg.MegakernelRenderer if best["name"] == "megakernel" else pkg.WavefrontRenderer
         r = cls(app, (w, h), None, depth, spp)
-        accum_t = torch.as_tensor(DevAccum(r.device_accum_ptr), device="cuda") if dist else None
+        accum_t = torch.as_tensor(DevAccum(r.device_accum_ptr), device="cuda") if dist and not gather_peer else None
         host_img = torch.empty((h, w, 4), dtype=torch.uint8).pin_memory()
+        if gather_peer:
+            attach_gather(r)
+            dev_img = torch.as_tensor(DevImage(r.device_rgba8_ptr), device="cuda")
         h2d = sum(i.positions.nbytes + i.normals.nbytes + i.uvs.nbytes + i.indices.nbytes + 64 + 40 for i in data.instances)
         h2d += (data.textures.nbytes if data.textures is not None else 0) + 56 + 24
         d2h = w * h * 4 + 8
@@ -416,7 +454,14 @@ def main():
             sc = pkg.Scene(app, data)  # H2D of the scene from host memory + GPU BVH build
             t_b = time.perf_counter()
             e2e_step.create_s += t_b - t_a
-            if dist:
+            if gather_peer:
+                barrier()  # rank 0 has read the previous frame before anybody stores into its image again
+                f = render(r, sc, want=(), shard=shard)
+                dist.all_reduce(token)
+                if rank == 0:
+                    host_img.copy_(dev_img, non_blocking=True)  # D2H of the gathered image
+                    torch.cuda.current_stream().synchronize()
+            elif dist:
                 f = render(r, sc, want=(), shard=shard)
                 dist.all_reduce(accum_t)
                 pkg.resolve(app, accum_t, spp_total, w, h, host_img)  # D2H of the image
@@ -456,7 +501,9 @@ def main():
                "ms_per_step": dt / args.steps * 1e3, "render_device_ms_per_step": e_dev_ms / args.steps,
                "scene_upload_and_build_ms_per_step": e2e_step.create_s / args.steps * 1e3,
                "render_call_ms_per_step": e2e_step.render_s / args.steps * 1e3, "clocks": e_clocks,
-               "includes": "scene upload from host + BVH build + render" + (" + NCCL all-reduce" if dist else "") + " + image read-back, every step"}
+               "includes": "scene upload from host + BVH build + render" + ((" + peer-memory gather" if gather_peer else " + NCCL all-reduce") if dist else "") + " + image read-back, every step"}
+        if gather_peer:
+            detach_gather(r)
         r.close()
 
     if rank != 0:
@@ -508,11 +555,12 @@ def main():
         "config": {"workload": args.workload, "triangles": int(stats["triangle_count"]), "width": w, "height": h, "spp": spp,
                    "max_depth": depth, "renderer": best["name"],
                    "progressive": (f"{-(-spp // batch)} frames of {batch} spp chained with RT_RENDER_RESUME" if batch and batch < spp else None), "l2": "flushed between timed steps (256 MB write)",
-                   "sharding": "none" if world == 1 else ("image tiles: 64x64 tiles round robin over ranks, bit-identical to 1 GPU, NCCL all-reduce (sum) of the fp32 accumulation buffer" if tiles else f"spp slices: {spp} spp per GPU, distinct seed salts, NCCL all-reduce of the fp32 accumulation buffer"),
+                   "sharding": "none" if world == 1 else (("image tiles: 64x64 tiles round robin over ranks, bit-identical to 1 GPU; " + ("finished RGBA8 pixels stored by the render kernel straight into rank 0's image over NVLink peer memory (CUDA IPC), 4-byte all-reduce as the frame barrier" if gather_peer else "NCCL all-reduce (sum) of the fp32 accumulation buffer + resolve on rank 0")) if tiles else f"spp slices: {spp} spp per GPU, distinct seed salts, NCCL all-reduce of the fp32 accumulation buffer"),
                    "bvh": {"nodes": int(stats["node_count"]), "depth": int(stats["wide_depth"]), "build_ms": float(stats["build_ms"])}},
         "renderers": {x["name"]: {"mrays_per_s": x["rays"] / (x["ms"] * 1e-3) / 1e6, "ms_per_step": x["ms"] / args.steps,
                                   "msamples_per_s": samples_total / (x["ms"] * 1e-3) / 1e6,
-                                  "kernel_launches_per_step": x["last_launches"], "clocks": x["clocks"]} for x in results},
+                                  "kernel_launches_per_step": x["last_launches"], "clocks": x["clocks"],
+                                  **({"gather_complete": x["gather_complete"]} if x.get("gather_complete") is not None else {})} for x in results},
         "also": also, "clocks": best["clocks"], "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
         "gpu_launches": int(best["launches"]),
     }

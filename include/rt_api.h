@@ -195,6 +195,26 @@ rt_status rt_render_frame(rt_renderer *r, const rt_scene *scene, const rt_camera
  * fp32 RGBA accumulation (W*H*4 floats) and RGBA8 image. For zero-copy hand-off to NCCL. */
 float *rt_renderer_device_accum(rt_renderer *r);
 uint8_t *rt_renderer_device_rgba8(rt_renderer *r);
+/* ---- image-tile shards: gather over peer memory (no collective) --------------------------
+ * Under image-tile sharding every pixel is finished by exactly one rank, so its final RGBA8 value
+ * can be stored straight into ONE destination image by the render kernel itself (4-byte stores
+ * over NVLink / NVSwitch peer memory, overlapped with the rendering) instead of all-reducing the
+ * fp32 accumulation buffers afterwards:
+ *   destination rank : rt_renderer_export_image(r, &h)   -> send h to the other ranks (64 opaque bytes)
+ *   every other rank : rt_renderer_set_gather(r, &h, NULL)   (another process: CUDA IPC handle)
+ *                  or  rt_renderer_set_gather(r, NULL, ptr)  (same process: a device pointer this
+ *                                                             device can store to, W*H*4 bytes)
+ * From then on each tile-sharded rt_render_frame of r also stores its owned pixels to the target;
+ * the destination renderer stops clearing the pixels it does not own. The caller orders the
+ * frames: all ranks must have returned from rt_render_frame (+ a barrier) before the destination
+ * image (rt_renderer_device_rgba8 of the exporting renderer) is read, and it must not be read
+ * while peers render the next frame. rt_renderer_set_gather(r, NULL, NULL) detaches. */
+typedef struct rt_ipc_handle {
+    uint8_t bytes[64];
+} rt_ipc_handle;
+rt_status rt_renderer_export_image(rt_renderer *r, rt_ipc_handle *out);
+rt_status rt_renderer_set_gather(rt_renderer *r, const rt_ipc_handle *handle, void *device_rgba8);
+
 /* (re)compute the RGBA8 image from an accumulation buffer holding the sum over `sample_count`
  * samples — used after a cross-GPU reduction (src/render_wavefront.cpp:360-394 + F10).
  * accum, rgba8: ANY-space. */

@@ -284,6 +284,24 @@ class IRenderer:
     def device_rgba8_ptr(self):
         return self._lib.rt_renderer_device_rgba8(self.handle)
 
+    def export_image(self):
+        """Make this renderer's device RGBA8 image the gather destination of tile-sharded peers:
+        returns the 64 opaque bytes to send them (rt_renderer_export_image)."""
+        h = _capi.rt_ipc_handle()
+        self.app.check(self._lib.rt_renderer_export_image(self.handle, C.byref(h)), "rt_renderer_export_image")
+        return bytes(h.bytes)
+
+    def set_gather(self, handle=None, device_ptr=None):
+        """Tile shards: also store owned pixels' RGBA8 into a peer's image — `handle` = bytes from the
+        destination's export_image() (another process) or `device_ptr` (same process); neither = detach."""
+        hp = None
+        if handle is not None:
+            hs = _capi.rt_ipc_handle()
+            C.memmove(hs.bytes, bytes(handle), 64)
+            hp = C.byref(hs)
+        self.app.check(self._lib.rt_renderer_set_gather(self.handle, hp, C.c_void_p(int(device_ptr)) if device_ptr else None),
+                       "rt_renderer_set_gather")
+
     def close(self):
         if getattr(self, "handle", None) and getattr(self.app, "handle", None):
             self._lib.rt_renderer_destroy(self.handle)

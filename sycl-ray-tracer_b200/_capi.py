@@ -49,6 +49,10 @@ class rt_shard(C.Structure):
                 ("seed_salt", C.c_uint32)]
 
 
+class rt_ipc_handle(C.Structure):
+    _fields_ = [("bytes", C.c_uint8 * 64)]
+
+
 class rt_render_params(C.Structure):
     _fields_ = [("max_depth", C.c_uint32), ("sample_count", C.c_uint32), ("shard", rt_shard), ("flags", C.c_uint32)]
 
@@ -87,6 +91,8 @@ SYMBOLS = {
                                   C.POINTER(rt_render_params), C.POINTER(rt_frame)]),
     "rt_renderer_device_accum": (C.c_void_p, [C.c_void_p]),
     "rt_renderer_device_rgba8": (C.c_void_p, [C.c_void_p]),
+    "rt_renderer_export_image": (C.c_int, [C.c_void_p, C.POINTER(rt_ipc_handle)]),
+    "rt_renderer_set_gather": (C.c_int, [C.c_void_p, C.POINTER(rt_ipc_handle), C.c_void_p]),
     "rt_resolve": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_int32, C.c_int32, C.c_void_p]),
 }
 

@@ -147,8 +147,16 @@ __global__ void __launch_bounds__(kMegaBlock, RT_MEGA_MIN_BLOCKS) k_megakernel(R
                                                            uint32_t *work_counter, unsigned long long *ray_counter) {
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
-    const uint32_t tiles_x = ((uint32_t)p.cam.w + 7u) / 8u, tiles_y = ((uint32_t)p.cam.h + 3u) / 4u;
-    const uint32_t n_work = tiles_x * tiles_y * 32u; /* pixel slots in 8x4-tile-major order */
+    /* Pixel slots are handed out in 8x4-block-major order (32 consecutive slots = one coherent block).
+     * Unsharded: blocks row-major over the image. Image-tile shards: only this rank's tiles are
+     * enumerated (the k-th owned tile is tile k * world + rank), blocks row-major inside each tile. */
+    const bool tiled = p.world > 1 && p.tile_size != 0;
+    const uint32_t ts = tiled ? p.tile_size : 0u;
+    const uint32_t blocks_x = ((uint32_t)p.cam.w + 7u) / 8u, blocks_y = ((uint32_t)p.cam.h + 3u) / 4u;
+    const uint32_t tiles_px = tiled ? ((uint32_t)p.cam.w + ts - 1u) / ts : 0u, tiles_py = tiled ? ((uint32_t)p.cam.h + ts - 1u) / ts : 0u;
+    const uint32_t n_tiles = tiles_px * tiles_py;
+    const uint32_t owned_tiles = tiled ? (n_tiles > p.rank ? (n_tiles - p.rank + p.world - 1u) / p.world : 0u) : 0u;
+    const uint32_t n_work = tiled ? owned_tiles * ts * ts : blocks_x * blocks_y * 32u;
     unsigned long long rays = 0;
     int mode = kNeedPixel;
     int x = 0, y = 0;
@@ -203,7 +211,9 @@ __global__ void __launch_bounds__(kMegaBlock, RT_MEGA_MIN_BLOCKS) k_megakernel(R
                     const size_t pix = (size_t)y * (size_t)p.cam.w + (size_t)x;
                     const float count = base_count + (float)p.spp;
                     out.accum[pix] = make_float4(sum.x, sum.y, sum.z, count);
-                    out.rgba8[pix] = rt_resolve_pixel(sum.x, sum.y, sum.z, count);
+                    const uint32_t px = rt_resolve_pixel(sum.x, sum.y, sum.z, count);
+                    out.rgba8[pix] = px;
+                    if (out.gather) out.gather[pix] = px; /* tile shards: straight into the destination rank's image */
                     out.rng[pix] = rng.a;
                     mode = kNeedPixel;
                 } else {
@@ -223,9 +233,18 @@ __global__ void __launch_bounds__(kMegaBlock, RT_MEGA_MIN_BLOCKS) k_megakernel(R
                 if (idx >= n_work) {
                     mode = kExhausted;
                 } else {
-                    const uint32_t tile = idx >> 5, in = idx & 31u;
-                    x = (int)((tile % tiles_x) * 8u + (in & 7u));
-                    y = (int)((tile / tiles_x) * 4u + (in >> 3));
+                    const uint32_t in = idx & 31u;
+                    uint32_t blk = idx >> 5, bx0 = 0, by0 = 0, bw = blocks_x;
+                    if (tiled) { /* tile_size is a multiple of 8: (ts/8) x (ts/4) blocks per tile */
+                        const uint32_t per_tile = (ts >> 3) * (ts >> 2);
+                        const uint32_t t = (blk / per_tile) * p.world + p.rank;
+                        blk %= per_tile;
+                        bw = ts >> 3;
+                        bx0 = (t % tiles_px) * ts;
+                        by0 = (t / tiles_px) * ts;
+                    }
+                    x = (int)(bx0 + (blk % bw) * 8u + (in & 7u));
+                    y = (int)(by0 + (blk / bw) * 4u + (in >> 3));
                     if (x < p.cam.w && y < p.cam.h && rt_owns_pixel(p, x, y)) {
                         if (p.resume) { /* carry on where the previous frame stopped */
                             const size_t pix = (size_t)y * (size_t)p.cam.w + (size_t)x;
@@ -393,8 +412,10 @@ __global__ void k_resolve_owned(RtFrameParams p, const float4 *accum, const uint
     const int x = (int)(i % (uint32_t)p.cam.w), y = (int)(i / (uint32_t)p.cam.w);
     if (rt_owns_pixel(p, x, y)) {
         const float4 a = accum[i];
-        out.rgba8[i] = rt_resolve_pixel(a.x, a.y, a.z, a.w); /* a.w = samples accumulated (= spp, or more after resumes) */
-    } else {
+        const uint32_t px = rt_resolve_pixel(a.x, a.y, a.z, a.w); /* a.w = samples accumulated (= spp, or more after resumes) */
+        out.rgba8[i] = px;
+        if (out.gather) out.gather[i] = px;
+    } else if (!p.keep_foreign) {
         out.rgba8[i] = 0u;
     }
     out.rng[i] = rng_state[i];

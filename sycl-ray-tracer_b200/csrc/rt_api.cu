@@ -36,6 +36,9 @@ struct rt_renderer {
     int grid_mega = 0, grid_extend = 0, grid_shade = 0;
     cudaEvent_t ev_batch[2] = {nullptr, nullptr}; /* wavefront: per-batch queue-length read-back */
     bool has_frame = false; /* a frame has been rendered: RT_RENDER_RESUME is allowed */
+    uint32_t *gather = nullptr;   /* tile shards: owned pixels are also stored here (peer memory) */
+    bool gather_ipc = false;      /* gather was opened from an IPC handle (close it) */
+    bool exported = false;        /* d_rgba8 is a gather destination: never clear foreign pixels */
     int tune_refill = 12; /* lanes that must run dry before a warp refills (RT_TUNE_REFILL overrides; 12-14 measured best) */
 };
 
@@ -468,9 +471,16 @@ rt_status rt_renderer_create(rt_context *ctx, rt_renderer_kind kind, int32_t wid
     return RT_OK;
 }
 
+static void gather_detach(rt_renderer *r) {
+    if (r->gather && r->gather_ipc) cudaIpcCloseMemHandle(r->gather);
+    r->gather = nullptr;
+    r->gather_ipc = false;
+}
+
 void rt_renderer_destroy(rt_renderer *r) {
     if (!r) return;
     cudaSetDevice(r->ctx->device);
+    gather_detach(r);
     cudaFree(r->d_accum);
     cudaFree(r->d_rgba8);
     cudaFree(r->d_rng);
@@ -493,6 +503,39 @@ void rt_renderer_destroy(rt_renderer *r) {
     delete r;
 }
 
+rt_status rt_renderer_export_image(rt_renderer *r, rt_ipc_handle *out) {
+    if (!r) return RT_ERR_INVALID;
+    rt_context *ctx = r->ctx;
+    if (!out) return rt_set_error(ctx, RT_ERR_INVALID, "rt_renderer_export_image", "out is NULL");
+    static_assert(sizeof(cudaIpcMemHandle_t) == sizeof(rt_ipc_handle), "rt_ipc_handle must hold a cudaIpcMemHandle_t");
+    RT_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    cudaIpcMemHandle_t h;
+    RT_CUDA_TRY(ctx, cudaIpcGetMemHandle(&h, r->d_rgba8));
+    memcpy(out->bytes, &h, sizeof(h));
+    r->exported = true;
+    return RT_OK;
+}
+
+rt_status rt_renderer_set_gather(rt_renderer *r, const rt_ipc_handle *handle, void *device_rgba8) {
+    if (!r) return RT_ERR_INVALID;
+    rt_context *ctx = r->ctx;
+    if (handle && device_rgba8) return rt_set_error(ctx, RT_ERR_INVALID, "rt_renderer_set_gather", "pass a handle or a pointer, not both");
+    RT_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    RT_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream)); /* no frame may still be storing to the old target */
+    gather_detach(r);
+    if (handle) {
+        cudaIpcMemHandle_t h;
+        memcpy(&h, handle->bytes, sizeof(h));
+        void *p = nullptr;
+        RT_CUDA_TRY(ctx, cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+        r->gather = (uint32_t *)p;
+        r->gather_ipc = true;
+    } else if (device_rgba8) {
+        r->gather = (uint32_t *)device_rgba8;
+    }
+    return RT_OK;
+}
+
 float *rt_renderer_device_accum(rt_renderer *r) { return r ? (float *)r->d_accum : nullptr; }
 uint8_t *rt_renderer_device_rgba8(rt_renderer *r) { return r ? (uint8_t *)r->d_rgba8 : nullptr; }
 
@@ -508,6 +551,7 @@ rt_status rt_render_frame(rt_renderer *r, const rt_scene *scene, const rt_camera
     const rt_shard &sh = params->shard;
     if (sh.world > 1 && sh.rank >= sh.world) return rt_set_error(ctx, RT_ERR_INVALID, "rt_render_frame", "shard rank >= world");
     if (sh.world > 1 && sh.tile_size % 8 != 0) return rt_set_error(ctx, RT_ERR_INVALID, "rt_render_frame", "tile_size must be a multiple of 8");
+    if (params->flags & ~RT_RENDER_RESUME) return rt_set_error(ctx, RT_ERR_INVALID, "rt_render_frame", "unknown bits in rt_render_params.flags");
     RT_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
 
@@ -528,6 +572,8 @@ rt_status rt_render_frame(rt_renderer *r, const rt_scene *scene, const rt_camera
     out.accum = r->d_accum;
     out.rgba8 = r->d_rgba8;
     out.rng = r->d_rng;
+    out.gather = (sh.world > 1 && sh.tile_size) ? r->gather : nullptr;
+    p.keep_foreign = r->exported ? 1 : 0;
     const size_t n = (size_t)r->w * (size_t)r->h;
     uint32_t launches = 0;
 
@@ -537,7 +583,7 @@ rt_status rt_render_frame(rt_renderer *r, const rt_scene *scene, const rt_camera
         RT_CUDA_TRY(ctx, cudaMemsetAsync(r->d_work, 0, sizeof(uint32_t), st));
         if (sh.world > 1 && sh.tile_size && !p.resume) { /* pixels of other ranks stay zero */
             RT_CUDA_TRY(ctx, cudaMemsetAsync(r->d_accum, 0, n * sizeof(float4), st));
-            RT_CUDA_TRY(ctx, cudaMemsetAsync(r->d_rgba8, 0, n * 4, st));
+            if (!r->exported) RT_CUDA_TRY(ctx, cudaMemsetAsync(r->d_rgba8, 0, n * 4, st));
             RT_CUDA_TRY(ctx, cudaMemsetAsync(r->d_rng, 0, n * 4, st));
         }
         RT_CUDA_TRY(ctx, rt_launch_megakernel(st, r->grid_mega, scene->view, p, out, r->d_work, r->d_rays));

@@ -232,6 +232,7 @@ struct RtFrameParams {
     int32_t wavefront_seed; /* F3: 0 = x*H_pad + y, 1 = x + y*W */
     int32_t clamp_samples;  /* F9: wavefront clamps every sample to [0,1] */
     int32_t resume;         /* continue the streams / accumulation left by the previous frame */
+    int32_t keep_foreign;   /* tile shards: leave other ranks' RGBA8 pixels alone (this image is a gather destination) */
     /* scheduling knobs of the persistent kernels (no effect on results) */
     int32_t tune_refill;    /* leave the traversal loop once this many lanes have finished */
 };

@@ -12,6 +12,7 @@ struct RtFrameOut {
     rt_float4 *accum; /* W*H: linear sum rgb, sample count in w */
     uint32_t *rgba8;  /* W*H */
     uint32_t *rng;    /* W*H: final xorshift state */
+    uint32_t *gather; /* optional second destination of owned pixels' RGBA8 (peer memory, tile shards) */
 };
 
 /* per-pixel ray state (Buffers, src/render_wavefront.hpp:10-37): fp32 origin padded to 16 B

@@ -425,6 +425,7 @@ uint64_t emu_render(const emu_scene *s, int kind, const rt_camera *camera, const
         out.accum = acc.data();
         out.rgba8 = bytes.data();
         out.rng = rng_final.data();
+        out.gather = nullptr;
         for (uint32_t pix = 0; pix < n_pix; pix++)
             if (rt_wf_generate_pixel(p, w, out, pix)) w.queue[0][counts[0]++] = pix;
         int cur = 0;

@@ -200,6 +200,43 @@ def test_tile_shards_sum_to_unsharded(pkg, app, scenes):
     scene.close()
 
 
+@pytest.mark.parametrize("kind", [0, 1])
+def test_tile_shards_gather_into_one_image(pkg, app, scenes, kind):
+    """tile shards with the peer-memory gather: every rank's kernel stores its finished pixels straight
+    into the destination renderer's image (here: a second renderer on the same device; across processes
+    the pointer comes from the CUDA IPC handle of rt_renderer_export_image) — the destination image equals
+    the unsharded frame without any reduction"""
+    data = scenes.cornell_scene(3)
+    scene = pkg.Scene(app, data)
+    w, h = 200, 120
+    cam = pkg.Camera((w, h), data.camera_position, data.camera_direction, data.camera_focal_length)
+    cls = pkg.MegakernelRenderer if kind == 0 else pkg.WavefrontRenderer
+    ref, dest, peer = cls(app, (w, h), None, 8, 3), cls(app, (w, h), None, 8, 3), cls(app, (w, h), None, 8, 3)
+    full = ref.render_frame(cam, scene).rgba8.copy()
+    dest.max_depth = 1
+    other = dest.render_frame(cam, scene).rgba8.copy()   # the destination starts out holding a different image
+    dest.max_depth = 8
+    tiles = (np.arange(h)[:, None] // 32) * ((w + 31) // 32) + np.arange(w)[None, :] // 32
+    foreign = tiles % 4 != 0
+    assert (other != full).any(-1)[foreign].any()
+    assert len(dest.export_image()) == 64                # from now on dest leaves foreign pixels alone
+    peer.set_gather(device_ptr=dest.device_rgba8_ptr)
+    for rank in (1, 2, 3):
+        peer.render_frame(cam, scene, want=(), shard={"rank": rank, "world": 4, "tile_size": 32})
+    f = dest.render_frame(cam, scene, want=("rgba8",), shard={"rank": 0, "world": 4, "tile_size": 32})
+    assert np.array_equal(f.rgba8, full)
+    peer.set_gather()                                    # detached: the next peer frame no longer touches dest
+    peer.max_depth = 1
+    peer.render_frame(cam, scene, want=(), shard={"rank": 1, "world": 4, "tile_size": 32})
+    f = dest.render_frame(cam, scene, want=("rgba8",), shard={"rank": 0, "world": 4, "tile_size": 32})
+    assert np.array_equal(f.rgba8, full)
+    with pytest.raises(pkg.RtError):
+        peer.set_gather(handle=b"\0" * 64, device_ptr=dest.device_rgba8_ptr)
+    for r in (ref, dest, peer):
+        r.close()
+    scene.close()
+
+
 def test_spp_shards_match_salted_oracle_and_resolve(pkg, oracle, app, scenes):
     """spp sharding (config 5's mode): each shard is its own stream (seed ^ salt); the reduced
     buffer resolved by rt_resolve equals the oracle's per-shard sum"""
