@@ -120,6 +120,9 @@ __device__ __forceinline__ void traverse_phase(const RtBvh &bvh, RtTravState &tv
     const unsigned full = 0xffffffffu;
     const bool trav = mode == kTraversing;
     const unsigned m_trav = __ballot_sync(full, trav); /* does not change inside the node loop */
+    /* the refill threshold scales with the lanes that still have work: in the drain of a frame (most lanes
+     * exhausted) a finished lane must not wait for every other ray of its warp */
+    const int thr = max(1, (__popc(m_trav) * refill + 31) >> 5);
     for (;;) {
         if (trav && rt_trav_has_node(tv)) rt_trav_node_step(bvh, tv, ks);
         const bool node = trav && rt_trav_has_node(tv);
@@ -127,7 +130,7 @@ __device__ __forceinline__ void traverse_phase(const RtBvh &bvh, RtTravState &tv
         /* leave when no lane has nodes left, `refill` lanes have run dry, or a lane's triangle stack
          * is full (draining on a pending-triangle count instead was measured and never paid off) */
         const bool out = trav && rt_trav_tri_full(tv);
-        if (!m_node || __popc(m_trav & ~m_node) >= refill || __any_sync(full, out)) break;
+        if (!m_node || __popc(m_trav & ~m_node) >= thr || __any_sync(full, out)) break;
     }
     for (;;) { /* drain: lanes that are out of nodes (or nearly out of triangle-stack room) must
                   finish their triangles; every other lane with triangles pending joins in, and
