@@ -23,6 +23,8 @@
  */
 #include "rt_render.h"
 
+#include <cub/device/device_radix_sort.cuh>
+
 namespace {
 
 constexpr int kMegaBlock = 128;
@@ -51,6 +53,99 @@ __global__ void k_intersect(RtScene scene, const RtInstance *inst, uint64_t n, c
         o_v[i] = h.v;
         o_t[i] = h.t;
     }
+}
+
+/* ------------------------------------------------------------------------------ pixel blocks */
+/* Pixels are handed to the persistent lanes in 8x4 blocks (32 consecutive slots = one coherent block).
+ * Unsharded: blocks row-major over the image. Image-tile shards: only this rank's tiles are enumerated
+ * (the k-th owned tile is tile k * world + rank), blocks row-major inside each tile. */
+struct BlockGeom {
+    uint32_t tiled, ts, blocks_x, tiles_px, per_tile, n_blocks;
+};
+__host__ __device__ inline BlockGeom block_geom(const RtFrameParams &p) {
+    BlockGeom g;
+    g.tiled = (p.world > 1 && p.tile_size != 0) ? 1u : 0u;
+    g.ts = g.tiled ? p.tile_size : 0u;
+    g.blocks_x = ((uint32_t)p.cam.w + 7u) / 8u;
+    const uint32_t blocks_y = ((uint32_t)p.cam.h + 3u) / 4u;
+    g.tiles_px = g.tiled ? ((uint32_t)p.cam.w + g.ts - 1u) / g.ts : 0u;
+    const uint32_t tiles_py = g.tiled ? ((uint32_t)p.cam.h + g.ts - 1u) / g.ts : 0u;
+    const uint32_t n_tiles = g.tiles_px * tiles_py;
+    const uint32_t owned = g.tiled ? (n_tiles > p.rank ? (n_tiles - p.rank + p.world - 1u) / p.world : 0u) : 0u;
+    g.per_tile = (g.ts >> 3) * (g.ts >> 2); /* tile_size is a multiple of 8 */
+    g.n_blocks = g.tiled ? owned * g.per_tile : g.blocks_x * blocks_y;
+    return g;
+}
+/* top-left pixel of block `blk` of this rank's enumeration */
+__device__ __forceinline__ void block_origin(const RtFrameParams &p, const BlockGeom &g, uint32_t blk, uint32_t &x0, uint32_t &y0) {
+    uint32_t bx0 = 0, by0 = 0, bw = g.blocks_x;
+    if (g.tiled) {
+        const uint32_t t = (blk / g.per_tile) * p.world + p.rank;
+        blk %= g.per_tile;
+        bw = g.ts >> 3;
+        bx0 = (t % g.tiles_px) * g.ts;
+        by0 = (t / g.tiles_px) * g.ts;
+    }
+    x0 = bx0 + (blk % bw) * 8u;
+    y0 = by0 + (blk / bw) * 4u;
+}
+
+/* Cost probe for the block order. A frame ends when its slowest lane finishes its last pixel, and a pixel
+ * is a strictly sequential chain (spp samples on one xorshift stream, F4), so expensive pixels handed out
+ * last stretch the tail of the kernel by up to a whole pixel time. The probe traces one throw-away path
+ * per block (own seed: the pixels' streams are untouched, nothing is accumulated or counted) and adds the
+ * traversal steps it took to the block's 64x64-pixel region; blocks are then handed out by decreasing cost
+ * class of their REGION (128 probes each: smooth, and neighbouring blocks stay together), image order
+ * within a class. Scheduling only: results are bit-identical for any order. */
+constexpr uint32_t kRegion = 64;
+__device__ __forceinline__ uint32_t region_of(const RtFrameParams &p, uint32_t x0, uint32_t y0) {
+    return (y0 / kRegion) * (((uint32_t)p.cam.w + kRegion - 1u) / kRegion) + x0 / kRegion;
+}
+__global__ void __launch_bounds__(128) k_block_cost(RtScene scene, RtFrameParams p, BlockGeom g, uint32_t *region_cost, uint32_t *vals) {
+    const uint32_t blk = blockIdx.x * blockDim.x + threadIdx.x;
+    if (blk >= g.n_blocks) return;
+    uint32_t x0, y0;
+    block_origin(p, g, blk, x0, y0);
+    uint32_t cost = 0;
+    if (x0 < (uint32_t)p.cam.w && y0 < (uint32_t)p.cam.h) {
+        const int x = min((int)x0 + 3, p.cam.w - 1), y = min((int)y0 + 1, p.cam.h - 1);
+        XorShift32 rng;
+        rng.a = (((uint32_t)x * 0x9E3779B1u) ^ ((uint32_t)y * 0x85EBCA77u)) | 1u;
+        const RtRayState r = rt_camera_ray(p.cam, x, y, rng);
+        f3 org = r.org, dir = r.dir, att = r.att, rad = r.rad, res;
+        for (uint32_t depth = 0; depth < p.max_depth; depth++) {
+            RtTravState tv;
+            RtTravStacks ks;
+            rt_trav_init(tv, org, dir, 0.0001f, INFINITY);
+            cost += 2; /* ray set-up + shading, in units of one traversal step */
+            while (rt_trav_has_node(tv)) {
+                rt_trav_node_step(scene.bvh, tv, ks);
+                cost++;
+                while (rt_trav_has_tri(tv)) {
+                    rt_trav_tri_step(scene.bvh, tv, ks);
+                    cost++;
+                }
+            }
+            if (rt_shade_segment(scene, tv.best, rng, org, dir, att, rad, res)) break;
+        }
+        atomicAdd(region_cost + region_of(p, x0, y0), cost);
+    }
+    vals[blk] = (y0 << 16) | x0;
+}
+
+__global__ void __launch_bounds__(128) k_block_key(RtFrameParams p, BlockGeom g, const uint32_t *region_cost, const uint32_t *vals,
+                                                   uint32_t *keys) {
+    const uint32_t blk = blockIdx.x * blockDim.x + threadIdx.x;
+    if (blk >= g.n_blocks) return;
+    const uint32_t x0 = vals[blk] & 0xffffu, y0 = vals[blk] >> 16;
+    /* cost class: log2 with two mantissa bits (8 bits, one radix pass); 0 = outside the image */
+    uint32_t key = 0;
+    if (x0 < (uint32_t)p.cam.w && y0 < (uint32_t)p.cam.h) {
+        const uint32_t cost = region_cost[region_of(p, x0, y0)] | 1u;
+        const int e = 31 - __clz(cost);
+        key = ((uint32_t)(e << 2) | ((e >= 2 ? cost >> (e - 2) : cost << (2 - e)) & 3u)) + 1u;
+    }
+    keys[blk] = key;
 }
 
 /* ------------------------------------------------------------------------------ megakernel */
@@ -143,23 +238,19 @@ __device__ __forceinline__ void traverse_phase(const RtBvh &bvh, RtTravState &tv
     if (mode == kTraversing && !rt_trav_has_node(tv)) mode = kHitPending;
 }
 
+#ifndef RT_PIXEL_ORDER
+#define RT_PIXEL_ORDER 0
+#endif
 #ifndef RT_MEGA_MIN_BLOCKS
 #define RT_MEGA_MIN_BLOCKS 8
 #endif
 __global__ void __launch_bounds__(kMegaBlock, RT_MEGA_MIN_BLOCKS) k_megakernel(RtScene scene, RtFrameParams p, RtFrameOut out,
-                                                           uint32_t *work_counter, unsigned long long *ray_counter) {
+                                                           uint32_t *work_counter, unsigned long long *ray_counter,
+                                                           const uint32_t *__restrict__ order) {
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
-    /* Pixel slots are handed out in 8x4-block-major order (32 consecutive slots = one coherent block).
-     * Unsharded: blocks row-major over the image. Image-tile shards: only this rank's tiles are
-     * enumerated (the k-th owned tile is tile k * world + rank), blocks row-major inside each tile. */
-    const bool tiled = p.world > 1 && p.tile_size != 0;
-    const uint32_t ts = tiled ? p.tile_size : 0u;
-    const uint32_t blocks_x = ((uint32_t)p.cam.w + 7u) / 8u, blocks_y = ((uint32_t)p.cam.h + 3u) / 4u;
-    const uint32_t tiles_px = tiled ? ((uint32_t)p.cam.w + ts - 1u) / ts : 0u, tiles_py = tiled ? ((uint32_t)p.cam.h + ts - 1u) / ts : 0u;
-    const uint32_t n_tiles = tiles_px * tiles_py;
-    const uint32_t owned_tiles = tiled ? (n_tiles > p.rank ? (n_tiles - p.rank + p.world - 1u) / p.world : 0u) : 0u;
-    const uint32_t n_work = tiled ? owned_tiles * ts * ts : blocks_x * blocks_y * 32u;
+    const BlockGeom g = block_geom(p);
+    const uint32_t n_work = g.n_blocks * 32u; /* pixel slots, 32 per 8x4 block */
     unsigned long long rays = 0;
     int mode = kNeedPixel;
     int x = 0, y = 0;
@@ -237,17 +328,16 @@ __global__ void __launch_bounds__(kMegaBlock, RT_MEGA_MIN_BLOCKS) k_megakernel(R
                     mode = kExhausted;
                 } else {
                     const uint32_t in = idx & 31u;
-                    uint32_t blk = idx >> 5, bx0 = 0, by0 = 0, bw = blocks_x;
-                    if (tiled) { /* tile_size is a multiple of 8: (ts/8) x (ts/4) blocks per tile */
-                        const uint32_t per_tile = (ts >> 3) * (ts >> 2);
-                        const uint32_t t = (blk / per_tile) * p.world + p.rank;
-                        blk %= per_tile;
-                        bw = ts >> 3;
-                        bx0 = (t % tiles_px) * ts;
-                        by0 = (t / tiles_px) * ts;
+                    uint32_t x0, y0;
+                    if (order) { /* blocks sorted by decreasing cost class (k_block_cost) */
+                        const uint32_t e = __ldg(order + (idx >> 5));
+                        x0 = e & 0xffffu;
+                        y0 = e >> 16;
+                    } else {
+                        block_origin(p, g, idx >> 5, x0, y0);
                     }
-                    x = (int)(bx0 + (blk % bw) * 8u + (in & 7u));
-                    y = (int)(by0 + (blk / bw) * 4u + (in >> 3));
+                    x = (int)(x0 + (in & 7u));
+                    y = (int)(y0 + (in >> 3));
                     if (x < p.cam.w && y < p.cam.h && rt_owns_pixel(p, x, y)) {
                         if (p.resume) { /* carry on where the previous frame stopped */
                             const size_t pix = (size_t)y * (size_t)p.cam.w + (size_t)x;
@@ -453,9 +543,34 @@ cudaError_t rt_megakernel_grid(int sm_count, int *grid) {
 }
 
 cudaError_t rt_launch_megakernel(cudaStream_t st, int grid, const RtScene &scene, const RtFrameParams &p,
-                                 const RtFrameOut &out, uint32_t *work_counter, unsigned long long *ray_counter) {
-    k_megakernel<<<grid, kMegaBlock, 0, st>>>(scene, p, out, work_counter, ray_counter);
+                                 const RtFrameOut &out, uint32_t *work_counter, unsigned long long *ray_counter,
+                                 const uint32_t *order) {
+    k_megakernel<<<grid, kMegaBlock, 0, st>>>(scene, p, out, work_counter, ray_counter, order);
     return cudaGetLastError();
+}
+
+uint32_t rt_block_count(const RtFrameParams &p) { return block_geom(p).n_blocks; }
+
+cudaError_t rt_block_order_temp_bytes(uint32_t n_blocks, size_t *bytes) {
+    *bytes = 0;
+    return cub::DeviceRadixSort::SortPairsDescending(nullptr, *bytes, (const uint32_t *)nullptr, (uint32_t *)nullptr,
+                                                     (const uint32_t *)nullptr, (uint32_t *)nullptr, (int)n_blocks, 0, 8);
+}
+
+uint32_t rt_region_count(int w, int h) { return (((uint32_t)w + kRegion - 1u) / kRegion) * (((uint32_t)h + kRegion - 1u) / kRegion); }
+
+cudaError_t rt_launch_block_order(cudaStream_t st, const RtScene &scene, const RtFrameParams &p, uint32_t *region_cost, uint32_t *keys_in,
+                                  uint32_t *keys_out, uint32_t *vals_in, uint32_t *vals_out, void *temp, size_t temp_bytes) {
+    const BlockGeom g = block_geom(p);
+    if (g.n_blocks == 0) return cudaSuccess;
+    cudaError_t e = cudaMemsetAsync(region_cost, 0, rt_region_count(p.cam.w, p.cam.h) * sizeof(uint32_t), st);
+    if (e != cudaSuccess) return e;
+    k_block_cost<<<(g.n_blocks + 127) / 128, 128, 0, st>>>(scene, p, g, region_cost, vals_in);
+    k_block_key<<<(g.n_blocks + 127) / 128, 128, 0, st>>>(p, g, region_cost, vals_in, keys_in);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    /* stable, descending: expensive classes first, enumeration (image) order inside a class */
+    return cub::DeviceRadixSort::SortPairsDescending(temp, temp_bytes, keys_in, keys_out, vals_in, vals_out, (int)g.n_blocks, 0, 8, st);
 }
 
 cudaError_t rt_wavefront_grid(int sm_count, int *grid_extend, int *grid_shade) {

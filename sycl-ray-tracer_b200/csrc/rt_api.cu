@@ -36,6 +36,12 @@ struct rt_renderer {
     int grid_mega = 0, grid_extend = 0, grid_shade = 0;
     cudaEvent_t ev_batch[2] = {nullptr, nullptr}; /* wavefront: per-batch queue-length read-back */
     bool has_frame = false; /* a frame has been rendered: RT_RENDER_RESUME is allowed */
+    uint32_t *d_order[4] = {nullptr, nullptr, nullptr, nullptr}; /* block order: keys in/out, values in/out */
+    void *d_order_temp = nullptr;
+    uint32_t *d_region_cost = nullptr;
+    size_t order_temp_bytes = 0;
+    uint32_t order_capacity = 0;
+    int block_order = 1;          /* megakernel: hand blocks out by decreasing probed cost (RT_BLOCK_ORDER=0 disables) */
     uint32_t *gather = nullptr;   /* tile shards: owned pixels are also stored here (peer memory) */
     bool gather_ipc = false;      /* gather was opened from an IPC handle (close it) */
     bool exported = false;        /* d_rgba8 is a gather destination: never clear foreign pixels */
@@ -430,6 +436,7 @@ rt_status rt_renderer_create(rt_context *ctx, rt_renderer_kind kind, int32_t wid
     r->w = width;
     r->h = height;
     if (const char *e = getenv("RT_TUNE_REFILL")) r->tune_refill = atoi(e) > 0 ? atoi(e) : r->tune_refill;
+    if (const char *e = getenv("RT_BLOCK_ORDER")) r->block_order = atoi(e);
     const size_t n = (size_t)width * (size_t)height;
     cudaError_t e = cudaSuccess;
     do {
@@ -481,6 +488,9 @@ void rt_renderer_destroy(rt_renderer *r) {
     if (!r) return;
     cudaSetDevice(r->ctx->device);
     gather_detach(r);
+    for (uint32_t *q : r->d_order) cudaFree(q);
+    cudaFree(r->d_order_temp);
+    cudaFree(r->d_region_cost);
     cudaFree(r->d_accum);
     cudaFree(r->d_rgba8);
     cudaFree(r->d_rng);
@@ -586,7 +596,33 @@ rt_status rt_render_frame(rt_renderer *r, const rt_scene *scene, const rt_camera
             if (!r->exported) RT_CUDA_TRY(ctx, cudaMemsetAsync(r->d_rgba8, 0, n * 4, st));
             RT_CUDA_TRY(ctx, cudaMemsetAsync(r->d_rng, 0, n * 4, st));
         }
-        RT_CUDA_TRY(ctx, rt_launch_megakernel(st, r->grid_mega, scene->view, p, out, r->d_work, r->d_rays));
+        /* block order: the probe is a fixed cost (one low-occupancy path per block), the tail it removes grows
+         * with the length of a pixel's sequential chain: measured +10 % on C2 (64 spp), +1.5 % on C3, -1.5 % on
+         * C4 at 16 spp -> only from 32 spp */
+        const uint32_t *order = nullptr;
+        const uint32_t n_blocks = rt_block_count(p);
+        if (r->block_order && p.spp >= 32 && p.max_depth >= 2 && n_blocks >= 1024 && r->w <= 65535 && r->h <= 65535) {
+            if (n_blocks > r->order_capacity) { /* first frame (or a coarser tiling): (re)allocate */
+                RT_CUDA_TRY(ctx, cudaStreamSynchronize(st));
+                for (uint32_t *&q : r->d_order) {
+                    cudaFree(q);
+                    q = nullptr;
+                }
+                cudaFree(r->d_order_temp);
+                r->d_order_temp = nullptr;
+                r->order_capacity = 0;
+                for (uint32_t *&q : r->d_order) RT_CUDA_TRY(ctx, dev_alloc(&q, n_blocks));
+                RT_CUDA_TRY(ctx, rt_block_order_temp_bytes(n_blocks, &r->order_temp_bytes));
+                RT_CUDA_TRY(ctx, cudaMalloc(&r->d_order_temp, r->order_temp_bytes ? r->order_temp_bytes : 1));
+                if (!r->d_region_cost) RT_CUDA_TRY(ctx, dev_alloc(&r->d_region_cost, rt_region_count(r->w, r->h)));
+                r->order_capacity = n_blocks;
+            }
+            RT_CUDA_TRY(ctx, rt_launch_block_order(st, scene->view, p, r->d_region_cost, r->d_order[0], r->d_order[1], r->d_order[2], r->d_order[3],
+                                                   r->d_order_temp, r->order_temp_bytes));
+            order = r->d_order[3];
+            launches += 2;
+        }
+        RT_CUDA_TRY(ctx, rt_launch_megakernel(st, r->grid_mega, scene->view, p, out, r->d_work, r->d_rays, order));
         launches++;
     } else {
         RT_CUDA_TRY(ctx, cudaMemsetAsync(r->d_counts, 0, 4 * sizeof(uint32_t), st));

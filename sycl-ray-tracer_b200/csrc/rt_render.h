@@ -13,7 +13,14 @@ cudaError_t rt_launch_intersect(cudaStream_t st, const RtScene &scene, const RtI
                                 int32_t *o_prim, float *o_u, float *o_v, float *o_t);
 cudaError_t rt_megakernel_grid(int sm_count, int *grid);
 cudaError_t rt_launch_megakernel(cudaStream_t st, int grid, const RtScene &scene, const RtFrameParams &p,
-                                 const RtFrameOut &out, uint32_t *work_counter, unsigned long long *ray_counter);
+                                 const RtFrameOut &out, uint32_t *work_counter, unsigned long long *ray_counter,
+                                 const uint32_t *order /* NULL: enumeration order */);
+/* block order of the megakernel: cost probe + one-pass stable radix sort (k_block_cost in render.cu) */
+uint32_t rt_block_count(const RtFrameParams &p);
+cudaError_t rt_block_order_temp_bytes(uint32_t n_blocks, size_t *bytes);
+uint32_t rt_region_count(int w, int h);
+cudaError_t rt_launch_block_order(cudaStream_t st, const RtScene &scene, const RtFrameParams &p, uint32_t *region_cost, uint32_t *keys_in,
+                                  uint32_t *keys_out, uint32_t *vals_in, uint32_t *vals_out, void *temp, size_t temp_bytes);
 cudaError_t rt_wavefront_grid(int sm_count, int *grid_extend, int *grid_shade);
 cudaError_t rt_launch_wf_generate(cudaStream_t st, int grid, const RtFrameParams &p, const RtWavefrontState &w,
                                   const RtFrameOut &out);

@@ -200,6 +200,39 @@ def test_tile_shards_sum_to_unsharded(pkg, app, scenes):
     scene.close()
 
 
+def test_cost_ordered_block_handout_changes_nothing(pkg, oracle, app, scenes, monkeypatch):
+    """from 32 spp the megakernel hands its 8x4 pixel blocks out by decreasing probed cost (k_block_cost):
+    scheduling only — every output equals the enumeration-order frame (RT_BLOCK_ORDER=0) and the oracle,
+    also under tile sharding"""
+    data = scenes.cornell_scene(3)
+    scene = pkg.Scene(app, data)
+    w, h = 256, 256                                      # 32 x 64 blocks: the ordering is active, also per rank at world 2
+    cam = pkg.Camera((w, h), data.camera_position, data.camera_direction, data.camera_focal_length)
+    ordered = pkg.MegakernelRenderer(app, (w, h), None, 6, 32)
+    monkeypatch.setenv("RT_BLOCK_ORDER", "0")
+    plain = pkg.MegakernelRenderer(app, (w, h), None, 6, 32)
+    monkeypatch.delenv("RT_BLOCK_ORDER")
+    a, b = ordered.render_frame(cam, scene), plain.render_frame(cam, scene)
+    assert a.kernel_launches == 3 and b.kernel_launches == 1   # probe + key + megakernel vs megakernel alone
+    assert a.ray_count == b.ray_count
+    for k in ("rgba8", "rng_state"):
+        assert np.array_equal(getattr(a, k), getattr(b, k))
+    assert np.array_equal(a.accum.view(np.uint32), b.accum.view(np.uint32))
+    crop = (96, 104, 160, 136)
+    o = oracle.Scene(data).render(oracle.camera_for(data, w, h), 0, 6, 32, use_bvh=True, crop=crop)
+    assert np.array_equal(a.accum[104:136, 96:160].view(np.uint32), o["accum"][104:136, 96:160].view(np.uint32))
+    acc, rays = np.zeros_like(a.accum), 0
+    for rank in range(2):
+        f = ordered.render_frame(cam, scene, shard={"rank": rank, "world": 2, "tile_size": 16})
+        assert f.kernel_launches == 3
+        acc += f.accum
+        rays += f.ray_count
+    assert np.array_equal(acc.view(np.uint32), a.accum.view(np.uint32)) and rays == a.ray_count
+    ordered.close()
+    plain.close()
+    scene.close()
+
+
 @pytest.mark.parametrize("kind", [0, 1])
 def test_tile_shards_gather_into_one_image(pkg, app, scenes, kind):
     """tile shards with the peer-memory gather: every rank's kernel stores its finished pixels straight
