@@ -22,6 +22,7 @@
  *  per-pixel results; they differ only in seed mapping (F3) and per-sample clamp (F9).
  */
 #include "rt_render.h"
+#include "rt_blocks.h"
 
 #include <cub/device/device_radix_sort.cuh>
 
@@ -55,41 +56,7 @@ __global__ void k_intersect(RtScene scene, const RtInstance *inst, uint64_t n, c
     }
 }
 
-/* ------------------------------------------------------------------------------ pixel blocks */
-/* Pixels are handed to the persistent lanes in 8x4 blocks (32 consecutive slots = one coherent block).
- * Unsharded: blocks row-major over the image. Image-tile shards: only this rank's tiles are enumerated
- * (the k-th owned tile is tile k * world + rank), blocks row-major inside each tile. */
-struct BlockGeom {
-    uint32_t tiled, ts, blocks_x, tiles_px, per_tile, n_blocks;
-};
-__host__ __device__ inline BlockGeom block_geom(const RtFrameParams &p) {
-    BlockGeom g;
-    g.tiled = (p.world > 1 && p.tile_size != 0) ? 1u : 0u;
-    g.ts = g.tiled ? p.tile_size : 0u;
-    g.blocks_x = ((uint32_t)p.cam.w + 7u) / 8u;
-    const uint32_t blocks_y = ((uint32_t)p.cam.h + 3u) / 4u;
-    g.tiles_px = g.tiled ? ((uint32_t)p.cam.w + g.ts - 1u) / g.ts : 0u;
-    const uint32_t tiles_py = g.tiled ? ((uint32_t)p.cam.h + g.ts - 1u) / g.ts : 0u;
-    const uint32_t n_tiles = g.tiles_px * tiles_py;
-    const uint32_t owned = g.tiled ? (n_tiles > p.rank ? (n_tiles - p.rank + p.world - 1u) / p.world : 0u) : 0u;
-    g.per_tile = (g.ts >> 3) * (g.ts >> 2); /* tile_size is a multiple of 8 */
-    g.n_blocks = g.tiled ? owned * g.per_tile : g.blocks_x * blocks_y;
-    return g;
-}
-/* top-left pixel of block `blk` of this rank's enumeration */
-__device__ __forceinline__ void block_origin(const RtFrameParams &p, const BlockGeom &g, uint32_t blk, uint32_t &x0, uint32_t &y0) {
-    uint32_t bx0 = 0, by0 = 0, bw = g.blocks_x;
-    if (g.tiled) {
-        const uint32_t t = (blk / g.per_tile) * p.world + p.rank;
-        blk %= g.per_tile;
-        bw = g.ts >> 3;
-        bx0 = (t % g.tiles_px) * g.ts;
-        by0 = (t / g.tiles_px) * g.ts;
-    }
-    x0 = bx0 + (blk % bw) * 8u;
-    y0 = by0 + (blk / bw) * 4u;
-}
-
+/* ------------------------------------------------------------------------------ block order */
 /* Cost probe for the block order. A frame ends when its slowest lane finishes its last pixel, and a pixel
  * is a strictly sequential chain (spp samples on one xorshift stream, F4), so expensive pixels handed out
  * last stretch the tail of the kernel by up to a whole pixel time. The probe traces one throw-away path
@@ -101,11 +68,11 @@ constexpr uint32_t kRegion = 64;
 __device__ __forceinline__ uint32_t region_of(const RtFrameParams &p, uint32_t x0, uint32_t y0) {
     return (y0 / kRegion) * (((uint32_t)p.cam.w + kRegion - 1u) / kRegion) + x0 / kRegion;
 }
-__global__ void __launch_bounds__(128) k_block_cost(RtScene scene, RtFrameParams p, BlockGeom g, uint32_t *region_cost, uint32_t *vals) {
+__global__ void __launch_bounds__(128) k_block_cost(RtScene scene, RtFrameParams p, RtBlockGeom g, uint32_t *region_cost, uint32_t *vals) {
     const uint32_t blk = blockIdx.x * blockDim.x + threadIdx.x;
     if (blk >= g.n_blocks) return;
     uint32_t x0, y0;
-    block_origin(p, g, blk, x0, y0);
+    rt_block_origin(p, g, blk, x0, y0);
     uint32_t cost = 0;
     if (x0 < (uint32_t)p.cam.w && y0 < (uint32_t)p.cam.h) {
         const int x = min((int)x0 + 3, p.cam.w - 1), y = min((int)y0 + 1, p.cam.h - 1);
@@ -133,7 +100,7 @@ __global__ void __launch_bounds__(128) k_block_cost(RtScene scene, RtFrameParams
     vals[blk] = (y0 << 16) | x0;
 }
 
-__global__ void __launch_bounds__(128) k_block_key(RtFrameParams p, BlockGeom g, const uint32_t *region_cost, const uint32_t *vals,
+__global__ void __launch_bounds__(128) k_block_key(RtFrameParams p, RtBlockGeom g, const uint32_t *region_cost, const uint32_t *vals,
                                                    uint32_t *keys) {
     const uint32_t blk = blockIdx.x * blockDim.x + threadIdx.x;
     if (blk >= g.n_blocks) return;
@@ -249,7 +216,7 @@ __global__ void __launch_bounds__(kMegaBlock, RT_MEGA_MIN_BLOCKS) k_megakernel(R
                                                            const uint32_t *__restrict__ order) {
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
-    const BlockGeom g = block_geom(p);
+    const RtBlockGeom g = rt_block_geom(p);
     const uint32_t n_work = g.n_blocks * 32u; /* pixel slots, 32 per 8x4 block */
     unsigned long long rays = 0;
     int mode = kNeedPixel;
@@ -334,7 +301,7 @@ __global__ void __launch_bounds__(kMegaBlock, RT_MEGA_MIN_BLOCKS) k_megakernel(R
                         x0 = e & 0xffffu;
                         y0 = e >> 16;
                     } else {
-                        block_origin(p, g, idx >> 5, x0, y0);
+                        rt_block_origin(p, g, idx >> 5, x0, y0);
                     }
                     x = (int)(x0 + (in & 7u));
                     y = (int)(y0 + (in >> 3));
@@ -549,7 +516,7 @@ cudaError_t rt_launch_megakernel(cudaStream_t st, int grid, const RtScene &scene
     return cudaGetLastError();
 }
 
-uint32_t rt_block_count(const RtFrameParams &p) { return block_geom(p).n_blocks; }
+uint32_t rt_block_count(const RtFrameParams &p) { return rt_block_geom(p).n_blocks; }
 
 cudaError_t rt_block_order_temp_bytes(uint32_t n_blocks, size_t *bytes) {
     *bytes = 0;
@@ -561,7 +528,7 @@ uint32_t rt_region_count(int w, int h) { return (((uint32_t)w + kRegion - 1u) / 
 
 cudaError_t rt_launch_block_order(cudaStream_t st, const RtScene &scene, const RtFrameParams &p, uint32_t *region_cost, uint32_t *keys_in,
                                   uint32_t *keys_out, uint32_t *vals_in, uint32_t *vals_out, void *temp, size_t temp_bytes) {
-    const BlockGeom g = block_geom(p);
+    const RtBlockGeom g = rt_block_geom(p);
     if (g.n_blocks == 0) return cudaSuccess;
     cudaError_t e = cudaMemsetAsync(region_cost, 0, rt_region_count(p.cam.w, p.cam.h) * sizeof(uint32_t), st);
     if (e != cudaSuccess) return e;

@@ -25,6 +25,7 @@ static unsigned long long g_count_node = 0, g_count_tri = 0;
 #include "../../include/rt_api.h"
 #include "../../sycl-ray-tracer_b200/csrc/rt_build.h"
 #include "../../sycl-ray-tracer_b200/csrc/rt_wavefront.h"
+#include "../../sycl-ray-tracer_b200/csrc/rt_blocks.h"
 
 namespace {
 
@@ -512,4 +513,31 @@ extern "C" void emu_scene_tree_stats(const emu_scene *s, uint64_t *out) {
         }
         out[n]++;
     }
+}
+
+/* megakernel pixel-slot enumeration (rt_blocks.h): counts[y*w+x] += 1 for every in-image pixel of every
+ * block this rank enumerates; returns the number of blocks */
+extern "C" uint32_t emu_enumerate_blocks(int w, int h, uint32_t rank, uint32_t world, uint32_t tile_size, uint32_t *counts,
+                                         uint32_t *foreign_out) {
+    RtFrameParams p;
+    memset(&p, 0, sizeof(p));
+    p.cam.w = w;
+    p.cam.h = h;
+    p.rank = rank;
+    p.world = world;
+    p.tile_size = tile_size;
+    const RtBlockGeom g = rt_block_geom(p);
+    uint32_t foreign = 0;
+    for (uint32_t blk = 0; blk < g.n_blocks; blk++) {
+        uint32_t x0, y0;
+        rt_block_origin(p, g, blk, x0, y0);
+        for (uint32_t in = 0; in < 32; in++) {
+            const int x = (int)(x0 + (in & 7u)), y = (int)(y0 + (in >> 3));
+            if (x >= w || y >= h) continue;
+            if (!rt_owns_pixel(p, x, y)) foreign++;
+            counts[(size_t)y * w + x]++;
+        }
+    }
+    *foreign_out = foreign;
+    return g.n_blocks;
 }

@@ -164,3 +164,26 @@ def test_coincident_centroids_and_flat_scene(oracle, hostemu):
     a, b = orc.intersect(org, d), emu.intersect(org, d)
     assert np.array_equal(a["prim"], b["prim"]) and np.array_equal(a["t"].view(np.uint32), b["t"].view(np.uint32))
     assert (a["prim"] >= 0).mean() > 0.5
+
+
+@pytest.mark.parametrize("size", [(200, 120), (256, 256), (33, 7), (8, 4), (1920, 1080)])
+def test_megakernel_block_enumeration_covers_owned_pixels_once(hostemu, size):
+    """rt_blocks.h: the pixel slots the megakernel hands out cover every pixel of the rank exactly once —
+    unsharded and for image tiles (only the rank's own tiles are enumerated), partial edge tiles included"""
+    import ctypes as C
+    L = hostemu.lib()
+    L.emu_enumerate_blocks.restype = C.c_uint32
+    L.emu_enumerate_blocks.argtypes = [C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]
+    w, h = size
+    for world, ts in [(1, 0), (2, 16), (4, 32), (8, 64), (3, 8), (8, 0), (5, 128)]:
+        total = np.zeros((h, w), np.uint32)
+        for rank in range(world if ts else 1):
+            counts, foreign = np.zeros((h, w), np.uint32), C.c_uint32()
+            n = L.emu_enumerate_blocks(w, h, rank, world, ts, counts.ctypes.data, C.byref(foreign))
+            assert foreign.value == 0 and counts.max() <= 1
+            if ts and world > 1:
+                tiles = (np.arange(h)[:, None] // ts) * ((w + ts - 1) // ts) + np.arange(w)[None, :] // ts
+                assert np.array_equal(counts == 1, tiles % world == rank)
+                assert n % ((ts // 8) * (ts // 4)) == 0
+            total += counts
+        assert (total == 1).all()
