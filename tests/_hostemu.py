@@ -67,15 +67,20 @@ class Scene:
                             prim.ctypes.data, u.ctypes.data, v.ctypes.data, t.ctypes.data)
         return dict(inst=inst, prim=prim, u=u, v=v, t=t)
 
-    def render(self, camera, kind, max_depth, spp, shard=None):
+    def render(self, camera, kind, max_depth, spp, shard=None, resume=None):
+        """resume = the dict a previous render() returned: continue it (RT_RENDER_RESUME)"""
         w, h = camera.img_size
         p = self.cap.rt_render_params()
         p.max_depth, p.sample_count = max_depth, spp
+        p.flags = self.cap.RT_RENDER_RESUME if resume else 0
         if shard:
             p.shard.rank, p.shard.world = shard.get("rank", 0), shard.get("world", 1)
             p.shard.tile_size, p.shard.seed_salt = shard.get("tile_size", 0), shard.get("seed_salt", 0)
         accum, rgba8 = np.empty((h, w, 4), np.float32), np.empty((h, w, 4), np.uint8)
         rng = np.empty((h, w), np.uint32)
+        if resume:
+            accum[...] = resume["accum"]
+            rng[...] = resume["rng_state"]
         rays = lib().emu_render(self.h, kind, C.addressof(camera.c), C.addressof(p), accum.ctypes.data,
                                 rgba8.ctypes.data, rng.ctypes.data)
         return dict(accum=accum, rgba8=rgba8, rng_state=rng, ray_count=int(rays))

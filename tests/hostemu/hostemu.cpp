@@ -388,27 +388,34 @@ uint64_t emu_render(const emu_scene *s, int kind, const rt_camera *camera, const
     p.tile_size = params->shard.tile_size;
     p.wavefront_seed = kind == 1;
     p.clamp_samples = kind == 1;
-    p.resume = 0;
+    p.resume = (params->flags & RT_RENDER_RESUME) ? 1 : 0; /* accum / rng_out then hold the previous frame (in/out) */
+    p.keep_foreign = 0;
     p.tune_refill = 8;
     const uint32_t n_pix = (uint32_t)p.cam.w * (uint32_t)p.cam.h;
     std::vector<rt_float4> acc(n_pix, rt_mk_float4(0, 0, 0, 0));
     std::vector<uint32_t> bytes(n_pix, 0), rng_final(n_pix, 0);
+    if (p.resume) {
+        memcpy(acc.data(), accum, (size_t)n_pix * 16);
+        memcpy(rng_final.data(), rng_out, (size_t)n_pix * 4);
+    }
     unsigned long long rays = 0;
     if (kind == 0) {
         for (int y = 0; y < p.cam.h; y++)
             for (int x = 0; x < p.cam.w; x++) {
                 if (!rt_owns_pixel(p, x, y)) continue;
-                XorShift32 rng;
-                const f3 sum = rt_megakernel_pixel(s->view, p, x, y, rng, rays);
                 const size_t pix = (size_t)y * p.cam.w + x;
-                acc[pix] = rt_mk_float4(sum.x, sum.y, sum.z, (float)p.spp);
-                bytes[pix] = rt_resolve_pixel(sum.x, sum.y, sum.z, (float)p.spp);
+                XorShift32 rng;
+                rng.a = rng_final[pix];
+                const float count = (p.resume ? acc[pix].w : 0.0f) + (float)p.spp;
+                const f3 sum = rt_megakernel_pixel(s->view, p, x, y, rng, rays, mk3(acc[pix].x, acc[pix].y, acc[pix].z), p.resume != 0);
+                acc[pix] = rt_mk_float4(sum.x, sum.y, sum.z, count);
+                bytes[pix] = rt_resolve_pixel(sum.x, sum.y, sum.z, count);
                 rng_final[pix] = rng.a;
             }
     } else {
         std::vector<rt_float4> org(n_pix), hit(n_pix);
         std::vector<rt_uint2> dir(n_pix), att(n_pix), rad(n_pix), prog(n_pix);
-        std::vector<uint32_t> rng(n_pix), q0(n_pix), q1(n_pix);
+        std::vector<uint32_t> rng(rng_final), q0(n_pix), q1(n_pix); /* resume: the renderer's own rng buffer lives on */
         uint32_t counts[2] = {0, 0};
         RtWavefrontState w;
         w.org = org.data();
@@ -442,7 +449,7 @@ uint64_t emu_render(const emu_scene *s, int kind, const rt_camera *camera, const
         }
         for (uint32_t pix = 0; pix < n_pix; pix++) {
             const int x = (int)(pix % (uint32_t)p.cam.w), y = (int)(pix / (uint32_t)p.cam.w);
-            if (rt_owns_pixel(p, x, y)) bytes[pix] = rt_resolve_pixel(acc[pix].x, acc[pix].y, acc[pix].z, (float)p.spp);
+            if (rt_owns_pixel(p, x, y)) bytes[pix] = rt_resolve_pixel(acc[pix].x, acc[pix].y, acc[pix].z, acc[pix].w);
             rng_final[pix] = rng[pix];
         }
     }

@@ -187,3 +187,26 @@ def test_megakernel_block_enumeration_covers_owned_pixels_once(hostemu, size):
                 assert n % ((ts // 8) * (ts // 4)) == 0
             total += counts
         assert (total == 1).all()
+
+
+@pytest.mark.parametrize("kind", [0, 1])
+def test_progressive_resume_on_the_cpu(pkg, oracle, hostemu, scenes, kind):
+    """RT_RENDER_RESUME in the kernels' own per-pixel code (rt_megakernel_pixel, rt_wf_generate_pixel):
+    2 + 3 + 1 samples continue the streams and sums of the previous frame and equal one 6-sample frame,
+    which equals the oracle"""
+    data = scenes.cornell_scene(2)
+    emu = hostemu.Scene(data)
+    w, h = 40, 24
+    cam = pkg.Camera((w, h), data.camera_position, data.camera_direction, data.camera_focal_length)
+    one = emu.render(cam, kind, 7, 6)
+    o = oracle.Scene(data).render(oracle.camera_for(data, w, h), kind, 7, 6, use_bvh=True)
+    assert np.array_equal(one["accum"].view(np.uint32), o["accum"].view(np.uint32)) and one["ray_count"] == o["ray_count"]
+    for shard in (None, {"rank": 1, "world": 2, "tile_size": 8}):
+        full = emu.render(cam, kind, 7, 6, shard=shard)
+        f, rays = None, 0
+        for n in (2, 3, 1):
+            f = emu.render(cam, kind, 7, n, shard=shard, resume=f)
+            rays += f["ray_count"]
+        assert rays == full["ray_count"]
+        assert np.array_equal(f["accum"].view(np.uint32), full["accum"].view(np.uint32))
+        assert np.array_equal(f["rgba8"], full["rgba8"]) and np.array_equal(f["rng_state"], full["rng_state"])
