@@ -216,8 +216,9 @@ rt_status rt_scene_create(rt_context *ctx, const rt_scene_desc *desc, rt_scene *
             return rt_set_error(ctx, RT_ERR_INVALID, "rt_scene_create", "bad material type");
         if (in.material.albedo_image >= (int32_t)desc->texture_layer_count)
             return rt_set_error(ctx, RT_ERR_INVALID, "rt_scene_create", "albedo_image out of range");
-        for (uint32_t k = 0; k < in.index_count; k++)
-            if (in.indices[k] >= in.vertex_count) return rt_set_error(ctx, RT_ERR_INVALID, "rt_scene_create", "index out of range");
+        uint32_t max_index = 0; /* branch-free so that the compiler vectorises it: 30 M indices at config 4 */
+        for (uint32_t k = 0; k < in.index_count; k++) max_index = in.indices[k] > max_index ? in.indices[k] : max_index;
+        if (in.index_count && max_index >= in.vertex_count) return rt_set_error(ctx, RT_ERR_INVALID, "rt_scene_create", "index out of range");
         n_verts += in.vertex_count;
         n_idx += in.index_count;
     }
