@@ -21,6 +21,20 @@
  *  and consumes its stream sequentially (F4), both formulations produce the reference's
  *  per-pixel results; they differ only in seed mapping (F3) and per-sample clamp (F9).
  */
+#ifdef RT_GPU_COUNTERS /* development build only (tools/): node visits / triangle tests of the render kernels */
+#include <cstdint>
+__device__ unsigned long long g_rt_counters[2];
+#define RT_COUNTERS 1
+__host__ __device__ inline void rt_count(int i) {
+#ifdef __CUDA_ARCH__
+    atomicAdd(&g_rt_counters[i], 1ull);
+#else
+    (void)i;
+#endif
+}
+#define RT_COUNT_NODE() rt_count(0)
+#define RT_COUNT_TRI() rt_count(1)
+#endif
 #include "rt_render.h"
 #include "rt_blocks.h"
 
@@ -514,6 +528,19 @@ cudaError_t rt_launch_megakernel(cudaStream_t st, int grid, const RtScene &scene
                                  const uint32_t *order) {
     k_megakernel<<<grid, kMegaBlock, 0, st>>>(scene, p, out, work_counter, ray_counter, order);
     return cudaGetLastError();
+}
+
+void rt_counters_read(unsigned long long out[2], bool reset) {
+    out[0] = out[1] = 0;
+#ifdef RT_GPU_COUNTERS
+    cudaMemcpyFromSymbol(out, g_rt_counters, sizeof(unsigned long long) * 2);
+    if (reset) {
+        const unsigned long long z[2] = {0, 0};
+        cudaMemcpyToSymbol(g_rt_counters, z, sizeof(z));
+    }
+#else
+    (void)reset;
+#endif
 }
 
 uint32_t rt_block_count(const RtFrameParams &p) { return rt_block_geom(p).n_blocks; }

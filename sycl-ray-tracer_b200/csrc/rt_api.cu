@@ -691,6 +691,14 @@ rt_status rt_render_frame(rt_renderer *r, const rt_scene *scene, const rt_camera
     frame->ray_count = *r->h_rays;
     frame->kernel_launches = launches;
     r->has_frame = true;
+#ifdef RT_GPU_COUNTERS
+    {
+        unsigned long long c[2];
+        rt_counters_read(c, true);
+        fprintf(stderr, "[rt counters] %s: %llu rays, %.3f node visits/ray, %.3f triangle tests/ray\n", r->kind == RT_MEGAKERNEL ? "megakernel" : "wavefront",
+                (unsigned long long)frame->ray_count, (double)c[0] / (double)frame->ray_count, (double)c[1] / (double)frame->ray_count);
+    }
+#endif
     return RT_OK;
 }
 

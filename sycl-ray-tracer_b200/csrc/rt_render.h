@@ -31,6 +31,8 @@ cudaError_t rt_launch_wf_shade(cudaStream_t st, int grid, const RtScene &scene, 
 cudaError_t rt_launch_resolve(cudaStream_t st, const float *accum, uint32_t *rgba8, uint32_t n_pix, float spp);
 cudaError_t rt_launch_resolve_owned(cudaStream_t st, const RtFrameParams &p, const float *accum,
                                     const uint32_t *rng_state, const RtFrameOut &out);
+/* RT_GPU_COUNTERS builds: traversal steps since the last reset (zeros otherwise) */
+void rt_counters_read(unsigned long long out[2], bool reset);
 cudaError_t rt_launch_selftest(cudaStream_t st, float a, float b, float c, float *o);
 
 #endif
