@@ -98,7 +98,7 @@ typedef struct rt_camera {
 typedef struct rt_shard {
     uint32_t rank;       /* this context's shard */
     uint32_t world;      /* number of shards; 0 or 1 = unsharded */
-    uint32_t tile_size;  /* > 0: image-tile sharding. Tiles of tile_size^2 pixels, numbered row
+    uint32_t tile_size;  /* > 0: image-tile sharding (a multiple of 8, <= 16384). Tiles of tile_size^2 pixels, numbered row
                             major, tile t belongs to rank t % world. Pixels of other ranks are left
                             untouched (zero) in accum/rgba8, so a SUM over ranks is the full image,
                             bit-identical to the unsharded render. */

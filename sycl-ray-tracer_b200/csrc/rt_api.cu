@@ -562,6 +562,7 @@ rt_status rt_render_frame(rt_renderer *r, const rt_scene *scene, const rt_camera
     const rt_shard &sh = params->shard;
     if (sh.world > 1 && sh.rank >= sh.world) return rt_set_error(ctx, RT_ERR_INVALID, "rt_render_frame", "shard rank >= world");
     if (sh.world > 1 && sh.tile_size % 8 != 0) return rt_set_error(ctx, RT_ERR_INVALID, "rt_render_frame", "tile_size must be a multiple of 8");
+    if (sh.world > 1 && sh.tile_size > 16384u) return rt_set_error(ctx, RT_ERR_INVALID, "rt_render_frame", "tile_size must be <= 16384");
     if (params->flags & ~RT_RENDER_RESUME) return rt_set_error(ctx, RT_ERR_INVALID, "rt_render_frame", "unknown bits in rt_render_params.flags");
     RT_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
