@@ -36,6 +36,22 @@ void glb_instance(void *h, uint32_t i, uint32_t *n_verts, uint32_t *n_idx, const
     node_mesh_prim[0] = in.node; node_mesh_prim[1] = in.mesh; node_mesh_prim[2] = in.primitive;
 }
 int glb_png_write(const char *path, const uint8_t *rgba, uint32_t w, uint32_t h) { return raytracer::glb::png_write(path, rgba, w, h) ? 1 : 0; }
+/* any embedded image (PNG / JPEG) -> RGBA8; comp = channels in the file (stbi's `comp`) */
+int glb_image_decode(const uint8_t *data, size_t n, uint8_t *rgba_out, uint32_t cap, uint32_t *w, uint32_t *h, int *comp) {
+    try {
+        raytracer::img::Image im = raytracer::img::decode_rgba8(data, n);
+        *w = im.w; *h = im.h; *comp = im.channels_in_file;
+        if (im.rgba.size() > cap) { g_err = "output buffer too small"; return 0; }
+        memcpy(rgba_out, im.rgba.data(), im.rgba.size());
+        return 1;
+    } catch (const std::exception &e) { g_err = e.what(); return 0; }
+}
+/* the bake's resize to one 512x512 RGBA8 layer (src/image_manager.hpp:52-62) */
+void glb_resize_to_layer(const uint8_t *rgba, uint32_t w, uint32_t h, uint8_t *out) {
+    std::vector<uint8_t> src(rgba, rgba + (size_t)w * h * 4);
+    std::vector<uint8_t> layer = raytracer::glb::resize_to_layer(src, w, h);
+    memcpy(out, layer.data(), layer.size());
+}
 int glb_png_read(const uint8_t *data, size_t n, uint8_t *rgba_out, uint32_t cap, uint32_t *w, uint32_t *h) {
     try {
         auto px = raytracer::glb::png_decode(data, n, *w, *h);

@@ -2,7 +2,7 @@
  * glb_loader.hpp — binary glTF (.glb) -> rt_scene_desc, following the reference loader's rules
  * (src/scene.cpp:54-129 Scene::Scene, :148-162 load_images, :164-442 load_primitives,
  * :444-510 load_node). The reference uses tinygltf + stb; this is a from-scratch reader (own JSON
- * parser, zlib for embedded PNGs) that reproduces what reaches the kernels:
+ * parser, own PNG / JPEG decoders) that reproduces what reaches the kernels:
  *
  *   - one instance per glTF node x mesh primitive, in node-index order then primitive order
  *     (= Embree attach order = instID, F11); POSITION / NORMAL / TEXCOORD_0 and indices required
@@ -18,9 +18,10 @@
  *   - camera node: position = global[3], direction = normalize(rotation * (0,0,-1)),
  *     focal = 1 / tan(yfov / 2) (:109-128);
  *   - images: every image is resized to 512x512 RGBA8 and baked into the layer array
- *     (src/image_manager.hpp:39-100). Embedded PNG (8-bit, non-interlaced) is decoded here; the resize
- *     is an sRGB-aware box / bilinear filter, NOT stb_image_resize2's default kernel, so textures
- *     that are not already 512x512 differ from the reference in the filtered texels (documented gap).
+ *     (src/image_manager.hpp:39-100). Embedded PNG and JPEG are decoded by image_codecs.hpp to exactly
+ *     the bytes stb_image hands the reference; the resize is an sRGB-aware box / bilinear filter, NOT
+ *     stb_image_resize2's default kernel, so textures that are not already 512x512 differ from the
+ *     reference in the filtered texels (documented gap).
  *
  * Explicit fallbacks where the reference relies on undefined behaviour (F15): a primitive without a
  * material -> diffuse 0.8 grey; no camera node -> position (0,0,0), direction (0,0,-1), focal 1.
@@ -29,6 +30,7 @@
 
 #include <zlib.h>
 
+#include <algorithm>
 #include <array>
 #include <cmath>
 #include <cstdint>
@@ -42,6 +44,7 @@
 #include <vector>
 
 #include "../../include/rt_api.h"
+#include "image_codecs.hpp"
 
 namespace raytracer {
 namespace glb {
@@ -190,59 +193,14 @@ inline Mat4 from_quat(const float q[4] /* x y z w */) {
     return r;
 }
 
-/* ------------------------------------------------------------------ PNG (zlib) */
-inline uint32_t be32(const uint8_t *p) { return (uint32_t)p[0] << 24 | p[1] << 16 | p[2] << 8 | p[3]; }
-
-/* decode an 8-bit, non-interlaced grey / grey+alpha / RGB / RGBA PNG to RGBA8 */
+/* ------------------------------------------------------------------ images */
+/* embedded PNG / JPEG -> RGBA8 exactly as stbi_load_from_memory(..., 4) delivers it to the reference
+ * (image_codecs.hpp) */
 inline std::vector<uint8_t> png_decode(const uint8_t *d, size_t n, uint32_t &w, uint32_t &h) {
-    static const uint8_t sig[8] = {0x89, 'P', 'N', 'G', 0x0d, 0x0a, 0x1a, 0x0a};
-    if (n < 8 || memcmp(d, sig, 8)) throw std::runtime_error("unsupported image (only embedded PNG is decoded)");
-    std::vector<uint8_t> idat;
-    int depth = 0, ctype = 0, interlace = 0;
-    for (size_t o = 8; o + 12 <= n;) {
-        const uint32_t len = be32(d + o);
-        const char *ty = (const char *)d + o + 4;
-        if (!strncmp(ty, "IHDR", 4)) {
-            w = be32(d + o + 8); h = be32(d + o + 12);
-            depth = d[o + 16]; ctype = d[o + 17]; interlace = d[o + 20];
-        } else if (!strncmp(ty, "IDAT", 4)) idat.insert(idat.end(), d + o + 8, d + o + 8 + len);
-        else if (!strncmp(ty, "IEND", 4)) break;
-        o += 12 + len;
-    }
-    const int ch = ctype == 0 ? 1 : ctype == 2 ? 3 : ctype == 4 ? 2 : ctype == 6 ? 4 : 0;
-    if (depth != 8 || !ch || interlace) throw std::runtime_error("unsupported PNG variant (need 8-bit, non-interlaced, non-palette)");
-    const size_t stride = (size_t)w * ch;
-    std::vector<uint8_t> raw((stride + 1) * h);
-    uLongf out_len = raw.size();
-    if (uncompress(raw.data(), &out_len, idat.data(), idat.size()) != Z_OK || out_len != raw.size())
-        throw std::runtime_error("PNG inflate failed");
-    std::vector<uint8_t> px(stride * h), out((size_t)w * h * 4);
-    for (uint32_t y = 0; y < h; y++) {
-        const uint8_t ft = raw[(stride + 1) * y], *src = &raw[(stride + 1) * y + 1];
-        uint8_t *cur = &px[stride * y];
-        const uint8_t *up = y ? &px[stride * (y - 1)] : nullptr;
-        for (size_t x = 0; x < stride; x++) {
-            const int a = x >= (size_t)ch ? cur[x - ch] : 0, b = up ? up[x] : 0, c = (up && x >= (size_t)ch) ? up[x - ch] : 0;
-            int pred = 0;
-            if (ft == 1) pred = a;
-            else if (ft == 2) pred = b;
-            else if (ft == 3) pred = (a + b) / 2;
-            else if (ft == 4) {
-                const int p = a + b - c, pa = std::abs(p - a), pb = std::abs(p - b), pc = std::abs(p - c);
-                pred = (pa <= pb && pa <= pc) ? a : (pb <= pc ? b : c);
-            }
-            cur[x] = (uint8_t)(src[x] + pred);
-        }
-    }
-    for (size_t i = 0; i < (size_t)w * h; i++) {
-        const uint8_t *s = &px[i * ch];
-        uint8_t *o = &out[i * 4];
-        if (ch == 1) { o[0] = o[1] = o[2] = s[0]; o[3] = 255; }
-        else if (ch == 2) { o[0] = o[1] = o[2] = s[0]; o[3] = s[1]; }
-        else if (ch == 3) { o[0] = s[0]; o[1] = s[1]; o[2] = s[2]; o[3] = 255; }
-        else memcpy(o, s, 4);
-    }
-    return out;
+    img::Image im = img::decode_rgba8(d, n);
+    w = im.w;
+    h = im.h;
+    return std::move(im.rgba);
 }
 
 /* RGBA8 PNG writer (filter 0, one zlib stream) — what stbi_write_png does for out.png (src/util.hpp:27) */
@@ -277,32 +235,107 @@ inline bool png_write(const std::string &path, const uint8_t *rgba, uint32_t w, 
     return (bool)f;
 }
 
-/* resize to 512x512 in linear light (sRGB decode -> box/bilinear -> sRGB encode); see header note */
+/* Resize to one 512x512 layer the way the reference's bake does (stbir_resize_uint8_srgb(..., STBIR_RGBA),
+ * src/image_manager.hpp:52-62) — stb_image_resize2's defaults, restated: colour in linear light (sRGB decode
+ * / encode), alpha linear and used as a weight (colour is premultiplied by alpha + 2^-120 before filtering and
+ * divided afterwards), edge clamp, separable polyphase filtering with the Catmull-Rom kernel along an axis that
+ * is enlarged and the Mitchell-Netravali (B = C = 1/3) kernel, stretched by the scale, along one that is
+ * reduced; every output tap set is normalised to sum 1. stb evaluates the same sums in single precision with
+ * SIMD in a cost-chosen pass order and encodes sRGB through a table, so individual texels can differ by one
+ * (rarely two) code values (tests/test_image_codecs.py measures it against the reference's output); an image
+ * that already is 512x512 passes through untouched. */
+inline float resize_kernel_catmull_rom(float x) {
+    x = std::fabs(x);
+    if (x < 1.0f) return 1.0f - x * x * (2.5f - 1.5f * x);
+    if (x < 2.0f) return 2.0f - x * (4.0f + x * (0.5f * x - 2.5f));
+    return 0.0f;
+}
+inline float resize_kernel_mitchell(float x) {
+    x = std::fabs(x);
+    if (x < 1.0f) return (16.0f + x * x * (21.0f * x - 36.0f)) / 18.0f;
+    if (x < 2.0f) return (32.0f + x * (-60.0f + x * (36.0f - 7.0f * x))) / 18.0f;
+    return 0.0f;
+}
+struct ResizeTaps {
+    std::vector<int> first;               /* per output index: first input index (may be < 0: clamped when read) */
+    std::vector<std::vector<float>> w;    /* weights of first, first + 1, ... */
+};
+inline ResizeTaps resize_taps(int in_n, int out_n) {
+    ResizeTaps t;
+    t.first.resize(out_n);
+    t.w.resize(out_n);
+    const double scale = (double)out_n / (double)in_n;
+    for (int o = 0; o < out_n; o++) {
+        int lo, hi;
+        if (scale >= 1.0) { /* enlarge: kernel in input space, support 2 input pixels */
+            const double c = (o + 0.5) / scale;
+            lo = (int)std::floor(c - 2.0 + 0.5);
+            hi = (int)std::floor(c + 2.0 - 0.5);
+            for (int i = lo; i <= hi; i++) t.w[o].push_back(resize_kernel_catmull_rom((float)((i + 0.5) - c)));
+        } else { /* reduce: kernel in output space, support 2 output pixels = 2 / scale input pixels */
+            const double c = o + 0.5;
+            lo = (int)std::floor((c - 2.0) / scale - 0.5);
+            hi = (int)std::ceil((c + 2.0) / scale - 0.5);
+            for (int i = lo; i <= hi; i++) t.w[o].push_back(resize_kernel_mitchell((float)((i + 0.5) * scale - c)) * (float)scale);
+        }
+        t.first[o] = lo;
+        double sum = 0;
+        for (float v : t.w[o]) sum += v;
+        for (float &v : t.w[o]) v = (float)(v / sum);
+    }
+    return t;
+}
 inline std::vector<uint8_t> resize_to_layer(const std::vector<uint8_t> &src, uint32_t w, uint32_t h) {
     const uint32_t N = RT_TEX_SIZE;
     if (w == N && h == N) return src;
-    auto to_lin = [](uint8_t v) { float c = v / 255.0f; return c <= 0.04045f ? c / 12.92f : std::pow((c + 0.055f) / 1.055f, 2.4f); };
-    auto to_srgb = [](float l) {
-        float c = l <= 0.0031308f ? l * 12.92f : 1.055f * std::pow(l, 1.0f / 2.4f) - 0.055f;
-        return (uint8_t)std::lround(std::fmin(std::fmax(c, 0.0f), 1.0f) * 255.0f);
-    };
+    static float lin[256];
+    static bool lin_ready = false;
+    if (!lin_ready) {
+        for (int v = 0; v < 256; v++) {
+            const double c = v / 255.0;
+            lin[v] = (float)(c <= 0.04045 ? c / 12.92 : std::pow((c + 0.055) / 1.055, 2.4));
+        }
+        lin_ready = true;
+    }
+    const float tiny = std::ldexp(1.0f, -120);
+    /* decode: premultiplied linear colour + alpha */
+    std::vector<float> a((size_t)w * h * 4);
+    for (size_t i = 0; i < (size_t)w * h; i++) {
+        const float al = src[i * 4 + 3] / 255.0f + tiny;
+        for (int c = 0; c < 3; c++) a[i * 4 + c] = lin[src[i * 4 + c]] * al;
+        a[i * 4 + 3] = al;
+    }
+    /* vertical pass: h -> N rows */
+    const ResizeTaps ty = resize_taps((int)h, (int)N), tx = resize_taps((int)w, (int)N);
+    std::vector<float> b((size_t)w * N * 4, 0.0f);
+    for (uint32_t y = 0; y < N; y++)
+        for (size_t k = 0; k < ty.w[y].size(); k++) {
+            const int sy = std::min(std::max(ty.first[y] + (int)k, 0), (int)h - 1);
+            const float wt = ty.w[y][k];
+            const float *in = &a[(size_t)sy * w * 4];
+            float *o = &b[(size_t)y * w * 4];
+            for (size_t i = 0; i < (size_t)w * 4; i++) o[i] += wt * in[i];
+        }
+    /* horizontal pass + encode */
     std::vector<uint8_t> out((size_t)N * N * 4);
     for (uint32_t y = 0; y < N; y++)
         for (uint32_t x = 0; x < N; x++) {
-            const double x0 = (double)x * w / N, x1 = (double)(x + 1) * w / N, y0 = (double)y * h / N, y1 = (double)(y + 1) * h / N;
-            double acc[4] = {0, 0, 0, 0}, wsum = 0;
-            for (uint32_t sy = (uint32_t)y0; sy < h && sy < (uint32_t)std::ceil(y1); sy++)
-                for (uint32_t sx = (uint32_t)x0; sx < w && sx < (uint32_t)std::ceil(x1); sx++) {
-                    const double wx = std::fmin(x1, sx + 1.0) - std::fmax(x0, (double)sx), wy = std::fmin(y1, sy + 1.0) - std::fmax(y0, (double)sy);
-                    const double wt = std::fmax(wx, 1e-9) * std::fmax(wy, 1e-9);
-                    const uint8_t *p = &src[((size_t)sy * w + sx) * 4];
-                    for (int c = 0; c < 3; c++) acc[c] += wt * to_lin(p[c]);
-                    acc[3] += wt * p[3] / 255.0;
-                    wsum += wt;
-                }
+            float acc[4] = {0, 0, 0, 0};
+            for (size_t k = 0; k < tx.w[x].size(); k++) {
+                const int sx = std::min(std::max(tx.first[x] + (int)k, 0), (int)w - 1);
+                const float wt = tx.w[x][k];
+                const float *in = &b[((size_t)y * w + sx) * 4];
+                for (int c = 0; c < 4; c++) acc[c] += wt * in[c];
+            }
             uint8_t *o = &out[((size_t)y * N + x) * 4];
-            for (int c = 0; c < 3; c++) o[c] = to_srgb((float)(acc[c] / wsum));
-            o[3] = (uint8_t)std::lround(acc[3] / wsum * 255.0);
+            const float al = acc[3];
+            for (int c = 0; c < 3; c++) {
+                float l = al >= tiny ? acc[c] / al : acc[c];
+                l = std::fmin(std::fmax(l, 0.0f), 1.0f);
+                const double e = l <= 0.0031308f ? l * 12.92 : 1.055 * std::pow((double)l, 1.0 / 2.4) - 0.055;
+                o[c] = (uint8_t)std::lround(std::fmin(std::fmax(e, 0.0), 1.0) * 255.0);
+            }
+            o[3] = (uint8_t)std::fmin(std::fmax(std::floor((al - tiny) * 255.0f + 0.5f), 0.0f), 255.0f);
         }
     return out;
 }

@@ -45,7 +45,7 @@ def _png(rgba):
     return b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", w, h, 8, 6, 0, 0, 0)) + chunk(b"IDAT", zlib.compress(raw)) + chunk(b"IEND", b"")
 
 
-def _write_glb(path, tex):
+def _write_glb(path, tex, extra_images=()):
     """two meshes under a parent/child hierarchy, u8/u16/u32 indices, an interleaved (strided) vertex
     buffer, diffuse-textured / metallic / dielectric / emissive materials, sky extras, a camera node"""
     rs = np.random.RandomState(4)
@@ -79,6 +79,7 @@ def _write_glb(path, tex):
         prims.append({"attributes": {"POSITION": a[0], "NORMAL": a[1], "TEXCOORD_0": a[2]}, "indices": ia, "material": k})
         expect.append((pos, nrm, uv, idx.astype(np.uint32)))
     img_view = add_view(_png(tex))
+    extra_views = [(add_view(bytes(data)), mime) for data, mime in extra_images]
     prims.append({"attributes": prims[0]["attributes"], "indices": prims[0]["indices"]})   # no material: F15 fallback
     expect.append(expect[0])
     q = np.array([0.0, np.sin(0.35), 0.0, np.cos(0.35)])          # rotation about Y
@@ -101,7 +102,7 @@ def _write_glb(path, tex):
                         "emissiveFactor": [1.0, 1.0, 1.0]},       # no emissive_strength extension -> emissive 0
                        {"pbrMetallicRoughness": {"metallicFactor": 0.9},
                         "extensions": {"KHR_materials_ior": {"ior": 1.33}, "KHR_materials_transmission": {"transmissionFactor": 1}}}],
-         "textures": [{"source": 0}], "images": [{"bufferView": img_view, "mimeType": "image/png"}],
+         "textures": [{"source": 0}], "images": [{"bufferView": img_view, "mimeType": "image/png"}] + [{"bufferView": v, "mimeType": m} for v, m in extra_views],
          "accessors": accessors, "bufferViews": views, "buffers": [{"byteLength": sum(len(b) for b in blobs)}]}
     js = json.dumps(j).encode()
     js += b" " * ((-len(js)) % 4)
@@ -217,3 +218,24 @@ def test_cli_renders_a_glb_to_png(glb, oracle, scenes, tmp_path):
     assert "Total rays:" in r.stdout and "Writing image to disk" in r.stdout
     img = np.array(Image.open(png))
     assert img.shape == (64, 96, 4) and (img[..., 3] == 255).all() and img[..., :3].std() > 1.0
+
+
+def test_embedded_jpeg_and_small_png_are_baked_like_the_reference(glb, tmp_path):
+    """images other than a 512x512 RGBA PNG: a JPEG (4:2:0) and a palette PNG with tRNS, decoded to stb_image's
+    bytes (tests/golden/images.npz) and resized by the bake's filter"""
+    gold = np.load(os.path.join(ROOT, "tests", "golden", "images.npz"))
+    tex = (np.random.RandomState(1).rand(512, 512, 4) * 255).astype(np.uint8)
+    path = str(tmp_path / "images.glb")
+    _write_glb(path, tex, [(gold["in_jpg_baseline_420"], "image/jpeg"), (gold["in_png_palette_trns"], "image/png")])
+    h = glb.glb_load(path.encode())
+    assert h, glb.glb_last_error()
+    assert glb.glb_layer_count(h) == 3
+    layers = np.ctypeslib.as_array(glb.glb_layers(h), (3, 512, 512, 4))
+    assert np.array_equal(layers[0], tex)
+    glb.glb_resize_to_layer.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]
+    for k, name in ((1, "jpg_baseline_420"), (2, "png_palette_trns")):
+        src = np.ascontiguousarray(gold["out_" + name])
+        want = np.zeros((512, 512, 4), np.uint8)
+        glb.glb_resize_to_layer(src.ctypes.data, src.shape[1], src.shape[0], want.ctypes.data)
+        assert np.array_equal(layers[k], want)
+    glb.glb_free(h)
