@@ -422,6 +422,47 @@ struct Reader {
 };
 } // namespace detail
 
+/* bytes behind a glTF "uri": RFC 2397 data URI (base64) or a file relative to the directory of the .glb */
+inline std::vector<uint8_t> read_uri(const std::string &uri, const std::string &glb_path) {
+    if (uri.compare(0, 5, "data:") == 0) {
+        const size_t comma = uri.find(',');
+        if (comma == std::string::npos || comma < 7 || uri.compare(comma - 7, 7, ";base64") != 0)
+            throw std::runtime_error("Failed to load .glTF : unsupported data URI");
+        std::vector<uint8_t> out;
+        uint32_t acc = 0;
+        int bits = 0;
+        for (size_t i = comma + 1; i < uri.size(); i++) {
+            const char c = uri[i];
+            int v;
+            if (c >= 'A' && c <= 'Z') v = c - 'A';
+            else if (c >= 'a' && c <= 'z') v = c - 'a' + 26;
+            else if (c >= '0' && c <= '9') v = c - '0' + 52;
+            else if (c == '+' || c == '-') v = 62;
+            else if (c == '/' || c == '_') v = 63;
+            else continue; /* '=' padding, whitespace */
+            acc = (acc << 6) | (uint32_t)v;
+            bits += 6;
+            if (bits >= 8) {
+                bits -= 8;
+                out.push_back((uint8_t)(acc >> bits));
+            }
+        }
+        return out;
+    }
+    std::string decoded; /* percent-decoding, as tinygltf does before opening the file */
+    for (size_t i = 0; i < uri.size(); i++) {
+        if (uri[i] == '%' && i + 2 < uri.size() && isxdigit((unsigned char)uri[i + 1]) && isxdigit((unsigned char)uri[i + 2])) {
+            decoded.push_back((char)std::stoi(uri.substr(i + 1, 2), nullptr, 16));
+            i += 2;
+        } else decoded.push_back(uri[i]);
+    }
+    const size_t slash = glb_path.find_last_of("/\\");
+    const std::string full = (slash == std::string::npos || decoded[0] == '/') ? decoded : glb_path.substr(0, slash + 1) + decoded;
+    std::ifstream f(full, std::ios::binary);
+    if (!f) throw std::runtime_error("Failed to load .glTF : cannot open " + full);
+    return std::vector<uint8_t>((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+}
+
 inline LoadedScene load(const std::string &path, const float global_scale[3] = nullptr) {
     std::ifstream f(path, std::ios::binary);
     if (!f) throw std::runtime_error("Failed to load .glTF : cannot open " + path); /* src/scene.cpp:68-70 */
@@ -446,12 +487,23 @@ inline LoadedScene load(const std::string &path, const float global_scale[3] = n
     if (n_images > RT_MAX_IMAGES) throw std::runtime_error("Too many images uploaded"); /* src/image_manager.hpp:41-44 */
     for (size_t i = 0; i < n_images; i++) {
         const Json &im = j["images"][i];
-        if (!im.has("bufferView")) throw std::runtime_error("Failed to load .glTF : external image URIs are not supported");
-        size_t stride;
-        const Json &v = j["bufferViews"][(size_t)im["bufferView"].integer(0)];
-        const uint8_t *p = rd.view_ptr(im["bufferView"].integer(0), 0, stride);
+        std::vector<uint8_t> ext; /* an image given by "uri" (data: URI or a file next to the .glb, as tinygltf resolves it) */
+        const uint8_t *p = nullptr;
+        size_t n_bytes = 0;
+        if (im.has("bufferView")) {
+            size_t stride;
+            const Json &v = j["bufferViews"][(size_t)im["bufferView"].integer(0)];
+            p = rd.view_ptr(im["bufferView"].integer(0), 0, stride);
+            n_bytes = (size_t)v["byteLength"].integer(0);
+        } else if (im.has("uri")) {
+            ext = read_uri(im["uri"].str, path);
+            p = ext.data();
+            n_bytes = ext.size();
+        } else {
+            throw std::runtime_error("Failed to load .glTF : image without bufferView or uri");
+        }
         uint32_t w = 0, h = 0;
-        std::vector<uint8_t> px = png_decode(p, (size_t)v["byteLength"].integer(0), w, h);
+        std::vector<uint8_t> px = png_decode(p, n_bytes, w, h);
         std::vector<uint8_t> layer = resize_to_layer(px, w, h);
         out.texture_layers.insert(out.texture_layers.end(), layer.begin(), layer.end());
         out.texture_layer_count++;

@@ -45,7 +45,7 @@ def _png(rgba):
     return b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", w, h, 8, 6, 0, 0, 0)) + chunk(b"IDAT", zlib.compress(raw)) + chunk(b"IEND", b"")
 
 
-def _write_glb(path, tex, extra_images=()):
+def _write_glb(path, tex, extra_images=(), uri_images=()):
     """two meshes under a parent/child hierarchy, u8/u16/u32 indices, an interleaved (strided) vertex
     buffer, diffuse-textured / metallic / dielectric / emissive materials, sky extras, a camera node"""
     rs = np.random.RandomState(4)
@@ -102,7 +102,7 @@ def _write_glb(path, tex, extra_images=()):
                         "emissiveFactor": [1.0, 1.0, 1.0]},       # no emissive_strength extension -> emissive 0
                        {"pbrMetallicRoughness": {"metallicFactor": 0.9},
                         "extensions": {"KHR_materials_ior": {"ior": 1.33}, "KHR_materials_transmission": {"transmissionFactor": 1}}}],
-         "textures": [{"source": 0}], "images": [{"bufferView": img_view, "mimeType": "image/png"}] + [{"bufferView": v, "mimeType": m} for v, m in extra_views],
+         "textures": [{"source": 0}], "images": [{"bufferView": img_view, "mimeType": "image/png"}] + [{"bufferView": v, "mimeType": m} for v, m in extra_views] + [{"uri": u} for u in uri_images],
          "accessors": accessors, "bufferViews": views, "buffers": [{"byteLength": sum(len(b) for b in blobs)}]}
     js = json.dumps(j).encode()
     js += b" " * ((-len(js)) % 4)
@@ -239,3 +239,27 @@ def test_embedded_jpeg_and_small_png_are_baked_like_the_reference(glb, tmp_path)
         glb.glb_resize_to_layer(src.ctypes.data, src.shape[1], src.shape[0], want.ctypes.data)
         assert np.array_equal(layers[k], want)
     glb.glb_free(h)
+
+
+def test_images_by_uri(glb, tmp_path):
+    """tinygltf also resolves image "uri"s inside a .glb: base64 data URIs and files next to the .glb"""
+    import base64
+    gold = np.load(os.path.join(ROOT, "tests", "golden", "images.npz"))
+    tex = (np.random.RandomState(1).rand(512, 512, 4) * 255).astype(np.uint8)
+    (tmp_path / "side car.jpg").write_bytes(gold["in_jpg_progressive_422"].tobytes())
+    data_uri = "data:image/png;base64," + base64.b64encode(gold["in_png_h_rgb8_adam7"].tobytes()).decode()
+    path = str(tmp_path / "uris.glb")
+    _write_glb(path, tex, uri_images=[data_uri, "side%20car.jpg"])
+    h = glb.glb_load(path.encode())
+    assert h, glb.glb_last_error()
+    assert glb.glb_layer_count(h) == 3
+    layers = np.ctypeslib.as_array(glb.glb_layers(h), (3, 512, 512, 4))
+    glb.glb_resize_to_layer.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]
+    for k, name in ((1, "png_h_rgb8_adam7"), (2, "jpg_progressive_422")):
+        src = np.ascontiguousarray(gold["out_" + name])
+        want = np.zeros((512, 512, 4), np.uint8)
+        glb.glb_resize_to_layer(src.ctypes.data, src.shape[1], src.shape[0], want.ctypes.data)
+        assert np.array_equal(layers[k], want)
+    glb.glb_free(h)
+    _write_glb(path, tex, uri_images=["missing.png"])
+    assert not glb.glb_load(path.encode()) and b"cannot open" in glb.glb_last_error()
