@@ -144,6 +144,7 @@ inline Image decode(const uint8_t *d, size_t n) {
             const uint32_t pw = (uint32_t)(((int64_t)im.w - xo[p] + xs[p] - 1) / xs[p]), ph = (uint32_t)(((int64_t)im.h - yo[p] + ys[p] - 1) / ys[p]);
             if (pw && ph) raw_len += (stride_of(pw) + 1) * ph;
         }
+    if (raw_len > ((size_t)1 << 30)) fail("PNG: image too large");
     std::vector<uint8_t> raw(raw_len);
     {
         z_stream zs;
@@ -373,7 +374,7 @@ struct Decoder {
         if (t > 16) fail("JPEG: bad DC size");
         const int diff = t ? extend_receive(t) : 0;
         c.dc_pred += diff;
-        data[0] = (int16_t)(c.dc_pred * dq[0]);
+        data[0] = (int16_t)((int64_t)c.dc_pred * dq[0]);
         int k = 1;
         do {
             const int rs = decode(ac), s = rs & 15, r = rs >> 4;
@@ -395,7 +396,7 @@ struct Decoder {
             if (t > 16) fail("JPEG: bad DC size");
             const int diff = t ? extend_receive(t) : 0;
             c.dc_pred += diff;
-            data[0] = (int16_t)(c.dc_pred * (1 << succ_low));
+            data[0] = (int16_t)((int64_t)c.dc_pred * (1 << succ_low));
         } else if (get_bit()) {
             data[0] = (int16_t)(data[0] + (1 << succ_low));
         }
@@ -471,7 +472,7 @@ struct Decoder {
     static inline int f2f(double x) { return (int)(x * 4096 + 0.5); }
     static void idct(uint8_t *out, int stride, const int16_t d[64]) {
 #define RT_IDCT_1D(s0, s1, s2, s3, s4, s5, s6, s7)                                       \
-    int t0, t1, t2, t3, p1, p2, p3, p4, p5, x0, x1, x2, x3;                               \
+    int64_t t0, t1, t2, t3, p1, p2, p3, p4, p5, x0, x1, x2, x3; /* 64-bit: corrupt data cannot overflow */ \
     p2 = s2;                                                                             \
     p3 = s6;                                                                             \
     p1 = (p2 + p3) * c0541;                                                              \
@@ -517,20 +518,20 @@ struct Decoder {
             } else {
                 RT_IDCT_1D(d[0], d[8], d[16], d[24], d[32], d[40], d[48], d[56])
                 x0 += 512; x1 += 512; x2 += 512; x3 += 512;
-                v[0] = (x0 + t3) >> 10;  v[56] = (x0 - t3) >> 10;
-                v[8] = (x1 + t2) >> 10;  v[48] = (x1 - t2) >> 10;
-                v[16] = (x2 + t1) >> 10; v[40] = (x2 - t1) >> 10;
-                v[24] = (x3 + t0) >> 10; v[32] = (x3 - t0) >> 10;
+                v[0] = (int)((x0 + t3) >> 10);  v[56] = (int)((x0 - t3) >> 10);
+                v[8] = (int)((x1 + t2) >> 10);  v[48] = (int)((x1 - t2) >> 10);
+                v[16] = (int)((x2 + t1) >> 10); v[40] = (int)((x2 - t1) >> 10);
+                v[24] = (int)((x3 + t0) >> 10); v[32] = (int)((x3 - t0) >> 10);
             }
         }
         v = val;
         for (int i = 0; i < 8; i++, v += 8, out += stride) {
             RT_IDCT_1D(v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7])
             x0 += 65536 + (128 << 17); x1 += 65536 + (128 << 17); x2 += 65536 + (128 << 17); x3 += 65536 + (128 << 17);
-            out[0] = clamp8((x0 + t3) >> 17); out[7] = clamp8((x0 - t3) >> 17);
-            out[1] = clamp8((x1 + t2) >> 17); out[6] = clamp8((x1 - t2) >> 17);
-            out[2] = clamp8((x2 + t1) >> 17); out[5] = clamp8((x2 - t1) >> 17);
-            out[3] = clamp8((x3 + t0) >> 17); out[4] = clamp8((x3 - t0) >> 17);
+            out[0] = clamp8((int)((x0 + t3) >> 17)); out[7] = clamp8((int)((x0 - t3) >> 17));
+            out[1] = clamp8((int)((x1 + t2) >> 17)); out[6] = clamp8((int)((x1 - t2) >> 17));
+            out[2] = clamp8((int)((x2 + t1) >> 17)); out[5] = clamp8((int)((x2 - t1) >> 17));
+            out[3] = clamp8((int)((x3 + t0) >> 17)); out[4] = clamp8((int)((x3 - t0) >> 17));
         }
 #undef RT_IDCT_1D
     }
@@ -545,6 +546,11 @@ struct Decoder {
     }
     void scan() {
         reset_entropy();
+        for (int k = 0; k < scan_n; k++) { /* the tables this scan decodes with must have been defined */
+            const Component &c = comp[order[k]];
+            const bool need_dc = !progressive || spec_start == 0, need_ac = !progressive || spec_start != 0;
+            if ((need_dc && !(progressive && succ_high) && !hdc[c.hd].present) || (need_ac && !hac[c.ha].present)) fail("JPEG: scan uses an undefined Huffman table");
+        }
         int16_t blk[64];
         if (!progressive) {
             if (scan_n == 1) {
@@ -642,6 +648,7 @@ struct Decoder {
         img_h = get16();
         img_w = get16();
         if (!img_h || !img_w) fail("JPEG: bad size");
+        if ((size_t)img_h * (size_t)img_w > ((size_t)1 << 28)) fail("JPEG: image too large");
         ncomp = get8();
         if (ncomp != 1 && ncomp != 3) fail(ncomp == 4 ? "JPEG: CMYK / YCCK is not supported" : "JPEG: bad component count");
         if (len != 8 + 3 * ncomp) fail("JPEG: bad SOF length");
