@@ -374,6 +374,7 @@ struct Decoder {
         if (t > 16) fail("JPEG: bad DC size");
         const int diff = t ? extend_receive(t) : 0;
         c.dc_pred += diff;
+        if (c.dc_pred > (1 << 24) || c.dc_pred < -(1 << 24)) fail("JPEG: bad DC delta");
         data[0] = (int16_t)((int64_t)c.dc_pred * dq[0]);
         int k = 1;
         do {
@@ -396,6 +397,7 @@ struct Decoder {
             if (t > 16) fail("JPEG: bad DC size");
             const int diff = t ? extend_receive(t) : 0;
             c.dc_pred += diff;
+            if (c.dc_pred > (1 << 24) || c.dc_pred < -(1 << 24)) fail("JPEG: bad DC delta");
             data[0] = (int16_t)((int64_t)c.dc_pred * (1 << succ_low));
         } else if (get_bit()) {
             data[0] = (int16_t)(data[0] + (1 << succ_low));
