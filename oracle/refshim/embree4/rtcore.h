@@ -5,6 +5,7 @@
  * brute-force closest-hit search (refshim.cpp), everything else is a stub.
  */
 #pragma once
+#include <cstddef>
 #include <cstdint>
 #define RTC_INVALID_GEOMETRY_ID ((unsigned int)-1)
 #define RTC_MAX_INSTANCE_LEVEL_COUNT 1
@@ -29,6 +30,21 @@ typedef struct RTCDeviceTy *RTCDevice;
 typedef struct RTCGeometryTy *RTCGeometry;
 void rtcIntersect1(RTCScene scene, RTCRayHit *rayhit);
 void *rtcGetGeometryUserDataFromScene(RTCScene scene, unsigned int geomID);
+/* scene construction (src/scene.cpp): recorded by oracle/refshim/scenref.cpp, unused elsewhere */
+enum RTCGeometryType { RTC_GEOMETRY_TYPE_TRIANGLE = 0, RTC_GEOMETRY_TYPE_INSTANCE = 121 };
+enum RTCBufferType { RTC_BUFFER_TYPE_INDEX = 0, RTC_BUFFER_TYPE_VERTEX = 1 };
+enum RTCFormat { RTC_FORMAT_UINT3 = 0x5003, RTC_FORMAT_FLOAT3 = 0x9003, RTC_FORMAT_FLOAT4X4_COLUMN_MAJOR = 0x9244 };
+RTCScene rtcNewScene(RTCDevice device);
+RTCGeometry rtcNewGeometry(RTCDevice device, RTCGeometryType type);
+void rtcSetSharedGeometryBuffer(RTCGeometry geometry, RTCBufferType type, unsigned int slot, RTCFormat format, const void *ptr,
+                                size_t byteOffset, size_t byteStride, size_t itemCount);
+void rtcCommitGeometry(RTCGeometry geometry);
+unsigned int rtcAttachGeometry(RTCScene scene, RTCGeometry geometry);
+void rtcCommitScene(RTCScene scene);
+void rtcSetGeometryTimeStepCount(RTCGeometry geometry, unsigned int timeStepCount);
+void rtcSetGeometryInstancedScene(RTCGeometry geometry, RTCScene scene);
+void rtcSetGeometryTransform(RTCGeometry geometry, unsigned int timeStep, RTCFormat format, const void *xfm);
+void rtcSetGeometryUserData(RTCGeometry geometry, void *ptr);
 inline void rtcReleaseGeometry(RTCGeometry) {}
 inline void rtcReleaseScene(RTCScene) {}
 inline void rtcReleaseDevice(RTCDevice) {}

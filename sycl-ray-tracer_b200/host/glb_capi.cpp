@@ -13,6 +13,15 @@ void *glb_load(const char *path) {
         return nullptr;
     }
 }
+void *glb_load_scaled(const char *path, float sx, float sy, float sz) { /* Scene(app, path, global_scale), src/scene.hpp:91-93 */
+    try {
+        const float gs[3] = {sx, sy, sz};
+        return new LoadedScene(raytracer::glb::load(path, gs));
+    } catch (const std::exception &e) {
+        g_err = e.what();
+        return nullptr;
+    }
+}
 const char *glb_last_error() { return g_err.c_str(); }
 void glb_free(void *h) { delete (LoadedScene *)h; }
 uint32_t glb_instance_count(void *h) { return (uint32_t)((LoadedScene *)h)->instances.size(); }

@@ -237,8 +237,9 @@ inline bool png_write(const std::string &path, const uint8_t *rgba, uint32_t w, 
 
 /* Resize to one 512x512 layer the way the reference's bake does (stbir_resize_uint8_srgb(..., STBIR_RGBA),
  * src/image_manager.hpp:52-62) — stb_image_resize2's defaults, restated: colour in linear light (sRGB decode
- * / encode), alpha linear and used as a weight (colour is premultiplied by alpha + 2^-120 before filtering and
- * divided afterwards), edge clamp, separable polyphase filtering with the Catmull-Rom kernel along an axis that
+ / encode), alpha linear and used as a weight ("fancy" alpha weighting: colour and alpha-weighted colour are
+ * both filtered, the quotient weighted / alpha is the result unless the filtered alpha is below 2^-120, where the
+ * plainly filtered colour is kept), edge clamp, separable polyphase filtering with the Catmull-Rom kernel along an axis that
  * is enlarged and the Mitchell-Netravali (B = C = 1/3) kernel, stretched by the scale, along one that is
  * reduced; every output tap set is normalised to sum 1. stb evaluates the same sums in single precision with
  * SIMD in a cost-chosen pass order and encodes sRGB through a table, so individual texels can differ by one
@@ -298,44 +299,49 @@ inline std::vector<uint8_t> resize_to_layer(const std::vector<uint8_t> &src, uin
         lin_ready = true;
     }
     const float tiny = std::ldexp(1.0f, -120);
-    /* decode: premultiplied linear colour + alpha */
-    std::vector<float> a((size_t)w * h * 4);
+    /* decode to 7 planes per pixel: linear colour, alpha, alpha-weighted linear colour ("fancy" alpha weighting:
+     * where the filtered alpha vanishes the plainly filtered colour is kept instead of dividing by ~0) */
+    const int CH = 7;
+    std::vector<float> a((size_t)w * h * CH);
     for (size_t i = 0; i < (size_t)w * h; i++) {
-        const float al = src[i * 4 + 3] / 255.0f + tiny;
-        for (int c = 0; c < 3; c++) a[i * 4 + c] = lin[src[i * 4 + c]] * al;
-        a[i * 4 + 3] = al;
+        const float al = src[i * 4 + 3] / 255.0f;
+        for (int c = 0; c < 3; c++) {
+            a[i * CH + c] = lin[src[i * 4 + c]];
+            a[i * CH + 4 + c] = lin[src[i * 4 + c]] * al;
+        }
+        a[i * CH + 3] = al;
     }
     /* vertical pass: h -> N rows */
     const ResizeTaps ty = resize_taps((int)h, (int)N), tx = resize_taps((int)w, (int)N);
-    std::vector<float> b((size_t)w * N * 4, 0.0f);
+    std::vector<float> b((size_t)w * N * CH, 0.0f);
     for (uint32_t y = 0; y < N; y++)
         for (size_t k = 0; k < ty.w[y].size(); k++) {
             const int sy = std::min(std::max(ty.first[y] + (int)k, 0), (int)h - 1);
             const float wt = ty.w[y][k];
-            const float *in = &a[(size_t)sy * w * 4];
-            float *o = &b[(size_t)y * w * 4];
-            for (size_t i = 0; i < (size_t)w * 4; i++) o[i] += wt * in[i];
+            const float *in = &a[(size_t)sy * w * CH];
+            float *o = &b[(size_t)y * w * CH];
+            for (size_t i = 0; i < (size_t)w * CH; i++) o[i] += wt * in[i];
         }
     /* horizontal pass + encode */
     std::vector<uint8_t> out((size_t)N * N * 4);
     for (uint32_t y = 0; y < N; y++)
         for (uint32_t x = 0; x < N; x++) {
-            float acc[4] = {0, 0, 0, 0};
+            float acc[CH] = {0, 0, 0, 0, 0, 0, 0};
             for (size_t k = 0; k < tx.w[x].size(); k++) {
                 const int sx = std::min(std::max(tx.first[x] + (int)k, 0), (int)w - 1);
                 const float wt = tx.w[x][k];
-                const float *in = &b[((size_t)y * w + sx) * 4];
-                for (int c = 0; c < 4; c++) acc[c] += wt * in[c];
+                const float *in = &b[((size_t)y * w + sx) * CH];
+                for (int c = 0; c < CH; c++) acc[c] += wt * in[c];
             }
             uint8_t *o = &out[((size_t)y * N + x) * 4];
             const float al = acc[3];
             for (int c = 0; c < 3; c++) {
-                float l = al >= tiny ? acc[c] / al : acc[c];
+                float l = al >= tiny ? acc[4 + c] / al : acc[c];
                 l = std::fmin(std::fmax(l, 0.0f), 1.0f);
                 const double e = l <= 0.0031308f ? l * 12.92 : 1.055 * std::pow((double)l, 1.0 / 2.4) - 0.055;
                 o[c] = (uint8_t)std::lround(std::fmin(std::fmax(e, 0.0), 1.0) * 255.0);
             }
-            o[3] = (uint8_t)std::fmin(std::fmax(std::floor((al - tiny) * 255.0f + 0.5f), 0.0f), 255.0f);
+            o[3] = (uint8_t)std::fmin(std::fmax(std::floor(al * 255.0f + 0.5f), 0.0f), 255.0f);
         }
     return out;
 }
@@ -606,10 +612,30 @@ inline LoadedScene load(const std::string &path, const float global_scale[3] = n
     if (camera_node >= 0) {
         const Mat4 m = global_matrix(camera_node);
         for (int k = 0; k < 3; k++) out.camera_position[k] = m.m[12 + k];
-        /* rotation * (0,0,-1) with the rotation part normalised (glm::quat_cast of the 3x3) */
-        float c2[3] = {m.m[8], m.m[9], m.m[10]};
-        const float len = std::sqrt(c2[0] * c2[0] + c2[1] * c2[1] + c2[2] * c2[2]);
-        for (int k = 0; k < 3; k++) out.camera_direction[k] = len > 0 ? -c2[k] / len : (k == 2 ? -1.0f : 0.0f);
+        /* glm::quat_cast of the global matrix's upper 3x3 — scale and all, as the reference does (:116) —
+         * then normalize(q * (0,0,-1)) (:120-121). With a pure rotation (and uniform scale) this is minus the
+         * third column, normalised; a non-uniform scale above the camera skews it exactly like the reference. */
+        const float m00 = m.m[0], m01 = m.m[1], m02 = m.m[2], m10 = m.m[4], m11 = m.m[5], m12 = m.m[6], m20 = m.m[8], m21 = m.m[9], m22 = m.m[10];
+        const float fx = m00 - m11 - m22, fy = m11 - m00 - m22, fz = m22 - m00 - m11, fw = m00 + m11 + m22;
+        int big = 0;
+        float fb = fw;
+        if (fx > fb) { fb = fx; big = 1; }
+        if (fy > fb) { fb = fy; big = 2; }
+        if (fz > fb) { fb = fz; big = 3; }
+        const float bv = std::sqrt(fb + 1.0f) * 0.5f, mult = 0.25f / bv;
+        float qw, qx, qy, qz;
+        if (big == 0) { qw = bv; qx = (m12 - m21) * mult; qy = (m20 - m02) * mult; qz = (m01 - m10) * mult; }
+        else if (big == 1) { qw = (m12 - m21) * mult; qx = bv; qy = (m01 + m10) * mult; qz = (m20 + m02) * mult; }
+        else if (big == 2) { qw = (m20 - m02) * mult; qx = (m01 + m10) * mult; qy = bv; qz = (m12 + m21) * mult; }
+        else { qw = (m01 - m10) * mult; qx = (m20 + m02) * mult; qy = (m12 + m21) * mult; qz = bv; }
+        /* q * v = v + 2 * (w * (qv x v) + qv x (qv x v)), v = (0, 0, -1) */
+        const float v[3] = {0.0f, 0.0f, -1.0f}, qv[3] = {qx, qy, qz};
+        const float uv[3] = {qv[1] * v[2] - v[1] * qv[2], qv[2] * v[0] - v[2] * qv[0], qv[0] * v[1] - v[0] * qv[1]};
+        const float uuv[3] = {qv[1] * uv[2] - uv[1] * qv[2], qv[2] * uv[0] - uv[2] * qv[0], qv[0] * uv[1] - uv[0] * qv[1]};
+        float d[3];
+        for (int k = 0; k < 3; k++) d[k] = v[k] + ((uv[k] * qw) + uuv[k]) * 2.0f;
+        const float inv = 1.0f / std::sqrt((d[0] * d[0] + d[1] * d[1]) + d[2] * d[2]);
+        for (int k = 0; k < 3; k++) out.camera_direction[k] = d[k] * inv;
         const Json &cam = j["cameras"][(size_t)j["nodes"][(size_t)camera_node]["camera"].integer(0)];
         const float yfov = (float)cam["perspective"]["yfov"].number(1.0);
         out.camera_focal_length = 1.0f / std::tan(yfov / 2.0f);

@@ -45,7 +45,7 @@ def _png(rgba):
     return b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", w, h, 8, 6, 0, 0, 0)) + chunk(b"IDAT", zlib.compress(raw)) + chunk(b"IEND", b"")
 
 
-def _write_glb(path, tex, extra_images=(), uri_images=()):
+def _write_glb(path, tex, extra_images=(), uri_images=(), f15=True):
     """two meshes under a parent/child hierarchy, u8/u16/u32 indices, an interleaved (strided) vertex
     buffer, diffuse-textured / metallic / dielectric / emissive materials, sky extras, a camera node"""
     rs = np.random.RandomState(4)
@@ -81,6 +81,8 @@ def _write_glb(path, tex, extra_images=(), uri_images=()):
     img_view = add_view(_png(tex))
     extra_views = [(add_view(bytes(data)), mime) for data, mime in extra_images]
     prims.append({"attributes": prims[0]["attributes"], "indices": prims[0]["indices"]})   # no material: F15 fallback
+    if not f15:                      # ... which is undefined behaviour in the reference loader itself (materials[-1])
+        prims[-1]["material"] = 1
     expect.append(expect[0])
     q = np.array([0.0, np.sin(0.35), 0.0, np.cos(0.35)])          # rotation about Y
     qc = np.array([np.sin(0.2), 0.0, 0.0, np.cos(0.2)])           # camera pitch
@@ -263,3 +265,76 @@ def test_images_by_uri(glb, tmp_path):
     glb.glb_free(h)
     _write_glb(path, tex, uri_images=["missing.png"])
     assert not glb.glb_load(path.encode()) and b"cannot open" in glb.glb_last_error()
+
+
+def _mine_scaled(glb, pkg, path, scale):
+    """host/glb_loader.hpp's view of a .glb in the same shape as tests/_scenref.load()"""
+    h = glb.glb_load_scaled(path.encode(), *[float(v) for v in scale])
+    assert h, glb.glb_last_error()
+    out = {"instances": []}
+    fp, up = C.POINTER(C.c_float), C.POINTER(C.c_uint32)
+    for i in range(glb.glb_instance_count(h)):
+        nv, ni = C.c_uint32(), C.c_uint32()
+        pos, nrm, uv, idx = fp(), fp(), fp(), up()
+        T, mat, nmp = (C.c_float * 16)(), pkg._capi.rt_material(), (C.c_int32 * 3)()
+        glb.glb_instance(h, i, C.byref(nv), C.byref(ni), C.byref(pos), C.byref(nrm), C.byref(uv), C.byref(idx), T, C.byref(mat), nmp)
+        out["instances"].append(dict(
+            positions=np.ctypeslib.as_array(pos, (nv.value, 3)).copy(), normals=np.ctypeslib.as_array(nrm, (nv.value, 3)).copy(),
+            uvs=np.ctypeslib.as_array(uv, (nv.value, 2)).copy(), indices=np.ctypeslib.as_array(idx, (ni.value,)).copy(),
+            transform=np.array(T, np.float32), type=mat.type, albedo_image=mat.albedo_image, albedo=np.array(mat.albedo_color, np.float32),
+            roughness=mat.roughness, ior=mat.ior, emissive=np.array(mat.emissive, np.float32)))
+    g = (C.c_float * 16)()
+    glb.glb_globals(h, g)
+    out.update(sky=np.array(g[0:3], np.float32), camera_position=np.array(g[3:6], np.float32), camera_direction=np.array(g[6:9], np.float32),
+               focal=float(g[9]))
+    n = glb.glb_layer_count(h)
+    out["layers"] = list(np.ctypeslib.as_array(glb.glb_layers(h), (n, 512, 512, 4)).copy()) if n else []
+    glb.glb_free(h)
+    return out
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/src"), reason="needs the reference sources (build container only)")
+def test_loader_equals_the_references_own_loader(glb, pkg, oracle, tmp_path):
+    """the reference's OWN src/scene.cpp (+ its vendored tinygltf / stb), compiled in place through the API shims
+    (oracle/refshim/scenref.cpp -> oracle/_ref/libscenref.so), loads the same .glb files: instance order,
+    buffers, transforms, normal matrices, material records, sky, camera and baked image layers must agree"""
+    import _scenref
+    gold = np.load(os.path.join(ROOT, "tests", "golden", "images.npz"))
+    tex = (np.random.RandomState(1).rand(512, 512, 4) * 255).astype(np.uint8)
+    path = str(tmp_path / "both.glb")
+    _write_glb(path, tex, [(gold["in_jpg_baseline_420"], "image/jpeg"), (gold["in_png_palette_trns"], "image/png")], f15=False)
+    for scale in ((1.0, 1.0, 1.0), (0.5, 2.0, 3.0)):
+        ref = _scenref.load(path, scale)
+        subprocess.run(["make", "-s", "-C", HOST], check=True)
+        glb.glb_load_scaled.restype = C.c_void_p
+        glb.glb_load_scaled.argtypes = [C.c_char_p, C.c_float, C.c_float, C.c_float]
+        mine = _mine_scaled(glb, pkg, path, scale)
+        assert len(mine["instances"]) == len(ref["instances"]) == 7
+        TYPE = {1: pkg._capi.RT_MAT_DIFFUSE, 2: pkg._capi.RT_MAT_METALLIC, 3: pkg._capi.RT_MAT_DIELECTRIC}
+        for a, b in zip(mine["instances"], ref["instances"]):
+            for k in ("positions", "normals", "uvs", "indices"):
+                assert np.array_equal(a[k], b[k]), k
+            assert np.allclose(a["transform"], b["transform"], rtol=2e-6, atol=1e-6)
+            assert a["type"] == TYPE[b["type"]]
+            if b["type"] != 3:
+                assert a["albedo_image"] == (b["albedo_image"] if b["albedo_is_image"] else -1)
+                if not b["albedo_is_image"]:
+                    assert np.array_equal(a["albedo"], b["albedo"])
+                assert np.array_equal(a["emissive"], b["emissive"])
+            if b["type"] == 2:
+                assert a["roughness"] == b["roughness"]
+            if b["type"] == 3:
+                assert a["ior"] == b["ior"]
+            # the normal matrix of the reference's GeometryData against the oracle's restatement, same matrix in
+            nm = np.zeros(9, np.float32)
+            oracle.lib().orc_normal_matrix(np.ascontiguousarray(b["transform"]).ctypes.data_as(oracle.f32p), nm.ctypes.data_as(oracle.f32p))
+            assert np.array_equal(nm.view(np.uint32), b["normal_matrix"].view(np.uint32))
+        assert np.array_equal(mine["sky"], ref["sky"])
+        assert np.allclose(mine["camera_position"], ref["camera_position"], atol=1e-6)
+        assert np.allclose(mine["camera_direction"], ref["camera_direction"], atol=1e-6)
+        assert np.isclose(mine["focal"], ref["focal"], rtol=1e-6)
+        assert len(mine["layers"]) == len(ref["layers"]) == 3
+        assert np.array_equal(mine["layers"][0], ref["layers"][0])            # 512x512: verbatim in both
+        for k in (1, 2):                                                       # resized: within one code value
+            d = np.abs(mine["layers"][k].astype(int) - ref["layers"][k].astype(int))
+            assert d.max() <= 1 and (d > 0).mean() < 0.02

@@ -24,8 +24,10 @@ RESIZE_PROCEDURAL = [(700, 600, 21), (1000, 100, 22), (515, 2048, 23), (512, 300
 
 
 def stbref():
-    subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "ref"], check=True)
-    L = C.CDLL(os.path.join(ROOT, "oracle", "_ref", "libstbref.so"))
+    so = os.path.join(ROOT, "oracle", "_ref", "libstbref.so")
+    if not os.path.exists(so):
+        subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "ref"], check=True)
+    L = C.CDLL(so)
     L.stbref_load_rgba.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_void_p, C.c_int]
     L.stbref_resize_srgb_rgba.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int]
     L.stbref_failure_reason.restype = C.c_char_p
