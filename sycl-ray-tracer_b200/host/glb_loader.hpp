@@ -24,7 +24,9 @@
  *     reference in the filtered texels (documented gap).
  *
  * Explicit fallbacks where the reference relies on undefined behaviour (F15): a primitive without a
- * material -> diffuse 0.8 grey; no camera node -> position (0,0,0), direction (0,0,-1), focal 1.
+ * material -> diffuse 0.8 grey; no camera node -> position (0,0,0), direction (0,0,-1), focal 1. (The reference
+ * tests `if (camera_node_index)` with -1 meaning "none", :109, so it also skips a camera that is node 0 and
+ * leaves the camera fields uninitialised; here node 0 is a camera like any other.)
  */
 #pragma once
 
