@@ -65,10 +65,16 @@ struct Json {
         auto it = obj.find(k);
         return it == obj.end() ? null_json : it->second;
     }
-    const Json &operator[](size_t i) const { return arr[i]; }
+    const Json &operator[](size_t i) const { /* out of range (also a negative index cast to size_t): null, like a missing key */
+        static const Json null_json;
+        return (type == Arr && i < arr.size()) ? arr[i] : null_json;
+    }
     size_t size() const { return type == Arr ? arr.size() : 0; }
     double number(double dflt) const { return type == Num ? num : dflt; }
-    int integer(int dflt) const { return type == Num ? (int)num : dflt; }
+    int integer(int dflt) const {
+        if (type != Num || !(num == num)) return dflt;
+        return num >= 2147483647.0 ? 2147483647 : (num <= -2147483648.0 ? (-2147483647 - 1) : (int)num);
+    }
 };
 
 class JsonParser {
@@ -394,36 +400,53 @@ namespace detail {
 struct Reader {
     Json j;
     std::vector<uint8_t> bin;
-    const uint8_t *view_ptr(int view, size_t extra, size_t &stride_out) const {
+    [[noreturn]] static void bad(const char *what) { throw std::runtime_error(std::string("Failed to load .glTF : ") + what); }
+    /* start of a buffer view (+ extra bytes) and how many bytes remain in it; every read is checked against that */
+    const uint8_t *view_ptr(int view, size_t extra, size_t &stride_out, size_t *avail_out = nullptr) const {
+        if (view < 0 || (size_t)view >= j["bufferViews"].size()) bad("bufferView index out of range");
         const Json &v = j["bufferViews"][(size_t)view];
-        stride_out = (size_t)v["byteStride"].integer(0);
-        const size_t off = (size_t)v["byteOffset"].integer(0) + extra;
-        if (off > bin.size()) throw std::runtime_error("Failed to load .glTF : buffer view out of range");
-        return bin.data() + off;
+        if (v["buffer"].integer(0) != 0) bad("only the GLB-embedded buffer 0 is supported");
+        const int off_i = v["byteOffset"].integer(0), len_i = v["byteLength"].integer(0), stride_i = v["byteStride"].integer(0);
+        if (off_i < 0 || len_i < 0 || stride_i < 0 || stride_i > 4096) bad("bad bufferView");
+        stride_out = (size_t)stride_i;
+        const size_t off = (size_t)off_i, len = (size_t)len_i;
+        if (off > bin.size() || len > bin.size() - off || extra > len) bad("buffer view out of range");
+        if (avail_out) *avail_out = len - extra;
+        return bin.data() + off + extra;
+    }
+    const Json &accessor_at(int accessor) const {
+        if (accessor < 0 || (size_t)accessor >= j["accessors"].size()) bad("accessor index out of range");
+        const Json &a = j["accessors"][(size_t)accessor];
+        if (a["byteOffset"].integer(0) < 0 || a["count"].integer(0) < 0) bad("bad accessor");
+        if (a.has("sparse")) bad("sparse accessors are not supported");
+        return a;
     }
     std::vector<float> floats(int accessor, int comps) const {
-        const Json &a = j["accessors"][(size_t)accessor];
-        if (a["componentType"].integer(0) != 5126) throw std::runtime_error("Failed to load .glTF : float accessor expected");
-        size_t stride = 0;
-        const uint8_t *p = view_ptr(a["bufferView"].integer(0), (size_t)a["byteOffset"].integer(0), stride);
+        const Json &a = accessor_at(accessor);
+        if (a["componentType"].integer(0) != 5126) bad("float accessor expected");
+        size_t stride = 0, avail = 0;
+        const uint8_t *p = view_ptr(a["bufferView"].integer(-1), (size_t)a["byteOffset"].integer(0), stride, &avail);
         if (!stride) stride = (size_t)comps * 4;
         const size_t n = (size_t)a["count"].integer(0);
+        if (n && ((n - 1) > (avail / stride) || (n - 1) * stride + (size_t)comps * 4 > avail)) bad("accessor reads past its buffer view");
         std::vector<float> out(n * comps);
         for (size_t i = 0; i < n; i++) memcpy(&out[i * comps], p + i * stride, (size_t)comps * 4);
         return out;
     }
     std::vector<uint32_t> indices(int accessor) const {
-        const Json &a = j["accessors"][(size_t)accessor];
-        size_t stride = 0;
-        const uint8_t *p = view_ptr(a["bufferView"].integer(0), (size_t)a["byteOffset"].integer(0), stride);
+        const Json &a = accessor_at(accessor);
+        size_t stride = 0, avail = 0;
+        const uint8_t *p = view_ptr(a["bufferView"].integer(-1), (size_t)a["byteOffset"].integer(0), stride, &avail);
         const size_t n = (size_t)a["count"].integer(0);
         const int ct = a["componentType"].integer(0);
+        const size_t es = ct == 5125 ? 4 : ct == 5123 ? 2 : ct == 5121 ? 1 : 0;
+        if (!es) throw std::runtime_error("Index component type not supported!"); /* src/scene.cpp:394-400 */
+        if (n > avail / es) bad("accessor reads past its buffer view");
         std::vector<uint32_t> out(n);
         for (size_t i = 0; i < n; i++) {
             if (ct == 5125) { uint32_t v; memcpy(&v, p + i * 4, 4); out[i] = v; }
             else if (ct == 5123) { uint16_t v; memcpy(&v, p + i * 2, 2); out[i] = v; }
-            else if (ct == 5121) out[i] = p[i];
-            else throw std::runtime_error("Index component type not supported!"); /* src/scene.cpp:394-400 */
+            else out[i] = p[i];
         }
         return out;
     }
@@ -491,6 +514,7 @@ inline LoadedScene load(const std::string &path, const float global_scale[3] = n
     const float *gs = global_scale ? global_scale : gs_default;
 
     /* images -> 512x512 layers (src/scene.cpp:148-162) */
+    if (j.type != Json::Obj) throw std::runtime_error("Failed to load .glTF : no JSON chunk");
     const size_t n_images = j["images"].size();
     if (n_images > RT_MAX_IMAGES) throw std::runtime_error("Too many images uploaded"); /* src/image_manager.hpp:41-44 */
     for (size_t i = 0; i < n_images; i++) {
@@ -500,9 +524,7 @@ inline LoadedScene load(const std::string &path, const float global_scale[3] = n
         size_t n_bytes = 0;
         if (im.has("bufferView")) {
             size_t stride;
-            const Json &v = j["bufferViews"][(size_t)im["bufferView"].integer(0)];
-            p = rd.view_ptr(im["bufferView"].integer(0), 0, stride);
-            n_bytes = (size_t)v["byteLength"].integer(0);
+            p = rd.view_ptr(im["bufferView"].integer(-1), 0, stride, &n_bytes);
         } else if (im.has("uri")) {
             ext = read_uri(im["uri"].str, path);
             p = ext.data();
@@ -539,11 +561,15 @@ inline LoadedScene load(const std::string &path, const float global_scale[3] = n
     while (!stack.empty()) {
         const int n = stack.back();
         stack.pop_back();
+        if (n < 0 || (size_t)n >= n_nodes) throw std::runtime_error("Failed to load .glTF : node index out of range");
+        if (reached[(size_t)n]) continue; /* a valid glTF is a forest; never follow a node twice (cycles) */
         reached[(size_t)n] = 1;
         const Json &nd = j["nodes"][(size_t)n];
         if (nd.has("camera")) camera_node = n;
         for (size_t k = 0; k < nd["children"].size(); k++) {
-            const int c = nd["children"][k].integer(0);
+            const int c = nd["children"][k].integer(-1);
+            if (c < 0 || (size_t)c >= n_nodes) throw std::runtime_error("Failed to load .glTF : node index out of range");
+            if (reached[(size_t)c]) continue;
             parent[(size_t)c] = n;
             stack.push_back(c);
         }
@@ -592,7 +618,8 @@ inline LoadedScene load(const std::string &path, const float global_scale[3] = n
                 if (ext.has("KHR_materials_emissive_strength")) strength = (float)ext["KHR_materials_emissive_strength"]["emissiveStrength"].number(1.0);
                 for (int k = 0; k < 3; k++) m.emissive[k] = (mat["emissiveFactor"].size() == 3 ? (float)mat["emissiveFactor"][k].num : 0.0f) * strength;
                 const int tex = pbr["baseColorTexture"]["index"].integer(-1);
-                const int image = tex >= 0 ? j["textures"][(size_t)tex]["source"].integer(-1) : -1;
+                int image = tex >= 0 ? j["textures"][(size_t)tex]["source"].integer(-1) : -1;
+                if (image < -1 || image >= (int)n_images) throw std::runtime_error("Failed to load .glTF : texture source out of range");
                 if (ext.has("KHR_materials_ior") && ext.has("KHR_materials_transmission")) {
                     m.type = RT_MAT_DIELECTRIC;
                     m.ior = (float)ext["KHR_materials_ior"]["ior"].number(1.5);

