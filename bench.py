@@ -263,7 +263,6 @@ def main():
     if args.impl == "reference":
         return run_reference(args)
 
-    import numpy as np
     import torch
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

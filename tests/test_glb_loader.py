@@ -343,7 +343,6 @@ def test_loader_equals_the_references_own_loader(glb, pkg, oracle, tmp_path):
 def test_malformed_files_are_rejected_not_trusted(glb, tmp_path):
     """indices, offsets and counts in the JSON are untrusted input: out-of-range accessors / buffer views /
     node and texture indices and cyclic hierarchies raise (the loader ran 20 k mutated files under ASan + UBSan)"""
-    import re
     tex = np.zeros((8, 8, 4), np.uint8)
     path = str(tmp_path / "base.glb")
     _write_glb(path, tex)
