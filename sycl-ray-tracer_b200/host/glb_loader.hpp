@@ -7,7 +7,8 @@
  *   - one instance per glTF node x mesh primitive, in node-index order then primitive order
  *     (= Embree attach order = instID, F11); POSITION / NORMAL / TEXCOORD_0 and indices required
  *     (:256-276), indices u8/u16/u32 widened to u32 (:359-401), byteStride honoured (:289-292);
- *   - node transform local = T * R * S * matrix (:18-21), global = parents... * (local * scale(gs))
+ *   - node transform local = T * R * S * matrix (:18-21; tinygltf drops T/R/S when "matrix" is given), global =
+ *     parents... * (local * scale(gs))
  *     (:137-146); a node without rotation keeps glm::quat{} = (0,0,0,0) whose mat4 cast is the
  *     identity (src/scene.hpp:48);
  *   - material classification (:188-254): KHR_materials_ior && KHR_materials_transmission ->
@@ -548,10 +549,16 @@ inline LoadedScene load(const std::string &path, const float global_scale[3] = n
         const Json &nd = j["nodes"][n];
         float t[3] = {0, 0, 0}, s[3] = {1, 1, 1}, q[4] = {0, 0, 0, 0};
         Mat4 m = Mat4::identity();
-        if (nd["translation"].size() == 3) for (int k = 0; k < 3; k++) t[k] = (float)nd["translation"][k].num;
-        if (nd["rotation"].size() == 4) for (int k = 0; k < 4; k++) q[k] = (float)nd["rotation"][k].num;
-        if (nd["scale"].size() == 3) for (int k = 0; k < 3; k++) s[k] = (float)nd["scale"][k].num;
-        if (nd["matrix"].size() == 16) for (int k = 0; k < 16; k++) m.m[k] = (float)nd["matrix"][k].num;
+        /* tinygltf treats "matrix" and T/R/S as exclusive: once a node has a numeric "matrix" array it does not even
+         * parse translation / rotation / scale (deps/include/tiny_gltf.h:5113-5118) */
+        bool has_matrix = nd["matrix"].type == Json::Arr;
+        for (size_t k = 0; has_matrix && k < nd["matrix"].size(); k++) has_matrix = nd["matrix"][k].type == Json::Num;
+        if (!has_matrix) {
+            if (nd["translation"].size() == 3) for (int k = 0; k < 3; k++) t[k] = (float)nd["translation"][k].num;
+            if (nd["rotation"].size() == 4) for (int k = 0; k < 4; k++) q[k] = (float)nd["rotation"][k].num;
+            if (nd["scale"].size() == 3) for (int k = 0; k < 3; k++) s[k] = (float)nd["scale"][k].num;
+        }
+        if (has_matrix && nd["matrix"].size() == 16) for (int k = 0; k < 16; k++) m.m[k] = (float)nd["matrix"][k].num;
         local[n] = mul(mul(mul(translate(t), from_quat(q)), scale(s)), m); /* T * R * S * matrix */
     }
     const Json &scene = j["scenes"][(size_t)std::max(0, j["scene"].integer(0))];
@@ -615,14 +622,14 @@ inline LoadedScene load(const std::string &path, const float global_scale[3] = n
                 for (int k = 0; k < 3; k++) m.albedo_color[k] = pbr["baseColorFactor"].size() >= 3 ? (float)pbr["baseColorFactor"][k].num : 1.0f;
                 const Json &ext = mat["extensions"];
                 float strength = 0.0f; /* 0 when the extension is absent (src/scene.cpp:203-211) */
-                if (ext.has("KHR_materials_emissive_strength")) strength = (float)ext["KHR_materials_emissive_strength"]["emissiveStrength"].number(1.0);
+                if (ext.has("KHR_materials_emissive_strength")) strength = (float)ext["KHR_materials_emissive_strength"]["emissiveStrength"].number(0.0); /* a missing key reads as 0 in tinygltf */
                 for (int k = 0; k < 3; k++) m.emissive[k] = (mat["emissiveFactor"].size() == 3 ? (float)mat["emissiveFactor"][k].num : 0.0f) * strength;
                 const int tex = pbr["baseColorTexture"]["index"].integer(-1);
                 int image = tex >= 0 ? j["textures"][(size_t)tex]["source"].integer(-1) : -1;
                 if (image < -1 || image >= (int)n_images) throw std::runtime_error("Failed to load .glTF : texture source out of range");
                 if (ext.has("KHR_materials_ior") && ext.has("KHR_materials_transmission")) {
                     m.type = RT_MAT_DIELECTRIC;
-                    m.ior = (float)ext["KHR_materials_ior"]["ior"].number(1.5);
+                    m.ior = (float)ext["KHR_materials_ior"]["ior"].number(0.0); /* tinygltf: Value::Get of a missing key -> 0 */
                 } else if ((float)pbr["metallicFactor"].number(1.0) > 0.01f) { /* glTF default metallicFactor = 1 */
                     m.type = RT_MAT_METALLIC;
                     m.roughness = (float)pbr["roughnessFactor"].number(1.0);

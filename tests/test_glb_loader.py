@@ -381,3 +381,140 @@ def test_malformed_files_are_rejected_not_trusted(glb, tmp_path):
     a = json.loads(js); a["nodes"][1]["children"] = [0]; a["nodes"][2]["children"] = [2]     # cycles: must terminate
     assert load(json.dumps(a))[0]
     assert not load(js[: len(js) // 2])[0] and not load("[1, 2")[0] and not load('{"nodes": 3')[0]
+
+
+def _write_random_glb(path, seed, n_nodes=60, n_meshes=9, n_materials=7):
+    """a random forest of nodes (TRS and/or matrix, some unreachable), meshes with 1-3 primitives, every
+    material class, PNG images of odd sizes; the camera is never node 0 and every primitive has a material,
+    so the reference loader itself stays clear of its F15 undefined behaviour"""
+    rs = np.random.RandomState(seed)
+    blobs, views, accessors = [], [], []
+
+    def add_view(data, stride=None):
+        off = sum(len(b) for b in blobs)
+        blobs.append(data + b"\x00" * ((-len(data)) % 4))
+        v = {"buffer": 0, "byteOffset": off, "byteLength": len(data)}
+        if stride:
+            v["byteStride"] = stride
+        views.append(v)
+        return len(views) - 1
+
+    def add_acc(view, ctype, count, typ, offset=0):
+        accessors.append({"bufferView": view, "componentType": ctype, "count": count, "type": typ, "byteOffset": offset})
+        return len(accessors) - 1
+
+    images = []
+    for k in range(3):
+        w, h = rs.randint(3, 40), rs.randint(3, 40)
+        images.append({"bufferView": add_view(_png(rs.randint(0, 256, (h, w, 4)).astype(np.uint8))), "mimeType": "image/png"})
+    materials = []
+    for k in range(n_materials):
+        pbr = {"baseColorFactor": [float(v) for v in rs.rand(3)] + [1.0], "metallicFactor": float(rs.choice([0.0, 0.005, 0.02, 0.8])),
+               "roughnessFactor": float(rs.rand())}
+        if rs.rand() < 0.5:
+            pbr["baseColorTexture"] = {"index": int(rs.randint(3))}
+        m = {"pbrMetallicRoughness": pbr, "emissiveFactor": [float(v) for v in rs.rand(3)]}
+        ext = {}
+        if rs.rand() < 0.5:
+            ext["KHR_materials_emissive_strength"] = {"emissiveStrength": float(rs.rand() * 10)} if rs.rand() < 0.8 else {}
+        if rs.rand() < 0.3:
+            ext["KHR_materials_ior"] = {"ior": float(1 + rs.rand())} if rs.rand() < 0.8 else {}
+            if rs.rand() < 0.7:
+                ext["KHR_materials_transmission"] = {"transmissionFactor": 1.0}
+        if ext:
+            m["extensions"] = ext
+        materials.append(m)
+    meshes = []
+    for k in range(n_meshes):
+        prims = []
+        for _ in range(rs.randint(1, 4)):
+            nv, ntri = rs.randint(3, 30), rs.randint(1, 20)
+            pos, nrm, uv = rs.randn(nv, 3).astype(np.float32), rs.randn(nv, 3).astype(np.float32), rs.rand(nv, 2).astype(np.float32)
+            ict, dt = [(5121, np.uint8), (5123, np.uint16), (5125, np.uint32)][rs.randint(3)]
+            idx = rs.randint(0, nv, ntri * 3).astype(dt)
+            if rs.rand() < 0.5:                                  # interleaved vertex buffer
+                inter = np.concatenate([pos, nrm, uv], axis=1).astype(np.float32)
+                v = add_view(inter.tobytes(), 32)
+                a = (add_acc(v, 5126, nv, "VEC3", 0), add_acc(v, 5126, nv, "VEC3", 12), add_acc(v, 5126, nv, "VEC2", 24))
+            else:
+                a = (add_acc(add_view(pos.tobytes()), 5126, nv, "VEC3"), add_acc(add_view(nrm.tobytes()), 5126, nv, "VEC3"),
+                     add_acc(add_view(uv.tobytes()), 5126, nv, "VEC2"))
+            prims.append({"attributes": {"POSITION": a[0], "NORMAL": a[1], "TEXCOORD_0": a[2]},
+                          "indices": add_acc(add_view(idx.tobytes()), ict, ntri * 3, "SCALAR"), "material": int(rs.randint(n_materials))})
+        meshes.append({"primitives": prims})
+    nodes = []
+    for n in range(n_nodes):
+        nd = {}
+        if rs.rand() < 0.7:
+            nd["translation"] = [float(v) for v in rs.randn(3)]
+        if rs.rand() < 0.6:
+            q = rs.randn(4)
+            nd["rotation"] = [float(v) for v in q / np.linalg.norm(q)]
+        if rs.rand() < 0.5:
+            nd["scale"] = [float(v) for v in 0.5 + rs.rand(3)]
+        if rs.rand() < 0.2:
+            nd["matrix"] = [float(v) for v in (np.eye(4) + 0.3 * rs.randn(4, 4) * np.array([1, 1, 1, 0])[None, :]).T.reshape(-1)]
+        if rs.rand() < 0.6:
+            nd["mesh"] = int(rs.randint(n_meshes))
+        nodes.append(nd)
+    roots = []
+    for n in range(n_nodes):                                     # parent has a lower index or none: a forest
+        r = rs.rand()
+        if n == 0 or r < 0.15:
+            roots.append(n)
+        elif r < 0.9:
+            nodes[rs.randint(0, n)].setdefault("children", []).append(n)
+        # else: unreachable node, ignored by both loaders
+    cam = int(rs.randint(1, n_nodes))                            # a root, so that it is reachable for sure
+    nodes[cam]["camera"] = 0
+    for nd in nodes:
+        if cam in nd.get("children", []):
+            nd["children"].remove(cam)
+    if cam not in roots:
+        roots.append(cam)
+    j = {"asset": {"version": "2.0"}, "scene": 0, "scenes": [{"nodes": roots, "extras": {"sky_color": [0.1, 0.2, 0.3]}}], "nodes": nodes,
+         "cameras": [{"type": "perspective", "perspective": {"yfov": 0.9, "aspectRatio": 1.7, "znear": 0.1}}], "meshes": meshes,
+         "materials": materials, "textures": [{"source": 2}, {"source": 0}, {"source": 1}], "images": images,
+         "accessors": accessors, "bufferViews": views, "buffers": [{"byteLength": sum(len(b) for b in blobs)}]}
+    js = json.dumps(j).encode()
+    js += b" " * ((-len(js)) % 4)
+    binc = b"".join(blobs)
+    with open(path, "wb") as f:
+        f.write(struct.pack("<4sII", b"glTF", 2, 12 + 8 + len(js) + 8 + len(binc)) + struct.pack("<II", len(js), 0x4E4F534A) + js +
+                struct.pack("<II", len(binc), 0x004E4942) + binc)
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/src"), reason="needs the reference sources (build container only)")
+@pytest.mark.parametrize("seed", [1, 2, 3, 4, 5, 6, 7, 8])
+def test_random_scenes_load_like_the_reference(glb, pkg, tmp_path, seed):
+    """random node forests / meshes / materials through the reference's own loader and through ours"""
+    import _scenref
+    path = str(tmp_path / f"random{seed}.glb")
+    _write_random_glb(path, seed)
+    ref = _scenref.load(path)
+    glb.glb_load_scaled.restype = C.c_void_p
+    glb.glb_load_scaled.argtypes = [C.c_char_p, C.c_float, C.c_float, C.c_float]
+    mine = _mine_scaled(glb, pkg, path, (1.0, 1.0, 1.0))
+    assert len(mine["instances"]) == len(ref["instances"]) > 20
+    TYPE = {1: pkg._capi.RT_MAT_DIFFUSE, 2: pkg._capi.RT_MAT_METALLIC, 3: pkg._capi.RT_MAT_DIELECTRIC}
+    for a, b in zip(mine["instances"], ref["instances"]):
+        for k in ("positions", "normals", "uvs", "indices"):
+            assert np.array_equal(a[k], b[k]), k
+        assert np.allclose(a["transform"], b["transform"], rtol=1e-5, atol=1e-5)
+        assert a["type"] == TYPE[b["type"]]
+        if b["type"] != 3:
+            assert a["albedo_image"] == (b["albedo_image"] if b["albedo_is_image"] else -1)
+            if not b["albedo_is_image"]:
+                assert np.array_equal(a["albedo"], b["albedo"])
+            assert np.array_equal(a["emissive"], b["emissive"])
+        if b["type"] == 2:
+            assert a["roughness"] == b["roughness"]
+        if b["type"] == 3:
+            assert a["ior"] == b["ior"]
+    assert np.array_equal(mine["sky"], ref["sky"])
+    assert np.allclose(mine["camera_position"], ref["camera_position"], rtol=1e-5, atol=1e-5)
+    assert np.allclose(mine["camera_direction"], ref["camera_direction"], atol=2e-5)
+    assert len(mine["layers"]) == len(ref["layers"]) == 3
+    for k in range(3):
+        d = np.abs(mine["layers"][k].astype(int) - ref["layers"][k].astype(int))
+        assert d.max() <= 1 and (d > 0).mean() < 0.02
