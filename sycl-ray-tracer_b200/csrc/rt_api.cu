@@ -603,7 +603,8 @@ rt_status rt_render_frame(rt_renderer *r, const rt_scene *scene, const rt_camera
          * C4 at 16 spp -> only from 32 spp */
         const uint32_t *order = nullptr;
         const uint32_t n_blocks = rt_block_count(p);
-        if (r->block_order && p.spp >= 32 && p.max_depth >= 2 && n_blocks >= 1024 && r->w <= 65535 && r->h <= 65535) {
+        if (r->block_order && p.spp >= 32 && p.max_depth >= 2 && n_blocks >= 1024 &&
+            (uint64_t)r->w + sh.tile_size <= 65536u && (uint64_t)r->h + sh.tile_size <= 65536u) { /* block origins are packed 16 + 16 bits, partial edge tiles included */
             if (n_blocks > r->order_capacity) { /* first frame (or a coarser tiling): (re)allocate */
                 RT_CUDA_TRY(ctx, cudaStreamSynchronize(st));
                 for (uint32_t *&q : r->d_order) {
