@@ -32,9 +32,10 @@ def codec():
 
 
 def test_fixture_covers_the_variants():
-    assert len(NAMES) >= 45
+    assert len(NAMES) >= 55
     for must in ("png_h_rgba16_adam7", "png_palette_trns", "png_h_grey2_colorkey", "jpg_progressive_420", "jpg_restart",
-                 "jpg_rgb_adobe", "jpg_grey_progressive", "jpg_odd_9x17_420"):
+                 "jpg_rgb_adobe", "jpg_grey_progressive", "jpg_odd_9x17_420", "jpg_h_440", "jpg_h_411", "jpg_h_mixed", "jpg_h_4x4",
+                 "jpg_h_1px_wide"):
         assert must in NAMES
 
 

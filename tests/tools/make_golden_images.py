@@ -123,6 +123,7 @@ def cases():
         save("jpg_440", big, "JPEG", quality=85, subsampling="4:4:0")
     except Exception:
         pass
+    out.update(handmade_jpegs())
     return {k: v for k, v in out.items() if v is not None}
 
 
@@ -213,6 +214,109 @@ def handmade_pngs():
     out["png_h_grey_alpha16"] = make(rs.randint(0, 65536, (h, w, 2)), w, h, 2, 16, 4)
     out["png_h_small_adam7_2x3"] = make(rs.randint(0, 256, (3, 2, 4)), 2, 3, 4, 8, 6, True)
     return out
+
+
+def handmade_jpegs():
+    """sampling layouts Pillow cannot write (4:4:0, 4:1:1, mixed chroma factors, 3x / 4x factors): a minimal
+    baseline encoder that entropy-codes RANDOM quantised coefficients (no forward DCT needed: any coefficient
+    set is a valid image) with flat 8-bit Huffman tables, interleaved MCUs, optional restart markers."""
+    import struct
+    zig = [0, 1, 8, 16, 9, 2, 3, 10, 17, 24, 32, 25, 18, 11, 4, 5, 12, 19, 26, 33, 40, 48, 41, 34, 27, 20, 13, 6, 7, 14, 21, 28, 35, 42, 49, 56,
+           57, 50, 43, 36, 29, 22, 15, 23, 30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63]
+    dc_syms = list(range(12))                                                    # 12 codes of 4 bits
+    ac_syms = [0x00, 0xF0] + [(r << 4) | sz for r in range(16) for sz in range(1, 11)]   # 162 codes of 8 bits
+    dc_code = {v: (i, 4) for i, v in enumerate(dc_syms)}
+    ac_code = {v: (i, 8) for i, v in enumerate(ac_syms)}
+
+    class Bits:
+        def __init__(self):
+            self.out, self.acc, self.n = bytearray(), 0, 0
+
+        def put(self, code, length):
+            self.acc = (self.acc << length) | (code & ((1 << length) - 1))
+            self.n += length
+            while self.n >= 8:
+                b = (self.acc >> (self.n - 8)) & 255
+                self.out.append(b)
+                if b == 255:
+                    self.out.append(0)
+                self.n -= 8
+
+        def flush(self):
+            if self.n:
+                self.put((1 << (8 - self.n)) - 1, 8 - self.n)
+
+    def mag(v):
+        sz = int(abs(v)).bit_length()
+        return sz, (v if v >= 0 else v + (1 << sz) - 1)
+
+    def make(w, h, factors, seed, restart=0, qscale=6):
+        rs = np.random.RandomState(seed)
+        hmax, vmax = max(f[0] for f in factors), max(f[1] for f in factors)
+        mx, my = -(-w // (8 * hmax)), -(-h // (8 * vmax))
+        seg = lambda m, d: b"\xff" + bytes([m]) + struct.pack(">H", len(d) + 2) + d
+        out = b"\xff\xd8" + seg(0xE0, b"JFIF\0\1\1\0\0\1\0\1\0\0")
+        q = bytes(int(min(255, qscale + (i // 8 + i % 8))) for i in range(64))
+        out += seg(0xDB, b"\0" + q) + seg(0xDB, b"\1" + bytes(min(255, 2 * v) for v in q))
+        out += seg(0xC0, struct.pack(">BHHB", 8, h, w, len(factors)) + b"".join(bytes([i + 1, (f[0] << 4) | f[1], 0 if i == 0 else 1]) for i, f in enumerate(factors)))
+        out += seg(0xC4, b"\x00" + bytes([0, 0, 0, 12] + [0] * 12) + bytes(dc_syms))
+        out += seg(0xC4, b"\x10" + bytes([0, 0, 0, 0, 0, 0, 0, 162] + [0] * 8) + bytes(ac_syms))
+        if restart:
+            out += seg(0xDD, struct.pack(">H", restart))
+        out += seg(0xDA, bytes([len(factors)]) + b"".join(bytes([i + 1, 0x00]) for i in range(len(factors))) + b"\0\x3f\0")
+        bits, pred, count, rst = Bits(), [0] * len(factors), 0, 0
+        for _ in range(mx * my):
+            for c, (fh, fv) in enumerate(factors):
+                for _b in range(fh * fv):
+                    coef = np.zeros(64, np.int64)
+                    coef[0] = int(np.clip(pred[c] + rs.randint(-12, 13), -60, 60))
+                    for k in rs.choice(np.arange(1, 64), rs.randint(0, 7), replace=False):
+                        coef[k] = rs.randint(-9, 10) if k < 12 else rs.randint(-2, 3)
+                    if rs.rand() < 0.1:
+                        coef[rs.randint(40, 64)] = rs.randint(1, 3)             # long zero runs (ZRL)
+                    sz, extra = mag(int(coef[0] - pred[c]))
+                    pred[c] = int(coef[0])
+                    bits.put(*dc_code[sz])
+                    if sz:
+                        bits.put(extra, sz)
+                    run = 0
+                    last = max([k for k in range(1, 64) if coef[zig[k]] != 0], default=0)
+                    for k in range(1, last + 1):
+                        v = int(coef[zig[k]])
+                        if v == 0:
+                            run += 1
+                            continue
+                        while run > 15:
+                            bits.put(*ac_code[0xF0])
+                            run -= 16
+                        sz, extra = mag(v)
+                        bits.put(*ac_code[(run << 4) | sz])
+                        bits.put(extra, sz)
+                        run = 0
+                    if last < 63:
+                        bits.put(*ac_code[0x00])
+            count += 1
+            if restart and count % restart == 0 and count < mx * my:
+                bits.flush()
+                bits.out += bytes([0xFF, 0xD0 + rst])
+                bits.acc = bits.n = 0
+                rst = (rst + 1) & 7
+                pred = [0] * len(factors)
+        bits.flush()
+        return out + bytes(bits.out) + b"\xff\xd9"
+
+    return {
+        "jpg_h_440": make(45, 37, [(1, 2), (1, 1), (1, 1)], 1),                 # h1v2: vertical 3:1 filter
+        "jpg_h_411": make(53, 21, [(4, 1), (1, 1), (1, 1)], 2),                 # 4x horizontal: replicated samples
+        "jpg_h_mixed": make(40, 40, [(2, 2), (2, 1), (1, 2)], 3),               # Cb h1v2, Cr h2v1 against a 2x2 luma
+        "jpg_h_4x4": make(37, 33, [(4, 4), (1, 1), (1, 1)], 4),                 # 32x32 MCUs
+        "jpg_h_3x1": make(50, 9, [(3, 1), (1, 1), (1, 1)], 5),
+        "jpg_h_42": make(70, 31, [(4, 2), (2, 1), (1, 1)], 6, restart=2),       # mixed ratios 1, 2 and 4 + restart markers
+        "jpg_h_grey_odd": make(13, 29, [(1, 1)], 7),
+        "jpg_h_chroma_major": make(33, 18, [(1, 1), (2, 2), (2, 2)], 8),        # luma subsampled instead of chroma
+        "jpg_h_1px_wide": make(1, 40, [(2, 2), (1, 1), (1, 1)], 9),             # w_lores == 1 special cases
+        "jpg_h_2px_422": make(2, 9, [(2, 1), (1, 1), (1, 1)], 10),
+    }
 
 
 def main():
