@@ -206,7 +206,7 @@ inline Mat4 from_quat(const float q[4] /* x y z w */) {
 /* embedded PNG / JPEG -> RGBA8 exactly as stbi_load_from_memory(..., 4) delivers it to the reference
  * (image_codecs.hpp) */
 inline std::vector<uint8_t> png_decode(const uint8_t *d, size_t n, uint32_t &w, uint32_t &h) {
-    img::Image im = img::decode_rgba8(d, n);
+    img::Image im = img::decode_rgba8(d, n, /* tinygltf_16bit_quirk = */ true);
     w = im.w;
     h = im.h;
     return std::move(im.rgba);

@@ -7,7 +7,8 @@
  *
  *   PNG  : all colour types (grey, RGB, palette, grey+alpha, RGBA), bit depths 1/2/4/8/16, tRNS
  *          (palette alpha and colour key), Adam7 interlace. Sub-byte grey is scaled by 255/(2^d-1),
- *          16-bit samples keep their high byte; ancillary chunks (gAMA, iCCP, ...) are ignored.
+ *          16-bit samples keep their high byte (or, on request, come out the way the reference's tinygltf + bake
+ *          combination misreads them); ancillary chunks (gAMA, iCCP, ...) are ignored.
  *   JPEG : baseline / extended sequential and progressive Huffman, 8-bit, 1 or 3 components, any
  *          sampling factors, restart intervals, 8- and 16-bit quantisation tables, Adobe APP14
  *          transform flag and R/G/B component ids. The inverse DCT is the 12-bit fixed-point
@@ -73,7 +74,7 @@ inline void unfilter(const uint8_t *src, size_t src_len, uint32_t rows, size_t s
     }
 }
 
-inline Image decode(const uint8_t *d, size_t n) {
+inline Image decode(const uint8_t *d, size_t n, bool tinygltf_16bit_quirk = false) {
     static const uint8_t sig[8] = {0x89, 'P', 'N', 'G', 0x0d, 0x0a, 0x1a, 0x0a};
     if (n < 8 || memcmp(d, sig, 8)) fail("not a PNG");
     Image im;
@@ -231,6 +232,27 @@ inline Image decode(const uint8_t *d, size_t n) {
         } else {
             o[0] = to8(s[0]); o[1] = to8(s[1]); o[2] = to8(s[2]); o[3] = to8(s[3]);
         }
+    }
+    if (depth == 16 && tinygltf_16bit_quirk) {
+        /* What the REFERENCE sees for a 16-bit PNG: tinygltf notices stbi_is_16_bit and loads 16-bit samples
+         * (deps/include/tiny_gltf.h:2618-2626), the reference's bake then reads that buffer as if it were 8-bit
+         * RGBA of the same width and height (src/scene.cpp:157-160, src/image_manager.hpp:39): the first w*h*4
+         * BYTES of the little-endian 16-bit RGBA stream, i.e. pixel p = (R.lo, R.hi, G.lo, G.hi) of 16-bit pixel p/2
+         * for even p and (B.lo, B.hi, A.lo, A.hi) for odd p. Reproduced, not fixed (same class as F15). */
+        std::vector<uint8_t> stream((size_t)im.w * im.h * 8);
+        for (size_t i = 0; i < (size_t)im.w * im.h; i++) {
+            const uint16_t *s = &samp[i * ch];
+            uint16_t px[4];
+            if (ctype == 0) { px[0] = px[1] = px[2] = s[0]; px[3] = (has_trns && s[0] == key16[0]) ? 0 : 65535; }
+            else if (ctype == 4) { px[0] = px[1] = px[2] = s[0]; px[3] = s[1]; }
+            else if (ctype == 2) { px[0] = s[0]; px[1] = s[1]; px[2] = s[2]; px[3] = (has_trns && s[0] == key16[0] && s[1] == key16[1] && s[2] == key16[2]) ? 0 : 65535; }
+            else { px[0] = s[0]; px[1] = s[1]; px[2] = s[2]; px[3] = s[3]; }
+            for (int c = 0; c < 4; c++) {
+                stream[i * 8 + c * 2] = (uint8_t)(px[c] & 255);
+                stream[i * 8 + c * 2 + 1] = (uint8_t)(px[c] >> 8);
+            }
+        }
+        memcpy(im.rgba.data(), stream.data(), im.rgba.size());
     }
     return im;
 }
@@ -933,8 +955,8 @@ inline Image decode(const uint8_t *d, size_t n) {
 } // namespace jpeg
 
 /* what stbi_load_from_memory(bytes, size, &w, &h, &comp, 4) returns for the formats glTF allows */
-inline Image decode_rgba8(const uint8_t *d, size_t n) {
-    if (n >= 8 && d[0] == 0x89 && d[1] == 'P' && d[2] == 'N' && d[3] == 'G') return png::decode(d, n);
+inline Image decode_rgba8(const uint8_t *d, size_t n, bool tinygltf_16bit_quirk = false) {
+    if (n >= 8 && d[0] == 0x89 && d[1] == 'P' && d[2] == 'N' && d[3] == 'G') return png::decode(d, n, tinygltf_16bit_quirk);
     if (n >= 3 && d[0] == 0xff && d[1] == 0xd8) return jpeg::decode(d, n);
     fail("unsupported image format (glTF allows image/png and image/jpeg)");
 }

@@ -302,7 +302,9 @@ def test_loader_equals_the_references_own_loader(glb, pkg, oracle, tmp_path):
     gold = np.load(os.path.join(ROOT, "tests", "golden", "images.npz"))
     tex = (np.random.RandomState(1).rand(512, 512, 4) * 255).astype(np.uint8)
     path = str(tmp_path / "both.glb")
-    _write_glb(path, tex, [(gold["in_jpg_baseline_420"], "image/jpeg"), (gold["in_png_palette_trns"], "image/png")], f15=False)
+    _write_glb(path, tex, [(gold["in_jpg_baseline_420"], "image/jpeg"), (gold["in_png_palette_trns"], "image/png"),
+                           (gold["in_png_h_rgba16_adam7"], "image/png"), (gold["in_png_grey16"], "image/png"),   # 16-bit: misread by the reference
+                           (gold["in_png_h_rgb16_colorkey"], "image/png")], f15=False)
     for scale in ((1.0, 1.0, 1.0), (0.5, 2.0, 3.0)):
         ref = _scenref.load(path, scale)
         subprocess.run(["make", "-s", "-C", HOST], check=True)
@@ -333,9 +335,9 @@ def test_loader_equals_the_references_own_loader(glb, pkg, oracle, tmp_path):
         assert np.allclose(mine["camera_position"], ref["camera_position"], atol=1e-6)
         assert np.allclose(mine["camera_direction"], ref["camera_direction"], atol=1e-6)
         assert np.isclose(mine["focal"], ref["focal"], rtol=1e-6)
-        assert len(mine["layers"]) == len(ref["layers"]) == 3
+        assert len(mine["layers"]) == len(ref["layers"]) == 6
         assert np.array_equal(mine["layers"][0], ref["layers"][0])            # 512x512: verbatim in both
-        for k in (1, 2):                                                       # resized: within one code value
+        for k in (1, 2, 3, 4, 5):                                              # resized: within one code value
             d = np.abs(mine["layers"][k].astype(int) - ref["layers"][k].astype(int))
             assert d.max() <= 1 and (d > 0).mean() < 0.02
 
