@@ -520,3 +520,24 @@ def test_random_scenes_load_like_the_reference(glb, pkg, tmp_path, seed):
     for k in range(3):
         d = np.abs(mine["layers"][k].astype(int) - ref["layers"][k].astype(int))
         assert d.max() <= 1 and (d > 0).mean() < 0.02
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/src"), reason="needs the reference sources (build container only)")
+def test_uri_images_load_like_the_reference(glb, pkg, tmp_path):
+    """image "uri"s (base64 data URI, percent-encoded file name next to the .glb) through tinygltf and through ours"""
+    import base64
+    import _scenref
+    gold = np.load(os.path.join(ROOT, "tests", "golden", "images.npz"))
+    tex = (np.random.RandomState(1).rand(512, 512, 4) * 255).astype(np.uint8)
+    (tmp_path / "side car.jpg").write_bytes(gold["in_jpg_progressive_422"].tobytes())
+    data_uri = "data:image/png;base64," + base64.b64encode(gold["in_png_h_rgb8_adam7"].tobytes()).decode()
+    path = str(tmp_path / "uris.glb")
+    _write_glb(path, tex, uri_images=[data_uri, "side%20car.jpg"], f15=False)
+    ref = _scenref.load(path)
+    glb.glb_load_scaled.restype = C.c_void_p
+    glb.glb_load_scaled.argtypes = [C.c_char_p, C.c_float, C.c_float, C.c_float]
+    mine = _mine_scaled(glb, pkg, path, (1.0, 1.0, 1.0))
+    assert len(mine["layers"]) == len(ref["layers"]) == 3
+    for k in range(3):
+        d = np.abs(mine["layers"][k].astype(int) - ref["layers"][k].astype(int))
+        assert d.max() <= 1 and (d > 0).mean() < 0.02
