@@ -316,7 +316,7 @@ def test_loader_equals_the_references_own_loader(glb, pkg, oracle, tmp_path):
         for a, b in zip(mine["instances"], ref["instances"]):
             for k in ("positions", "normals", "uvs", "indices"):
                 assert np.array_equal(a[k], b[k]), k
-            assert np.allclose(a["transform"], b["transform"], rtol=2e-6, atol=1e-6)
+            assert np.array_equal(a["transform"].view(np.uint32), b["transform"].view(np.uint32))     # same arithmetic order as glm
             assert a["type"] == TYPE[b["type"]]
             if b["type"] != 3:
                 assert a["albedo_image"] == (b["albedo_image"] if b["albedo_is_image"] else -1)
@@ -332,9 +332,9 @@ def test_loader_equals_the_references_own_loader(glb, pkg, oracle, tmp_path):
             oracle.lib().orc_normal_matrix(np.ascontiguousarray(b["transform"]).ctypes.data_as(oracle.f32p), nm.ctypes.data_as(oracle.f32p))
             assert np.array_equal(nm.view(np.uint32), b["normal_matrix"].view(np.uint32))
         assert np.array_equal(mine["sky"], ref["sky"])
-        assert np.allclose(mine["camera_position"], ref["camera_position"], atol=1e-6)
-        assert np.allclose(mine["camera_direction"], ref["camera_direction"], atol=1e-6)
-        assert np.isclose(mine["focal"], ref["focal"], rtol=1e-6)
+        assert np.array_equal(mine["camera_position"], ref["camera_position"])
+        assert np.array_equal(mine["camera_direction"], ref["camera_direction"])
+        assert mine["focal"] == ref["focal"]
         assert len(mine["layers"]) == len(ref["layers"]) == 6
         assert np.array_equal(mine["layers"][0], ref["layers"][0])            # 512x512: verbatim in both
         for k in (1, 2, 3, 4, 5):                                              # resized: within one code value
@@ -502,7 +502,7 @@ def test_random_scenes_load_like_the_reference(glb, pkg, tmp_path, seed):
     for a, b in zip(mine["instances"], ref["instances"]):
         for k in ("positions", "normals", "uvs", "indices"):
             assert np.array_equal(a[k], b[k]), k
-        assert np.allclose(a["transform"], b["transform"], rtol=1e-5, atol=1e-5)
+        assert np.array_equal(a["transform"].view(np.uint32), b["transform"].view(np.uint32))
         assert a["type"] == TYPE[b["type"]]
         if b["type"] != 3:
             assert a["albedo_image"] == (b["albedo_image"] if b["albedo_is_image"] else -1)
@@ -514,8 +514,8 @@ def test_random_scenes_load_like_the_reference(glb, pkg, tmp_path, seed):
         if b["type"] == 3:
             assert a["ior"] == b["ior"]
     assert np.array_equal(mine["sky"], ref["sky"])
-    assert np.allclose(mine["camera_position"], ref["camera_position"], rtol=1e-5, atol=1e-5)
-    assert np.allclose(mine["camera_direction"], ref["camera_direction"], atol=2e-5)
+    assert np.array_equal(mine["camera_position"], ref["camera_position"])
+    assert np.array_equal(mine["camera_direction"], ref["camera_direction"]) and mine["focal"] == ref["focal"]
     assert len(mine["layers"]) == len(ref["layers"]) == 3
     for k in range(3):
         d = np.abs(mine["layers"][k].astype(int) - ref["layers"][k].astype(int))
@@ -541,3 +541,42 @@ def test_uri_images_load_like_the_reference(glb, pkg, tmp_path):
     for k in range(3):
         d = np.abs(mine["layers"][k].astype(int) - ref["layers"][k].astype(int))
         assert d.max() <= 1 and (d > 0).mean() < 0.02
+
+
+def _scene_data(pkg, mine):
+    """our loader's output as the SceneData the oracle (and the CUDA path) render"""
+    insts = [pkg.InstanceData(i["positions"], i["normals"], i["uvs"], i["indices"], i["transform"],
+                              pkg.Material(i["type"], tuple(i["albedo"]), i["albedo_image"], i["roughness"], i["ior"], tuple(i["emissive"])))
+             for i in mine["instances"]]
+    tex = np.stack(mine["layers"]) if mine["layers"] else None
+    return pkg.SceneData(insts, tex, tuple(mine["sky"]), tuple(mine["camera_position"]), tuple(mine["camera_direction"]), mine["focal"], "glb")
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/src"), reason="needs the reference sources (build container only)")
+@pytest.mark.parametrize("kind", [0, 1])
+def test_whole_reference_program_equals_loader_plus_oracle(glb, pkg, oracle, tmp_path, kind):
+    """END TO END on the CPU: the reference's whole program — src/scene.cpp loader, Camera, Megakernel /
+    WavefrontRenderer::render_frame, write_image, i.e. src/main.cpp:30-70 compiled in place
+    (oracle/refshim/fullref.cpp -> oracle/_ref/libfullref.so) — renders a .glb; our loader + the oracle's renderer
+    (the thing every CUDA result is compared with) must produce the same out.png bytes and the same ray count."""
+    so = os.path.join(ROOT, "oracle", "_ref", "libfullref.so")
+    if not os.path.exists(so):
+        subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "ref"], check=True)
+    F = C.CDLL(so)
+    F.fullref_main.restype = C.c_uint64
+    F.fullref_main.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_void_p]
+    F.fullref_last_error.restype = C.c_char_p
+    tex = (np.random.RandomState(1).rand(512, 512, 4) * 255).astype(np.uint8)      # 512x512: baked verbatim by both
+    path = str(tmp_path / "e2e.glb")
+    _write_glb(path, tex, f15=False)
+    w, h, depth, spp = 72, 48, 6, 3
+    ref_img = np.zeros((h, w, 4), np.uint8)
+    rays = F.fullref_main(path.encode(), 1 if kind == 0 else 0, w, h, depth, spp, ref_img.ctypes.data)
+    assert rays != 2 ** 64 - 1, F.fullref_last_error()
+    glb.glb_load_scaled.restype = C.c_void_p
+    glb.glb_load_scaled.argtypes = [C.c_char_p, C.c_float, C.c_float, C.c_float]
+    data = _scene_data(pkg, _mine_scaled(glb, pkg, path, (1.0, 1.0, 1.0)))
+    o = oracle.Scene(data).render(oracle.camera_for(data, w, h), kind, depth, spp, use_bvh=False)
+    assert o["ray_count"] == rays > w * h * spp
+    assert np.array_equal(o["rgba8"], ref_img)
+    assert ref_img[..., :3].std() > 5 and (ref_img[..., 3] == 255).all()
