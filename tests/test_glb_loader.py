@@ -385,7 +385,7 @@ def test_malformed_files_are_rejected_not_trusted(glb, tmp_path):
     assert not load(js[: len(js) // 2])[0] and not load("[1, 2")[0] and not load('{"nodes": 3')[0]
 
 
-def _write_random_glb(path, seed, n_nodes=60, n_meshes=9, n_materials=7):
+def _write_random_glb(path, seed, n_nodes=60, n_meshes=9, n_materials=7, tex512=False):
     """a random forest of nodes (TRS and/or matrix, some unreachable), meshes with 1-3 primitives, every
     material class, PNG images of odd sizes; the camera is never node 0 and every primitive has a material,
     so the reference loader itself stays clear of its F15 undefined behaviour"""
@@ -407,7 +407,7 @@ def _write_random_glb(path, seed, n_nodes=60, n_meshes=9, n_materials=7):
 
     images = []
     for k in range(3):
-        w, h = rs.randint(3, 40), rs.randint(3, 40)
+        w, h = (512, 512) if tex512 else (rs.randint(3, 40), rs.randint(3, 40))   # 512x512 is baked verbatim by both loaders
         images.append({"bufferView": add_view(_png(rs.randint(0, 256, (h, w, 4)).astype(np.uint8))), "mimeType": "image/png"})
     materials = []
     for k in range(n_materials):
@@ -580,3 +580,25 @@ def test_whole_reference_program_equals_loader_plus_oracle(glb, pkg, oracle, tmp
     assert o["ray_count"] == rays > w * h * spp
     assert np.array_equal(o["rgba8"], ref_img)
     assert ref_img[..., :3].std() > 5 and (ref_img[..., 3] == 255).all()
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/src"), reason="needs the reference sources (build container only)")
+@pytest.mark.parametrize("seed", [11, 12])
+def test_whole_reference_program_on_random_scenes(glb, pkg, oracle, tmp_path, seed):
+    """the end-to-end comparison on random scenes: ~60 instances under a random node forest, textured diffuse /
+    metallic / dielectric / emissive materials, both renderers"""
+    F = C.CDLL(os.path.join(ROOT, "oracle", "_ref", "libfullref.so"))
+    F.fullref_main.restype = C.c_uint64
+    F.fullref_main.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_void_p]
+    path = str(tmp_path / "e2e_random.glb")
+    _write_random_glb(path, seed, n_nodes=40, tex512=True)
+    glb.glb_load_scaled.restype = C.c_void_p
+    glb.glb_load_scaled.argtypes = [C.c_char_p, C.c_float, C.c_float, C.c_float]
+    data = _scene_data(pkg, _mine_scaled(glb, pkg, path, (1.0, 1.0, 1.0)))
+    w, h, depth, spp = 48, 32, 5, 2
+    for kind in (0, 1):
+        ref_img = np.zeros((h, w, 4), np.uint8)
+        rays = F.fullref_main(path.encode(), 1 if kind == 0 else 0, w, h, depth, spp, ref_img.ctypes.data)
+        o = oracle.Scene(data).render(oracle.camera_for(data, w, h), kind, depth, spp, use_bvh=False)
+        assert o["ray_count"] == rays > w * h * spp * 1.02     # some paths do bounce
+        assert np.array_equal(o["rgba8"], ref_img)
