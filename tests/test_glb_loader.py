@@ -602,3 +602,50 @@ def test_whole_reference_program_on_random_scenes(glb, pkg, oracle, tmp_path, se
         o = oracle.Scene(data).render(oracle.camera_for(data, w, h), kind, depth, spp, use_bvh=False)
         assert o["ray_count"] == rays > w * h * spp * 1.02     # some paths do bounce
         assert np.array_equal(o["rgba8"], ref_img)
+
+
+E2E_GOLDEN = os.path.join(ROOT, "tests", "golden", "reference_program_e2e.npz")
+E2E_CASE = dict(w=72, h=48, depth=6, spp=3)
+
+
+def _e2e_glb(path):
+    tex = (np.random.RandomState(1).rand(512, 512, 4) * 255).astype(np.uint8)
+    _write_glb(path, tex, f15=False)
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/src"), reason="needs the reference sources (build container only)")
+def test_e2e_golden_is_what_the_reference_program_renders_today(tmp_path):
+    """tests/golden/reference_program_e2e.npz = out.png bytes + ray counts of the reference's whole program
+    (libfullref.so) on the generated .glb; regenerate with RT_WRITE_GOLDEN=1"""
+    F = C.CDLL(os.path.join(ROOT, "oracle", "_ref", "libfullref.so"))
+    F.fullref_main.restype = C.c_uint64
+    F.fullref_main.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_void_p]
+    path = str(tmp_path / "e2e.glb")
+    _e2e_glb(path)
+    out = {"glb_crc": np.uint32(zlib.crc32(open(path, "rb").read()))}
+    for kind, name in ((0, "megakernel"), (1, "wavefront")):
+        img = np.zeros((E2E_CASE["h"], E2E_CASE["w"], 4), np.uint8)
+        rays = F.fullref_main(path.encode(), 1 if kind == 0 else 0, E2E_CASE["w"], E2E_CASE["h"], E2E_CASE["depth"], E2E_CASE["spp"], img.ctypes.data)
+        out["img_" + name], out["rays_" + name] = img, np.uint64(rays)
+    if os.environ.get("RT_WRITE_GOLDEN"):
+        np.savez_compressed(E2E_GOLDEN, **out)
+    gold = np.load(E2E_GOLDEN)
+    for k in out:
+        assert np.array_equal(gold[k], out[k]), k
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("flag,name", [("-m", "megakernel"), ("-w", "wavefront")])
+def test_cli_output_equals_the_reference_programs(glb, tmp_path, flag, name):
+    """`raytracer [-m|-w] scene.glb` on the B200 writes the out.png the reference's whole program writes
+    (fixture rendered by the reference's own code, see above) and prints the same ray count"""
+    from PIL import Image
+    gold = np.load(E2E_GOLDEN)
+    path = str(tmp_path / "e2e.glb")
+    _e2e_glb(path)
+    assert zlib.crc32(open(path, "rb").read()) == int(gold["glb_crc"])        # the very file the fixture was rendered from
+    png = str(tmp_path / "out.png")
+    r = subprocess.run([os.path.join(HOST, "raytracer"), flag, "-d", str(E2E_CASE["depth"]), "-s", str(E2E_CASE["spp"]),
+                        "--size", f"{E2E_CASE['w']}x{E2E_CASE['h']}", "--png", png, path], capture_output=True, text=True, check=True)
+    assert f"Total rays: {int(gold['rays_' + name])}" in r.stdout
+    assert np.array_equal(np.array(Image.open(png)), gold["img_" + name])
