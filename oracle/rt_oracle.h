@@ -15,7 +15,12 @@
  * "embree 4", CMakeLists.txt:13) has no source to follow: it is restated as a
  * brute-force closest-hit search with the Woop/Benthin/Wald watertight test,
  * honouring Embree's documented conventions (u,v weights of v1,v2;
- * tnear < t <= tfar; double sided; instID/primID).
+ * tnear < t <= tfar; double sided; instID/primID); its closest-hit answer is
+ * checked against exact rational arithmetic (tests/test_oracle_bvh.py). The
+ * reference's whole program (loader + renderers + write_image, compiled in
+ * place: oracle/_ref/libfullref.so) renders .glb files to the bytes and ray
+ * counts this oracle produces from the product's loader output
+ * (tests/test_glb_loader.py).
  *
  * Every function cites the reference file:line it follows.
  */
