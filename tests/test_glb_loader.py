@@ -605,28 +605,29 @@ def test_whole_reference_program_on_random_scenes(glb, pkg, oracle, tmp_path, se
 
 
 E2E_GOLDEN = os.path.join(ROOT, "tests", "golden", "reference_program_e2e.npz")
-E2E_CASE = dict(w=72, h=48, depth=6, spp=3)
-
-
-def _e2e_glb(path):
-    tex = (np.random.RandomState(1).rand(512, 512, 4) * 255).astype(np.uint8)
-    _write_glb(path, tex, f15=False)
+# name -> (writer, width, height, max_depth, samples)
+E2E_CASES = {
+    "synthetic": (lambda p: _write_glb(p, (np.random.RandomState(1).rand(512, 512, 4) * 255).astype(np.uint8), f15=False), 72, 48, 6, 3),
+    "random11": (lambda p: _write_random_glb(p, 11, n_nodes=40, tex512=True), 48, 32, 5, 2),   # ~50 textured instances
+}
 
 
 @pytest.mark.skipif(not os.path.isdir("/root/reference/src"), reason="needs the reference sources (build container only)")
 def test_e2e_golden_is_what_the_reference_program_renders_today(tmp_path):
     """tests/golden/reference_program_e2e.npz = out.png bytes + ray counts of the reference's whole program
-    (libfullref.so) on the generated .glb; regenerate with RT_WRITE_GOLDEN=1"""
+    (libfullref.so) on generated .glb files; regenerate with RT_WRITE_GOLDEN=1"""
     F = C.CDLL(os.path.join(ROOT, "oracle", "_ref", "libfullref.so"))
     F.fullref_main.restype = C.c_uint64
     F.fullref_main.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_void_p]
-    path = str(tmp_path / "e2e.glb")
-    _e2e_glb(path)
-    out = {"glb_crc": np.uint32(zlib.crc32(open(path, "rb").read()))}
-    for kind, name in ((0, "megakernel"), (1, "wavefront")):
-        img = np.zeros((E2E_CASE["h"], E2E_CASE["w"], 4), np.uint8)
-        rays = F.fullref_main(path.encode(), 1 if kind == 0 else 0, E2E_CASE["w"], E2E_CASE["h"], E2E_CASE["depth"], E2E_CASE["spp"], img.ctypes.data)
-        out["img_" + name], out["rays_" + name] = img, np.uint64(rays)
+    out = {}
+    for case, (writer, w, h, depth, spp) in E2E_CASES.items():
+        path = str(tmp_path / f"{case}.glb")
+        writer(path)
+        out[f"{case}_glb_crc"] = np.uint32(zlib.crc32(open(path, "rb").read()))
+        for kind, name in ((0, "megakernel"), (1, "wavefront")):
+            img = np.zeros((h, w, 4), np.uint8)
+            rays = F.fullref_main(path.encode(), 1 if kind == 0 else 0, w, h, depth, spp, img.ctypes.data)
+            out[f"{case}_img_{name}"], out[f"{case}_rays_{name}"] = img, np.uint64(rays)
     if os.environ.get("RT_WRITE_GOLDEN"):
         np.savez_compressed(E2E_GOLDEN, **out)
     gold = np.load(E2E_GOLDEN)
@@ -635,17 +636,19 @@ def test_e2e_golden_is_what_the_reference_program_renders_today(tmp_path):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("case", sorted(E2E_CASES))
 @pytest.mark.parametrize("flag,name", [("-m", "megakernel"), ("-w", "wavefront")])
-def test_cli_output_equals_the_reference_programs(glb, tmp_path, flag, name):
+def test_cli_output_equals_the_reference_programs(glb, tmp_path, flag, name, case):
     """`raytracer [-m|-w] scene.glb` on the B200 writes the out.png the reference's whole program writes
     (fixture rendered by the reference's own code, see above) and prints the same ray count"""
     from PIL import Image
     gold = np.load(E2E_GOLDEN)
+    writer, w, h, depth, spp = E2E_CASES[case]
     path = str(tmp_path / "e2e.glb")
-    _e2e_glb(path)
-    assert zlib.crc32(open(path, "rb").read()) == int(gold["glb_crc"])        # the very file the fixture was rendered from
+    writer(path)
+    assert zlib.crc32(open(path, "rb").read()) == int(gold[f"{case}_glb_crc"])   # the very file the fixture was rendered from
     png = str(tmp_path / "out.png")
-    r = subprocess.run([os.path.join(HOST, "raytracer"), flag, "-d", str(E2E_CASE["depth"]), "-s", str(E2E_CASE["spp"]),
-                        "--size", f"{E2E_CASE['w']}x{E2E_CASE['h']}", "--png", png, path], capture_output=True, text=True, check=True)
-    assert f"Total rays: {int(gold['rays_' + name])}" in r.stdout
-    assert np.array_equal(np.array(Image.open(png)), gold["img_" + name])
+    r = subprocess.run([os.path.join(HOST, "raytracer"), flag, "-d", str(depth), "-s", str(spp), "--size", f"{w}x{h}", "--png", png, path],
+                       capture_output=True, text=True, check=True)
+    assert f"Total rays: {int(gold[f'{case}_rays_{name}'])}" in r.stdout
+    assert np.array_equal(np.array(Image.open(png)), gold[f"{case}_img_{name}"])
