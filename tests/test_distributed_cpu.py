@@ -30,7 +30,14 @@ def _worker(rank, world, port, mode, out):
         shard = {"rank": rank, "world": world, "tile_size": 16, "seed_salt": 0}
     else:
         shard = {"rank": rank, "world": world, "tile_size": 0, "seed_salt": (rank * 0x9E3779B9) & 0xFFFFFFFF}
-    f = emu.render(cam, 1, 6, 2, shard=shard)
+    if mode == "progressive":   # config 5: spp slices rendered in batches chained with RT_RENDER_RESUME, one reduction at the end
+        f, rays_total = None, 0
+        for n in (1, 2, 1):
+            f = emu.render(cam, 1, 6, n, shard=shard, resume=f)
+            rays_total += f["ray_count"]
+        f["ray_count"] = rays_total
+    else:
+        f = emu.render(cam, 1, 6, 2, shard=shard)
     acc = torch.from_numpy(f["accum"].copy())
     rays = torch.tensor([f["ray_count"]], dtype=torch.int64)
     dist.all_reduce(acc)
@@ -42,10 +49,10 @@ def _worker(rank, world, port, mode, out):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("mode", ["tile", "spp"])
+@pytest.mark.parametrize("mode", ["tile", "spp", "progressive"])
 def test_two_ranks_gloo(tmp_path, mode, pkg, scenes, hostemu):
     out = str(tmp_path / f"acc_{mode}.npy")
-    port = 29500 + (os.getpid() % 2000) + (0 if mode == "tile" else 1)
+    port = 29500 + (os.getpid() % 2000) + {"tile": 0, "spp": 1, "progressive": 2}[mode]
     mp.spawn(_worker, args=(2, port, mode, out), nprocs=2, join=True)
     acc, rays = np.load(out), int(np.load(out + ".rays.npy")[0])
     data = scenes.cornell_scene(2)
@@ -54,6 +61,11 @@ def test_two_ranks_gloo(tmp_path, mode, pkg, scenes, hostemu):
     if mode == "tile":   # bit-identical to the unsharded frame
         full = emu.render(cam, 1, 6, 2)
         assert np.array_equal(acc.view(np.uint32), full["accum"].view(np.uint32)) and rays == full["ray_count"]
+    elif mode == "progressive":   # 1 + 2 + 1 samples per rank = one 4-sample frame per rank, reduced once
+        parts = [emu.render(cam, 1, 6, 4, shard={"rank": r, "world": 2, "tile_size": 0, "seed_salt": (r * 0x9E3779B9) & 0xFFFFFFFF})
+                 for r in range(2)]
+        assert np.array_equal(acc.view(np.uint32), (parts[0]["accum"] + parts[1]["accum"]).view(np.uint32))
+        assert (acc[..., 3] == 8).all() and rays == parts[0]["ray_count"] + parts[1]["ray_count"]
     else:                # sum of independently salted streams; sample count adds up
         parts = [emu.render(cam, 1, 6, 2, shard={"rank": r, "world": 2, "tile_size": 0, "seed_salt": (r * 0x9E3779B9) & 0xFFFFFFFF})
                  for r in range(2)]
