@@ -548,3 +548,50 @@ extern "C" uint32_t emu_enumerate_blocks(int w, int h, uint32_t rank, uint32_t w
     *foreign_out = foreign;
     return g.n_blocks;
 }
+
+/* scheduling studies (tools/simd_model.py): per ray segment of pixel (x, y) the node steps and triangle tests of
+ * the simple traversal, and whether the segment is the first of a sample. Returns the number of segments. */
+extern "C" uint32_t emu_pixel_costs(const emu_scene *s, int wavefront_seed, const rt_camera *camera, const rt_render_params *params,
+                                    int x, int y, uint16_t *node_steps, uint16_t *tri_steps, uint8_t *first_of_sample, uint32_t max_rays) {
+    RtCamera cam;
+    cam.center = mk3(camera->center[0], camera->center[1], camera->center[2]);
+    cam.pixel00 = mk3(camera->pixel00_loc[0], camera->pixel00_loc[1], camera->pixel00_loc[2]);
+    cam.du = mk3(camera->pixel_delta_u[0], camera->pixel_delta_u[1], camera->pixel_delta_u[2]);
+    cam.dv = mk3(camera->pixel_delta_v[0], camera->pixel_delta_v[1], camera->pixel_delta_v[2]);
+    cam.w = camera->img_size[0];
+    cam.h = camera->img_size[1];
+    XorShift32 rng;
+    rng.a = rt_pixel_seed(wavefront_seed, x, y, cam.w, cam.h) ^ params->shard.seed_salt;
+    uint32_t n = 0;
+    for (uint32_t sidx = 0; sidx < params->sample_count; sidx++) {
+        RtRayState r = rt_camera_ray(cam, x, y, rng);
+        for (uint32_t depth = 0; depth < params->max_depth; depth++) {
+            RtTravState tv;
+            RtTravStacks ks;
+            rt_trav_init(tv, r.org, r.dir, 0.0001f, INFINITY);
+            uint32_t nn = 0, nt = 0;
+            while (rt_trav_has_node(tv)) {
+                rt_trav_node_step(s->view.bvh, tv, ks);
+                nn++;
+                while (rt_trav_has_tri(tv)) {
+                    rt_trav_tri_step(s->view.bvh, tv, ks);
+                    nt++;
+                }
+            }
+            if (n < max_rays) {
+                node_steps[n] = (uint16_t)std::min(nn, 65535u);
+                tri_steps[n] = (uint16_t)std::min(nt, 65535u);
+                first_of_sample[n] = depth == 0;
+            }
+            n++;
+            f3 org = r.org, dir = r.dir, att = r.att, rad = r.rad, res;
+            const bool done = rt_shade_segment(s->view, tv.best, rng, org, dir, att, rad, res);
+            r.org = org;
+            r.dir = round_half3(dir);
+            r.att = round_half3(att);
+            r.rad = round_half3(rad);
+            if (done) break;
+        }
+    }
+    return n;
+}
