@@ -54,9 +54,12 @@ def simulate(pixels, n_warps, refill=12, pooled_tris=False, coop_tail=False, tst
 
     warps = [dict(pix=[None] * 32, ray=[0] * 32, node=[0] * 32, tri=[0] * 32, pend=[0] * 32, trav=[False] * 32, need=[True] * 32, dead=[False] * 32) for _ in range(n_warps)]
     live = list(range(n_warps))
+    clock = [0.0] * n_warps            # warp instructions issued by each warp: its time line (equal issue rates)
     while live:
-        for wi in list(live):
+        # the warp that is furthest behind runs next, so pixels are handed out in time order like the global counter
+        for wi in sorted(live, key=lambda i: clock[i])[:1]:
             wp = warps[wi]
+            before = sum(v[0] for v in stats.values())
             # ---- regenerate: lanes whose ray finished shade it / start the next ray / fetch a pixel
             shading = 0
             for l in range(32):
@@ -87,6 +90,7 @@ def simulate(pixels, n_warps, refill=12, pooled_tris=False, coop_tail=False, tst
                 stats["shade"][1] += W_SHADE * shading
             if all(wp["dead"]):
                 live.remove(wi)
+                clock[wi] += sum(v[0] for v in stats.values()) - before
                 continue
             # ---- traverse phase
             trav0 = [l for l in range(32) if wp["trav"][l]]
@@ -132,6 +136,8 @@ def simulate(pixels, n_warps, refill=12, pooled_tris=False, coop_tail=False, tst
             for l in trav0:
                 if wp["node"][l] == 0 and wp["pend"][l] == 0:
                     wp["trav"][l] = False
+            clock[wi] += sum(v[0] for v in stats.values()) - before
+    stats["_makespan"] = [max(clock), sum(clock) / n_warps]
     return stats
 
 
@@ -232,10 +238,12 @@ def simulate_k(pixels, n_warps, refill=12, K=2, tstack=8):
 
 
 def report(tag, st):
+    span = st.pop("_makespan", None)
     tot_w = sum(v[0] for v in st.values())
     tot_l = sum(v[1] for v in st.values())
     parts = "  ".join(f"{k} {100 * v[0] / tot_w:4.1f}% @ {v[1] / max(v[0], 1):4.1f}" for k, v in st.items())
-    print(f"{tag:34s} warp-instr {tot_w / 1e6:8.2f} M   avg lanes {tot_l / tot_w:5.2f}   {parts}")
+    tail = f"   makespan / mean warp time {span[0] / span[1]:.3f}" if span else ""
+    print(f"{tag:34s} warp-instr {tot_w / 1e6:8.2f} M   avg lanes {tot_l / tot_w:5.2f}   {parts}{tail}")
     return tot_w
 
 
@@ -256,6 +264,16 @@ if __name__ == "__main__":
         report(f"refill {r}", simulate(px, a.warps, r))
     t = report("pooled triangle drain", simulate(px, a.warps, 12, pooled_tris=True))
     print(f"pooled drain: {100 * (base - t) / base:.1f} % fewer warp instructions")
+    # the tail: few pixels per lane (as under 8-way tile sharding) and the order they are handed out in
+    cost = [float(p[0].sum()) * W_NODE + float(p[1].sum()) * W_TRI + len(p[0]) * W_SHADE for p in px]
+    blocks = [list(range(i, min(i + 32, len(px)))) for i in range(0, len(px), 32)]
+    def by_blocks(order):
+        return [px[i] for b in order for i in blocks[b]]
+    bcost = [sum(cost[i] for i in b) for b in blocks]
+    many = max(2, len(px) // (32 * 5))                           # ~5 pixels per lane
+    report(f"tail: image order, {many} warps", simulate(px, many, 12))
+    report("tail: expensive blocks first", simulate(by_blocks(sorted(range(len(blocks)), key=lambda b: -bcost[b])), many, 12))
+    report("tail: cheap blocks first", simulate(by_blocks(sorted(range(len(blocks)), key=lambda b: bcost[b])), many, 12))
     for K in (2, 3):
         t = report(f"{K} ray contexts per lane", simulate_k(px, max(1, a.warps // K), 12, K))
         print(f"{K} contexts: {100 * (base - t) / base:.1f} % fewer warp instructions")
