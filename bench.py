@@ -528,9 +528,20 @@ def main():
             traffic = json.load(open(tp)).get(args.workload, {}).get(best["name"], {}).get("dram_bytes_per_launch")
         except Exception:
             traffic = None
+    # the realistic byte model next to the floor — visits*80 + tests*48 + 128 (+96) with the node visits and
+    # triangle tests per ray counted inside the real kernels (RT_GPU_COUNTERS build, recorded in profiles/)
+    realistic = None
+    try:
+        steps = json.load(open(tp)).get(args.workload, {}).get(best["name"], {}).get("traversal_steps")
+        if steps:
+            rb = steps["node_visits_per_ray"] * 80 + steps["triangle_tests_per_ray"] * 48 + 128 + (96 if wave else 0)
+            realistic = {"node_visits_per_ray": steps["node_visits_per_ray"], "triangle_tests_per_ray": steps["triangle_tests_per_ray"],
+                         "bytes_per_ray": rb, "achieved_gbs": (mega["rays"] * rb + samples_total * 16) / world / kernel_s / 1e9}
+    except Exception:
+        realistic = None
     roofline = {"bound": "hbm", "kernel": "k_megakernel" if not wave else "k_wf_extend+k_wf_shade",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                "peak_source": peak_src, "algorithmic_bytes_per_ray": bpr,
+                "peak_source": peak_src, "algorithmic_bytes_per_ray": bpr, "realistic_model": realistic,
                 "algorithmic_bytes_per_launch": alg_bytes_total / max(1, n_launch),
                 "launch_ms": mega["kernel_ms"] / max(1, n_launch / world),
                 "note": ("scene (BVH+shading = %.1f MB) %s" % ((stats["bvh_bytes"] + stats["shading_bytes"]) / 1e6,
