@@ -84,7 +84,7 @@ __global__ void k_wide_emit(RtBuild b, uint32_t n_items) {
     if (i < n_items) rt_wide_emit(b, i);
 }
 
-/* a root with eight empty slots (inverted boxes, meta 0): every ray misses */
+/* a root with eight empty slots (inverted boxes, imask = tmask = 0): every ray misses */
 __global__ void k_empty_root(rt_uint4 *nodes) {
     const uint32_t ff = 0xffffffffu;
     nodes[0] = make_uint4(0, 0, 0, 1u | (1u << 8) | (1u << 16));

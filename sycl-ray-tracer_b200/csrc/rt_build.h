@@ -9,7 +9,7 @@
  *   karras       binary radix tree over the sorted codes (Karras, HPG 2012)
  *   fit          bottom-up AABB fit, one atomic flag per inner node
  *   wide_select  greedy surface-area collapse of the binary tree into <= 8 children
- *   wide_emit    quantise child boxes, assign octant-ordered slots, write the 80-byte node,
+ *   wide_emit    quantise child boxes, assign octant-ordered slots, write the 80-byte node (imask / tmask),
  *                leaf-ordered triangles and the pre-gathered shading records
  *
  * Each function handles ONE item and is wrapped by a thin kernel in bvh_build.cu.
@@ -19,7 +19,7 @@
 
 #include "rt_shade.h"
 
-#define RT_LEAF_MAX 3 /* triangles per leaf child (unary count in 3 meta bits) */
+#define RT_LEAF_MAX 3 /* triangles per leaf child (unary count in the slot's 3 tmask bits) */
 
 struct RtInstanceGeom {
     float transform[16]; /* column-major */
@@ -477,7 +477,7 @@ RT_HD void rt_wide_emit(const RtBuild &b, uint32_t item) {
                    ez = rt_quant_exponent(plo.z, phi.z);
     const float sx = rt_u2f(ex << 23), sy = rt_u2f(ey << 23), sz = rt_u2f(ez << 23);
 
-    uint32_t imask = 0, meta[2] = {0, 0};
+    uint32_t imask = 0, tmask = 0;
     uint32_t q[6][2]; /* qlo x,y,z, qhi x,y,z ; two words of four bytes */
     for (int a = 0; a < 6; a++) {
         q[a][0] = 0;
@@ -504,12 +504,10 @@ RT_HD void rt_wide_emit(const RtBuild &b, uint32_t item) {
         const uint32_t cnt = rt_subtree_count(b, id);
         if (!rt_child_is_leaf(b, id)) {
             imask |= 1u << s;
-            meta[w] |= (0x20u | (24u + (uint32_t)s)) << sh;
             b.next_items[(child_base - b.next_level_first_node) + inner_rank] = id;
             inner_rank++;
         } else {
-            const uint32_t unary = (1u << cnt) - 1u;
-            meta[w] |= ((unary << 5) | tri_off) << sh;
+            tmask |= ((1u << cnt) - 1u) << (3 * s); /* unary count; triangles follow in slot order */
             const uint32_t first = rt_subtree_first(b, id);
             for (uint32_t t = 0; t < cnt; t++) {
                 const uint32_t gid = b.vals[first + t];
@@ -528,7 +526,7 @@ RT_HD void rt_wide_emit(const RtBuild &b, uint32_t item) {
     rt_uint4 n0, n1, n2, n3, n4;
     n0.x = rt_f2u(plo.x); n0.y = rt_f2u(plo.y); n0.z = rt_f2u(plo.z);
     n0.w = ex | (ey << 8) | (ez << 16) | (imask << 24);
-    n1.x = child_base; n1.y = tri_base; n1.z = meta[0]; n1.w = meta[1];
+    n1.x = child_base; n1.y = tri_base; n1.z = tmask; n1.w = 0u;
     n2.x = q[0][0]; n2.y = q[0][1]; n2.z = q[1][0]; n2.w = q[1][1];
     n3.x = q[2][0]; n3.y = q[2][1]; n3.z = q[3][0]; n3.w = q[3][1];
     n4.x = q[4][0]; n4.y = q[4][1]; n4.z = q[5][0]; n4.w = q[5][1];

@@ -14,12 +14,15 @@
  * Node format (80 bytes = 5 x 16-byte vector loads, after Ylitie, Karras, Laine, "Efficient
  * Incoherent Ray Traversal on GPUs Through Compressed Wide BVHs", HPG 2017):
  *   n0 = { p.x, p.y, p.z, ex | ey<<8 | ez<<16 | imask<<24 }
- *   n1 = { child_base, tri_base, meta[0..3], meta[4..7] }
+ *   n1 = { child_base, tri_base, tmask, 0 }
  *   n2 = { qlo_x[0..3], qlo_x[4..7], qlo_y[0..3], qlo_y[4..7] }
  *   n3 = { qlo_z[0..3], qlo_z[4..7], qhi_x[0..3], qhi_x[4..7] }
  *   n4 = { qhi_y[0..3], qhi_y[4..7], qhi_z[0..3], qhi_z[4..7] }
  * child box k = p + q * 2^(e-127)  (e = biased fp32 exponent byte).
- * meta: 0 = empty slot; inner child = 0x20 | (24 + slot); leaf = unary(count) << 5 | offset.
+ * imask bit s = slot s is an inner child (child node = child_base + rank of s among the imask bits).
+ * tmask bits 3s..3s+2 = unary triangle count (1..3) of leaf slot s; the node's leaf triangles are
+ * stored contiguously in slot order from tri_base, so triangle position b (a set bit of tmask) is
+ * tri_base + popc(tmask below b). Empty slots have neither bit and an inverted box.
  * Triangles: 3 x float4 in leaf order: {v0, 0}, {v1, 0}, {v2, global_id_bits}.
  */
 #ifndef RT_TRAVERSE_H
@@ -124,19 +127,6 @@ RT_HD void rt_ldg2(const rt_float4 *p, rt_float4 &a, rt_float4 &b) {
 #endif
 }
 
-/* replicate the msb of every byte over the byte (PRMT with sign-replicate selectors) */
-RT_HD uint32_t rt_sign_extend_s8x4(uint32_t x) {
-#if RT_DEVICE_CODE
-    uint32_t r; /* __byte_perm() masks the selector to 3 bits; the replicate bit needs raw prmt */
-    asm("prmt.b32 %0, %1, %1, 0xba98;" : "=r"(r) : "r"(x));
-    return r;
-#else
-    uint32_t r = 0;
-    for (int i = 0; i < 4; i++)
-        if (x & (0x80u << (8 * i))) r |= 0xffu << (8 * i);
-    return r;
-#endif
-}
 /* byte j of w -> the float 1 + b * 2^-15, built with ONE byte permute (no I2F: the conversion
  * pipe is the narrowest one on sm_100a and 48 conversions per node visit made it the busiest):
  * 0x3F800000 | b << 8. The node test folds the "1 +" and the 2^-15 into its per-node constants. */
@@ -254,7 +244,7 @@ struct RtRayBox {
     f3 org;
     f3 rcp;          /* 1 / dir with |dir| clamped away from 0 */
     uint32_t neg;    /* bit0: dir.x < 0, bit1: dir.y < 0, bit2: dir.z < 0 */
-    uint32_t oct_inv4;
+    uint32_t oct_inv; /* 7 - octant: the inner child in slot s has visiting priority s ^ oct_inv */
 };
 
 RT_HD RtRayBox rt_ray_box_setup(f3 org, f3 dir) {
@@ -268,48 +258,60 @@ RT_HD RtRayBox rt_ray_box_setup(f3 org, f3 dir) {
     r.neg = (dx < 0.0f ? 1u : 0u) | (dy < 0.0f ? 2u : 0u) | (dz < 0.0f ? 4u : 0u);
     /* slot s is visited in order of increasing (s ^ octant), octant = x<<2 | y<<1 | z sign bits */
     uint32_t octant = (dx < 0.0f ? 4u : 0u) | (dy < 0.0f ? 2u : 0u) | (dz < 0.0f ? 1u : 0u);
-    r.oct_inv4 = (7u - octant) * 0x01010101u;
+    r.oct_inv = 7u - octant;
     return r;
 }
 
-/* returns the hit mask of one wide node: bits 24..31 inner children in visiting priority,
- * bits 0..23 leaf triangles (offsets from tri_base) */
+/* bit i of x -> bit i ^ k (k = 0..7): the octant permutation of a byte of child-hit flags */
+RT_HD uint32_t rt_xor_perm8(uint32_t x, uint32_t k) {
+    if (k & 1u) x = ((x & 0x55u) << 1) | ((x >> 1) & 0x55u);
+    if (k & 2u) x = ((x & 0x33u) << 2) | ((x >> 2) & 0x33u);
+    if (k & 4u) x = ((x & 0x0fu) << 4) | ((x >> 4) & 0x0fu);
+    return x;
+}
+
+/* hits |= BIT when the slab interval is not empty: FSETP + one predicated LOP3 with an immediate */
+template <uint32_t BIT>
+RT_HD void rt_or_if_le(float a, float b, uint32_t &hits) {
+#if RT_DEVICE_CODE
+    asm("{\n\t.reg .pred p;\n\tsetp.le.f32 p, %1, %2;\n\t@p or.b32 %0, %0, %3;\n\t}" : "+r"(hits) : "f"(a), "f"(b), "n"(BIT));
+#else
+    if (a <= b) hits |= BIT;
+#endif
+}
+
+/* one child: slot 4 * H + J, planes = byte J of the six quantised-plane words of half H */
 template <int J, int H>
 RT_HD void rt_child_test(uint32_t nx, uint32_t ny, uint32_t nz, uint32_t fx, uint32_t fy, uint32_t fz, float Sx,
                          float Sy, float Sz, float onx, float ony, float onz, float ofx, float ofy, float ofz,
-                         float tmin, float tmax_pad, uint32_t child_bits4, uint32_t bit_index4, uint32_t one,
-                         uint32_t &hitmask) {
+                         float tmin, float tmax_pad, uint32_t one, uint32_t &hits) {
     float tnx, tny, tnz, tfx, tfy, tfz; /* near and far plane of one axis share the multiplier: one FFMA2 */
     rt_fma2(rt_byte_to_unit<J, 1 + 0 + 6 * J + 24 * H>(nx, one), rt_byte_to_unit<J, 1 + 3 + 6 * J + 24 * H>(fx, one), Sx, onx, ofx, tnx, tfx);
     rt_fma2(rt_byte_to_unit<J, 1 + 1 + 6 * J + 24 * H>(ny, one), rt_byte_to_unit<J, 1 + 4 + 6 * J + 24 * H>(fy, one), Sy, ony, ofy, tny, tfy);
     rt_fma2(rt_byte_to_unit<J, 1 + 2 + 6 * J + 24 * H>(nz, one), rt_byte_to_unit<J, 1 + 5 + 6 * J + 24 * H>(fz, one), Sz, onz, ofz, tnz, tfz);
     const float cmin = rt_max(rt_max3(tnx, tny, tnz), tmin);
     const float cmax = rt_min(rt_min3(tfx, tfy, tfz), tmax_pad);
-    const uint32_t bits = (child_bits4 >> (8 * J)) & 0xffu;
-    const uint32_t idxb = (bit_index4 >> (8 * J)) & 0xffu;
-    hitmask |= (cmin <= cmax) ? (bits << idxb) : 0u;
+    rt_or_if_le<1u << (4 * H + J)>(cmin, cmax, hits);
 }
 
 /* four children (one 32-bit word of every quantised plane) */
 template <int H>
-RT_HD void rt_half_test(const RtRayBox &rb, uint32_t meta4, uint32_t qlox, uint32_t qloy, uint32_t qloz, uint32_t qhix,
+RT_HD void rt_half_test(const RtRayBox &rb, uint32_t qlox, uint32_t qloy, uint32_t qloz, uint32_t qhix,
                         uint32_t qhiy, uint32_t qhiz, float Sx, float Sy, float Sz, float onx, float ony, float onz,
-                        float ofx, float ofy, float ofz, float tmin, float tmax_pad, uint32_t one, uint32_t &hitmask) {
-    const uint32_t is_inner4 = (meta4 & (meta4 << 1)) & 0x10101010u;
-    const uint32_t inner_mask4 = rt_sign_extend_s8x4(is_inner4 << 3);
-    const uint32_t bit_index4 = (meta4 ^ (rb.oct_inv4 & inner_mask4)) & 0x1f1f1f1fu;
-    const uint32_t child_bits4 = (meta4 >> 5) & 0x07070707u;
+                        float ofx, float ofy, float ofz, float tmin, float tmax_pad, uint32_t one, uint32_t &hits) {
     const uint32_t nx = (rb.neg & 1u) ? qhix : qlox, fx = (rb.neg & 1u) ? qlox : qhix;
     const uint32_t ny = (rb.neg & 2u) ? qhiy : qloy, fy = (rb.neg & 2u) ? qloy : qhiy;
     const uint32_t nz = (rb.neg & 4u) ? qhiz : qloz, fz = (rb.neg & 4u) ? qloz : qhiz;
-    rt_child_test<0, H>(nx, ny, nz, fx, fy, fz, Sx, Sy, Sz, onx, ony, onz, ofx, ofy, ofz, tmin, tmax_pad, child_bits4, bit_index4, one, hitmask);
-    rt_child_test<1, H>(nx, ny, nz, fx, fy, fz, Sx, Sy, Sz, onx, ony, onz, ofx, ofy, ofz, tmin, tmax_pad, child_bits4, bit_index4, one, hitmask);
-    rt_child_test<2, H>(nx, ny, nz, fx, fy, fz, Sx, Sy, Sz, onx, ony, onz, ofx, ofy, ofz, tmin, tmax_pad, child_bits4, bit_index4, one, hitmask);
-    rt_child_test<3, H>(nx, ny, nz, fx, fy, fz, Sx, Sy, Sz, onx, ony, onz, ofx, ofy, ofz, tmin, tmax_pad, child_bits4, bit_index4, one, hitmask);
+    rt_child_test<0, H>(nx, ny, nz, fx, fy, fz, Sx, Sy, Sz, onx, ony, onz, ofx, ofy, ofz, tmin, tmax_pad, one, hits);
+    rt_child_test<1, H>(nx, ny, nz, fx, fy, fz, Sx, Sy, Sz, onx, ony, onz, ofx, ofy, ofz, tmin, tmax_pad, one, hits);
+    rt_child_test<2, H>(nx, ny, nz, fx, fy, fz, Sx, Sy, Sz, onx, ony, onz, ofx, ofy, ofz, tmin, tmax_pad, one, hits);
+    rt_child_test<3, H>(nx, ny, nz, fx, fy, fz, Sx, Sy, Sz, onx, ony, onz, ofx, ofy, ofz, tmin, tmax_pad, one, hits);
 }
 
-RT_HD uint32_t rt_node_test(const RtRayBox &rb, rt_uint4 n0, rt_uint4 n1, rt_uint4 n2,
-                            rt_uint4 n3, rt_uint4 n4, float tmin, float tmax_pad) {
+/* returns the hit flags of one wide node in SLOT order: bit s = the ray's interval [tmin, tmax_pad]
+ * overlaps the (conservatively padded) box of slot s. Empty slots never hit (inverted boxes). */
+RT_HD uint32_t rt_node_test(const RtRayBox &rb, rt_uint4 n0, rt_uint4 n2, rt_uint4 n3, rt_uint4 n4, float tmin,
+                            float tmax_pad) {
     const float sx = rt_u2f((n0.w & 0xffu) << 23), sy = rt_u2f(((n0.w >> 8) & 0xffu) << 23),
                 sz = rt_u2f(((n0.w >> 16) & 0xffu) << 23);
     /* plane t = q*id + o with id = 2^e/d, o = (p - org)/d */
@@ -330,11 +332,11 @@ RT_HD uint32_t rt_node_test(const RtRayBox &rb, rt_uint4 n0, rt_uint4 n1, rt_uin
                 ez = rt_fma(fabsf(idz), 0.00390625f, fabsf(oz) * 4.76837158e-7f);
     const float onx = (ox - ex) - Sx, ony = (oy - ey) - Sy, onz = (oz - ez) - Sz;
     const float ofx = (ox + ex) - Sx, ofy = (oy + ey) - Sy, ofz = (oz + ez) - Sz;
-    uint32_t hitmask = 0;
+    uint32_t hits = 0;
     const uint32_t one = rt_unit_bits();
-    rt_half_test<0>(rb, n1.z, n2.x, n2.z, n3.x, n3.z, n4.x, n4.z, Sx, Sy, Sz, onx, ony, onz, ofx, ofy, ofz, tmin, tmax_pad, one, hitmask);
-    rt_half_test<1>(rb, n1.w, n2.y, n2.w, n3.y, n3.w, n4.y, n4.w, Sx, Sy, Sz, onx, ony, onz, ofx, ofy, ofz, tmin, tmax_pad, one, hitmask);
-    return hitmask;
+    rt_half_test<0>(rb, n2.x, n2.z, n3.x, n3.z, n4.x, n4.z, Sx, Sy, Sz, onx, ony, onz, ofx, ofy, ofz, tmin, tmax_pad, one, hits);
+    rt_half_test<1>(rb, n2.y, n2.w, n3.y, n3.w, n4.y, n4.w, Sx, Sy, Sz, onx, ony, onz, ofx, ofy, ofz, tmin, tmax_pad, one, hits);
+    return hits;
 }
 
 /* ---- traversal ------------------------------------------------------------------------ */
@@ -362,7 +364,11 @@ struct RtTravState {
 };
 
 /* The dynamically indexed storage is kept apart from RtTravState so that the scalar state is
- * promoted to registers; entries are (base, bits) pairs packed in 64 bits (one access each). */
+ * promoted to registers; entries are (base, bits) pairs packed in 64 bits (one access each).
+ *   node entry: (child_base, inner hit flags in PRIORITY order << 24 | imask)
+ *   tri entry : (tri_base, leaf hit flags in slot order << 24 | tmask)
+ * perm() is the octant permutation of a byte of hit flags (bit s -> bit s ^ k); the persistent
+ * kernels replace it by a 2 KB shared-memory table (render.cu). */
 struct RtTravStacks {
     uint64_t node[RT_STACK_SIZE];  /* pending node groups */
     uint64_t tri[RT_TSTACK_SIZE];  /* pending triangle groups */
@@ -370,6 +376,7 @@ struct RtTravStacks {
     RT_HD void node_put(int i, uint64_t v) { node[i] = v; }
     RT_HD uint64_t tri_get(int i) const { return tri[i]; }
     RT_HD void tri_put(int i, uint64_t v) { tri[i] = v; }
+    RT_HD uint32_t perm(uint32_t k, uint32_t x) const { return rt_xor_perm8(x, k); }
 };
 RT_HD uint64_t rt_pack2(uint32_t x, uint32_t y) { return (uint64_t)x | ((uint64_t)y << 32); }
 
@@ -386,7 +393,7 @@ RT_HD void rt_trav_init(RtTravState &s, f3 org, f3 dir, float tnear, float tfar)
     s.sp = 0;
     s.tsp = 0;
     s.ng_x = 0;
-    s.ng_y = 0x80000000u; /* the root, as the only child of a virtual group */
+    s.ng_y = 0x80000000u; /* the root, as the only child of a virtual group (imask 0: rank 0 for any slot) */
 }
 
 RT_HD bool rt_trav_has_node(const RtTravState &s) { return s.ng_y > 0x00ffffffu; }
@@ -396,7 +403,6 @@ RT_HD bool rt_trav_tri_full(const RtTravState &s) { return s.tsp >= RT_TSTACK_SI
 /* precondition: rt_trav_has_node(s) && !rt_trav_tri_full(s) */
 template <class Stacks>
 RT_HD void rt_trav_node_step(const RtBvh &bvh, RtTravState &s, Stacks &k) {
-    const uint32_t oct_inv = s.rb.oct_inv4 & 7u;
     const uint32_t imask = s.ng_y & 0xffu;
     const int bit = rt_bfind(s.ng_y);
     s.ng_y &= ~(1u << bit);
@@ -404,7 +410,7 @@ RT_HD void rt_trav_node_step(const RtBvh &bvh, RtTravState &s, Stacks &k) {
         k.node_put(s.sp, rt_pack2(s.ng_x, s.ng_y));
         s.sp++;
     }
-    const uint32_t slot = ((uint32_t)bit - 24u) ^ oct_inv;
+    const uint32_t slot = ((uint32_t)bit - 24u) ^ s.rb.oct_inv;
     const uint32_t rel = (uint32_t)rt_popc(imask & ~(0xffffffffu << slot));
     const rt_uint4 *np = bvh.nodes + (size_t)(s.ng_x + rel) * RT_NODE_VEC4;
     rt_uint4 n0, n1, n2, n3, n4;
@@ -418,11 +424,13 @@ RT_HD void rt_trav_node_step(const RtBvh &bvh, RtTravState &s, Stacks &k) {
     n4 = rt_ldg(np + 4);
 #endif
     RT_COUNT_NODE();
-    const uint32_t hm = rt_node_test(s.rb, n0, n1, n2, n3, n4, s.tnear, s.tmax_pad);
+    const uint32_t hits = rt_node_test(s.rb, n0, n2, n3, n4, s.tnear, s.tmax_pad);
+    const uint32_t im = n0.w >> 24;
+    const uint32_t leaf = hits & ~im;
     s.ng_x = n1.x;
-    s.ng_y = (hm & 0xff000000u) | (n0.w >> 24);
-    if (hm & 0x00ffffffu) {
-        k.tri_put(s.tsp, rt_pack2(n1.y, hm & 0x00ffffffu));
+    s.ng_y = (k.perm(s.rb.oct_inv, hits & im) << 24) | im;
+    if (leaf) {
+        k.tri_put(s.tsp, rt_pack2(n1.y, (leaf << 24) | n1.z));
         s.tsp++;
     }
     if (s.ng_y <= 0x00ffffffu && s.sp > 0) { /* no child hit: next pending group */
@@ -433,17 +441,22 @@ RT_HD void rt_trav_node_step(const RtBvh &bvh, RtTravState &s, Stacks &k) {
     }
 }
 
-/* precondition: rt_trav_has_tri(s) */
+/* precondition: rt_trav_has_tri(s). Tests ONE triangle of the top group: the lowest remaining
+ * triangle position of the lowest hit leaf slot. */
 template <class Stacks>
 RT_HD void rt_trav_tri_step(const RtBvh &bvh, RtTravState &s, Stacks &k) {
     const uint64_t e = k.tri_get(s.tsp - 1);
     const uint32_t base = (uint32_t)e;
-    uint32_t bits = (uint32_t)(e >> 32);
-    const int i = rt_ctz(bits);
-    bits &= bits - 1;
-    if (bits) k.tri_put(s.tsp - 1, rt_pack2(base, bits));
+    uint32_t w = (uint32_t)(e >> 32);
+    const uint32_t j = (uint32_t)rt_ctz(w >> 24), sh = 3u * j;  /* lowest hit leaf slot, first bit of its unary count */
+    const uint32_t pos = sh + (uint32_t)rt_ctz((w >> sh) & 7u); /* its lowest untested triangle */
+    const uint32_t tslot = base + (uint32_t)rt_popc(w & ((1u << pos) - 1u)); /* pos < 24: only tmask bits are counted */
+    /* the tested position leaves the mask; every later position of this group lies above it, so
+     * the base moves up by one to keep  slot = base + popc(mask below position)  true */
+    w &= ~(1u << pos);
+    if (((w >> sh) & 7u) == 0u) w &= ~(0x01000000u << j);
+    if (w > 0x00ffffffu) k.tri_put(s.tsp - 1, rt_pack2(base + 1u, w));
     else s.tsp--;
-    const uint32_t tslot = base + (uint32_t)i;
     const rt_float4 *tp = bvh.tris + (size_t)tslot * RT_TRI_VEC4;
     rt_float4 a, b, c;
     rt_ldg2(tp, a, b);

@@ -299,19 +299,17 @@ int emu_scene_validate(const emu_scene *s) {
                                   {np[3].z, np[3].w}, {np[4].x, np[4].y}, {np[4].z, np[4].w}};
         uint32_t rank = 0;
         for (int slot = 0; slot < 8; slot++) {
-            const uint32_t meta = ((slot < 4 ? np[1].z : np[1].w) >> ((slot & 3) * 8)) & 0xffu;
+            const uint32_t tmask = np[1].z, unary = (tmask >> (3 * slot)) & 7u;
             const bool inner = (imask >> slot) & 1u;
-            if (meta == 0) {
-                if (inner) return 1;
-                continue;
-            }
+            if (tmask >> 24) return 1;
+            if (inner && unary) return 2;
+            if (!inner && !unary) continue; /* empty slot */
             float lo[3], hi[3];
             for (int a = 0; a < 3; a++) {
                 lo[a] = p[a] + (float)((q[a][slot >> 2] >> ((slot & 3) * 8)) & 0xffu) * sc[a];
                 hi[a] = p[a] + (float)((q[3 + a][slot >> 2] >> ((slot & 3) * 8)) & 0xffu) * sc[a];
             }
             if (inner) {
-                if (meta != (0x20u | (24u + (uint32_t)slot))) return 2;
                 const uint32_t child = np[1].x + rank++;
                 if (child >= s->n_nodes || seen_node[child]) return 3;
                 seen_node[child] = 1;
@@ -322,8 +320,8 @@ int emu_scene_validate(const emu_scene *s) {
                     if (cpv[a] < lo[a] || cpv[a] > hi[a]) return 4;
                 stack.push_back(child);
             } else {
-                const uint32_t cnt = rt_popc(meta >> 5), off = meta & 31u;
-                if (cnt < 1 || cnt > 3 || (meta >> 5) != (1u << cnt) - 1u) return 5;
+                const uint32_t cnt = rt_popc(unary), off = rt_popc(tmask & ((1u << (3 * slot)) - 1u));
+                if (cnt < 1 || cnt > 3 || unary != (1u << cnt) - 1u) return 5;
                 for (uint32_t t = 0; t < cnt; t++) {
                     const uint32_t tri = np[1].y + off + t;
                     if (tri >= n || seen_tri[tri]) return 6;
@@ -509,13 +507,14 @@ extern "C" void emu_scene_tree_stats(const emu_scene *s, uint64_t *out) {
         const rt_uint4 *np = &s->nodes[(size_t)ni * RT_NODE_VEC4];
         int n = 0;
         for (int slot = 0; slot < 8; slot++) {
-            const uint32_t meta = ((slot < 4 ? np[1].z : np[1].w) >> ((slot & 3) * 8)) & 0xffu;
-            if (!meta) continue;
+            const uint32_t unary = (np[1].z >> (3 * slot)) & 7u;
+            const bool inner = (np[0].w >> 24) & (1u << slot);
+            if (!inner && !unary) continue;
             n++;
-            if ((np[0].w >> 24) & (1u << slot)) out[10]++;
+            if (inner) out[10]++;
             else {
                 out[9]++;
-                out[10 + rt_popc(meta >> 5)]++;
+                out[10 + rt_popc(unary)]++;
             }
         }
         out[n]++;
