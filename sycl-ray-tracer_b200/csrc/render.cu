@@ -363,6 +363,248 @@ __global__ void __launch_bounds__(kMegaBlock, RT_MEGA_MIN_BLOCKS) k_megakernel(R
     if (lane == 0 && rays) atomicAdd(ray_counter, rays);
 }
 
+/* ------------------------------------------------------------------------------ megakernel, K contexts per lane */
+/* Round-2 scheduling of K1. A lane owns K pixels ("contexts"); everything a pixel needs between two
+ * rays is PARKED in local memory (7 x 16 bytes per context) instead of being held in registers across
+ * the traversal loop, so the node loop runs on the traversal state alone (the round-1 kernel re-loaded
+ * spilled ray constants on every node visit). One context at a time is under traversal; the others
+ * are READY (a ray waiting to be traced, its direction-only set-up already computed) or HIT (a
+ * closest hit waiting to be shaded). The warp alternates between
+ *   shade   : every lane with a HIT (or brand-new) context shades ONE of them, regenerates the next
+ *             ray / sample / pixel exactly like k_megakernel, runs the six divisions of the ray set-up
+ *             and parks the context as READY. Runs when `tune_shade` lanes have something to shade, or
+ *             `tune_idle` lanes can neither traverse nor switch — so shading runs with most lanes active
+ *             instead of the 8-13 of the one-context scheme;
+ *   switch  : lanes whose traversal finished park the hit (16 bytes) and load a READY context
+ *             (3 x 16 bytes + a few selects): cheap, so the refill threshold of the node loop is low;
+ *   traverse: traverse_phase(), as before.
+ * Per-pixel arithmetic and the order of a pixel's draws are those of rt_megakernel_pixel (a pixel still
+ * has one ray in flight and its own stream, F4); only the interleaving of pixels changes, so results are
+ * bit-identical to k_megakernel and to the oracle.
+ *   context: q0 = {org, rng}  q1 = {dir, s}  q2 = {att, depth}  q3 = {rad, base_count}  q4 = {sum, x}
+ *            q5 = READY: {nSx, nSy, Sz, code}, HIT: {t, u, v, tri}   q6 = {rcp, y} */
+constexpr int kCtxQ = 7;
+enum { cNew = 0, cReady = 1, cTrav = 2, cHit = 3, cDone = 4 };
+
+__device__ __forceinline__ int opaque_index(int i) { /* keeps the context arrays in local memory for K = 1 too */
+    asm volatile("" : "+r"(i));
+    return i;
+}
+
+template <int K>
+__global__ void __launch_bounds__(kMegaBlock, RT_MEGA_MIN_BLOCKS) k_megakernel_ctx(RtScene scene, RtFrameParams p, RtFrameOut out,
+                                                                                  uint32_t *work_counter, unsigned long long *ray_counter,
+                                                                                  const uint32_t *__restrict__ order) {
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const RtBlockGeom g = rt_block_geom(p);
+    const uint32_t n_work = g.n_blocks * 32u; /* pixel slots, 32 per 8x4 block */
+    float4 cx[K * kCtxQ];
+    uint32_t st = 0; /* 3 bits per context, all cNew */
+    int cur = -1;    /* context under traversal */
+    unsigned long long rays = 0;
+    RtTravState tv;
+    SmemStacks<kMegaBlock> ks;
+#if RT_SMEM_TRI || RT_SMEM_NODE
+    __shared__ uint64_t s_stacks[RT_SMEM_ENTRIES * kMegaBlock];
+    ks.sm = s_stacks + threadIdx.x;
+#endif
+    fill_perm_table();
+    __syncthreads();
+    tv.sp = 0;
+    tv.tsp = 0;
+    tv.ng_y = 0;
+
+    for (;;) {
+        /* ---------------- shade passes ---------------- */
+        for (;;) {
+            int c = -1;
+            bool ready = false, alive = false;
+#pragma unroll
+            for (int i = K - 1; i >= 0; i--) {
+                const uint32_t s_i = (st >> (3 * i)) & 7u;
+                if (s_i == cNew || s_i == cHit) c = i;
+                ready |= s_i == cReady;
+                alive |= s_i != cDone;
+            }
+            const unsigned m_pend = __ballot_sync(full, c >= 0);
+            if (!m_pend) break;
+            const unsigned m_go = __ballot_sync(full, cur >= 0 || ready);
+            const unsigned m_alive = __ballot_sync(full, alive);
+            /* thresholds scale with the lanes that still have work (the drain of a frame) */
+            const int n_alive = __popc(m_alive);
+            const int t_shade = max(1, (n_alive * p.tune_shade + 31) >> 5), t_idle = max(1, (n_alive * p.tune_idle + 31) >> 5);
+            if (m_go && __popc(m_pend) < t_shade && __popc(m_pend & ~m_go) < t_idle) break;
+
+            /* ---- one pass: lanes with c >= 0 shade / regenerate context c ---- */
+            int mode = kExhausted; /* not taking part */
+            int x = 0, y = 0;
+            uint32_t s = 0, depth = 0;
+            XorShift32 rng;
+            rng.a = 0;
+            f3 sum = mk3(0.0f, 0.0f, 0.0f);
+            float base_count = 0.0f;
+            RtRayState r;
+            r.org = r.dir = r.att = r.rad = sum;
+            float4 *q = cx + opaque_index((c < 0 ? 0 : c) * kCtxQ);
+            if (c >= 0) {
+                if (((st >> (3 * c)) & 7u) == cNew) {
+                    mode = kNeedPixel;
+                } else {
+                    const float4 q0 = q[0], q1 = q[1], q2 = q[2], q3 = q[3], q4 = q[4], q5 = q[5];
+                    rng.a = __float_as_uint(q0.w);
+                    s = __float_as_uint(q1.w);
+                    depth = __float_as_uint(q2.w);
+                    base_count = q3.w;
+                    sum = mk3(q4.x, q4.y, q4.z);
+                    x = (int)__float_as_uint(q4.w);
+                    y = (int)__float_as_uint(q[6].w);
+                    RtHit h;
+                    h.t = q5.x;
+                    h.u = q5.y;
+                    h.v = q5.z;
+                    h.tri = __float_as_uint(q5.w);
+                    h.gid = 0;
+                    f3 org = mk3(q0.x, q0.y, q0.z), dir = mk3(q1.x, q1.y, q1.z), att = mk3(q2.x, q2.y, q2.z),
+                       rad = mk3(q3.x, q3.y, q3.z), res = mk3(0.0f, 0.0f, 0.0f);
+                    bool done = rt_shade_segment(scene, h, rng, org, dir, att, rad, res);
+                    r.org = org; /* src/render_megakernel.cpp:41-55: re-quantise the ray state (F6) */
+                    r.dir = round_half3(dir);
+                    r.att = round_half3(att);
+                    r.rad = round_half3(rad);
+                    depth++;
+                    if (!done && depth == p.max_depth) { /* :62, survivors are black (F7) */
+                        done = true;
+                        res = mk3(0.0f, 0.0f, 0.0f);
+                    }
+                    if (done) {
+                        if (p.clamp_samples) res = mk3(rt_clamp01(res.x), rt_clamp01(res.y), rt_clamp01(res.z));
+                        sum = sum + res;
+                        s++;
+                        mode = kNeedRay;
+                    } else {
+                        mode = kStart;
+                    }
+                }
+            }
+            for (;;) { /* warp-uniform: runs until no lane is waiting for a pixel */
+                if (mode == kNeedRay) {
+                    while (p.max_depth == 0 && s < p.spp) { /* the bounce loop never runs: black sample */
+                        rng.next();
+                        rng.next();
+                        s++;
+                    }
+                    if (s == p.spp) { /* pixel finished: :154-158 mean, gamma, image write */
+                        const size_t pix = (size_t)y * (size_t)p.cam.w + (size_t)x;
+                        const float count = base_count + (float)p.spp;
+                        out.accum[pix] = make_float4(sum.x, sum.y, sum.z, count);
+                        const uint32_t px = rt_resolve_pixel(sum.x, sum.y, sum.z, count);
+                        out.rgba8[pix] = px;
+                        if (out.gather) out.gather[pix] = px; /* tile shards: straight into the destination rank's image */
+                        out.rng[pix] = rng.a;
+                        mode = kNeedPixel;
+                    } else {
+                        r = rt_camera_ray(p.cam, x, y, rng); /* 2 draws (F5) */
+                        depth = 0;
+                        mode = kStart;
+                    }
+                }
+                const unsigned need = __ballot_sync(full, mode == kNeedPixel);
+                if (!need) break;
+                uint32_t base = 0;
+                const int leader = __ffs(need) - 1;
+                if (lane == leader) base = atomicAdd(work_counter, (uint32_t)__popc(need));
+                base = __shfl_sync(full, base, leader);
+                if (mode == kNeedPixel) {
+                    const uint32_t idx = base + (uint32_t)__popc(need & ((1u << lane) - 1u));
+                    if (idx >= n_work) {
+                        mode = kExhausted;
+                        st = (st & ~(7u << (3 * c))) | ((uint32_t)cDone << (3 * c));
+                    } else {
+                        const uint32_t in = idx & 31u;
+                        uint32_t x0, y0;
+                        if (order) { /* blocks sorted by decreasing cost class (k_block_cost) */
+                            const uint32_t e = __ldg(order + (idx >> 5));
+                            x0 = e & 0xffffu;
+                            y0 = e >> 16;
+                        } else {
+                            rt_block_origin(p, g, idx >> 5, x0, y0);
+                        }
+                        x = (int)(x0 + (in & 7u));
+                        y = (int)(y0 + (in >> 3));
+                        if (x < p.cam.w && y < p.cam.h && rt_owns_pixel(p, x, y)) {
+                            if (p.resume) { /* carry on where the previous frame stopped */
+                                const size_t pix = (size_t)y * (size_t)p.cam.w + (size_t)x;
+                                const float4 a = out.accum[pix];
+                                rng.a = out.rng[pix];
+                                sum = mk3(a.x, a.y, a.z);
+                                base_count = a.w;
+                            } else {
+                                rng.a = rt_pixel_seed(p.wavefront_seed, x, y, p.cam.w, p.cam.h) ^ p.seed_salt;
+                                sum = mk3(0.0f, 0.0f, 0.0f);
+                                base_count = 0.0f;
+                            }
+                            s = 0;
+                            mode = kNeedRay;
+                        } /* else: padding / another rank's pixel, fetch again */
+                    }
+                }
+            }
+            if (mode == kStart) { /* park the context with its ray ready to be traced */
+                const RtRayPre pre = rt_ray_pre(r.dir);
+                q[0] = make_float4(r.org.x, r.org.y, r.org.z, __uint_as_float(rng.a));
+                q[1] = make_float4(r.dir.x, r.dir.y, r.dir.z, __uint_as_float(s));
+                q[2] = make_float4(r.att.x, r.att.y, r.att.z, __uint_as_float(depth));
+                q[3] = make_float4(r.rad.x, r.rad.y, r.rad.z, base_count);
+                q[4] = make_float4(sum.x, sum.y, sum.z, __uint_as_float((uint32_t)x));
+                q[5] = make_float4(pre.nSx, pre.nSy, pre.Sz, __uint_as_float(pre.code));
+                q[6] = make_float4(pre.rcp.x, pre.rcp.y, pre.rcp.z, __uint_as_float((uint32_t)y));
+                st = (st & ~(7u << (3 * c))) | ((uint32_t)cReady << (3 * c));
+                rays++;
+            }
+        }
+        /* ---------------- switch ---------------- */
+        if (cur < 0) {
+            int c = -1;
+#pragma unroll
+            for (int i = K - 1; i >= 0; i--)
+                if (((st >> (3 * i)) & 7u) == cReady) c = i;
+            if (c >= 0) {
+                const float4 *q = cx + opaque_index(c * kCtxQ);
+                const float4 q0 = q[0], q5 = q[5], q6 = q[6];
+                RtRayPre pre;
+                pre.rcp = mk3(q6.x, q6.y, q6.z);
+                pre.nSx = q5.x;
+                pre.nSy = q5.y;
+                pre.Sz = q5.z;
+                pre.code = __float_as_uint(q5.w);
+                rt_trav_init_pre(tv, mk3(q0.x, q0.y, q0.z), pre, 0.0001f, INFINITY);
+                st = (st & ~(7u << (3 * c))) | ((uint32_t)cTrav << (3 * c));
+                cur = c;
+            }
+        }
+        /* ---------------- traverse ---------------- */
+        int mode = cur >= 0 ? kTraversing : kExhausted;
+        const unsigned act0 = __ballot_sync(full, mode == kTraversing);
+        if (!act0) {
+            bool alive = false;
+#pragma unroll
+            for (int i = 0; i < K; i++) alive |= ((st >> (3 * i)) & 7u) != cDone;
+            if (!__any_sync(full, alive)) break; /* every context of every lane is exhausted */
+            continue;                            /* only shading work is left: the next pass runs it */
+        }
+        traverse_phase(scene.bvh, tv, ks, mode, p.tune_refill);
+        if (mode == kHitPending) { /* park the hit; the lane switches at the top of the next round */
+            cx[opaque_index(cur * kCtxQ + 5)] = make_float4(tv.best.t, tv.best.u, tv.best.v, __uint_as_float(tv.best.tri));
+            st = (st & ~(7u << (3 * cur))) | ((uint32_t)cHit << (3 * cur));
+            cur = -1;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) rays += __shfl_xor_sync(full, rays, o);
+    if (lane == 0 && rays) atomicAdd(ray_counter, rays);
+}
+
 /* ------------------------------------------------------------------------------ wavefront */
 /* block-wide order-preserving compaction of `keep` flags: returns the global slot or ~0u */
 __device__ __forceinline__ uint32_t block_compact(bool keep, uint32_t *queue_count, uint32_t *s_warp, uint32_t *s_base) {
@@ -527,9 +769,16 @@ cudaError_t rt_launch_intersect(cudaStream_t st, const RtScene &scene, const RtI
     return cudaGetLastError();
 }
 
-cudaError_t rt_megakernel_grid(int sm_count, int *grid) {
+cudaError_t rt_megakernel_grid(int sm_count, int tune_ctx, int *grid) {
     int per_sm = 0;
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_megakernel, kMegaBlock, 0);
+    cudaError_t e = cudaSuccess;
+    switch (tune_ctx) {
+    case 1: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_megakernel_ctx<1>, kMegaBlock, 0); break;
+    case 2: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_megakernel_ctx<2>, kMegaBlock, 0); break;
+    case 3: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_megakernel_ctx<3>, kMegaBlock, 0); break;
+    case 4: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_megakernel_ctx<4>, kMegaBlock, 0); break;
+    default: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_megakernel, kMegaBlock, 0); break;
+    }
     if (e != cudaSuccess) return e;
     if (per_sm < 1) per_sm = 1;
     *grid = sm_count * per_sm;
@@ -539,7 +788,13 @@ cudaError_t rt_megakernel_grid(int sm_count, int *grid) {
 cudaError_t rt_launch_megakernel(cudaStream_t st, int grid, const RtScene &scene, const RtFrameParams &p,
                                  const RtFrameOut &out, uint32_t *work_counter, unsigned long long *ray_counter,
                                  const uint32_t *order) {
-    k_megakernel<<<grid, kMegaBlock, 0, st>>>(scene, p, out, work_counter, ray_counter, order);
+    switch (p.tune_ctx) {
+    case 1: k_megakernel_ctx<1><<<grid, kMegaBlock, 0, st>>>(scene, p, out, work_counter, ray_counter, order); break;
+    case 2: k_megakernel_ctx<2><<<grid, kMegaBlock, 0, st>>>(scene, p, out, work_counter, ray_counter, order); break;
+    case 3: k_megakernel_ctx<3><<<grid, kMegaBlock, 0, st>>>(scene, p, out, work_counter, ray_counter, order); break;
+    case 4: k_megakernel_ctx<4><<<grid, kMegaBlock, 0, st>>>(scene, p, out, work_counter, ray_counter, order); break;
+    default: k_megakernel<<<grid, kMegaBlock, 0, st>>>(scene, p, out, work_counter, ray_counter, order); break;
+    }
     return cudaGetLastError();
 }
 

@@ -46,6 +46,8 @@ struct rt_renderer {
     bool gather_ipc = false;      /* gather was opened from an IPC handle (close it) */
     bool exported = false;        /* d_rgba8 is a gather destination: never clear foreign pixels */
     int tune_refill = 12; /* lanes that must run dry before a warp refills (RT_TUNE_REFILL overrides; 12-14 measured best) */
+    int tune_ctx = 2;     /* megakernel: ray contexts per lane (RT_MEGA_CTX; 0 = round-1 kernel) */
+    int tune_shade = 24, tune_idle = 4; /* megakernel contexts: shade-pass triggers (RT_TUNE_SHADE, RT_TUNE_IDLE) */
 };
 
 namespace {
@@ -438,6 +440,10 @@ rt_status rt_renderer_create(rt_context *ctx, rt_renderer_kind kind, int32_t wid
     r->h = height;
     if (const char *e = getenv("RT_TUNE_REFILL")) r->tune_refill = atoi(e) > 0 ? atoi(e) : r->tune_refill;
     if (const char *e = getenv("RT_BLOCK_ORDER")) r->block_order = atoi(e);
+    if (const char *e = getenv("RT_MEGA_CTX")) r->tune_ctx = atoi(e) >= 0 && atoi(e) <= 4 ? atoi(e) : r->tune_ctx;
+    if (const char *e = getenv("RT_TUNE_SHADE")) r->tune_shade = atoi(e) > 0 ? atoi(e) : r->tune_shade;
+    if (const char *e = getenv("RT_TUNE_IDLE")) r->tune_idle = atoi(e) > 0 ? atoi(e) : r->tune_idle;
+    if (kind == RT_MEGAKERNEL && r->tune_ctx > 0 && !getenv("RT_TUNE_REFILL")) r->tune_refill = 4; /* switching is cheap */
     const size_t n = (size_t)width * (size_t)height;
     cudaError_t e = cudaSuccess;
     do {
@@ -452,7 +458,7 @@ rt_status rt_renderer_create(rt_context *ctx, rt_renderer_kind kind, int32_t wid
         if ((e = cudaEventCreateWithFlags(&r->ev_batch[0], cudaEventDisableTiming)) != cudaSuccess) break;
         if ((e = cudaEventCreateWithFlags(&r->ev_batch[1], cudaEventDisableTiming)) != cudaSuccess) break;
         if (kind == RT_MEGAKERNEL) {
-            if ((e = rt_megakernel_grid(ctx->sm_count, &r->grid_mega)) != cudaSuccess) break;
+            if ((e = rt_megakernel_grid(ctx->sm_count, r->tune_ctx, &r->grid_mega)) != cudaSuccess) break;
         } else {
             /* Buffers + rng_buffer, src/render_wavefront.hpp:18-37, .cpp:52-54 */
             if ((e = dev_alloc(&r->wf.org, n)) != cudaSuccess) break;
@@ -578,6 +584,9 @@ rt_status rt_render_frame(rt_renderer *r, const rt_scene *scene, const rt_camera
     p.wavefront_seed = r->kind == RT_WAVEFRONT ? 1 : 0;
     p.clamp_samples = r->kind == RT_WAVEFRONT ? 1 : 0;
     p.tune_refill = r->tune_refill;
+    p.tune_ctx = r->tune_ctx;
+    p.tune_shade = r->tune_shade;
+    p.tune_idle = r->tune_idle;
     p.resume = (params->flags & RT_RENDER_RESUME) ? 1 : 0;
     if (p.resume && !r->has_frame) return rt_set_error(ctx, RT_ERR_STATE, "rt_render_frame", "RT_RENDER_RESUME without a previous frame");
     RtFrameOut out;

@@ -11,7 +11,7 @@
 cudaError_t rt_launch_intersect(cudaStream_t st, const RtScene &scene, const RtInstance *inst, uint64_t n,
                                 const float *org, const float *dir, float tnear, float tfar, int32_t *o_inst,
                                 int32_t *o_prim, float *o_u, float *o_v, float *o_t);
-cudaError_t rt_megakernel_grid(int sm_count, int *grid);
+cudaError_t rt_megakernel_grid(int sm_count, int tune_ctx, int *grid);
 cudaError_t rt_launch_megakernel(cudaStream_t st, int grid, const RtScene &scene, const RtFrameParams &p,
                                  const RtFrameOut &out, uint32_t *work_counter, unsigned long long *ray_counter,
                                  const uint32_t *order /* NULL: enumeration order */);

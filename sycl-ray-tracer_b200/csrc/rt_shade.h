@@ -235,6 +235,9 @@ struct RtFrameParams {
     int32_t keep_foreign;   /* tile shards: leave other ranks' RGBA8 pixels alone (this image is a gather destination) */
     /* scheduling knobs of the persistent kernels (no effect on results) */
     int32_t tune_refill;    /* leave the traversal loop once this many lanes have finished */
+    int32_t tune_ctx;       /* megakernel: ray contexts per lane (0 = the round-1 one-pixel-in-registers kernel) */
+    int32_t tune_shade;     /* megakernel contexts: shade once this many lanes have a hit waiting ... */
+    int32_t tune_idle;      /* ... or this many lanes can neither traverse nor switch */
 };
 
 /* image-tile sharding: tile t (row major, tile_size^2 pixels) belongs to rank t % world */

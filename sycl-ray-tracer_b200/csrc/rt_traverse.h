@@ -173,9 +173,18 @@ struct RtRayTri {
 
 RT_HD float rt_shear(f3 p, f3 m) { return rt_fma(p.x, m.x, rt_fma(p.y, m.y, p.z * m.z)); }
 
-RT_HD RtRayTri rt_ray_tri_setup(f3 org, f3 dir) {
-    RtRayTri r;
-    r.org = org;
+/* The direction-only part of the per-ray set-up (six IEEE divisions), separated so that the persistent
+ * megakernel can compute it while it shades (many lanes active) and park it with the ray: starting the
+ * traversal later is then a handful of loads and selects. code = kx | ky << 2 | kz << 4 | neg << 6 |
+ * oct_inv << 9 (see RtRayBox). */
+struct RtRayPre {
+    f3 rcp;             /* 1 / dir with |dir| clamped away from 0 (box slabs) */
+    float nSx, nSy, Sz; /* -dir[kx]/dir[kz], -dir[ky]/dir[kz], 1/dir[kz] (triangle shear) */
+    uint32_t code;
+};
+
+RT_HD RtRayPre rt_ray_pre(f3 dir) {
+    RtRayPre r;
     float ax = fabsf(dir.x), ay = fabsf(dir.y), az = fabsf(dir.z);
     int kz = 0;
     float am = ax;
@@ -194,7 +203,26 @@ RT_HD RtRayTri rt_ray_tri_setup(f3 org, f3 dir) {
         kx = ky;
         ky = tmp;
     }
-    const float nSx = -rt_div(sel3(dir, kx), dz), nSy = -rt_div(sel3(dir, ky), dz), Sz = rt_div(1.0f, dz);
+    r.nSx = -rt_div(sel3(dir, kx), dz);
+    r.nSy = -rt_div(sel3(dir, ky), dz);
+    r.Sz = rt_div(1.0f, dz);
+    const float tiny = 1e-20f;
+    float dx = fabsf(dir.x) > tiny ? dir.x : copysignf(tiny, dir.x);
+    float dy = fabsf(dir.y) > tiny ? dir.y : copysignf(tiny, dir.y);
+    float dzz = fabsf(dir.z) > tiny ? dir.z : copysignf(tiny, dir.z);
+    r.rcp = mk3(rt_div(1.0f, dx), rt_div(1.0f, dy), rt_div(1.0f, dzz));
+    const uint32_t neg = (dx < 0.0f ? 1u : 0u) | (dy < 0.0f ? 2u : 0u) | (dzz < 0.0f ? 4u : 0u);
+    /* slot s is visited in order of increasing (s ^ octant), octant = x<<2 | y<<1 | z sign bits */
+    const uint32_t octant = (dx < 0.0f ? 4u : 0u) | (dy < 0.0f ? 2u : 0u) | (dzz < 0.0f ? 1u : 0u);
+    r.code = (uint32_t)kx | ((uint32_t)ky << 2) | ((uint32_t)kz << 4) | (neg << 6) | ((7u - octant) << 9);
+    return r;
+}
+
+RT_HD RtRayTri rt_ray_tri_from_pre(f3 org, const RtRayPre &q) {
+    RtRayTri r;
+    r.org = org;
+    const int kx = (int)(q.code & 3u), ky = (int)((q.code >> 2) & 3u), kz = (int)((q.code >> 4) & 3u);
+    const float nSx = q.nSx, nSy = q.nSy, Sz = q.Sz;
     r.mx = mk3(kx == 0 ? 1.0f : (kz == 0 ? nSx : 0.0f), kx == 1 ? 1.0f : (kz == 1 ? nSx : 0.0f),
                kx == 2 ? 1.0f : (kz == 2 ? nSx : 0.0f));
     r.my = mk3(ky == 0 ? 1.0f : (kz == 0 ? nSy : 0.0f), ky == 1 ? 1.0f : (kz == 1 ? nSy : 0.0f),
@@ -247,18 +275,12 @@ struct RtRayBox {
     uint32_t oct_inv; /* 7 - octant: the inner child in slot s has visiting priority s ^ oct_inv */
 };
 
-RT_HD RtRayBox rt_ray_box_setup(f3 org, f3 dir) {
+RT_HD RtRayBox rt_ray_box_from_pre(f3 org, const RtRayPre &q) {
     RtRayBox r;
     r.org = org;
-    const float tiny = 1e-20f;
-    float dx = fabsf(dir.x) > tiny ? dir.x : copysignf(tiny, dir.x);
-    float dy = fabsf(dir.y) > tiny ? dir.y : copysignf(tiny, dir.y);
-    float dz = fabsf(dir.z) > tiny ? dir.z : copysignf(tiny, dir.z);
-    r.rcp = mk3(rt_div(1.0f, dx), rt_div(1.0f, dy), rt_div(1.0f, dz));
-    r.neg = (dx < 0.0f ? 1u : 0u) | (dy < 0.0f ? 2u : 0u) | (dz < 0.0f ? 4u : 0u);
-    /* slot s is visited in order of increasing (s ^ octant), octant = x<<2 | y<<1 | z sign bits */
-    uint32_t octant = (dx < 0.0f ? 4u : 0u) | (dy < 0.0f ? 2u : 0u) | (dz < 0.0f ? 1u : 0u);
-    r.oct_inv = 7u - octant;
+    r.rcp = q.rcp;
+    r.neg = (q.code >> 6) & 7u;
+    r.oct_inv = (q.code >> 9) & 7u;
     return r;
 }
 
@@ -380,20 +402,24 @@ struct RtTravStacks {
 };
 RT_HD uint64_t rt_pack2(uint32_t x, uint32_t y) { return (uint64_t)x | ((uint64_t)y << 32); }
 
-RT_HD void rt_trav_init(RtTravState &s, f3 org, f3 dir, float tnear, float tfar) {
+RT_HD void rt_trav_init_pre(RtTravState &s, f3 org, const RtRayPre &pre, float tnear, float tfar) {
     s.best.t = tfar;
     s.best.u = 0.0f;
     s.best.v = 0.0f;
     s.best.tri = RT_MISS;
     s.best.gid = RT_MISS;
-    s.rt = rt_ray_tri_setup(org, dir);
-    s.rb = rt_ray_box_setup(org, dir);
+    s.rt = rt_ray_tri_from_pre(org, pre);
+    s.rb = rt_ray_box_from_pre(org, pre);
     s.tnear = tnear;
     s.tmax_pad = tfar * RT_BOX_PAD;
     s.sp = 0;
     s.tsp = 0;
     s.ng_x = 0;
     s.ng_y = 0x80000000u; /* the root, as the only child of a virtual group (imask 0: rank 0 for any slot) */
+}
+
+RT_HD void rt_trav_init(RtTravState &s, f3 org, f3 dir, float tnear, float tfar) {
+    rt_trav_init_pre(s, org, rt_ray_pre(dir), tnear, tfar);
 }
 
 RT_HD bool rt_trav_has_node(const RtTravState &s) { return s.ng_y > 0x00ffffffu; }

@@ -235,10 +235,37 @@ def sponza_scale_scene(field_cells=256, sphere_subdiv=4, n_spheres=25, seed=0x5E
     return SceneData(I, tex, (0.5, 0.7, 1.0), (0.0, 2.2, 7.6), (0.0, -0.22, -1.0), 1.5, "sponza_scale")
 
 
+def _cached(tag, make):
+    """the 10 M-triangle field takes ~45 s of numpy per process: keep the arrays of big meshes in a per-machine
+    scratch file (RT_SCENE_CACHE overrides the directory, empty disables). Deterministic content, so a cache hit
+    returns the same bytes the generator would."""
+    import os
+    import tempfile
+    d = os.environ.get("RT_SCENE_CACHE", tempfile.gettempdir())
+    path = os.path.join(d, f"rt_b200_scene_{tag}.npz") if d else None
+    if path and os.path.exists(path):
+        try:
+            z = np.load(path)
+            return z["pos"], z["nrm"], z["uv"], z["idx"]
+        except Exception:
+            pass
+    arrs = make()
+    if path:
+        try:
+            tmp = path + f".{os.getpid()}.tmp.npz"
+            np.savez(tmp, pos=arrs[0], nrm=arrs[1], uv=arrs[2], idx=arrs[3])
+            os.replace(tmp, path)
+        except Exception:
+            pass
+    return arrs
+
+
 def big_mesh_scene(cells=2236, seed=0x5EED0004):
     """C4: one displaced height field, 2 * cells^2 triangles (2236 -> 9,999,392), diffuse 0.7 grey,
     grazing camera so rays span the whole BVH."""
-    I = [InstanceData(*heightfield(cells, 50.0, 4.0, seed + 1, 12.0, 32.0), None, Material.diffuse((0.7, 0.7, 0.7)))]
+    mesh = (lambda: heightfield(cells, 50.0, 4.0, seed + 1, 12.0, 32.0))
+    arrs = _cached(f"heightfield_{cells}_{seed:x}", mesh) if cells >= 1024 else mesh()
+    I = [InstanceData(*arrs, None, Material.diffuse((0.7, 0.7, 0.7)))]
     return SceneData(I, None, (0.5, 0.7, 1.0), (0.0, 6.0, 49.0), (0.0, -0.08, -1.0), 1.5, f"heightfield_{cells}")
 
 
