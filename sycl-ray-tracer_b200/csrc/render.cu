@@ -159,12 +159,31 @@ enum { kNeedPixel = 0, kNeedRay = 1, kStart = 2, kTraversing = 3, kHitPending = 
 #define RT_SMEM_NODE 0
 #endif
 #define RT_SMEM_ENTRIES ((RT_SMEM_TRI ? RT_TSTACK_SIZE : 0) + RT_SMEM_NODE)
-/* octant permutation table of the child-hit flags (rt_trav_node_step): s_perm_tbl[k * 256 + x] =
+/* octant permutation table of the child-hit flags (rt_trav_node_step): s_perm_tbl[x * 8 + k] =
  * rt_xor_perm8(x, k). One LDS at a compile-time shared address instead of a dozen ALU instructions per
- * node visit; 2 KB per CTA of every kernel that traverses with SmemStacks. */
+ * node visit; 2 KB per CTA of every kernel that traverses with SmemStacks. Indexed [x][k]: most lanes
+ * carry a small x (0-2 inner children hit) and differ in k, which the [k][x] layout put on ONE bank
+ * (ncu: 7.2 wavefronts per LDS); here lanes with equal x share a word or sit on adjacent banks.
+ * RT_PERM_MODE 2 = no table, the three conditional swaps in registers. */
+#ifndef RT_PERM_MODE
+#define RT_PERM_MODE 1
+#endif
 __shared__ __align__(16) uint8_t s_perm_tbl[8 * 256];
 __device__ __forceinline__ void fill_perm_table() { /* the caller synchronises the CTA afterwards */
+#if RT_PERM_MODE == 0
     for (uint32_t i = threadIdx.x; i < 8u * 256u; i += blockDim.x) s_perm_tbl[i] = (uint8_t)rt_xor_perm8(i & 255u, i >> 8);
+#elif RT_PERM_MODE == 1
+    for (uint32_t i = threadIdx.x; i < 8u * 256u; i += blockDim.x) s_perm_tbl[i] = (uint8_t)rt_xor_perm8(i >> 3, i & 7u);
+#endif
+}
+__device__ __forceinline__ uint32_t perm_lookup(uint32_t k, uint32_t x) {
+#if RT_PERM_MODE == 0
+    return s_perm_tbl[k * 256u + x];
+#elif RT_PERM_MODE == 1
+    return s_perm_tbl[x * 8u + k];
+#else
+    return rt_xor_perm8(x, k);
+#endif
 }
 
 template <int BLOCK>
@@ -174,7 +193,7 @@ struct SmemStacks {
     uint64_t tri[RT_TSTACK_SIZE];
 #endif
     uint64_t *sm; /* this thread's column of the CTA's shared array */
-    __device__ __forceinline__ uint32_t perm(uint32_t k, uint32_t x) const { return s_perm_tbl[k * 256u + x]; }
+    __device__ __forceinline__ uint32_t perm(uint32_t k, uint32_t x) const { return perm_lookup(k, x); }
     __device__ __forceinline__ uint64_t node_get(int i) const {
 #if RT_SMEM_NODE
         if (i < RT_SMEM_NODE) return sm[((RT_SMEM_TRI ? RT_TSTACK_SIZE : 0) + i) * BLOCK];
@@ -726,6 +745,145 @@ __global__ void __launch_bounds__(kWfBlock) k_wf_shade(RtScene scene, RtFramePar
     }
 }
 
+/* ------------------------------------------------------------------------------ wavefront, persistent */
+/* The whole wavefront frame in ONE launch (K2-K6 of src/render_wavefront.cpp:62-417). The streaming kernels above pay
+ * a grid-wide ramp and tail for every one of the spp * max_depth bounce iterations (thousands of launches per frame).
+ * Here every CTA owns a fixed share of the image — the 8x4 pixel blocks b with b % gridDim.x == blockIdx.x, a
+ * regular lattice over the frame, so the shares cost the same to within a few per cent — and runs generate /
+ * {extend, shade}* / resolve for its own pixels with CTA-local queues: the iteration boundary is a __syncthreads() of
+ * one CTA, not a grid-wide barrier, the CTAs of an SM drift apart and fill each other's ramps and tails, and the L1
+ * keeps the upper BVH levels across iterations. A pixel's state, its queue entries and its accumulation are only
+ * ever touched by its own CTA (same SM, same L1), so no device-scope fence is needed. Per-pixel arithmetic is
+ * rt_wf_generate_pixel / traverse / rt_wf_shade_pixel, unchanged: results are bit-identical to the streaming form. */
+__device__ __forceinline__ bool wf_block_pixel(const RtFrameParams &p, const RtBlockGeom &g, uint32_t blk, int lane, uint32_t &pix) {
+    if (blk >= g.n_blocks) return false;
+    uint32_t x0, y0;
+    rt_block_origin(p, g, blk, x0, y0);
+    const int x = (int)(x0 + ((uint32_t)lane & 7u)), y = (int)(y0 + ((uint32_t)lane >> 3));
+    if (x >= p.cam.w || y >= p.cam.h || !rt_owns_pixel(p, x, y)) return false;
+    pix = (uint32_t)y * (uint32_t)p.cam.w + (uint32_t)x;
+    return true;
+}
+
+__global__ void __launch_bounds__(kWfBlock, RT_EXT_MIN_BLOCKS) k_wf_persistent(RtScene scene, RtFrameParams p, RtWavefrontState w, RtFrameOut out,
+                                                                              unsigned long long *ray_counter, uint32_t cap) {
+    __shared__ uint32_t s_warp[kWfBlock / 32];
+    __shared__ uint32_t s_base;
+    __shared__ uint32_t s_count[2];
+    __shared__ uint32_t s_head;
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr uint32_t kWarps = kWfBlock / 32;
+    const RtBlockGeom g = rt_block_geom(p);
+    uint32_t *queue[2] = {w.queue[0] + (size_t)blockIdx.x * cap, w.queue[1] + (size_t)blockIdx.x * cap};
+    const uint32_t my_blocks = g.n_blocks > blockIdx.x ? (g.n_blocks - blockIdx.x + gridDim.x - 1) / gridDim.x : 0u;
+    const uint32_t rounds = (my_blocks + kWarps - 1) / kWarps;
+    fill_perm_table();
+    if (threadIdx.x == 0) {
+        s_count[0] = 0u;
+        s_count[1] = 0u;
+        s_head = 0u;
+    }
+    __syncthreads();
+    /* ---- generate (K2 + first K3): seed, zero, first camera ray of every owned pixel ---- */
+    for (uint32_t it = 0; it < rounds; it++) {
+        const uint32_t k = it * kWarps + (uint32_t)warp;
+        uint32_t pix = 0;
+        bool live = k < my_blocks && wf_block_pixel(p, g, blockIdx.x + k * gridDim.x, lane, pix);
+        if (live) live = rt_wf_generate_pixel(p, w, out, pix);
+        const uint32_t slot = block_compact(live, &s_count[0], s_warp, &s_base);
+        if (live) queue[0][slot] = pix;
+    }
+    unsigned long long rays = 0;
+    RtTravState tv;
+    SmemStacks<kWfBlock> ks;
+#if RT_SMEM_TRI || RT_SMEM_NODE
+    __shared__ uint64_t s_stacks[RT_SMEM_ENTRIES * kWfBlock];
+    ks.sm = s_stacks + threadIdx.x;
+#endif
+    int cur = 0;
+    for (;;) {
+        __syncthreads(); /* queue[cur] and its length are complete */
+        const uint32_t count = s_count[cur];
+        if (count == 0u) break;
+        __syncthreads(); /* every thread has read the length before it is reused */
+        if (threadIdx.x == 0) {
+            s_count[cur ^ 1] = 0u;
+            s_head = 0u;
+            rays += count; /* src/render_wavefront.cpp:407 */
+        }
+        __syncthreads();
+        /* ---- extend: traversal only, persistent lanes with replacement from the CTA's queue ---- */
+        {
+            const uint32_t *q = queue[cur];
+            int mode = kNeedPixel;
+            uint32_t pix = 0;
+            tv.sp = 0;
+            tv.tsp = 0;
+            tv.ng_y = 0;
+            for (;;) {
+                if (mode == kHitPending) {
+                    w.hit[pix] = make_float4(tv.best.t, tv.best.u, tv.best.v, __uint_as_float(tv.best.tri));
+                    mode = kNeedPixel;
+                }
+                const unsigned need = __ballot_sync(full, mode == kNeedPixel);
+                if (need) {
+                    uint32_t base = 0;
+                    const int leader = __ffs(need) - 1;
+                    if (lane == leader) base = atomicAdd(&s_head, (uint32_t)__popc(need));
+                    base = __shfl_sync(full, base, leader);
+                    if (mode == kNeedPixel) {
+                        const uint32_t idx = base + (uint32_t)__popc(need & ((1u << lane) - 1u));
+                        if (idx >= count) {
+                            mode = kExhausted;
+                        } else {
+                            pix = q[idx];
+                            const float4 o = w.org[pix];
+                            rt_trav_init(tv, mk3(o.x, o.y, o.z), rt_unpack_half3(w.dir[pix]), 0.0001f, INFINITY);
+                            mode = kTraversing;
+                        }
+                    }
+                }
+                const unsigned act0 = __ballot_sync(full, mode == kTraversing);
+                if (!act0) break;
+                traverse_phase(scene.bvh, tv, ks, mode, p.tune_refill);
+            }
+        }
+        __syncthreads(); /* every hit record of this iteration is written */
+        /* ---- shade + connect + regenerate, survivors compacted into the other queue ---- */
+        {
+            const uint32_t *q = queue[cur];
+            uint32_t *nq = queue[cur ^ 1];
+            const uint32_t srounds = (count + kWfBlock - 1) / kWfBlock;
+            for (uint32_t it = 0; it < srounds; it++) {
+                const uint32_t i = it * kWfBlock + threadIdx.x;
+                bool keep = false;
+                uint32_t pix = 0;
+                if (i < count) {
+                    pix = q[i];
+                    keep = rt_wf_shade_pixel(scene, p, w, out, pix);
+                }
+                const uint32_t slot = block_compact(keep, &s_count[cur ^ 1], s_warp, &s_base);
+                if (keep) nq[slot] = pix;
+            }
+        }
+        cur ^= 1;
+    }
+    /* ---- resolve (K6/K7) of the owned pixels ---- */
+    for (uint32_t it = 0; it < rounds; it++) {
+        const uint32_t k = it * kWarps + (uint32_t)warp;
+        uint32_t pix = 0;
+        if (k < my_blocks && wf_block_pixel(p, g, blockIdx.x + k * gridDim.x, lane, pix)) {
+            const float4 a = out.accum[pix];
+            const uint32_t px = rt_resolve_pixel(a.x, a.y, a.z, a.w); /* a.w = samples accumulated (= spp, or more after resumes) */
+            out.rgba8[pix] = px;
+            if (out.gather) out.gather[pix] = px;
+            out.rng[pix] = w.rng[pix];
+        }
+    }
+    if (threadIdx.x == 0 && rays) atomicAdd(ray_counter, rays);
+}
+
 /* ------------------------------------------------------------------------------ resolve */
 __global__ void k_resolve(const float4 *accum, uint32_t *rgba8, uint32_t n_pix, float spp) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -843,6 +1001,20 @@ cudaError_t rt_wavefront_grid(int sm_count, int *grid_extend, int *grid_shade) {
     if (e != cudaSuccess) return e;
     *grid_extend = sm_count * (a < 1 ? 1 : a);
     *grid_shade = sm_count * (b < 1 ? 1 : b);
+    return cudaSuccess;
+}
+
+cudaError_t rt_launch_wf_persistent(cudaStream_t st, int grid, uint32_t cap, const RtScene &scene, const RtFrameParams &p,
+                                    const RtWavefrontState &w, const RtFrameOut &out, unsigned long long *ray_counter) {
+    k_wf_persistent<<<grid, kWfBlock, 0, st>>>(scene, p, w, out, ray_counter, cap);
+    return cudaGetLastError();
+}
+
+cudaError_t rt_wf_persistent_grid(int sm_count, int *grid) {
+    int a = 0;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, k_wf_persistent, kWfBlock, 0);
+    if (e != cudaSuccess) return e;
+    *grid = sm_count * (a < 1 ? 1 : a);
     return cudaSuccess;
 }
 

@@ -33,7 +33,9 @@ struct rt_renderer {
     uint32_t *d_counts = nullptr;           /* 2 queue lengths */
     uint32_t *h_counts = nullptr;           /* pinned mirror */
     unsigned long long *h_rays = nullptr;   /* pinned */
-    int grid_mega = 0, grid_extend = 0, grid_shade = 0;
+    int grid_mega = 0, grid_extend = 0, grid_shade = 0, grid_persist = 0;
+    size_t queue_capacity = 0;    /* slots per wavefront id queue */
+    int wf_persist = 1;           /* wavefront: the whole frame in one persistent launch (RT_WF_PERSIST=0: streaming kernels) */
     cudaEvent_t ev_batch[2] = {nullptr, nullptr}; /* wavefront: per-batch queue-length read-back */
     bool has_frame = false; /* a frame has been rendered: RT_RENDER_RESUME is allowed */
     uint32_t *d_order[4] = {nullptr, nullptr, nullptr, nullptr}; /* block order: keys in/out, values in/out */
@@ -440,6 +442,7 @@ rt_status rt_renderer_create(rt_context *ctx, rt_renderer_kind kind, int32_t wid
     r->h = height;
     if (const char *e = getenv("RT_TUNE_REFILL")) r->tune_refill = atoi(e) > 0 ? atoi(e) : r->tune_refill;
     if (const char *e = getenv("RT_BLOCK_ORDER")) r->block_order = atoi(e);
+    if (const char *e = getenv("RT_WF_PERSIST")) r->wf_persist = atoi(e);
     if (const char *e = getenv("RT_MEGA_CTX")) r->tune_ctx = atoi(e) >= 0 && atoi(e) <= 4 ? atoi(e) : r->tune_ctx;
     if (const char *e = getenv("RT_TUNE_SHADE")) r->tune_shade = atoi(e) > 0 ? atoi(e) : r->tune_shade;
     if (const char *e = getenv("RT_TUNE_IDLE")) r->tune_idle = atoi(e) > 0 ? atoi(e) : r->tune_idle;
@@ -468,12 +471,15 @@ rt_status rt_renderer_create(rt_context *ctx, rt_renderer_kind kind, int32_t wid
             if ((e = dev_alloc(&r->wf.hit, n)) != cudaSuccess) break;
             if ((e = dev_alloc(&r->wf.prog, n)) != cudaSuccess) break;
             if ((e = dev_alloc(&r->wf.rng, n)) != cudaSuccess) break;
-            if ((e = dev_alloc(&r->wf.queue[0], n)) != cudaSuccess) break;
-            if ((e = dev_alloc(&r->wf.queue[1], n)) != cudaSuccess) break;
+            if ((e = rt_wavefront_grid(ctx->sm_count, &r->grid_extend, &r->grid_shade)) != cudaSuccess) break;
+            if ((e = rt_wf_persistent_grid(ctx->sm_count, &r->grid_persist)) != cudaSuccess) break;
+            /* persistent form: one private queue segment per CTA, whole 8x4 blocks (rt_blocks.h) */
+            r->queue_capacity = ((size_t)((width + 7) / 8) * (size_t)((height + 3) / 4) + (size_t)r->grid_persist) * 32u;
+            if ((e = dev_alloc(&r->wf.queue[0], r->queue_capacity)) != cudaSuccess) break;
+            if ((e = dev_alloc(&r->wf.queue[1], r->queue_capacity)) != cudaSuccess) break;
             r->wf.count[0] = r->d_counts;
             r->wf.count[1] = r->d_counts + 1;
             r->wf.head = r->d_counts + 2;
-            if ((e = rt_wavefront_grid(ctx->sm_count, &r->grid_extend, &r->grid_shade)) != cudaSuccess) break;
         }
     } while (0);
     if (e != cudaSuccess) {
@@ -635,6 +641,30 @@ rt_status rt_render_frame(rt_renderer *r, const rt_scene *scene, const rt_camera
             launches += 2;
         }
         RT_CUDA_TRY(ctx, rt_launch_megakernel(st, r->grid_mega, scene->view, p, out, r->d_work, r->d_rays, order));
+        launches++;
+    } else if (r->wf_persist) {
+        /* the whole frame in one launch: every CTA runs generate / {extend, shade}* / resolve for its own lattice of
+         * 8x4 pixel blocks with CTA-local queues (k_wf_persistent) */
+        const uint32_t n_blocks = rt_block_count(p);
+        const uint32_t grid = (uint32_t)r->grid_persist;
+        const uint32_t cap = ((n_blocks + grid - 1) / grid) * 32u;
+        if ((size_t)grid * cap > r->queue_capacity) { /* a tiling whose partial edge tiles enumerate more blocks than the image has */
+            RT_CUDA_TRY(ctx, cudaStreamSynchronize(st));
+            cudaFree(r->wf.queue[0]);
+            cudaFree(r->wf.queue[1]);
+            r->wf.queue[0] = r->wf.queue[1] = nullptr;
+            r->queue_capacity = 0;
+            RT_CUDA_TRY(ctx, dev_alloc(&r->wf.queue[0], (size_t)grid * cap));
+            RT_CUDA_TRY(ctx, dev_alloc(&r->wf.queue[1], (size_t)grid * cap));
+            r->queue_capacity = (size_t)grid * cap;
+        }
+        if (sh.world > 1 && sh.tile_size && !p.resume) { /* pixels of other ranks stay zero (they are never enumerated) */
+            RT_CUDA_TRY(ctx, cudaMemsetAsync(r->d_accum, 0, n * sizeof(float4), st));
+            if (!r->exported) RT_CUDA_TRY(ctx, cudaMemsetAsync(r->d_rgba8, 0, n * 4, st));
+            RT_CUDA_TRY(ctx, cudaMemsetAsync(r->d_rng, 0, n * 4, st));
+            RT_CUDA_TRY(ctx, cudaMemsetAsync(r->wf.rng, 0, n * 4, st));
+        }
+        RT_CUDA_TRY(ctx, rt_launch_wf_persistent(st, (int)grid, cap, scene->view, p, r->wf, out, r->d_rays));
         launches++;
     } else {
         RT_CUDA_TRY(ctx, cudaMemsetAsync(r->d_counts, 0, 4 * sizeof(uint32_t), st));

@@ -22,6 +22,10 @@ uint32_t rt_region_count(int w, int h);
 cudaError_t rt_launch_block_order(cudaStream_t st, const RtScene &scene, const RtFrameParams &p, uint32_t *region_cost, uint32_t *keys_in,
                                   uint32_t *keys_out, uint32_t *vals_in, uint32_t *vals_out, void *temp, size_t temp_bytes);
 cudaError_t rt_wavefront_grid(int sm_count, int *grid_extend, int *grid_shade);
+/* the whole wavefront frame in one launch: CTA-local queues of `cap` slots each (render.cu) */
+cudaError_t rt_wf_persistent_grid(int sm_count, int *grid);
+cudaError_t rt_launch_wf_persistent(cudaStream_t st, int grid, uint32_t cap, const RtScene &scene, const RtFrameParams &p,
+                                    const RtWavefrontState &w, const RtFrameOut &out, unsigned long long *ray_counter);
 cudaError_t rt_launch_wf_generate(cudaStream_t st, int grid, const RtFrameParams &p, const RtWavefrontState &w,
                                   const RtFrameOut &out);
 cudaError_t rt_launch_wf_extend(cudaStream_t st, int grid, const RtScene &scene, const RtWavefrontState &w, int cur,

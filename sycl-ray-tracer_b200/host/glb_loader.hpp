@@ -563,22 +563,37 @@ inline LoadedScene load(const std::string &path, const float global_scale[3] = n
     }
     const Json &scene = j["scenes"][(size_t)std::max(0, j["scene"].integer(0))];
     int camera_node = -1;
-    std::vector<int> stack;
-    for (size_t k = 0; k < scene["nodes"].size(); k++) stack.push_back(scene["nodes"][k].integer(0));
+    /* Scene::load_node (src/scene.cpp:444-480) recurses in PRE-ORDER: scene roots in order, a node before its children,
+     * children in order. The last node WITH a camera that this order visits wins (:455-457), and a node reached a
+     * second time (not a valid glTF, but nothing stops it) gets the later visitor as its parent (:452). The explicit
+     * stack below reproduces that order (children pushed in reverse); a node is never followed into itself (the
+     * reference would recurse until its stack overflows), and a pathological DAG is cut off after 64 visits per node. */
+    struct Visit { int node, parent; bool leave; };
+    std::vector<Visit> stack;
+    std::vector<char> on_path(n_nodes, 0);
+    size_t visits = 0;
+    for (size_t k = scene["nodes"].size(); k-- > 0;) stack.push_back({scene["nodes"][k].integer(0), -1, false});
     while (!stack.empty()) {
-        const int n = stack.back();
+        const Visit v = stack.back();
         stack.pop_back();
+        const int n = v.node;
+        if (v.leave) {
+            on_path[(size_t)n] = 0;
+            continue;
+        }
         if (n < 0 || (size_t)n >= n_nodes) throw std::runtime_error("Failed to load .glTF : node index out of range");
-        if (reached[(size_t)n]) continue; /* a valid glTF is a forest; never follow a node twice (cycles) */
+        if (on_path[(size_t)n]) continue; /* a cycle: never follow a node into itself */
+        if (++visits > 64 * n_nodes) throw std::runtime_error("Failed to load .glTF : node graph is not a forest");
         reached[(size_t)n] = 1;
+        parent[(size_t)n] = v.parent;
         const Json &nd = j["nodes"][(size_t)n];
         if (nd.has("camera")) camera_node = n;
-        for (size_t k = 0; k < nd["children"].size(); k++) {
+        on_path[(size_t)n] = 1;
+        stack.push_back({n, v.parent, true});
+        for (size_t k = nd["children"].size(); k-- > 0;) {
             const int c = nd["children"][k].integer(-1);
             if (c < 0 || (size_t)c >= n_nodes) throw std::runtime_error("Failed to load .glTF : node index out of range");
-            if (reached[(size_t)c]) continue;
-            parent[(size_t)c] = n;
-            stack.push_back(c);
+            stack.push_back({c, n, false});
         }
     }
     auto global_matrix = [&](int n) { /* src/scene.cpp:137-146 */

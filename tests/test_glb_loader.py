@@ -652,3 +652,45 @@ def test_cli_output_equals_the_reference_programs(glb, tmp_path, flag, name, cas
                        capture_output=True, text=True, check=True)
     assert f"Total rays: {int(gold[f'{case}_rays_{name}'])}" in r.stdout
     assert np.array_equal(np.array(Image.open(png)), gold[f"{case}_img_{name}"])
+
+
+def _patch_glb_json(path, fn):
+    """rewrite the JSON chunk of a .glb in place (the BIN chunk is kept)"""
+    raw = open(path, "rb").read()
+    jlen = struct.unpack_from("<I", raw, 12)[0]
+    j = json.loads(raw[20:20 + jlen].decode())
+    fn(j)
+    js = json.dumps(j).encode()
+    js += b" " * ((-len(js)) % 4)
+    rest = raw[20 + jlen:]
+    with open(path, "wb") as f:
+        f.write(struct.pack("<4sII", b"glTF", 2, 12 + 8 + len(js) + len(rest)) + struct.pack("<II", len(js), 0x4E4F534A) + js + rest)
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/src"), reason="needs the reference sources (build container only)")
+@pytest.mark.parametrize("roots", [[0, 3, 5], [5, 0, 3], [3, 5, 0], [5, 3]])
+def test_several_cameras_pick_the_references_camera(glb, pkg, tmp_path, roots):
+    """Scene::load_node recurses in pre-order and the LAST camera node it visits wins (src/scene.cpp:444-457): sibling
+    camera roots, a camera below a camera, and every order of the scene roots must frame the image like the reference"""
+    import _scenref
+    tex = (np.random.RandomState(1).rand(512, 512, 4) * 255).astype(np.uint8)
+    path = str(tmp_path / "cams.glb")
+    _write_glb(path, tex, f15=False)
+
+    def patch(j):
+        j["nodes"].append({"translation": [3.0, 2.0, 1.0], "rotation": [0.0, np.sin(0.4), 0.0, np.cos(0.4)], "camera": 0, "children": [6, 7]})  # 5
+        j["nodes"].append({"translation": [0.0, 0.5, 1.0], "camera": 0})                                                                        # 6
+        j["nodes"].append({"translation": [1.0, 0.0, 0.0], "mesh": 1})                                                                          # 7: no camera
+        j["scenes"][0]["nodes"] = roots
+    _patch_glb_json(path, patch)
+    ref = _scenref.load(path)
+    glb.glb_load_scaled.restype = C.c_void_p
+    glb.glb_load_scaled.argtypes = [C.c_char_p, C.c_float, C.c_float, C.c_float]
+    mine = _mine_scaled(glb, pkg, path, (1.0, 1.0, 1.0))
+    assert ref["camera_node"] == {(0, 3, 5): 6, (5, 0, 3): 3, (3, 5, 0): 6, (5, 3): 3}[tuple(roots)]
+    assert np.array_equal(mine["camera_position"], ref["camera_position"])
+    assert np.array_equal(mine["camera_direction"], ref["camera_direction"])
+    assert mine["focal"] == ref["focal"]
+    assert len(mine["instances"]) == len(ref["instances"])
+    for a, b in zip(mine["instances"], ref["instances"]):
+        assert np.array_equal(a["transform"].view(np.uint32), b["transform"].view(np.uint32))
