@@ -43,7 +43,10 @@ __host__ __device__ inline void rt_count(int i) {
 namespace {
 
 constexpr int kMegaBlock = 128;
-constexpr int kWfBlock = 256;
+#ifndef RT_WF_BLOCK
+#define RT_WF_BLOCK 256
+#endif
+constexpr int kWfBlock = RT_WF_BLOCK;
 
 /* ------------------------------------------------------------------------------ intersect */
 __global__ void k_intersect(RtScene scene, const RtInstance *inst, uint64_t n, const float *org,
@@ -884,6 +887,142 @@ __global__ void __launch_bounds__(kWfBlock, RT_EXT_MIN_BLOCKS) k_wf_persistent(R
     if (threadIdx.x == 0 && rays) atomicAdd(ray_counter, rays);
 }
 
+/* ------------------------------------------------------------------------------ wavefront, queue-driven warps */
+/* k_wf_persistent still ends every bounce iteration with a drain (the CTA's last rays run in half-empty warps): making
+ * its CTAs smaller, down to one warp, changes nothing (profiles/README.md), the loss is the iteration itself. Here the
+ * unit is the WARP and there are no iterations. A warp keeps `tune_inflight` pixels in flight, claimed 8x4 block by
+ * block from a global counter (like the megakernel's hand-out, so the frame ends within one pixel time on every warp),
+ * and two private ring queues in global memory — pixels whose ray is ready to be traced, pixels whose hit is ready to
+ * be shaded — through which its pixels flow continuously:
+ *   claim  : while fewer than tune_inflight pixels are in flight, fetch the next block and generate its camera rays;
+ *   hits   : lanes whose traversal finished store the hit record and append the pixel to the hit ring;
+ *   shade  : as soon as 32 hits are queued (or nothing else can be done) the warp shades 32 of them with all lanes
+ *            (rt_wf_shade_pixel: material, rng, accumulate, regenerate), appends the survivors to the ray ring and
+ *            resolves the pixels that finished their samples (K6/K7);
+ *   refill : idle lanes take the next rays from the ray ring and start traversing;
+ *   traverse_phase(): node steps / triangle drain with the warp converged.
+ * No barrier, no atomics on the queues, no fences: a warp's rings and the state of the pixels it claimed are private to
+ * it, and warp-level program order (__syncwarp) is all the ordering they need. Per-pixel arithmetic is unchanged: a
+ * pixel has one ray in flight and its own stream, so results are bit-identical to the other two forms. */
+__device__ __forceinline__ void wf_resolve_pixel(const RtWavefrontState &w, const RtFrameOut &out, uint32_t pix) {
+    const float4 a = out.accum[pix];
+    const uint32_t px = rt_resolve_pixel(a.x, a.y, a.z, a.w); /* a.w = samples accumulated (= spp, or more after resumes) */
+    out.rgba8[pix] = px;
+    if (out.gather) out.gather[pix] = px;
+    out.rng[pix] = w.rng[pix];
+}
+
+__global__ void __launch_bounds__(kWfBlock, RT_EXT_MIN_BLOCKS) k_wf_flow(RtScene scene, RtFrameParams p, RtWavefrontState w, RtFrameOut out,
+                                                                        uint32_t *work_counter, unsigned long long *ray_counter,
+                                                                        uint32_t cap /* slots per ring, a power of two >= tune_inflight */) {
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const unsigned lt = (1u << lane) - 1u;
+    const uint32_t wid = blockIdx.x * (uint32_t)(kWfBlock / 32) + (threadIdx.x >> 5);
+    const RtBlockGeom g = rt_block_geom(p);
+    uint32_t *rayq = w.queue[0] + (size_t)wid * cap, *hitq = w.queue[1] + (size_t)wid * cap;
+    const uint32_t mask = cap - 1u;
+    fill_perm_table();
+    __syncthreads();
+    uint32_t ray_head = 0, ray_tail = 0, hit_head = 0, hit_tail = 0; /* warp-uniform ring cursors */
+    uint32_t inflight = 0;                                             /* pixels claimed and not finished */
+    bool more = true;                                                  /* blocks are left on the global counter */
+    unsigned long long rays = 0;
+    RtTravState tv;
+    SmemStacks<kWfBlock> ks;
+#if RT_SMEM_TRI || RT_SMEM_NODE
+    __shared__ uint64_t s_stacks[RT_SMEM_ENTRIES * kWfBlock];
+    ks.sm = s_stacks + threadIdx.x;
+#endif
+    tv.sp = 0;
+    tv.tsp = 0;
+    tv.ng_y = 0;
+    int mode = kNeedPixel; /* kNeedPixel = idle */
+    uint32_t pix = 0;
+    for (;;) {
+        /* ---- claim + generate (K2 + first K3) ---- */
+        while (more && inflight + 32u <= (uint32_t)p.tune_inflight) {
+            uint32_t blk = 0;
+            if (lane == 0) blk = atomicAdd(work_counter, 1u);
+            blk = __shfl_sync(full, blk, 0);
+            if (blk >= g.n_blocks) {
+                more = false;
+                break;
+            }
+            uint32_t gp = 0;
+            bool live = wf_block_pixel(p, g, blk, lane, gp);
+            if (live) {
+                live = rt_wf_generate_pixel(p, w, out, gp);
+                if (!live) wf_resolve_pixel(w, out, gp); /* no samples to trace */
+            }
+            const unsigned m = __ballot_sync(full, live);
+            if (live) rayq[(ray_tail + (uint32_t)__popc(m & lt)) & mask] = gp;
+            ray_tail += (uint32_t)__popc(m);
+            inflight += (uint32_t)__popc(m);
+            __syncwarp();
+        }
+        /* ---- finished traversals -> hit ring ---- */
+        {
+            const bool fin = mode == kHitPending;
+            const unsigned m = __ballot_sync(full, fin);
+            if (m) {
+                if (fin) {
+                    w.hit[pix] = make_float4(tv.best.t, tv.best.u, tv.best.v, __uint_as_float(tv.best.tri));
+                    hitq[(hit_tail + (uint32_t)__popc(m & lt)) & mask] = pix;
+                    mode = kNeedPixel;
+                }
+                hit_tail += (uint32_t)__popc(m);
+                __syncwarp();
+            }
+        }
+        const unsigned m_trav = __ballot_sync(full, mode == kTraversing);
+        /* ---- shade: 32 wide whenever possible; narrower only when the warp would otherwise starve ---- */
+        for (;;) {
+            const uint32_t n_hits = hit_tail - hit_head, n_rays = ray_tail - ray_head;
+            const int n_idle = 32 - __popc(m_trav);
+            if (!(n_hits >= 32u || (n_hits > 0u && n_rays == 0u && (n_idle >= p.tune_refill || !m_trav)))) break;
+            const uint32_t n = n_hits < 32u ? n_hits : 32u;
+            bool keep = false;
+            uint32_t spix = 0;
+            if ((uint32_t)lane < n) {
+                spix = hitq[(hit_head + (uint32_t)lane) & mask];
+                keep = rt_wf_shade_pixel(scene, p, w, out, spix);
+                if (!keep) wf_resolve_pixel(w, out, spix); /* the pixel's last sample: K6/K7 */
+            }
+            const unsigned mk = __ballot_sync(full, keep);
+            if (keep) rayq[(ray_tail + (uint32_t)__popc(mk & lt)) & mask] = spix;
+            hit_head += n;
+            ray_tail += (uint32_t)__popc(mk);
+            inflight -= n - (uint32_t)__popc(mk);
+            __syncwarp();
+        }
+        /* ---- refill idle lanes from the ray ring ---- */
+        {
+            const bool idle = mode == kNeedPixel;
+            const unsigned m = __ballot_sync(full, idle);
+            const uint32_t n_rays = ray_tail - ray_head;
+            if (m && n_rays) {
+                const uint32_t r = (uint32_t)__popc(m & lt);
+                if (idle && r < n_rays) {
+                    pix = rayq[(ray_head + r) & mask];
+                    const float4 o = w.org[pix];
+                    rt_trav_init(tv, mk3(o.x, o.y, o.z), rt_unpack_half3(w.dir[pix]), 0.0001f, INFINITY);
+                    mode = kTraversing;
+                }
+                const uint32_t take = min((uint32_t)__popc(m), n_rays);
+                ray_head += take;
+                rays += take; /* one rtcIntersect1 per segment, src/render_wavefront.cpp:407 */
+            }
+        }
+        if (!__ballot_sync(full, mode == kTraversing)) {
+            if (inflight == 0u && !more) break; /* every pixel this warp claimed has finished its samples */
+            continue;
+        }
+        traverse_phase(scene.bvh, tv, ks, mode, p.tune_refill);
+    }
+    if (lane == 0 && rays) atomicAdd(ray_counter, rays);
+}
+
 /* ------------------------------------------------------------------------------ resolve */
 __global__ void k_resolve(const float4 *accum, uint32_t *rgba8, uint32_t n_pix, float spp) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1008,6 +1147,21 @@ cudaError_t rt_launch_wf_persistent(cudaStream_t st, int grid, uint32_t cap, con
                                     const RtWavefrontState &w, const RtFrameOut &out, unsigned long long *ray_counter) {
     k_wf_persistent<<<grid, kWfBlock, 0, st>>>(scene, p, w, out, ray_counter, cap);
     return cudaGetLastError();
+}
+
+cudaError_t rt_launch_wf_flow(cudaStream_t st, int grid, uint32_t cap, const RtScene &scene, const RtFrameParams &p,
+                              const RtWavefrontState &w, const RtFrameOut &out, uint32_t *work_counter, unsigned long long *ray_counter) {
+    k_wf_flow<<<grid, kWfBlock, 0, st>>>(scene, p, w, out, work_counter, ray_counter, cap);
+    return cudaGetLastError();
+}
+
+cudaError_t rt_wf_flow_grid(int sm_count, int *grid, int *warps_per_block) {
+    int a = 0;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, k_wf_flow, kWfBlock, 0);
+    if (e != cudaSuccess) return e;
+    *grid = sm_count * (a < 1 ? 1 : a);
+    *warps_per_block = kWfBlock / 32;
+    return cudaSuccess;
 }
 
 cudaError_t rt_wf_persistent_grid(int sm_count, int *grid) {

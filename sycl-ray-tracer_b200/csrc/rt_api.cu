@@ -33,9 +33,9 @@ struct rt_renderer {
     uint32_t *d_counts = nullptr;           /* 2 queue lengths */
     uint32_t *h_counts = nullptr;           /* pinned mirror */
     unsigned long long *h_rays = nullptr;   /* pinned */
-    int grid_mega = 0, grid_extend = 0, grid_shade = 0, grid_persist = 0;
+    int grid_mega = 0, grid_extend = 0, grid_shade = 0, grid_persist = 0, grid_flow = 0, flow_warps = 8;
     size_t queue_capacity = 0;    /* slots per wavefront id queue */
-    int wf_persist = 1;           /* wavefront: the whole frame in one persistent launch (RT_WF_PERSIST=0: streaming kernels) */
+    int wf_persist = 2;           /* wavefront: 2 = queue-driven warps (one launch), 1 = per-CTA iterations (one launch), 0 = streaming kernels (RT_WF_PERSIST) */
     cudaEvent_t ev_batch[2] = {nullptr, nullptr}; /* wavefront: per-batch queue-length read-back */
     bool has_frame = false; /* a frame has been rendered: RT_RENDER_RESUME is allowed */
     uint32_t *d_order[4] = {nullptr, nullptr, nullptr, nullptr}; /* block order: keys in/out, values in/out */
@@ -49,6 +49,7 @@ struct rt_renderer {
     bool exported = false;        /* d_rgba8 is a gather destination: never clear foreign pixels */
     int tune_refill = 12; /* lanes that must run dry before a warp refills (RT_TUNE_REFILL overrides; 12-14 measured best) */
     int tune_ctx = 2;     /* megakernel: ray contexts per lane (RT_MEGA_CTX; 0 = round-1 kernel) */
+    int tune_inflight = 128; /* wavefront, queue-driven warps: pixels in flight per warp (RT_TUNE_INFLIGHT) */
     int tune_shade = 24, tune_idle = 4; /* megakernel contexts: shade-pass triggers (RT_TUNE_SHADE, RT_TUNE_IDLE) */
 };
 
@@ -443,6 +444,7 @@ rt_status rt_renderer_create(rt_context *ctx, rt_renderer_kind kind, int32_t wid
     if (const char *e = getenv("RT_TUNE_REFILL")) r->tune_refill = atoi(e) > 0 ? atoi(e) : r->tune_refill;
     if (const char *e = getenv("RT_BLOCK_ORDER")) r->block_order = atoi(e);
     if (const char *e = getenv("RT_WF_PERSIST")) r->wf_persist = atoi(e);
+    if (const char *e = getenv("RT_TUNE_INFLIGHT")) r->tune_inflight = atoi(e) >= 32 && atoi(e) <= 65536 ? (atoi(e) + 31) / 32 * 32 : r->tune_inflight;
     if (const char *e = getenv("RT_MEGA_CTX")) r->tune_ctx = atoi(e) >= 0 && atoi(e) <= 4 ? atoi(e) : r->tune_ctx;
     if (const char *e = getenv("RT_TUNE_SHADE")) r->tune_shade = atoi(e) > 0 ? atoi(e) : r->tune_shade;
     if (const char *e = getenv("RT_TUNE_IDLE")) r->tune_idle = atoi(e) > 0 ? atoi(e) : r->tune_idle;
@@ -473,6 +475,7 @@ rt_status rt_renderer_create(rt_context *ctx, rt_renderer_kind kind, int32_t wid
             if ((e = dev_alloc(&r->wf.rng, n)) != cudaSuccess) break;
             if ((e = rt_wavefront_grid(ctx->sm_count, &r->grid_extend, &r->grid_shade)) != cudaSuccess) break;
             if ((e = rt_wf_persistent_grid(ctx->sm_count, &r->grid_persist)) != cudaSuccess) break;
+            if ((e = rt_wf_flow_grid(ctx->sm_count, &r->grid_flow, &r->flow_warps)) != cudaSuccess) break;
             /* persistent form: one private queue segment per CTA, whole 8x4 blocks (rt_blocks.h) */
             r->queue_capacity = ((size_t)((width + 7) / 8) * (size_t)((height + 3) / 4) + (size_t)r->grid_persist) * 32u;
             if ((e = dev_alloc(&r->wf.queue[0], r->queue_capacity)) != cudaSuccess) break;
@@ -593,6 +596,7 @@ rt_status rt_render_frame(rt_renderer *r, const rt_scene *scene, const rt_camera
     p.tune_ctx = r->tune_ctx;
     p.tune_shade = r->tune_shade;
     p.tune_idle = r->tune_idle;
+    p.tune_inflight = r->tune_inflight;
     p.resume = (params->flags & RT_RENDER_RESUME) ? 1 : 0;
     if (p.resume && !r->has_frame) return rt_set_error(ctx, RT_ERR_STATE, "rt_render_frame", "RT_RENDER_RESUME without a previous frame");
     RtFrameOut out;
@@ -643,11 +647,19 @@ rt_status rt_render_frame(rt_renderer *r, const rt_scene *scene, const rt_camera
         RT_CUDA_TRY(ctx, rt_launch_megakernel(st, r->grid_mega, scene->view, p, out, r->d_work, r->d_rays, order));
         launches++;
     } else if (r->wf_persist) {
+        const uint32_t n_blocks = rt_block_count(p);
+        uint32_t grid, cap;
+        if (r->wf_persist >= 2) { /* one ray ring + one hit ring per warp, a power of two >= the pixels a warp keeps in flight */
+            grid = (uint32_t)r->grid_flow;
+            cap = 32u;
+            while (cap < (uint32_t)r->tune_inflight) cap <<= 1;
+            cap *= (uint32_t)r->flow_warps; /* per CTA, so that the allocation check below covers both forms */
+        } else {
+            grid = (uint32_t)r->grid_persist;
+            cap = ((n_blocks + grid - 1) / grid) * 32u;
+        }
         /* the whole frame in one launch: every CTA runs generate / {extend, shade}* / resolve for its own lattice of
          * 8x4 pixel blocks with CTA-local queues (k_wf_persistent) */
-        const uint32_t n_blocks = rt_block_count(p);
-        const uint32_t grid = (uint32_t)r->grid_persist;
-        const uint32_t cap = ((n_blocks + grid - 1) / grid) * 32u;
         if ((size_t)grid * cap > r->queue_capacity) { /* a tiling whose partial edge tiles enumerate more blocks than the image has */
             RT_CUDA_TRY(ctx, cudaStreamSynchronize(st));
             cudaFree(r->wf.queue[0]);
@@ -664,7 +676,11 @@ rt_status rt_render_frame(rt_renderer *r, const rt_scene *scene, const rt_camera
             RT_CUDA_TRY(ctx, cudaMemsetAsync(r->d_rng, 0, n * 4, st));
             RT_CUDA_TRY(ctx, cudaMemsetAsync(r->wf.rng, 0, n * 4, st));
         }
-        RT_CUDA_TRY(ctx, rt_launch_wf_persistent(st, (int)grid, cap, scene->view, p, r->wf, out, r->d_rays));
+        if (r->wf_persist >= 2) {
+            RT_CUDA_TRY(ctx, cudaMemsetAsync(r->d_work, 0, sizeof(uint32_t), st));
+            RT_CUDA_TRY(ctx, rt_launch_wf_flow(st, (int)grid, cap / (uint32_t)r->flow_warps, scene->view, p, r->wf, out, r->d_work, r->d_rays));
+        }
+        else RT_CUDA_TRY(ctx, rt_launch_wf_persistent(st, (int)grid, cap, scene->view, p, r->wf, out, r->d_rays));
         launches++;
     } else {
         RT_CUDA_TRY(ctx, cudaMemsetAsync(r->d_counts, 0, 4 * sizeof(uint32_t), st));

@@ -24,6 +24,10 @@ cudaError_t rt_launch_block_order(cudaStream_t st, const RtScene &scene, const R
 cudaError_t rt_wavefront_grid(int sm_count, int *grid_extend, int *grid_shade);
 /* the whole wavefront frame in one launch: CTA-local queues of `cap` slots each (render.cu) */
 cudaError_t rt_wf_persistent_grid(int sm_count, int *grid);
+/* queue-driven warps: one ray ring and one hit ring of `cap` (power of two >= tune_inflight) slots per warp */
+cudaError_t rt_wf_flow_grid(int sm_count, int *grid, int *warps_per_block);
+cudaError_t rt_launch_wf_flow(cudaStream_t st, int grid, uint32_t cap, const RtScene &scene, const RtFrameParams &p,
+                              const RtWavefrontState &w, const RtFrameOut &out, uint32_t *work_counter, unsigned long long *ray_counter);
 cudaError_t rt_launch_wf_persistent(cudaStream_t st, int grid, uint32_t cap, const RtScene &scene, const RtFrameParams &p,
                                     const RtWavefrontState &w, const RtFrameOut &out, unsigned long long *ray_counter);
 cudaError_t rt_launch_wf_generate(cudaStream_t st, int grid, const RtFrameParams &p, const RtWavefrontState &w,

@@ -238,6 +238,7 @@ struct RtFrameParams {
     int32_t tune_ctx;       /* megakernel: ray contexts per lane (0 = the round-1 one-pixel-in-registers kernel) */
     int32_t tune_shade;     /* megakernel contexts: shade once this many lanes have a hit waiting ... */
     int32_t tune_idle;      /* ... or this many lanes can neither traverse nor switch */
+    int32_t tune_inflight;  /* wavefront (queue-driven warps): pixels a warp keeps in flight, a multiple of 32 */
 };
 
 /* image-tile sharding: tile t (row major, tile_size^2 pixels) belongs to rank t % world */
