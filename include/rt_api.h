@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define RT_API_VERSION 1
+#define RT_API_VERSION 2
 #define RT_TEX_SIZE 512   /* src/image_manager.hpp:14  IMAGE_SIZE  */
 #define RT_MAX_IMAGES 128 /* src/image_manager.hpp:12  MAX_IMAGES  */
 
@@ -195,6 +195,7 @@ rt_status rt_render_frame(rt_renderer *r, const rt_scene *scene, const rt_camera
  * fp32 RGBA accumulation (W*H*4 floats) and RGBA8 image. For zero-copy hand-off to NCCL. */
 float *rt_renderer_device_accum(rt_renderer *r);
 uint8_t *rt_renderer_device_rgba8(rt_renderer *r);
+uint32_t *rt_renderer_device_rng(rt_renderer *r); /* W*H final xorshift32 states */
 /* ---- image-tile shards: gather over peer memory (no collective) --------------------------
  * Under image-tile sharding every pixel is finished by exactly one rank, so its final RGBA8 value
  * can be stored straight into ONE destination image by the render kernel itself (4-byte stores
@@ -220,6 +221,50 @@ rt_status rt_renderer_set_gather(rt_renderer *r, const rt_ipc_handle *handle, vo
  * accum, rgba8: ANY-space. */
 rt_status rt_resolve(rt_context *ctx, const float *accum, uint32_t sample_count, int32_t width,
                      int32_t height, uint8_t *rgba8);
+
+/* ---- several GPUs of one node behind one handle ---------------------------------------------
+ * No reference equivalent (App picks ONE device, src/app.hpp:43-55); this is what makes the reference's call
+ * sequence (src/main.cpp:57-70: scene, renderer, render_frame) run on N B200s from one process. The scene is
+ * replicated; a frame is sharded by image tiles or by samples and the one exchange step runs over NVLink peer
+ * memory inside the library's own kernels (csrc/rt_group.cu):
+ *   RT_GROUP_TILES  tile t of tile_size^2 pixels -> device t % N; finished RGBA8 pixels are stored by the render
+ *                   kernel straight into device 0's image. Image, accumulation, final stream states and ray
+ *                   count are BIT-IDENTICAL to one device rendering the frame.
+ *   RT_GROUP_SPP    device i renders every pixel with sample_count / N samples (the first sample_count % N devices
+ *                   one more) and seed salt i * 0x9E3779B9 (device 0 = the reference stream); one kernel per device
+ *                   then sums its 1/N slice of the pixels over all accumulation buffers in device order, resolves
+ *                   and stores into device 0's buffers (reduce-scatter + resolve + gather, fused). accum = that sum.
+ * All devices must be able to access each other's memory (NVLink / NVSwitch). Calls are synchronous. */
+typedef enum rt_group_mode { RT_GROUP_TILES = 0, RT_GROUP_SPP = 1 } rt_group_mode;
+typedef struct rt_group rt_group;
+typedef struct rt_group_scene rt_group_scene;
+typedef struct rt_group_renderer rt_group_renderer;
+typedef struct rt_group_params {
+    uint32_t max_depth;    /* -d */
+    uint32_t sample_count; /* -s: samples per pixel of the WHOLE frame (with RT_RENDER_RESUME: added by this call) */
+    uint32_t mode;         /* rt_group_mode */
+    uint32_t tile_size;    /* RT_GROUP_TILES: a multiple of 8; 0 = 64 */
+    uint32_t flags;        /* 0 or RT_RENDER_RESUME */
+} rt_group_params;
+
+/* devices = CUDA device indices (NULL: 0 .. n_devices-1), 1 <= n_devices <= 16 */
+rt_status rt_group_create(const int *devices, uint32_t n_devices, rt_group **out);
+void rt_group_destroy(rt_group *g);
+uint32_t rt_group_size(const rt_group *g);
+rt_context *rt_group_context(rt_group *g, uint32_t i); /* the i-th device's context (owned by the group) */
+const char *rt_group_last_error(rt_group *g);
+/* rt_scene_create + rt_scene_commit on every device, concurrently */
+rt_status rt_group_scene_create(rt_group *g, const rt_scene_desc *desc, rt_group_scene **out);
+void rt_group_scene_destroy(rt_group_scene *s);
+rt_scene *rt_group_scene_get(rt_group_scene *s, uint32_t i);
+rt_status rt_group_renderer_create(rt_group *g, rt_renderer_kind kind, int32_t width, int32_t height,
+                                   rt_group_renderer **out);
+void rt_group_renderer_destroy(rt_group_renderer *r);
+rt_renderer *rt_group_renderer_get(rt_group_renderer *r, uint32_t i);
+/* IRenderer::render_frame on the whole group. frame->ray_count is the sum over devices, device_ms the slowest
+ * device's render time plus the exchange, kernel_launches the sum; the pointers of `frame` are ANY-space. */
+rt_status rt_group_render_frame(rt_group_renderer *r, const rt_group_scene *scene, const rt_camera *camera,
+                                const rt_group_params *params, rt_frame *frame);
 
 #ifdef __cplusplus
 }

@@ -21,7 +21,7 @@ from ._capi import (RT_MAT_DIELECTRIC, RT_MAT_DIFFUSE, RT_MAT_METALLIC, RT_MAT_N
                     RT_WAVEFRONT)
 
 __all__ = ["App", "Scene", "Camera", "IRenderer", "MegakernelRenderer", "WavefrontRenderer", "Frame",
-           "SceneData", "InstanceData", "Material", "RtError", "intersect", "resolve"]
+           "SceneData", "InstanceData", "Material", "RtError", "intersect", "resolve", "Group", "GroupScene", "GroupRenderer"]
 
 
 class RtError(RuntimeError):
@@ -345,3 +345,122 @@ def resolve(app, accum, sample_count, width, height, rgba8=None):
     app.check(app._lib.rt_resolve(app.handle, _ptr(accum), int(sample_count), int(width), int(height), _ptr(rgba8)),
               "rt_resolve")
     return rgba8
+
+
+def device_count():
+    """CUDA devices visible to the library (0 without a GPU)."""
+    try:
+        import ctypes.util
+        rt = C.CDLL(ctypes.util.find_library("cudart") or "libcudart.so")
+    except OSError:
+        try:
+            import torch
+            return int(torch.cuda.device_count())
+        except Exception:
+            return 0
+    n = C.c_int(0)
+    return int(n.value) if rt.cudaGetDeviceCount(C.byref(n)) == 0 else 0
+
+
+class Group:
+    """Several GPUs of one node behind one handle (rt_group_*, include/rt_api.h): what lets the reference's
+    main() sequence (src/main.cpp:57-70) run on N B200s from one process."""
+
+    def __init__(self, devices):
+        self._lib = _capi.load()
+        devices = list(range(devices)) if isinstance(devices, int) else [int(d) for d in devices]
+        arr = (C.c_int * len(devices))(*devices)
+        h = C.c_void_p()
+        st = self._lib.rt_group_create(arr, len(devices), C.byref(h))
+        if st != _capi.RT_OK:
+            raise RtError(f"rt_group_create failed ({st}): {self._lib.rt_last_error(None).decode()}")
+        self.handle, self.devices = h, devices
+
+    def __len__(self):
+        return int(self._lib.rt_group_size(self.handle))
+
+    def check(self, st, what):
+        if st != _capi.RT_OK:
+            raise RtError(f"{what} failed ({st}): {self._lib.rt_group_last_error(self.handle).decode()}")
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self._lib.rt_group_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class GroupScene:
+    """Scene replicated on every device of a Group (upload + GPU BVH build run concurrently)."""
+
+    def __init__(self, group, data):
+        self.group, self.data, self._lib = group, data, group._lib
+        self._insts = fill_instances(_capi.rt_instance, _capi.rt_material, data)
+        desc = _capi.rt_scene_desc()
+        desc.instances = self._insts
+        desc.instance_count = len(data.instances)
+        if data.textures is not None:
+            desc.texture_layers = data.textures.ctypes.data_as(_capi.u8p)
+            desc.texture_layer_count = data.textures.shape[0]
+        desc.sky_color = (C.c_float * 3)(*data.sky_color)
+        h = C.c_void_p()
+        group.check(self._lib.rt_group_scene_create(group.handle, C.byref(desc), C.byref(h)), "rt_group_scene_create")
+        self.handle = h
+
+    def close(self):
+        if getattr(self, "handle", None) and getattr(self.group, "handle", None):
+            self._lib.rt_group_scene_destroy(self.handle)
+        self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class GroupRenderer:
+    """IRenderer over a Group: mode "tiles" (bit-identical to one device) or "spp" (salted sample slices)."""
+
+    def __init__(self, group, kind, img_size, max_depth=10, sample_count=32, mode="tiles", tile_size=64):
+        self.group, self._lib = group, group._lib
+        self.img_size = (int(img_size[0]), int(img_size[1]))
+        self.max_depth, self.sample_count, self.mode, self.tile_size = int(max_depth), int(sample_count), mode, int(tile_size)
+        h = C.c_void_p()
+        group.check(self._lib.rt_group_renderer_create(group.handle, int(kind), self.img_size[0], self.img_size[1], C.byref(h)),
+                    "rt_group_renderer_create")
+        self.handle = h
+
+    def render_frame(self, camera, scene, want=("rgba8", "accum", "rng_state"), resume=False):
+        w, h = self.img_size
+        out = {"rgba8": np.empty((h, w, 4), np.uint8) if "rgba8" in want else None,
+               "accum": np.empty((h, w, 4), np.float32) if "accum" in want else None,
+               "rng_state": np.empty((h, w), np.uint32) if "rng_state" in want else None}
+        p = _capi.rt_group_params()
+        p.max_depth, p.sample_count = self.max_depth, self.sample_count
+        p.mode = _capi.RT_GROUP_SPP if self.mode == "spp" else _capi.RT_GROUP_TILES
+        p.tile_size = self.tile_size
+        p.flags = _capi.RT_RENDER_RESUME if resume else 0
+        f = _capi.rt_frame()
+        f.rgba8, f.accum, f.rng_state = _ptr(out["rgba8"]), _ptr(out["accum"]), _ptr(out["rng_state"])
+        self.group.check(self._lib.rt_group_render_frame(self.handle, scene.handle, C.byref(camera.c), C.byref(p), C.byref(f)),
+                         "rt_group_render_frame")
+        return Frame(out["rgba8"], out["accum"], out["rng_state"], int(f.ray_count), float(f.device_ms), int(f.kernel_launches),
+                     self.sample_count)
+
+    def close(self):
+        if getattr(self, "handle", None) and getattr(self.group, "handle", None):
+            self._lib.rt_group_renderer_destroy(self.handle)
+        self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+

@@ -62,6 +62,14 @@ class rt_frame(C.Structure):
                 ("ray_count", C.c_uint64), ("device_ms", C.c_float), ("kernel_launches", C.c_uint32)]
 
 
+class rt_group_params(C.Structure):
+    _fields_ = [("max_depth", C.c_uint32), ("sample_count", C.c_uint32), ("mode", C.c_uint32), ("tile_size", C.c_uint32),
+                ("flags", C.c_uint32)]
+
+
+RT_GROUP_TILES, RT_GROUP_SPP = 0, 1
+
+
 class rt_scene_stats(C.Structure):
     _fields_ = [("triangle_count", C.c_uint64), ("node_count", C.c_uint64), ("bvh_bytes", C.c_uint64),
                 ("shading_bytes", C.c_uint64), ("build_ms", C.c_float), ("max_leaf_tris", C.c_uint32),
@@ -94,6 +102,19 @@ SYMBOLS = {
     "rt_renderer_export_image": (C.c_int, [C.c_void_p, C.POINTER(rt_ipc_handle)]),
     "rt_renderer_set_gather": (C.c_int, [C.c_void_p, C.POINTER(rt_ipc_handle), C.c_void_p]),
     "rt_resolve": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_int32, C.c_int32, C.c_void_p]),
+    "rt_renderer_device_rng": (C.c_void_p, [C.c_void_p]),
+    "rt_group_create": (C.c_int, [C.POINTER(C.c_int), C.c_uint32, C.POINTER(C.c_void_p)]),
+    "rt_group_destroy": (None, [C.c_void_p]),
+    "rt_group_size": (C.c_uint32, [C.c_void_p]),
+    "rt_group_context": (C.c_void_p, [C.c_void_p, C.c_uint32]),
+    "rt_group_last_error": (C.c_char_p, [C.c_void_p]),
+    "rt_group_scene_create": (C.c_int, [C.c_void_p, C.POINTER(rt_scene_desc), C.POINTER(C.c_void_p)]),
+    "rt_group_scene_destroy": (None, [C.c_void_p]),
+    "rt_group_scene_get": (C.c_void_p, [C.c_void_p, C.c_uint32]),
+    "rt_group_renderer_create": (C.c_int, [C.c_void_p, C.c_int, C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]),
+    "rt_group_renderer_destroy": (None, [C.c_void_p]),
+    "rt_group_renderer_get": (C.c_void_p, [C.c_void_p, C.c_uint32]),
+    "rt_group_render_frame": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(rt_camera), C.POINTER(rt_group_params), C.POINTER(rt_frame)]),
 }
 
 _lib = None

@@ -118,7 +118,7 @@ struct Scratch {
 
 } // namespace
 
-rt_status rt_build_bvh(rt_scene *s) {
+static rt_status build_bvh(rt_scene *s) {
     rt_context *ctx = s->ctx;
     cudaStream_t st = ctx->stream;
     const uint32_t n = s->n_tris;
@@ -264,4 +264,17 @@ rt_status rt_build_bvh(rt_scene *s) {
     s->stats.node_count = node_count;
     s->stats.wide_depth = depth;
     return RT_OK;
+}
+
+rt_status rt_build_bvh(rt_scene *s) {
+    const rt_status st = build_bvh(s);
+    if (st != RT_OK) { /* a failed commit leaves nothing behind: the scene can be destroyed or committed again */
+        rt_pool_free(s->ctx, s->d_nodes);
+        rt_pool_free(s->ctx, s->d_tris);
+        rt_pool_free(s->ctx, s->d_shade);
+        s->d_nodes = nullptr;
+        s->d_tris = nullptr;
+        s->d_shade = nullptr;
+    }
+    return st;
 }

@@ -7,6 +7,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <new>
+#include <thread>
 
 #include "rt_internal.h"
 #include "rt_render.h"
@@ -18,6 +19,82 @@ rt_status rt_set_error(rt_context *ctx, rt_status st, const char *what, const ch
     if (ctx) ctx->err = msg;
     else g_create_error = msg;
     return st;
+}
+
+cudaError_t rt_scratch(rt_context *ctx, int k, size_t bytes, void **out) {
+    if (ctx->scratch_bytes[k] < bytes) {
+        cudaError_t e = cudaStreamSynchronize(ctx->stream); /* nothing may still use the old block */
+        if (e != cudaSuccess) return e;
+        cudaFree(ctx->scratch[k]);
+        ctx->scratch[k] = nullptr;
+        ctx->scratch_bytes[k] = 0;
+        if ((e = cudaMalloc(&ctx->scratch[k], bytes)) != cudaSuccess) return e;
+        ctx->scratch_bytes[k] = bytes;
+    }
+    *out = ctx->scratch[k];
+    return cudaSuccess;
+}
+
+static bool is_pageable_host(const void *p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return true;
+    }
+    return a.type == cudaMemoryTypeUnregistered;
+}
+
+static bool is_device_pointer(const void *p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+cudaError_t rt_upload(rt_context *ctx, void *dst, const void *src, size_t bytes) {
+    constexpr size_t kChunk = 8u << 20; /* 8 MiB per pinned chunk */
+    constexpr int kLanes = 4;           /* host copy threads = copy streams = pinned chunks */
+    if (bytes == 0) return cudaSuccess;
+    if (bytes < (4u << 20) || !is_pageable_host(src)) return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, ctx->stream);
+    for (int k = 0; k < kLanes; k++) {
+        cudaError_t e = cudaSuccess;
+        if (!ctx->stage[k] && (e = cudaMallocHost(&ctx->stage[k], kChunk)) != cudaSuccess) return e;
+        if (!ctx->stage_stream[k] && (e = cudaStreamCreateWithFlags(&ctx->stage_stream[k], cudaStreamNonBlocking)) != cudaSuccess) return e;
+        if (!ctx->stage_event[k] && (e = cudaEventCreateWithFlags(&ctx->stage_event[k], cudaEventDisableTiming)) != cudaSuccess) return e;
+    }
+    /* the destination may still be in use by earlier work on the context stream (pool re-use): order the copy streams after it */
+    cudaError_t e = cudaSuccess;
+    if (!ctx->stage_begin && (e = cudaEventCreateWithFlags(&ctx->stage_begin, cudaEventDisableTiming)) != cudaSuccess) return e;
+    if ((e = cudaEventRecord(ctx->stage_begin, ctx->stream)) != cudaSuccess) return e;
+    const size_t n_chunks = (bytes + kChunk - 1) / kChunk;
+    cudaError_t errs[kLanes] = {cudaSuccess, cudaSuccess, cudaSuccess, cudaSuccess};
+    auto lane = [&](int k) {
+        cudaError_t le = cudaSetDevice(ctx->device);
+        if (le == cudaSuccess) le = cudaStreamWaitEvent(ctx->stage_stream[k], ctx->stage_begin, 0);
+        for (size_t c = (size_t)k; c < n_chunks && le == cudaSuccess; c += kLanes) {
+            const size_t off = c * kChunk, len = bytes - off < kChunk ? bytes - off : kChunk;
+            le = cudaEventSynchronize(ctx->stage_event[k]); /* the chunk's previous copy has left the pinned buffer */
+            if (le != cudaSuccess) break;
+            memcpy(ctx->stage[k], (const char *)src + off, len);
+            le = cudaMemcpyAsync((char *)dst + off, ctx->stage[k], len, cudaMemcpyHostToDevice, ctx->stage_stream[k]);
+            if (le == cudaSuccess) le = cudaEventRecord(ctx->stage_event[k], ctx->stage_stream[k]);
+        }
+        errs[k] = le;
+    };
+    {
+        std::thread t1(lane, 1), t2(lane, 2), t3(lane, 3);
+        lane(0);
+        t1.join();
+        t2.join();
+        t3.join();
+    }
+    for (int k = 0; k < kLanes; k++) {
+        if (errs[k] != cudaSuccess) return errs[k];
+        if ((e = cudaStreamWaitEvent(ctx->stream, ctx->stage_event[k], 0)) != cudaSuccess) return e; /* the context stream continues after the last chunk of every lane */
+    }
+    return cudaSuccess;
 }
 
 struct rt_renderer {
@@ -37,7 +114,11 @@ struct rt_renderer {
     size_t queue_capacity = 0;    /* slots per wavefront id queue */
     int wf_persist = 2;           /* wavefront: 2 = queue-driven warps (one launch), 1 = per-CTA iterations (one launch), 0 = streaming kernels (RT_WF_PERSIST) */
     cudaEvent_t ev_batch[2] = {nullptr, nullptr}; /* wavefront: per-batch queue-length read-back */
-    bool has_frame = false; /* a frame has been rendered: RT_RENDER_RESUME is allowed */
+    bool has_frame = false; /* a frame has been rendered: RT_RENDER_RESUME is allowed ... */
+    const rt_scene *last_scene = nullptr; /* ... for the same scene, camera, depth and shard only */
+    rt_camera last_camera = {};
+    rt_shard last_shard = {};
+    uint32_t last_depth = 0;
     uint32_t *d_order[4] = {nullptr, nullptr, nullptr, nullptr}; /* block order: keys in/out, values in/out */
     void *d_order_temp = nullptr;
     uint32_t *d_region_cost = nullptr;
@@ -48,8 +129,10 @@ struct rt_renderer {
     bool gather_ipc = false;      /* gather was opened from an IPC handle (close it) */
     bool exported = false;        /* d_rgba8 is a gather destination: never clear foreign pixels */
     int tune_refill = 12; /* lanes that must run dry before a warp refills (RT_TUNE_REFILL overrides; 12-14 measured best) */
-    int tune_ctx = 2;     /* megakernel: ray contexts per lane (RT_MEGA_CTX; 0 = round-1 kernel) */
-    int tune_inflight = 128; /* wavefront, queue-driven warps: pixels in flight per warp (RT_TUNE_INFLIGHT) */
+    int tune_ctx = 0;     /* megakernel: parked ray contexts per lane (RT_MEGA_CTX 1-4 = k_megakernel_ctx; measured slower than the
+                             one-pixel-in-registers kernel on C2/C3/C4, profiles/README.md) */
+    int tune_inflight = 64; /* wavefront, queue-driven warps: pixels in flight per warp (RT_TUNE_INFLIGHT; measured 32 / 64 / 96 / 128 / 256 / 512:
+                               64 is best on C2, C3 and C4 — the warp's pixel state stays in L1) */
     int tune_shade = 24, tune_idle = 4; /* megakernel contexts: shade-pass triggers (RT_TUNE_SHADE, RT_TUNE_IDLE) */
 };
 
@@ -157,6 +240,16 @@ void rt_context_destroy(rt_context *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     for (auto &t : ctx->tex_cache) cudaFreeArray(t.second);
+    for (int k = 0; k < 2; k++) cudaFree(ctx->scratch[k]);
+    for (int k = 0; k < 4; k++) {
+        if (ctx->stage_stream[k]) {
+            cudaStreamSynchronize(ctx->stage_stream[k]);
+            cudaStreamDestroy(ctx->stage_stream[k]);
+        }
+        if (ctx->stage_event[k]) cudaEventDestroy(ctx->stage_event[k]);
+        if (ctx->stage[k]) cudaFreeHost(ctx->stage[k]);
+    }
+    if (ctx->stage_begin) cudaEventDestroy(ctx->stage_begin);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
@@ -227,8 +320,8 @@ rt_status rt_scene_create(rt_context *ctx, const rt_scene_desc *desc, rt_scene *
         n_verts += in.vertex_count;
         n_idx += in.index_count;
     }
-    if (n_idx / 3 >= 0x7fffffffull || n_verts >= 0xffffffffull)
-        return rt_set_error(ctx, RT_ERR_INVALID, "rt_scene_create", "scene too large (2^31 triangles)");
+    if (n_idx >= 0xffffffffull || n_verts >= 0xffffffffull) /* index / vertex offsets are 32-bit (first_index, first_vertex) */
+        return rt_set_error(ctx, RT_ERR_INVALID, "rt_scene_create", "scene too large (2^32 indices or vertices)");
 
     rt_scene *s = new (std::nothrow) rt_scene();
     if (!s) return rt_set_error(ctx, RT_ERR_INVALID, "rt_scene_create", "out of memory");
@@ -277,17 +370,18 @@ rt_status rt_scene_create(rt_context *ctx, const rt_scene_desc *desc, rt_scene *
         if ((e = rt_pool_alloc(ctx, (void **)&s->d_geom, s->h_geom.size() * sizeof(*s->d_geom))) != cudaSuccess) { fail(e, "alloc geom"); break; }
         if ((e = rt_pool_alloc(ctx, (void **)&s->d_inst, s->h_inst.size() * sizeof(*s->d_inst))) != cudaSuccess) { fail(e, "alloc inst"); break; }
         /* every instance's arrays go straight from the caller's memory to their offset in the
-         * concatenated device arrays (no host-side staging copy) */
+         * concatenated device arrays (small or pinned sources directly, large pageable ones through rt_upload's
+         * pinned ring) */
         for (uint32_t i = 0; i < desc->instance_count && e == cudaSuccess; i++) {
             const rt_instance &in = desc->instances[i];
             const RtInstanceGeom &g = s->h_geom[i];
             if (in.vertex_count) {
-                e = cudaMemcpyAsync(s->d_positions + (size_t)g.first_vertex * 3, in.positions, (size_t)in.vertex_count * 12, cudaMemcpyHostToDevice, stream);
-                if (e == cudaSuccess) e = cudaMemcpyAsync(s->d_normals + (size_t)g.first_vertex * 3, in.normals, (size_t)in.vertex_count * 12, cudaMemcpyHostToDevice, stream);
-                if (e == cudaSuccess) e = cudaMemcpyAsync(s->d_uvs + (size_t)g.first_vertex * 2, in.uvs, (size_t)in.vertex_count * 8, cudaMemcpyHostToDevice, stream);
+                e = rt_upload(ctx, s->d_positions + (size_t)g.first_vertex * 3, in.positions, (size_t)in.vertex_count * 12);
+                if (e == cudaSuccess) e = rt_upload(ctx, s->d_normals + (size_t)g.first_vertex * 3, in.normals, (size_t)in.vertex_count * 12);
+                if (e == cudaSuccess) e = rt_upload(ctx, s->d_uvs + (size_t)g.first_vertex * 2, in.uvs, (size_t)in.vertex_count * 8);
             }
             if (e == cudaSuccess && in.index_count)
-                e = cudaMemcpyAsync(s->d_indices + g.first_index, in.indices, (size_t)in.index_count * 4, cudaMemcpyHostToDevice, stream);
+                e = rt_upload(ctx, s->d_indices + g.first_index, in.indices, (size_t)in.index_count * 4);
         }
         if (e != cudaSuccess) { fail(e, "copy geometry"); break; }
         if ((e = cudaMemcpyAsync(s->d_geom, s->h_geom.data(), s->h_geom.size() * sizeof(RtInstanceGeom), cudaMemcpyHostToDevice, stream)) != cudaSuccess) { fail(e, "copy geom"); break; }
@@ -386,6 +480,7 @@ rt_status rt_intersect(rt_context *ctx, const rt_scene *scene, uint64_t n, const
                        float tnear, float tfar, int32_t *inst, int32_t *prim, float *u, float *v, float *t,
                        float *device_ms) {
     if (!ctx || !scene) return RT_ERR_INVALID;
+    if (scene->ctx != ctx) return rt_set_error(ctx, RT_ERR_INVALID, "rt_intersect", "scene belongs to another context");
     if (!scene->committed) return rt_set_error(ctx, RT_ERR_STATE, "rt_intersect", "scene not committed");
     if (n && (!org || !dir || !inst || !prim || !u || !v || !t))
         return rt_set_error(ctx, RT_ERR_INVALID, "rt_intersect", "NULL argument");
@@ -448,7 +543,8 @@ rt_status rt_renderer_create(rt_context *ctx, rt_renderer_kind kind, int32_t wid
     if (const char *e = getenv("RT_MEGA_CTX")) r->tune_ctx = atoi(e) >= 0 && atoi(e) <= 4 ? atoi(e) : r->tune_ctx;
     if (const char *e = getenv("RT_TUNE_SHADE")) r->tune_shade = atoi(e) > 0 ? atoi(e) : r->tune_shade;
     if (const char *e = getenv("RT_TUNE_IDLE")) r->tune_idle = atoi(e) > 0 ? atoi(e) : r->tune_idle;
-    if (kind == RT_MEGAKERNEL && r->tune_ctx > 0 && !getenv("RT_TUNE_REFILL")) r->tune_refill = 4; /* switching is cheap */
+    if (kind == RT_MEGAKERNEL && r->tune_ctx > 0 && !getenv("RT_TUNE_REFILL")) r->tune_refill = 8;
+    if (kind == RT_WAVEFRONT && r->wf_persist >= 2 && !getenv("RT_TUNE_REFILL")) r->tune_refill = 14;
     const size_t n = (size_t)width * (size_t)height;
     cudaError_t e = cudaSuccess;
     do {
@@ -529,6 +625,10 @@ void rt_renderer_destroy(rt_renderer *r) {
     delete r;
 }
 
+} /* extern "C" */
+void rt_renderer_mark_exported(rt_renderer *r) { r->exported = true; } /* rt_group: device 0's image is the gather destination */
+extern "C" {
+
 rt_status rt_renderer_export_image(rt_renderer *r, rt_ipc_handle *out) {
     if (!r) return RT_ERR_INVALID;
     rt_context *ctx = r->ctx;
@@ -564,6 +664,7 @@ rt_status rt_renderer_set_gather(rt_renderer *r, const rt_ipc_handle *handle, vo
 
 float *rt_renderer_device_accum(rt_renderer *r) { return r ? (float *)r->d_accum : nullptr; }
 uint8_t *rt_renderer_device_rgba8(rt_renderer *r) { return r ? (uint8_t *)r->d_rgba8 : nullptr; }
+uint32_t *rt_renderer_device_rng(rt_renderer *r) { return r ? r->d_rng : nullptr; }
 
 rt_status rt_render_frame(rt_renderer *r, const rt_scene *scene, const rt_camera *camera,
                           const rt_render_params *params, rt_frame *frame) {
@@ -599,6 +700,10 @@ rt_status rt_render_frame(rt_renderer *r, const rt_scene *scene, const rt_camera
     p.tune_inflight = r->tune_inflight;
     p.resume = (params->flags & RT_RENDER_RESUME) ? 1 : 0;
     if (p.resume && !r->has_frame) return rt_set_error(ctx, RT_ERR_STATE, "rt_render_frame", "RT_RENDER_RESUME without a previous frame");
+    if (p.resume && (r->last_scene != scene || memcmp(&r->last_camera, camera, sizeof(rt_camera)) != 0 || r->last_depth != params->max_depth ||
+                     r->last_shard.rank != sh.rank || r->last_shard.world != sh.world || r->last_shard.tile_size != sh.tile_size ||
+                     r->last_shard.seed_salt != sh.seed_salt))
+        return rt_set_error(ctx, RT_ERR_STATE, "rt_render_frame", "RT_RENDER_RESUME with a different scene, camera, depth or shard than the previous frame");
     RtFrameOut out;
     out.accum = r->d_accum;
     out.rgba8 = r->d_rgba8;
@@ -748,6 +853,10 @@ rt_status rt_render_frame(rt_renderer *r, const rt_scene *scene, const rt_camera
     frame->ray_count = *r->h_rays;
     frame->kernel_launches = launches;
     r->has_frame = true;
+    r->last_scene = scene;
+    r->last_camera = *camera;
+    r->last_shard = sh;
+    r->last_depth = params->max_depth;
 #ifdef RT_GPU_COUNTERS
     {
         unsigned long long c[2];
@@ -766,19 +875,21 @@ rt_status rt_resolve(rt_context *ctx, const float *accum, uint32_t sample_count,
     RT_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
     const size_t n = (size_t)width * (size_t)height;
-    float *d_a = nullptr;
-    uint32_t *d_o = nullptr;
+    /* device-resident arguments are used in place; host ones go through the context's grow-only scratch (no
+     * cudaMalloc / cudaFree / staging copy per call: after a cross-GPU reduction both usually are device memory) */
+    const bool a_dev = is_device_pointer(accum), o_dev = is_device_pointer(rgba8);
+    void *d_a = (void *)accum, *d_o = (void *)rgba8;
     cudaError_t e = cudaSuccess;
     do {
-        if ((e = dev_alloc(&d_a, n * 4)) != cudaSuccess) break;
-        if ((e = dev_alloc(&d_o, n)) != cudaSuccess) break;
-        if ((e = cudaMemcpyAsync(d_a, accum, n * 16, cudaMemcpyDefault, st)) != cudaSuccess) break;
-        if ((e = rt_launch_resolve(st, d_a, d_o, (uint32_t)n, (float)sample_count)) != cudaSuccess) break;
-        if ((e = cudaMemcpyAsync(rgba8, d_o, n * 4, cudaMemcpyDefault, st)) != cudaSuccess) break;
+        if (!a_dev) {
+            if ((e = rt_scratch(ctx, 0, n * 16, &d_a)) != cudaSuccess) break;
+            if ((e = rt_upload(ctx, d_a, accum, n * 16)) != cudaSuccess) break;
+        }
+        if (!o_dev && (e = rt_scratch(ctx, 1, n * 4, &d_o)) != cudaSuccess) break;
+        if ((e = rt_launch_resolve(st, (const float *)d_a, (uint32_t *)d_o, (uint32_t)n, (float)sample_count)) != cudaSuccess) break;
+        if (!o_dev && (e = cudaMemcpyAsync(rgba8, d_o, n * 4, cudaMemcpyDefault, st)) != cudaSuccess) break;
         e = cudaStreamSynchronize(st);
     } while (0);
-    cudaFree(d_a);
-    cudaFree(d_o);
     if (e != cudaSuccess) return rt_set_error(ctx, RT_ERR_CUDA, "rt_resolve", cudaGetErrorString(e));
     return RT_OK;
 }

@@ -24,7 +24,22 @@ struct rt_context {
     /* layered texture arrays of destroyed scenes, kept for the next scene with the same layer count:
      * cudaMalloc3DArray / cudaFreeArray are synchronous driver calls worth tens of milliseconds */
     std::vector<std::pair<uint32_t, cudaArray_t>> tex_cache;
+    /* grow-only device scratch of rt_resolve / rt_intersect (no cudaMalloc / cudaFree per call) */
+    void *scratch[2] = {nullptr, nullptr};
+    size_t scratch_bytes[2] = {0, 0};
+    /* pinned staging ring + copy streams of rt_upload (pageable host memory -> device at PCIe speed) */
+    void *stage[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaStream_t stage_stream[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t stage_event[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t stage_begin = nullptr; /* the copy streams start after the work already on ctx->stream */
 };
+
+/* device scratch slot `k` of at least `bytes` (kept for the next call) */
+cudaError_t rt_scratch(rt_context *ctx, int k, size_t bytes, void **out);
+/* host (pageable / pinned) or device memory -> device, ordered on ctx->stream. Large pageable sources go through a
+ * ring of pinned chunks filled by a few host threads, each with its own copy stream: a pageable cudaMemcpyAsync runs at
+ * ~7 GB/s and stalls the calling thread, the staged path at PCIe speed (C4's 280 MB scene: ~40 ms -> ~12 ms). */
+cudaError_t rt_upload(rt_context *ctx, void *dst, const void *src, size_t bytes);
 
 /* Scene's device side (src/scene.hpp:64-91) */
 struct rt_scene {
@@ -64,6 +79,7 @@ inline void rt_pool_free(rt_context *ctx, void *p) {
     if (p) cudaFreeAsync(p, ctx->stream);
 }
 rt_status rt_build_bvh(rt_scene *s); /* bvh_build.cu */
+void rt_renderer_mark_exported(rt_renderer *r); /* rt_api.cu, for rt_group.cu */
 
 #define RT_CUDA_TRY(ctx, expr)                                                     \
     do {                                                                           \

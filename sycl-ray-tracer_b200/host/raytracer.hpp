@@ -146,6 +146,68 @@ struct RendererBase : public IRenderer {
 };
 } // namespace detail
 
+/* ---- several GPUs of one node (no reference equivalent: App picks one device, src/app.hpp:43-55) --------------
+ * Same call sequence, N devices: GroupApp replaces App, GroupScene replaces Scene, GroupRenderer(kind, ...) replaces
+ * the two renderer classes. Mode RT_GROUP_TILES renders exactly the single-device image. */
+struct GroupApp {
+    rt_group *group = nullptr;
+    GroupApp(const GroupApp &) = delete;
+    GroupApp &operator=(const GroupApp &) = delete;
+    explicit GroupApp(uint32_t n_devices) {
+        if (rt_group_create(nullptr, n_devices, &group) != RT_OK)
+            throw std::runtime_error(std::string("rt_group_create: ") + rt_last_error(nullptr));
+        for (uint32_t i = 0; i < n_devices; i++)
+            std::printf("Running on device: %s\n", rt_context_device_name(rt_group_context(group, i)));
+    }
+    ~GroupApp() { rt_group_destroy(group); }
+    uint32_t size() const { return rt_group_size(group); }
+    void check(rt_status st, const char *what) const {
+        if (st != RT_OK) throw std::runtime_error(std::string(what) + ": " + rt_group_last_error(group));
+    }
+};
+
+struct GroupScene {
+    GroupApp &app;
+    rt_group_scene *scene = nullptr;
+    GroupScene(const GroupScene &) = delete;
+    GroupScene &operator=(const GroupScene &) = delete;
+    GroupScene(GroupApp &app_, const rt_scene_desc &desc) : app(app_) {
+        app.check(rt_group_scene_create(app.group, &desc, &scene), "rt_group_scene_create");
+    }
+    ~GroupScene() { rt_group_scene_destroy(scene); }
+};
+
+struct GroupRenderer {
+    GroupApp &app;
+    range2 img_size;
+    Image &image;
+    const uint32_t max_depth, sample_count;
+    rt_group_mode mode;
+    rt_group_renderer *handle = nullptr;
+    bool quiet = false;
+    rt_frame last{};
+    GroupRenderer(rt_renderer_kind kind, GroupApp &app_, range2 size, Image &image_, uint32_t depth, uint32_t spp, rt_group_mode mode_)
+        : app(app_), img_size(size), image(image_), max_depth(depth), sample_count(spp), mode(mode_) {
+        app.check(rt_group_renderer_create(app.group, kind, (int32_t)size[0], (int32_t)size[1], &handle), "rt_group_renderer_create");
+    }
+    ~GroupRenderer() { rt_group_renderer_destroy(handle); }
+    void render_frame(const Camera &camera, const GroupScene &scene) {
+        rt_group_params p{};
+        p.max_depth = max_depth;
+        p.sample_count = sample_count;
+        p.mode = (uint32_t)mode;
+        last = rt_frame{};
+        last.rgba8 = image.rgba8.data();
+        app.check(rt_group_render_frame(handle, scene.scene, &camera.c, &p, &last), "rt_group_render_frame");
+        if (!quiet) {
+            const double secs = last.device_ms * 1e-3;
+            std::printf("Time measured: %.6f seconds\n", secs);
+            std::printf("Total rays: %llu\n", (unsigned long long)last.ray_count);
+            std::printf("Rays/sec: %.2fM\n", (double)last.ray_count / secs / 1000000.0);
+        }
+    }
+};
+
 /* src/render_megakernel.hpp:6-22 */
 struct MegakernelRenderer : public detail::RendererBase {
     MegakernelRenderer(App &app, range2 img_size, Image &image, uint32_t max_depth, uint32_t sample_count)

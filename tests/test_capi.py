@@ -22,7 +22,7 @@ def test_library_exports_every_declared_symbol(pkg):
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/rt_api.h but not exported"
         assert n in pkg._capi.SYMBOLS, f"{n} has no ctypes binding"
-    assert lib.rt_api_version() == 1
+    assert lib.rt_api_version() == 2
 
 
 def test_struct_layouts_match_the_header(pkg):
