@@ -18,9 +18,15 @@ wavefront. One "step" = one render_frame of that configuration.
   cpu_baseline  the oracle (CPU restatement of the reference, own SAH BVH instead of Embree)
              timed on the box's host cores on a bounded sample of the same workload
 
-N > 1 (torchrun): spp sharding, weak scaling — every rank renders the full frame with its own
-256 spp (distinct seed salt), the fp32 accumulation buffers are combined with an NCCL all-reduce
-over NVLink inside the timed region and rank 0 resolves the image.
+N > 1 (torchrun, one rank per GPU): STRONG scaling by default — the workload's total samples per pixel are split over
+the ranks (256 / N each on C3, distinct seed salts), every rank renders the full frame, and the one exchange step runs
+inside the timed region: the library's fused reduce-scatter + resolve + gather kernel over NVLink peer memory
+(rt_renderer_reduce_resolve: each rank sums its 1/N slice of the pixels over all ranks' accumulation buffers and stores
+the resolved RGBA8 pixels into rank 0's image), ordered by two 4-byte NCCL all-reduces. --exchange nccl uses an NCCL
+all-reduce of the fp32 buffers + rt_resolve instead; --sharding tiles is config 4's image-tile mode (peer-store gather
+fused into the render kernel, bit-identical to one GPU); --scaling weak keeps the per-GPU work fixed (round 1's mode,
+also reported under "also_weak" by the default run). The gathered image is checked, untimed, against a one-GPU render
+(tiles) or against the rank-ordered sum of the accumulation buffers (spp).
 """
 import argparse
 import importlib
@@ -178,25 +184,39 @@ def build_scene_data(workload):
 
 
 def cpu_reference_run(data, w, h, depth, mode, target_s, threads=0):
-    """Time the oracle (CPU restatement of the reference's trace_ray/material code, own SAH BVH in
-    place of Embree's rtcIntersect1) on a bounded sample of the workload: a centred crop of the full
-    frame at reduced spp (Mrays/s is spp-independent, benchmark_avg.csv:12-19)."""
+    """Time the oracle (CPU restatement of the reference's trace_ray/material code, own SAH BVH in place of Embree's
+    rtcIntersect1) on a bounded sample of the workload: a 6 x 4 lattice of tiles SPREAD OVER THE WHOLE FRAME (so the
+    sample sees the frame's mix of sky, floor, walls and spheres, not its centre) at reduced spp (Mrays/s is
+    spp-independent, benchmark_avg.csv:12-19)."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import _oracle
     osc = _oracle.Scene(data)
     ocam = _oracle.camera_for(data, w, h)
-    cw, ch = min(w, 480), min(h, 270)
-    crop = ((w - cw) // 2, (h - ch) // 2, (w - cw) // 2 + cw, (h - ch) // 2 + ch)
-    probe = osc.render(ocam, mode, depth, 1, use_bvh=True, crop=crop, threads=threads)  # also builds the BVH
-    probe = osc.render(ocam, mode, depth, 1, use_bvh=True, crop=crop, threads=threads)
-    rate = probe["ray_count"] / max(probe["seconds"], 1e-9)
-    spp = int(max(1, min(64, round(target_s * rate / max(probe["ray_count"], 1)))))
+    gx, gy = (6, 4) if w >= 480 and h >= 272 else (1, 1)
+    tw, th = min(w, 80), min(h, 68)
+    crops = []
+    for j in range(gy):
+        for i in range(gx):
+            x0 = (w - tw) * i // max(1, gx - 1) if gx > 1 else (w - tw) // 2
+            y0 = (h - th) * j // max(1, gy - 1) if gy > 1 else (h - th) // 2
+            crops.append((x0, y0, x0 + tw, y0 + th))
+
+    def once(spp):
+        rays = secs = 0
+        for c in crops:
+            r = osc.render(ocam, mode, depth, spp, use_bvh=True, crop=c, threads=threads)
+            rays, secs = rays + r["ray_count"], secs + r["seconds"]
+        return rays, secs
+    once(1)  # also builds the BVH
+    rays1, secs1 = once(1)
+    spp = int(max(1, min(64, round(target_s * (rays1 / max(secs1, 1e-9)) / max(rays1, 1)))))
     cores = _oracle.lib().orc_max_threads() if threads <= 0 else threads
-    sample = f"{cw}x{ch} centre crop of the {w}x{h} frame, {spp} spp, depth {depth}, {'wavefront' if mode else 'megakernel'} seeding"
+    sample = (f"{gx}x{gy} lattice of {tw}x{th} tiles spread over the whole {w}x{h} frame ({len(crops) * tw * th} pixels), {spp} spp, depth {depth}, "
+              f"{'wavefront' if mode else 'megakernel'} seeding")
 
     def step():
-        r = osc.render(ocam, mode, depth, spp, use_bvh=True, crop=crop, threads=threads)
-        return r["ray_count"], r["seconds"], cw * ch * spp
+        rays, secs = once(spp)
+        return rays, secs, len(crops) * tw * th * spp
     return step, cores, sample
 
 
@@ -222,7 +242,8 @@ def run_reference(args):
         "msamples_per_s": samples / secs / 1e6,
         "config": {"workload": args.workload, "triangles": data.triangle_count, "width": w, "height": h,
                    "spp": spp, "max_depth": depth, "renderer": "megakernel",
-                   "note": "reference algorithm on host cores: oracle C++ restatement + own SAH BVH (Embree/SYCL absent, reference unbuildable here)"},
+                   "note": "reference algorithm on host cores: oracle C++ restatement + own SAH BVH (Embree/SYCL absent, reference unbuildable here); "
+                           "each step renders the sample named in cpu_baseline.sample: tiles spread over the whole frame of this workload"},
         "cpu_baseline": {"value": val, "unit": "Mrays/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -248,18 +269,24 @@ def main():
     ap.add_argument("--batch-spp", type=int, default=-1, help="progressive rendering: samples per frame, frames chained with "
                     "RT_RENDER_RESUME (bit-identical to one frame); 0 = one frame, default: 256 for c5, else 0")
     ap.add_argument("--cpu-seconds", type=float, default=6.0, help="target seconds per CPU-baseline step")
-    ap.add_argument("--sharding", default="spp", choices=["spp", "tiles"],
-                    help="N>1: spp = every rank renders the full frame with its own spp (weak scaling, default); "
-                         "tiles = 64x64 image tiles dealt round robin, total work fixed (strong scaling, config 4's mode)")
-    ap.add_argument("--gather", default="peer", choices=["peer", "allreduce"],
-                    help="tile sharding: peer = every rank's kernel stores its finished RGBA8 pixels straight into rank 0's image "
-                         "over NVLink peer memory (CUDA IPC), a 4-byte all-reduce orders the frame; allreduce = NCCL all-reduce of the "
-                         "fp32 accumulation buffers + resolve on rank 0")
+    ap.add_argument("--sharding", default="auto", choices=["auto", "spp", "tiles"],
+                    help="N>1: spp = every rank renders the full frame with its share of the samples and its own seed salt; tiles = 64x64 "
+                         "image tiles dealt round robin (config 4's mode, bit-identical to one GPU); auto = tiles for c4, spp otherwise")
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
+                    help="N>1 with spp sharding: strong = the workload's total spp is split over the ranks (default); weak = every rank "
+                         "renders the workload's full spp (N times the work)")
+    ap.add_argument("--exchange", "--gather", dest="exchange", default="peer", choices=["peer", "nccl", "allreduce"],
+                    help="N>1: peer = the library's own kernels move the result over NVLink peer memory (tiles: the render kernel stores finished "
+                         "RGBA8 pixels into rank 0's image; spp: fused reduce-scatter + resolve + gather kernel), 4-byte NCCL all-reduces order "
+                         "the frame; nccl = NCCL all-reduce of the fp32 accumulation buffers + rt_resolve on rank 0")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--no-also", action="store_true", help="skip the quick secondary measurement of configs[1] (Cornell)")
+    ap.add_argument("--no-also", action="store_true", help="skip the quick secondary measurements (configs[1] Cornell at N=1, the weak-scaling line at N>1)")
+    ap.add_argument("--no-verify", action="store_true", help="N>1: skip the untimed check of the gathered image")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.exchange == "allreduce":
+        args.exchange = "nccl"
     if args.impl == "reference":
         return run_reference(args)
 
@@ -287,83 +314,145 @@ def main():
     scene = pkg.Scene(app, data)
     stats = scene.stats
     cam = pkg.Camera((w, h), data.camera_position, data.camera_direction, data.camera_focal_length)
-    tiles = args.sharding == "tiles" and world > 1
-    if world == 1:
-        shard = None
-    elif tiles:
-        shard = {"rank": rank, "world": world, "tile_size": 64, "seed_salt": 0}
-    else:
-        shard = {"rank": rank, "world": world, "tile_size": 0, "seed_salt": (rank * 0x9E3779B9) & 0xFFFFFFFF}
+    sharding = args.sharding if args.sharding != "auto" else ("tiles" if args.workload == "c4_heightfield_10m" else "spp")
+    tiles = sharding == "tiles" and world > 1
     batch = PROGRESSIVE.get(args.workload, 0) if args.batch_spp < 0 else args.batch_spp
-    split_total = args.workload in PROGRESSIVE and world > 1 and not tiles  # c5: the total spp is divided over the ranks
-    if split_total:
-        spp = max(1, spp // world)
-    spp_total = spp if (tiles or world == 1) else spp * world
-
-    def render(r, sc, **kw):
-        """one step's rendering: a single rt_render_frame, or a progressive chain of them"""
-        if not batch or batch >= spp:
-            return r.render_frame(cam, sc, **kw)
-        done, agg = 0, None
-        while done < spp:
-            r.sample_count = min(batch, spp - done)
-            f = r.render_frame(cam, sc, resume=done > 0, **kw)
-            done += r.sample_count
-            if agg is None:
-                agg = f
-            else:
-                agg.ray_count, agg.device_ms, agg.kernel_launches = agg.ray_count + f.ray_count, agg.device_ms + f.device_ms, agg.kernel_launches + f.kernel_launches
-        r.sample_count = spp
-        return agg
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
 
     class DevAccum:  # zero-copy view of the renderer's device accumulation buffer
         def __init__(self, ptr):
             self.__cuda_array_interface__ = {"shape": (h, w, 4), "typestr": "<f4", "data": (int(ptr), False), "version": 3}
 
+    class DevImage:  # zero-copy view of a renderer's device RGBA8 image
+        def __init__(self, ptr):
+            self.__cuda_array_interface__ = {"shape": (h, w, 4), "typestr": "|u1", "data": (int(ptr), False), "version": 3}
+
     def barrier():
         if dist:
             dist.barrier()
         torch.cuda.synchronize()
 
-    gather_peer = tiles and args.gather == "peer"
-    token = torch.zeros(1, dtype=torch.int32, device="cuda") if gather_peer else None
+    token = torch.zeros(1, dtype=torch.int32, device="cuda") if dist else None
 
-    class DevImage:  # zero-copy view of a renderer's device RGBA8 image
-        def __init__(self, ptr):
-            self.__cuda_array_interface__ = {"shape": (h, w, 4), "typestr": "|u1", "data": (int(ptr), False), "version": 3}
+    class Plan:
+        """how one step is sharded over the ranks: samples per rank, the shard descriptor, the exchange"""
 
-    def attach_gather(r):
-        """rank 0 exports its renderer's image, the others open it (CUDA IPC) as their gather target"""
+        def __init__(self, strong):
+            self.strong = strong or tiles
+            if world == 1:
+                self.spp_rank, self.spp_total, self.shard = spp, spp, None
+            elif tiles:
+                self.spp_rank, self.spp_total = spp, spp
+                self.shard = {"rank": rank, "world": world, "tile_size": 64, "seed_salt": 0}
+            else:
+                self.spp_rank = (spp // world + (1 if rank < spp % world else 0)) if strong else spp
+                self.spp_total = spp if strong else spp * world
+                self.shard = {"rank": rank, "world": world, "tile_size": 0, "seed_salt": (rank * 0x9E3779B9) & 0xFFFFFFFF}
+            self.peer = dist is not None and args.exchange == "peer"
+
+    def render(r, sc, n_spp, **kw):
+        """one step's rendering: a single rt_render_frame, or a progressive chain of them"""
+        if not batch or batch >= n_spp:
+            r.sample_count = n_spp
+            return r.render_frame(cam, sc, **kw)
+        done, agg = 0, None
+        while done < n_spp:
+            r.sample_count = min(batch, n_spp - done)
+            f = r.render_frame(cam, sc, resume=done > 0, **kw)
+            done += r.sample_count
+            if agg is None:
+                agg = f
+            else:
+                agg.ray_count, agg.device_ms, agg.kernel_launches = agg.ray_count + f.ray_count, agg.device_ms + f.device_ms, agg.kernel_launches + f.kernel_launches
+        r.sample_count = n_spp
+        return agg
+
+    def attach(r, plan):
+        """peer exchange: rank 0 exports its image (gather destination of every rank), spp slices also share every rank's
+        accumulation buffer (CUDA IPC handles, exchanged once per renderer)"""
+        if not plan.peer:
+            return
         box = [r.export_image() if rank == 0 else None]
         dist.broadcast_object_list(box, src=0)
         if rank != 0:
             r.set_gather(handle=box[0])
+        if not tiles:
+            handles = [None] * world
+            dist.all_gather_object(handles, r.export_accum())
+            r.set_peers(handles, rank)
         barrier()
 
-    def detach_gather(r):
+    def detach(r, plan):
+        if not plan.peer:
+            return
         barrier()
+        if not tiles:
+            r.set_peers(None)
         if rank != 0:
             r.set_gather()
         barrier()
 
-    def bench_renderer(cls, name):
-        r = cls(app, (w, h), None, depth, spp)
-        accum_t = torch.as_tensor(DevAccum(r.device_accum_ptr), device="cuda") if dist and not gather_peer else None
+    def exchange(r, plan, accum_t, out_rgba):
+        """the one exchange step of a sharded frame, enqueued on the stream the render ran on; returns the kernels it launched here"""
+        if not dist:
+            return 0
+        if plan.peer and tiles:      # the pixels are already in rank 0's image: order the frame across ranks
+            dist.all_reduce(token)
+            return 0
+        if plan.peer:                # every rank has rendered -> fused reduce-scatter + resolve + gather -> rank 0's image is complete
+            dist.all_reduce(token)
+            r.reduce_resolve()
+            dist.all_reduce(token)
+            return 1
+        dist.all_reduce(accum_t)     # library collective on the fp32 buffers, then resolve on rank 0
+        if rank == 0:
+            pkg.resolve(app, accum_t, plan.spp_total, w, h, out_rgba)
+            return 1
+        return 0
+
+    def verify(r, plan, cls, accum_t, out_rgba):
+        """untimed: the image the exchange produced on rank 0 against an independent computation"""
+        if not dist or args.no_verify:
+            return None
+        barrier()
+        got = torch.as_tensor(DevImage(r.device_rgba8_ptr), device="cuda").clone() if plan.peer else out_rgba.clone()
+        if tiles:   # bit-identical to ONE GPU rendering the whole frame
+            ok = None
+            if rank == 0:
+                solo = cls(app, (w, h), None, depth, spp)
+                f1 = render(solo, scene, spp, want=())
+                ok = bool(torch.equal(torch.as_tensor(DevImage(solo.device_rgba8_ptr), device="cuda"), got))
+                solo.close()
+            barrier()
+            return {"image_equals_one_gpu_render": ok}
+        # spp slices: the rank-ordered fp32 sum of every rank's accumulation buffer, resolved
+        mine = torch.as_tensor(DevAccum(r.device_accum_ptr), device="cuda").clone() if plan.peer else None
+        if mine is None:
+            return None     # the NCCL all-reduce overwrote the buffers in place (and its summation order is not defined)
+        parts = [torch.empty_like(mine) for _ in range(world)] if rank == 0 else None
+        dist.gather(mine, parts, dst=0)
+        ok = None
+        if rank == 0:
+            total = parts[0].clone()
+            for k in range(1, world):
+                total += parts[k]
+            want = torch.empty((h, w, 4), dtype=torch.uint8, device="cuda")
+            pkg.resolve(app, total, plan.spp_total, w, h, want)
+            ok = bool(torch.equal(want, got)) and bool((total[..., 3] == plan.spp_total).all().item())
+        barrier()
+        return {"image_equals_rank_ordered_sum": ok}
+
+    def bench_renderer(cls, name, plan, steps, warmup, check=True):
+        r = cls(app, (w, h), None, depth, plan.spp_rank)
+        accum_t = torch.as_tensor(DevAccum(r.device_accum_ptr), device="cuda") if dist and not plan.peer else None
         out_rgba = torch.empty((h, w, 4), dtype=torch.uint8, device="cuda")
-        if gather_peer:
-            attach_gather(r)
+        attach(r, plan)
 
         def step():
-            f = render(r, scene, want=(), shard=shard)
-            if gather_peer:  # the pixels are already in rank 0's image; order the frame across ranks on the stream
-                dist.all_reduce(token)
-            elif dist:  # combine the accumulation buffers over NVLink, then resolve the image
-                dist.all_reduce(accum_t)
-                if rank == 0:
-                    pkg.resolve(app, accum_t, spp_total, w, h, out_rgba)
+            f = render(r, scene, plan.spp_rank, want=(), shard=plan.shard)
+            f.kernel_launches += exchange(r, plan, accum_t, out_rgba)
             return f
-        for _ in range(args.warmup):
+        for _ in range(warmup):
             step()
         ms, kms, rays, launches = 0.0, 0.0, 0, 0
         try:
@@ -374,7 +463,7 @@ def main():
         barrier()
         if rank == 0:
             sampler.start()
-        for _ in range(args.steps):
+        for _ in range(steps):
             flush.fill_(1)  # L2 flush between timed iterations (outside the event pair)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             barrier()
@@ -385,7 +474,7 @@ def main():
             ms += e0.elapsed_time(e1)
             kms += f.device_ms
             rays += f.ray_count
-            launches += f.kernel_launches + (1 if (dist and rank == 0 and not gather_peer) else 0)
+            launches += f.kernel_launches
         clocks = sampler.stop() if rank == 0 else None
         barrier()
         t = torch.tensor([ms, kms, float(rays), float(launches)], dtype=torch.float64, device="cuda")
@@ -395,23 +484,32 @@ def main():
             sm = t.clone()
             dist.all_reduce(sm, op=dist.ReduceOp.SUM)
             ms, kms, rays, launches = float(mx[0]), float(mx[1]), int(sm[2]), int(sm[3])
-        gathered = None
-        if gather_peer:
-            barrier()
-            if rank == 0:  # untimed check: every pixel of rank 0's image was stored by its owner (alpha = 255 everywhere)
-                gathered = bool((torch.as_tensor(DevImage(r.device_rgba8_ptr), device="cuda")[..., 3] == 255).all().item())
-            detach_gather(r)
+        checked = verify(r, plan, cls, accum_t, out_rgba) if check else None
+        detach(r, plan)
         r.close()
-        return {"name": name, "gather_complete": gathered, "ms": ms, "kernel_ms": kms, "rays": rays, "launches": launches, "clocks": clocks,
-                "last_launches": f.kernel_launches}
+        return {"name": name, "verified": checked, "ms": ms, "kernel_ms": kms, "rays": rays, "launches": launches, "clocks": clocks,
+                "last_launches": f.kernel_launches, "steps": steps}
 
+    split_total = args.workload in PROGRESSIVE and world > 1 and not tiles   # c5 is defined by its total spp
+    plan = Plan(strong=(args.scaling == "strong" or split_total))
+    spp_total = plan.spp_total
     results = []
     if args.renderer in ("both", "megakernel"):
-        results.append(bench_renderer(pkg.MegakernelRenderer, "megakernel"))
+        results.append(bench_renderer(pkg.MegakernelRenderer, "megakernel", plan, args.steps, args.warmup))
     if args.renderer in ("both", "wavefront"):
-        results.append(bench_renderer(pkg.WavefrontRenderer, "wavefront"))
+        results.append(bench_renderer(pkg.WavefrontRenderer, "wavefront", plan, args.steps, args.warmup))
     best = max(results, key=lambda x: x["rays"] / x["ms"])
     samples_total = w * h * spp_total * args.steps
+
+    # ---- N > 1: the weak-scaling line next to the strong one (every rank renders the workload's full spp), quick ----
+    also_weak = None
+    if world > 1 and plan.strong and not tiles and not split_total and not args.no_also:
+        wplan = Plan(strong=False)
+        cls = pkg.MegakernelRenderer if best["name"] == "megakernel" else pkg.WavefrontRenderer
+        wr = bench_renderer(cls, best["name"], wplan, 3, 3, check=False)
+        also_weak = {"scaling": "weak", "spp_per_gpu": wplan.spp_rank, "renderer": best["name"], "steps": 3,
+                     "mrays_per_s": wr["rays"] / (wr["ms"] * 1e-3) / 1e6, "ms_per_step": wr["ms"] / 3,
+                     "msamples_per_s": w * h * wplan.spp_total * 3 / (wr["ms"] * 1e-3) / 1e6}
 
     # ---- the other single-GPU configuration of BASELINE.json (configs[1], Cornell, wavefront), quick ----
     also = None
@@ -438,12 +536,12 @@ def main():
     e2e = None
     if not args.no_e2e:
         cls = pkg.MegakernelRenderer if best["name"] == "megakernel" else pkg.WavefrontRenderer
-        r = cls(app, (w, h), None, depth, spp)
-        accum_t = torch.as_tensor(DevAccum(r.device_accum_ptr), device="cuda") if dist and not gather_peer else None
+        r = cls(app, (w, h), None, depth, plan.spp_rank)
+        accum_t = torch.as_tensor(DevAccum(r.device_accum_ptr), device="cuda") if dist and not plan.peer else None
         host_img = torch.empty((h, w, 4), dtype=torch.uint8).pin_memory()
-        if gather_peer:
-            attach_gather(r)
-            dev_img = torch.as_tensor(DevImage(r.device_rgba8_ptr), device="cuda")
+        out_rgba = torch.empty((h, w, 4), dtype=torch.uint8, device="cuda")
+        attach(r, plan)
+        dev_img = torch.as_tensor(DevImage(r.device_rgba8_ptr), device="cuda") if plan.peer else out_rgba
         h2d = sum(i.positions.nbytes + i.normals.nbytes + i.uvs.nbytes + i.indices.nbytes + 64 + 40 for i in data.instances)
         h2d += (data.textures.nbytes if data.textures is not None else 0) + 56 + 24
         d2h = w * h * 4 + 8
@@ -453,19 +551,16 @@ def main():
             sc = pkg.Scene(app, data)  # H2D of the scene from host memory + GPU BVH build
             t_b = time.perf_counter()
             e2e_step.create_s += t_b - t_a
-            if gather_peer:
-                barrier()  # rank 0 has read the previous frame before anybody stores into its image again
-                f = render(r, sc, want=(), shard=shard)
-                dist.all_reduce(token)
+            if dist:
+                if plan.peer:
+                    barrier()  # rank 0 has read the previous frame before anybody stores into its image again
+                f = render(r, sc, plan.spp_rank, want=(), shard=plan.shard)
+                exchange(r, plan, accum_t, out_rgba)
                 if rank == 0:
                     host_img.copy_(dev_img, non_blocking=True)  # D2H of the gathered image
                     torch.cuda.current_stream().synchronize()
-            elif dist:
-                f = render(r, sc, want=(), shard=shard)
-                dist.all_reduce(accum_t)
-                pkg.resolve(app, accum_t, spp_total, w, h, host_img)  # D2H of the image
             else:
-                f = render(r, sc, want=("rgba8",), outputs={"rgba8": host_img})  # D2H inside (every progressive frame)
+                f = render(r, sc, plan.spp_rank, want=("rgba8",), outputs={"rgba8": host_img})  # D2H inside (every progressive frame)
             e2e_step.render_s += time.perf_counter() - t_b
             sc.close()
             return f
@@ -500,9 +595,9 @@ def main():
                "ms_per_step": dt / args.steps * 1e3, "render_device_ms_per_step": e_dev_ms / args.steps,
                "scene_upload_and_build_ms_per_step": e2e_step.create_s / args.steps * 1e3,
                "render_call_ms_per_step": e2e_step.render_s / args.steps * 1e3, "clocks": e_clocks,
-               "includes": "scene upload from host + BVH build + render" + ((" + peer-memory gather" if gather_peer else " + NCCL all-reduce") if dist else "") + " + image read-back, every step"}
-        if gather_peer:
-            detach_gather(r)
+               "includes": "scene upload from host (pageable numpy arrays, staged through pinned chunks) + BVH build + render"
+                           + ((" + peer-memory exchange" if plan.peer else " + NCCL all-reduce + resolve") if dist else "") + " + image read-back, every step"}
+        detach(r, plan)
         r.close()
 
     if rank != 0:
@@ -516,16 +611,21 @@ def main():
     wave = best["name"] == "wavefront"
     bpr = algorithmic_bytes_per_ray(stats["triangle_count"], wave)
     # per launch: megakernel = 1 launch per step; wavefront = the extend+shade pair averaged over the step's launches
-    n_launch = args.steps * world if not wave else max(1, (mega["launches"] - 2 * args.steps * world))
+    n_launch = args.steps * world  # one render kernel per rank and step in both formulations (megakernel / queue-driven wavefront)
     alg_bytes_total = mega["rays"] * bpr + samples_total * 16
     # per GPU: bytes of one rank's steps / that rank's render-kernel device time (max over ranks)
     kernel_s = mega["kernel_ms"] * 1e-3
     achieved = alg_bytes_total / world / kernel_s / 1e9
-    traffic = None
+    # DRAM traffic comes from ncu (one --set full capture per workload and kernel, summarised under profiles/): recorded there as
+    # bytes per ray of that capture and scaled to this run's rays per launch — a cross-reference, not something this run measured
+    traffic, traffic_source = None, None
     tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.exists(tp):
         try:
-            traffic = json.load(open(tp)).get(args.workload, {}).get(best["name"], {}).get("dram_bytes_per_launch")
+            ent = json.load(open(tp)).get(args.workload, {}).get(best["name"], {})
+            if ent.get("dram_bytes_per_ray") is not None:
+                traffic = ent["dram_bytes_per_ray"] * mega["rays"] / max(1, n_launch)
+                traffic_source = f"ncu capture {ent.get('capture')}: {ent['dram_bytes_per_ray']:.2f} DRAM bytes per ray x this run's rays per launch"
         except Exception:
             traffic = None
     # the realistic byte model next to the floor — visits*80 + tests*48 + 128 (+96) with the node visits and
@@ -539,8 +639,8 @@ def main():
                          "bytes_per_ray": rb, "achieved_gbs": (mega["rays"] * rb + samples_total * 16) / world / kernel_s / 1e9}
     except Exception:
         realistic = None
-    roofline = {"bound": "hbm", "kernel": "k_megakernel" if not wave else "k_wf_extend+k_wf_shade",
-                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+    roofline = {"bound": "hbm", "kernel": "k_megakernel" if not wave else "k_wf_flow",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_source,
                 "peak_source": peak_src, "algorithmic_bytes_per_ray": bpr, "realistic_model": realistic,
                 "algorithmic_bytes_per_launch": alg_bytes_total / max(1, n_launch),
                 "launch_ms": mega["kernel_ms"] / max(1, n_launch / world),
@@ -559,19 +659,25 @@ def main():
     value = best["rays"] / (best["ms"] * 1e-3) / 1e6
     line = {
         "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": best["ms"] / args.steps, "higher_is_better": True, "scaling": "strong" if (tiles or split_total) else "weak", "vs_baseline": None,
+        "ms_per_step": best["ms"] / args.steps, "higher_is_better": True, "scaling": "strong" if plan.strong else "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "msamples_per_s": samples_total / (best["ms"] * 1e-3) / 1e6,
         "config": {"workload": args.workload, "triangles": int(stats["triangle_count"]), "width": w, "height": h, "spp": spp,
                    "max_depth": depth, "renderer": best["name"],
                    "progressive": (f"{-(-spp // batch)} frames of {batch} spp chained with RT_RENDER_RESUME" if batch and batch < spp else None), "l2": "flushed between timed steps (256 MB write)",
-                   "sharding": "none" if world == 1 else (("image tiles: 64x64 tiles round robin over ranks, bit-identical to 1 GPU; " + ("finished RGBA8 pixels stored by the render kernel straight into rank 0's image over NVLink peer memory (CUDA IPC), 4-byte all-reduce as the frame barrier" if gather_peer else "NCCL all-reduce (sum) of the fp32 accumulation buffer + resolve on rank 0")) if tiles else f"spp slices: {spp} spp per GPU, distinct seed salts, NCCL all-reduce of the fp32 accumulation buffer"),
+                   "spp_per_gpu": plan.spp_rank if world > 1 else None,
+                   "sharding": "none" if world == 1 else (
+                       ("image tiles: 64x64 tiles round robin over ranks, bit-identical to 1 GPU; " if tiles else
+                        f"spp slices: the frame's {spp_total} spp split over {world} ranks ({'strong' if plan.strong else 'weak'} scaling), distinct seed salts; ")
+                       + (("finished RGBA8 pixels stored by the render kernel straight into rank 0's image over NVLink peer memory (CUDA IPC), 4-byte all-reduce as the frame barrier"
+                           if tiles else "fused reduce-scatter + resolve + gather kernel over NVLink peer memory (rt_renderer_reduce_resolve), two 4-byte NCCL all-reduces as barriers")
+                          if plan.peer else "NCCL all-reduce (sum) of the fp32 accumulation buffer + resolve on rank 0")),
                    "bvh": {"nodes": int(stats["node_count"]), "depth": int(stats["wide_depth"]), "build_ms": float(stats["build_ms"])}},
         "renderers": {x["name"]: {"mrays_per_s": x["rays"] / (x["ms"] * 1e-3) / 1e6, "ms_per_step": x["ms"] / args.steps,
                                   "msamples_per_s": samples_total / (x["ms"] * 1e-3) / 1e6,
                                   "kernel_launches_per_step": x["last_launches"], "clocks": x["clocks"],
-                                  **({"gather_complete": x["gather_complete"]} if x.get("gather_complete") is not None else {})} for x in results},
-        "also": also, "clocks": best["clocks"], "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+                                  **({"verified": x["verified"]} if x.get("verified") is not None else {})} for x in results},
+        "also": also, "also_weak": also_weak, "clocks": best["clocks"], "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
         "gpu_launches": int(best["launches"]),
     }
     emit(line)

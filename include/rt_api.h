@@ -216,6 +216,20 @@ typedef struct rt_ipc_handle {
 rt_status rt_renderer_export_image(rt_renderer *r, rt_ipc_handle *out);
 rt_status rt_renderer_set_gather(rt_renderer *r, const rt_ipc_handle *handle, void *device_rgba8);
 
+/* ---- spp slices across PROCESSES: fused reduce-scatter + resolve + gather over peer memory -----------------
+ * One process per GPU (torchrun, MPI): every rank exports its accumulation buffer, collects all ranks' handles and
+ * attaches them; rank 0 also exports its image and the others attach it with rt_renderer_set_gather. After every
+ * rank has finished its frame (a barrier), rt_renderer_reduce_resolve ENQUEUES one kernel on the context stream
+ * that sums this rank's 1/world slice of the pixels over all ranks' buffers (peer loads, rank order), resolves it
+ * with the total sample count and stores the RGBA8 pixels into rank 0's image (peer stores); a second barrier
+ * tells rank 0 that the image is complete. No library collective touches the 16 bytes per pixel.
+ *   rt_renderer_export_accum(r, &h)                      -> all-gather h
+ *   rt_renderer_set_peers(r, handles, world, rank)       (handles[rank] is ignored; NULL / 0 detaches)
+ *   rt_renderer_reduce_resolve(r)                        (asynchronous on rt_context_stream) */
+rt_status rt_renderer_export_accum(rt_renderer *r, rt_ipc_handle *out);
+rt_status rt_renderer_set_peers(rt_renderer *r, const rt_ipc_handle *accum_handles, uint32_t world, uint32_t rank);
+rt_status rt_renderer_reduce_resolve(rt_renderer *r);
+
 /* (re)compute the RGBA8 image from an accumulation buffer holding the sum over `sample_count`
  * samples — used after a cross-GPU reduction (src/render_wavefront.cpp:360-394 + F10).
  * accum, rgba8: ANY-space. */

@@ -291,6 +291,27 @@ class IRenderer:
         self.app.check(self._lib.rt_renderer_export_image(self.handle, C.byref(h)), "rt_renderer_export_image")
         return bytes(h.bytes)
 
+    def export_accum(self):
+        """64 opaque bytes naming this renderer's device accumulation buffer for the other ranks (CUDA IPC)"""
+        h = _capi.rt_ipc_handle()
+        self.app.check(self._lib.rt_renderer_export_accum(self.handle, C.byref(h)), "rt_renderer_export_accum")
+        return bytes(h.bytes)
+
+    def set_peers(self, handles=None, rank=0):
+        """spp slices across processes: attach every rank's accumulation buffer (list of export_accum() bytes, own entry
+        ignored); None detaches"""
+        if not handles:
+            self.app.check(self._lib.rt_renderer_set_peers(self.handle, None, 0, 0), "rt_renderer_set_peers")
+            return
+        arr = (_capi.rt_ipc_handle * len(handles))()
+        for k, hb in enumerate(handles):
+            C.memmove(arr[k].bytes, bytes(hb), 64)
+        self.app.check(self._lib.rt_renderer_set_peers(self.handle, arr, len(handles), int(rank)), "rt_renderer_set_peers")
+
+    def reduce_resolve(self):
+        """enqueue the fused reduce-scatter + resolve + gather kernel for this rank's slice (asynchronous on the stream)"""
+        self.app.check(self._lib.rt_renderer_reduce_resolve(self.handle), "rt_renderer_reduce_resolve")
+
     def set_gather(self, handle=None, device_ptr=None):
         """Tile shards: also store owned pixels' RGBA8 into a peer's image — `handle` = bytes from the
         destination's export_image() (another process) or `device_ptr` (same process); neither = detach."""

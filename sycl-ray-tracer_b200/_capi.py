@@ -103,6 +103,9 @@ SYMBOLS = {
     "rt_renderer_set_gather": (C.c_int, [C.c_void_p, C.POINTER(rt_ipc_handle), C.c_void_p]),
     "rt_resolve": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_int32, C.c_int32, C.c_void_p]),
     "rt_renderer_device_rng": (C.c_void_p, [C.c_void_p]),
+    "rt_renderer_export_accum": (C.c_int, [C.c_void_p, C.POINTER(rt_ipc_handle)]),
+    "rt_renderer_set_peers": (C.c_int, [C.c_void_p, C.POINTER(rt_ipc_handle), C.c_uint32, C.c_uint32]),
+    "rt_renderer_reduce_resolve": (C.c_int, [C.c_void_p]),
     "rt_group_create": (C.c_int, [C.POINTER(C.c_int), C.c_uint32, C.POINTER(C.c_void_p)]),
     "rt_group_destroy": (None, [C.c_void_p]),
     "rt_group_size": (C.c_uint32, [C.c_void_p]),

@@ -128,6 +128,8 @@ struct rt_renderer {
     uint32_t *gather = nullptr;   /* tile shards: owned pixels are also stored here (peer memory) */
     bool gather_ipc = false;      /* gather was opened from an IPC handle (close it) */
     bool exported = false;        /* d_rgba8 is a gather destination: never clear foreign pixels */
+    const float4 *peer_accum[16] = {}; /* spp slices across processes: every rank's accumulation buffer (IPC mappings) */
+    uint32_t peer_world = 0, peer_rank = 0;
     int tune_refill = 12; /* lanes that must run dry before a warp refills (RT_TUNE_REFILL overrides; 12-14 measured best) */
     int tune_ctx = 0;     /* megakernel: parked ray contexts per lane (RT_MEGA_CTX 1-4 = k_megakernel_ctx; measured slower than the
                              one-pixel-in-registers kernel on C2/C3/C4, profiles/README.md) */
@@ -590,6 +592,13 @@ rt_status rt_renderer_create(rt_context *ctx, rt_renderer_kind kind, int32_t wid
     return RT_OK;
 }
 
+static void peers_detach(rt_renderer *r) {
+    for (uint32_t i = 0; i < r->peer_world; i++)
+        if (i != r->peer_rank && r->peer_accum[i]) cudaIpcCloseMemHandle((void *)r->peer_accum[i]);
+    memset(r->peer_accum, 0, sizeof(r->peer_accum));
+    r->peer_world = r->peer_rank = 0;
+}
+
 static void gather_detach(rt_renderer *r) {
     if (r->gather && r->gather_ipc) cudaIpcCloseMemHandle(r->gather);
     r->gather = nullptr;
@@ -600,6 +609,7 @@ void rt_renderer_destroy(rt_renderer *r) {
     if (!r) return;
     cudaSetDevice(r->ctx->device);
     gather_detach(r);
+    peers_detach(r);
     for (uint32_t *q : r->d_order) cudaFree(q);
     cudaFree(r->d_order_temp);
     cudaFree(r->d_region_cost);
@@ -659,6 +669,59 @@ rt_status rt_renderer_set_gather(rt_renderer *r, const rt_ipc_handle *handle, vo
     } else if (device_rgba8) {
         r->gather = (uint32_t *)device_rgba8;
     }
+    return RT_OK;
+}
+
+rt_status rt_renderer_export_accum(rt_renderer *r, rt_ipc_handle *out) {
+    if (!r) return RT_ERR_INVALID;
+    rt_context *ctx = r->ctx;
+    if (!out) return rt_set_error(ctx, RT_ERR_INVALID, "rt_renderer_export_accum", "out is NULL");
+    RT_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    cudaIpcMemHandle_t h;
+    RT_CUDA_TRY(ctx, cudaIpcGetMemHandle(&h, r->d_accum));
+    memcpy(out->bytes, &h, sizeof(h));
+    return RT_OK;
+}
+
+rt_status rt_renderer_set_peers(rt_renderer *r, const rt_ipc_handle *handles, uint32_t world, uint32_t rank) {
+    if (!r) return RT_ERR_INVALID;
+    rt_context *ctx = r->ctx;
+    RT_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    RT_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    peers_detach(r);
+    if (!handles || world == 0) return RT_OK;
+    if (world > 16 || rank >= world) return rt_set_error(ctx, RT_ERR_INVALID, "rt_renderer_set_peers", "world <= 16 and rank < world");
+    r->peer_world = world;
+    r->peer_rank = rank;
+    for (uint32_t i = 0; i < world; i++) {
+        if (i == rank) {
+            r->peer_accum[i] = r->d_accum;
+            continue;
+        }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, handles[i].bytes, sizeof(h));
+        void *p = nullptr;
+        const cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            peers_detach(r);
+            return rt_set_error(ctx, RT_ERR_CUDA, "cudaIpcOpenMemHandle", cudaGetErrorString(e));
+        }
+        r->peer_accum[i] = (const float4 *)p;
+    }
+    return RT_OK;
+}
+
+rt_status rt_renderer_reduce_resolve(rt_renderer *r) {
+    if (!r) return RT_ERR_INVALID;
+    rt_context *ctx = r->ctx;
+    if (!r->peer_world) return rt_set_error(ctx, RT_ERR_STATE, "rt_renderer_reduce_resolve", "no peers attached (rt_renderer_set_peers)");
+    uint32_t *dst = r->peer_rank == 0 ? r->d_rgba8 : r->gather;
+    if (!dst) return rt_set_error(ctx, RT_ERR_STATE, "rt_renderer_reduce_resolve", "no destination image (rt_renderer_set_gather with rank 0's handle)");
+    RT_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    const size_t n = (size_t)r->w * (size_t)r->h;
+    const uint32_t per = (uint32_t)((n + r->peer_world - 1) / r->peer_world), first = r->peer_rank * per;
+    const uint32_t count = first < n ? (uint32_t)(n - first < per ? n - first : per) : 0u;
+    RT_CUDA_TRY(ctx, rt_launch_reduce_resolve_peer(ctx->stream, r->peer_accum, r->peer_world, first, count, nullptr, dst));
     return RT_OK;
 }
 

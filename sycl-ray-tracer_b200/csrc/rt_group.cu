@@ -64,7 +64,7 @@ __global__ void k_reduce_resolve_peer(PeerPtrs p, uint32_t n_dev, uint32_t first
         s.z += a.z;
         s.w += a.w;
     }
-    sum_out[pix] = s;
+    if (sum_out) sum_out[pix] = s;
     rgba8_out[pix] = rt_resolve_pixel(s.x, s.y, s.z, s.w);
 }
 
@@ -99,6 +99,15 @@ rt_status for_each_device(rt_group *g, const char *what, F fn) {
 }
 
 } // namespace
+
+cudaError_t rt_launch_reduce_resolve_peer(cudaStream_t st, const float4 *const *accum, uint32_t world, uint32_t first, uint32_t count,
+                                          float4 *sum_out, uint32_t *rgba8_out) {
+    if (!count) return cudaSuccess;
+    PeerPtrs pp = {};
+    for (uint32_t i = 0; i < world && i < RT_GROUP_MAX; i++) pp.accum[i] = accum[i];
+    k_reduce_resolve_peer<<<(count + 255) / 256, 256, 0, st>>>(pp, world, first, count, sum_out, rgba8_out);
+    return cudaGetLastError();
+}
 
 extern "C" {
 

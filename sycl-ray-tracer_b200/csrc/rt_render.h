@@ -41,6 +41,10 @@ cudaError_t rt_launch_resolve_owned(cudaStream_t st, const RtFrameParams &p, con
                                     const uint32_t *rng_state, const RtFrameOut &out);
 /* RT_GPU_COUNTERS builds: traversal steps since the last reset (zeros otherwise) */
 void rt_counters_read(unsigned long long out[2], bool reset);
+/* reduce-scatter + resolve + gather over peer memory (rt_group.cu): pixels [first, first + count) summed over `world`
+ * accumulation buffers in rank order; sum_out may be NULL */
+cudaError_t rt_launch_reduce_resolve_peer(cudaStream_t st, const float4 *const *accum, uint32_t world, uint32_t first, uint32_t count,
+                                          float4 *sum_out, uint32_t *rgba8_out);
 cudaError_t rt_launch_selftest(cudaStream_t st, float a, float b, float c, float *o);
 
 #endif
