@@ -113,11 +113,22 @@ typedef struct rt_shard {
                               accumulation carry on, so k frames of n samples are bit-identical to one
                               frame of k*n samples (BASELINE config 5: 4096 spp in batches) */
 
+/* The two items the reference's roadmap leaves open (PLAN.md:23-27), as OPTIONS: both change the sampling order, so
+ * images are no longer the reference's bit for bit (the oracle implements the same options, tests/test_gpu_options.py). */
+#define RT_RENDER_ROULETTE 2u /* Russian roulette: from the third bounce on a path survives with probability
+                                q = clamp(max(attenuation), 0.05, 1) (one extra draw) and its attenuation is divided by q */
+
 typedef struct rt_render_params {
     uint32_t max_depth;    /* -d, src/main.cpp:11 */
     uint32_t sample_count; /* -s, src/main.cpp:13; with RT_RENDER_RESUME: samples ADDED by this call */
     rt_shard shard;
-    uint32_t flags;        /* 0 or RT_RENDER_RESUME */
+    uint32_t flags;        /* RT_RENDER_RESUME | RT_RENDER_ROULETTE */
+    uint32_t sample_chains; /* 0 or 1: one xorshift stream per pixel, samples strictly in sequence (the reference, F4).
+                               k = 2..16 ("splats", PLAN.md:26-27): k independent sample chains per pixel are in flight at
+                               once — chain c takes sample_count / k samples (the first sample_count % k chains one more)
+                               on the stream seed ^ c * 0x9E3779B9 and accumulates into its own plane; the planes are summed
+                               in chain order, so the result is deterministic and equals the sum of k seed-salted renders.
+                               Shortens a pixel's sequential chain k-fold (the tail of a frame with few pixels per GPU). */
 } rt_render_params;
 
 /* Result of one render_frame. Every pointer is optional (NULL = not wanted) and ANY-space. */
@@ -258,7 +269,8 @@ typedef struct rt_group_params {
     uint32_t sample_count; /* -s: samples per pixel of the WHOLE frame (with RT_RENDER_RESUME: added by this call) */
     uint32_t mode;         /* rt_group_mode */
     uint32_t tile_size;    /* RT_GROUP_TILES: a multiple of 8; 0 = 64 */
-    uint32_t flags;        /* 0 or RT_RENDER_RESUME */
+    uint32_t flags;        /* RT_RENDER_RESUME | RT_RENDER_ROULETTE */
+    uint32_t sample_chains; /* as in rt_render_params */
 } rt_group_params;
 
 /* devices = CUDA device indices (NULL: 0 .. n_devices-1), 1 <= n_devices <= 16 */

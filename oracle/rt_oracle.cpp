@@ -590,7 +590,7 @@ inline bool trace_ray(const orc_scene *s, bool use_bvh, Rng &rng, V3 &org, V3 &d
 /* src/render_megakernel.cpp:20-63 (the wavefront path runs the identical per-ray sequence,
  * src/render_wavefront.cpp:244-296, because every pixel has at most one ray in flight) */
 inline V3 render_sample(const orc_scene *s, const orc_camera &cam, bool use_bvh, Rng &rng, int x,
-                        int y, uint32_t max_depth, uint64_t &ray_count) {
+                        int y, uint32_t max_depth, uint64_t &ray_count, bool roulette = false) {
     RayState r = camera_get_ray(cam, x, y, rng);
     for (uint32_t i = 0; i < max_depth; i++) {
         ray_count++;
@@ -598,6 +598,15 @@ inline V3 render_sample(const orc_scene *s, const orc_camera &cam, bool use_bvh,
         V3 org = r.org, dir = r.dir;
         V3 res;
         bool done = trace_ray(s, use_bvh, rng, org, dir, att, rad, res);
+        if (!done && roulette && i + 1 >= 3 && i + 1 < max_depth) {
+            /* optional Russian roulette (not in the reference: PLAN.md:23-24 lists it as open). From the third bounce
+             * on the path survives with probability q = clamp(max(att), 0.05, 1) — one extra draw — and its
+             * attenuation is divided by q; a killed path contributes black like a path cut at max_depth. */
+            float q = std::fmin(std::fmax(std::fmax(std::fmax(att.x, att.y), att.z), 0.05f), 1.0f);
+            if (rng.next() > q) return v3(0, 0, 0);
+            float inv = 1.0f / q;
+            att = att * inv;
+        }
         r.org = org;
         r.dir = rh(dir);
         r.att = rh(att);
@@ -839,7 +848,7 @@ uint64_t orc_render(const orc_scene *cs, const orc_camera *cam, const orc_render
             uint64_t rays = 0;
             V3 sum = v3(0, 0, 0);
             for (uint32_t sidx = 0; sidx < spp; sidx++) {
-                V3 c = render_sample(s, *cam, use_bvh, rng, x, y, p->max_depth, rays);
+                V3 c = render_sample(s, *cam, use_bvh, rng, x, y, p->max_depth, rays, p->roulette != 0);
                 if (wave) /* src/render_wavefront.cpp:277: per-sample clamp (F9) */
                     c = v3(clamp01(c.x), clamp01(c.y), clamp01(c.z));
                 sum = sum + c; /* megakernel :151-152; wavefront merge_samples :350-352 */

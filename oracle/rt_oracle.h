@@ -80,6 +80,8 @@ typedef struct orc_render_params {
     int32_t threads;     /* OpenMP threads; <=0: all */
     /* crop window inside the full image (seeds always use the full image size) */
     int32_t x0, y0, x1, y1;
+    int32_t roulette;    /* 0 = the reference's path loop; 1 = Russian roulette from the third bounce on (PLAN.md:23-24, the
+                            RT_RENDER_ROULETTE option of the CUDA path): changes the number of draws, hence the streams */
 } orc_render_params;
 
 /* ---- primitives (for KATs) ---- */

@@ -252,7 +252,8 @@ class IRenderer:
                                                C.byref(h)), "rt_renderer_create")
         self.handle = h
 
-    def render_frame(self, camera, scene, want=("rgba8", "accum", "rng_state"), shard=None, outputs=None, resume=False):
+    def render_frame(self, camera, scene, want=("rgba8", "accum", "rng_state"), shard=None, outputs=None, resume=False,
+                     roulette=False, chains=0):
         """IRenderer::render_frame. `want` selects which host copies to make; `outputs` may map
         names to caller buffers (numpy arrays or torch tensors, host or device)."""
         w, h = self.img_size
@@ -265,7 +266,8 @@ class IRenderer:
             outputs["rng_state"] = np.empty((h, w), np.uint32)
         p = _capi.rt_render_params()
         p.max_depth, p.sample_count = self.max_depth, self.sample_count
-        p.flags = _capi.RT_RENDER_RESUME if resume else 0  # progressive: continue the previous frame
+        p.flags = (_capi.RT_RENDER_RESUME if resume else 0) | (_capi.RT_RENDER_ROULETTE if roulette else 0)
+        p.sample_chains = int(chains)  # > 1: independent sample chains per pixel (not the reference's order)
         if shard:
             p.shard.rank, p.shard.world = int(shard.get("rank", 0)), int(shard.get("world", 1))
             p.shard.tile_size, p.shard.seed_salt = int(shard.get("tile_size", 0)), int(shard.get("seed_salt", 0))
@@ -457,7 +459,7 @@ class GroupRenderer:
                     "rt_group_renderer_create")
         self.handle = h
 
-    def render_frame(self, camera, scene, want=("rgba8", "accum", "rng_state"), resume=False):
+    def render_frame(self, camera, scene, want=("rgba8", "accum", "rng_state"), resume=False, roulette=False, chains=0):
         w, h = self.img_size
         out = {"rgba8": np.empty((h, w, 4), np.uint8) if "rgba8" in want else None,
                "accum": np.empty((h, w, 4), np.float32) if "accum" in want else None,
@@ -466,7 +468,8 @@ class GroupRenderer:
         p.max_depth, p.sample_count = self.max_depth, self.sample_count
         p.mode = _capi.RT_GROUP_SPP if self.mode == "spp" else _capi.RT_GROUP_TILES
         p.tile_size = self.tile_size
-        p.flags = _capi.RT_RENDER_RESUME if resume else 0
+        p.flags = (_capi.RT_RENDER_RESUME if resume else 0) | (_capi.RT_RENDER_ROULETTE if roulette else 0)
+        p.sample_chains = int(chains)
         f = _capi.rt_frame()
         f.rgba8, f.accum, f.rng_state = _ptr(out["rgba8"]), _ptr(out["accum"]), _ptr(out["rng_state"])
         self.group.check(self._lib.rt_group_render_frame(self.handle, scene.handle, C.byref(camera.c), C.byref(p), C.byref(f)),

@@ -14,6 +14,7 @@ RT_MEGAKERNEL, RT_WAVEFRONT = 0, 1
 RT_MAT_NONE, RT_MAT_DIFFUSE, RT_MAT_METALLIC, RT_MAT_DIELECTRIC = 0, 1, 2, 3
 RT_TEX_SIZE, RT_MAX_IMAGES = 512, 128
 RT_RENDER_RESUME = 1
+RT_RENDER_ROULETTE = 2
 
 f32p = C.POINTER(C.c_float)
 u32p = C.POINTER(C.c_uint32)
@@ -54,7 +55,8 @@ class rt_ipc_handle(C.Structure):
 
 
 class rt_render_params(C.Structure):
-    _fields_ = [("max_depth", C.c_uint32), ("sample_count", C.c_uint32), ("shard", rt_shard), ("flags", C.c_uint32)]
+    _fields_ = [("max_depth", C.c_uint32), ("sample_count", C.c_uint32), ("shard", rt_shard), ("flags", C.c_uint32),
+                ("sample_chains", C.c_uint32)]
 
 
 class rt_frame(C.Structure):
@@ -64,7 +66,7 @@ class rt_frame(C.Structure):
 
 class rt_group_params(C.Structure):
     _fields_ = [("max_depth", C.c_uint32), ("sample_count", C.c_uint32), ("mode", C.c_uint32), ("tile_size", C.c_uint32),
-                ("flags", C.c_uint32)]
+                ("flags", C.c_uint32), ("sample_chains", C.c_uint32)]
 
 
 RT_GROUP_TILES, RT_GROUP_SPP = 0, 1

@@ -262,11 +262,13 @@ __global__ void __launch_bounds__(kMegaBlock, RT_MEGA_MIN_BLOCKS) k_megakernel(R
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const RtBlockGeom g = rt_block_geom(p);
-    const uint32_t n_work = g.n_blocks * 32u; /* pixel slots, 32 per 8x4 block */
+    const uint32_t n_chains = p.chains > 1u ? p.chains : 1u;
+    const uint32_t n_work = g.n_blocks * n_chains * 32u; /* pixel slots, 32 per (8x4 block, sample chain) */
+    const size_t n_pix = (size_t)p.cam.w * (size_t)p.cam.h;
     unsigned long long rays = 0;
     int mode = kNeedPixel;
     int x = 0, y = 0;
-    uint32_t s = 0, depth = 0;
+    uint32_t s = 0, depth = 0, chain = 0, spp_c = p.spp; /* sample chain of the lane's pixel, samples it contributes */
     XorShift32 rng;
     rng.a = 0;
     f3 sum = mk3(0.0f, 0.0f, 0.0f);
@@ -290,17 +292,12 @@ __global__ void __launch_bounds__(kMegaBlock, RT_MEGA_MIN_BLOCKS) k_megakernel(R
         if (mode == kHitPending) {
             f3 org = r.org, dir = r.dir, att = r.att, rad = r.rad, res = mk3(0.0f, 0.0f, 0.0f);
             bool done = rt_shade_segment(scene, tv.best, rng, org, dir, att, rad, res);
+            done = rt_after_segment(p, done, depth, att, rng, res);
             r.org = org; /* src/render_megakernel.cpp:41-55: re-quantise the ray state (F6) */
             r.dir = round_half3(dir);
             r.att = round_half3(att);
             r.rad = round_half3(rad);
-            depth++;
-            if (!done && depth == p.max_depth) { /* :62, survivors are black (F7) */
-                done = true;
-                res = mk3(0.0f, 0.0f, 0.0f);
-            }
             if (done) {
-                if (p.clamp_samples) res = mk3(rt_clamp01(res.x), rt_clamp01(res.y), rt_clamp01(res.z));
                 sum = sum + res;
                 s++;
                 mode = kNeedRay;
@@ -310,19 +307,21 @@ __global__ void __launch_bounds__(kMegaBlock, RT_MEGA_MIN_BLOCKS) k_megakernel(R
         }
         for (;;) { /* warp-uniform: runs until no lane is waiting for a pixel */
             if (mode == kNeedRay) {
-                while (p.max_depth == 0 && s < p.spp) { /* the bounce loop never runs: black sample */
+                while (p.max_depth == 0 && s < spp_c) { /* the bounce loop never runs: black sample */
                     rng.next();
                     rng.next();
                     s++;
                 }
-                if (s == p.spp) { /* pixel finished: :154-158 mean, gamma, image write */
-                    const size_t pix = (size_t)y * (size_t)p.cam.w + (size_t)x;
-                    const float count = base_count + (float)p.spp;
-                    out.accum[pix] = make_float4(sum.x, sum.y, sum.z, count);
-                    const uint32_t px = rt_resolve_pixel(sum.x, sum.y, sum.z, count);
-                    out.rgba8[pix] = px;
-                    if (out.gather) out.gather[pix] = px; /* tile shards: straight into the destination rank's image */
-                    out.rng[pix] = rng.a;
+                if (s == spp_c) { /* pixel finished: :154-158 mean, gamma, image write */
+                    const size_t pix = (size_t)y * (size_t)p.cam.w + (size_t)x, vp = (size_t)chain * n_pix + pix;
+                    const float count = base_count + (float)spp_c;
+                    out.accum[vp] = make_float4(sum.x, sum.y, sum.z, count);
+                    out.rng[vp] = rng.a;
+                    if (n_chains == 1u) { /* with sample chains k_combine_chains sums the planes and writes the image */
+                        const uint32_t px = rt_resolve_pixel(sum.x, sum.y, sum.z, count);
+                        out.rgba8[pix] = px;
+                        if (out.gather) out.gather[pix] = px; /* tile shards: straight into the destination rank's image */
+                    }
                     mode = kNeedPixel;
                 } else {
                     r = rt_camera_ray(p.cam, x, y, rng); /* 2 draws (F5) */
@@ -341,26 +340,28 @@ __global__ void __launch_bounds__(kMegaBlock, RT_MEGA_MIN_BLOCKS) k_megakernel(R
                 if (idx >= n_work) {
                     mode = kExhausted;
                 } else {
-                    const uint32_t in = idx & 31u;
+                    const uint32_t in = idx & 31u, item = idx >> 5, blk = item / n_chains; /* (block, chain) pairs */
                     uint32_t x0, y0;
                     if (order) { /* blocks sorted by decreasing cost class (k_block_cost) */
-                        const uint32_t e = __ldg(order + (idx >> 5));
+                        const uint32_t e = __ldg(order + blk);
                         x0 = e & 0xffffu;
                         y0 = e >> 16;
                     } else {
-                        rt_block_origin(p, g, idx >> 5, x0, y0);
+                        rt_block_origin(p, g, blk, x0, y0);
                     }
                     x = (int)(x0 + (in & 7u));
                     y = (int)(y0 + (in >> 3));
                     if (x < p.cam.w && y < p.cam.h && rt_owns_pixel(p, x, y)) {
+                        chain = item - blk * n_chains;
+                        spp_c = rt_chain_spp(p.spp, p.chains, chain);
                         if (p.resume) { /* carry on where the previous frame stopped */
-                            const size_t pix = (size_t)y * (size_t)p.cam.w + (size_t)x;
-                            const float4 a = out.accum[pix];
-                            rng.a = out.rng[pix];
+                            const size_t vp = (size_t)chain * n_pix + (size_t)y * (size_t)p.cam.w + (size_t)x;
+                            const float4 a = out.accum[vp];
+                            rng.a = out.rng[vp];
                             sum = mk3(a.x, a.y, a.z);
                             base_count = a.w;
                         } else {
-                            rng.a = rt_pixel_seed(p.wavefront_seed, x, y, p.cam.w, p.cam.h) ^ p.seed_salt;
+                            rng.a = rt_pixel_seed(p.wavefront_seed, x, y, p.cam.w, p.cam.h) ^ p.seed_salt ^ (chain * RT_CHAIN_SALT);
                             sum = mk3(0.0f, 0.0f, 0.0f);
                             base_count = 0.0f;
                         }
@@ -490,17 +491,12 @@ __global__ void __launch_bounds__(kMegaBlock, RT_MEGA_MIN_BLOCKS) k_megakernel_c
                     f3 org = mk3(q0.x, q0.y, q0.z), dir = mk3(q1.x, q1.y, q1.z), att = mk3(q2.x, q2.y, q2.z),
                        rad = mk3(q3.x, q3.y, q3.z), res = mk3(0.0f, 0.0f, 0.0f);
                     bool done = rt_shade_segment(scene, h, rng, org, dir, att, rad, res);
+                    done = rt_after_segment(p, done, depth, att, rng, res);
                     r.org = org; /* src/render_megakernel.cpp:41-55: re-quantise the ray state (F6) */
                     r.dir = round_half3(dir);
                     r.att = round_half3(att);
                     r.rad = round_half3(rad);
-                    depth++;
-                    if (!done && depth == p.max_depth) { /* :62, survivors are black (F7) */
-                        done = true;
-                        res = mk3(0.0f, 0.0f, 0.0f);
-                    }
                     if (done) {
-                        if (p.clamp_samples) res = mk3(rt_clamp01(res.x), rt_clamp01(res.y), rt_clamp01(res.z));
                         sum = sum + res;
                         s++;
                         mode = kNeedRay;
@@ -758,10 +754,17 @@ __global__ void __launch_bounds__(kWfBlock) k_wf_shade(RtScene scene, RtFramePar
  * keeps the upper BVH levels across iterations. A pixel's state, its queue entries and its accumulation are only
  * ever touched by its own CTA (same SM, same L1), so no device-scope fence is needed. Per-pixel arithmetic is
  * rt_wf_generate_pixel / traverse / rt_wf_shade_pixel, unchanged: results are bit-identical to the streaming form. */
-__device__ __forceinline__ bool wf_block_pixel(const RtFrameParams &p, const RtBlockGeom &g, uint32_t blk, int lane, uint32_t &pix) {
+__device__ __forceinline__ bool wf_block_pixel(const RtFrameParams &p, const RtBlockGeom &g, uint32_t blk, int lane, uint32_t &pix,
+                                               const uint32_t *order = nullptr) {
     if (blk >= g.n_blocks) return false;
     uint32_t x0, y0;
-    rt_block_origin(p, g, blk, x0, y0);
+    if (order) { /* blocks sorted by decreasing cost class (k_block_cost), like the megakernel's hand-out */
+        const uint32_t e = __ldg(order + blk);
+        x0 = e & 0xffffu;
+        y0 = e >> 16;
+    } else {
+        rt_block_origin(p, g, blk, x0, y0);
+    }
     const int x = (int)(x0 + ((uint32_t)lane & 7u)), y = (int)(y0 + ((uint32_t)lane >> 3));
     if (x >= p.cam.w || y >= p.cam.h || !rt_owns_pixel(p, x, y)) return false;
     pix = (uint32_t)y * (uint32_t)p.cam.w + (uint32_t)x;
@@ -914,7 +917,8 @@ __device__ __forceinline__ void wf_resolve_pixel(const RtWavefrontState &w, cons
 
 __global__ void __launch_bounds__(kWfBlock, RT_EXT_MIN_BLOCKS) k_wf_flow(RtScene scene, RtFrameParams p, RtWavefrontState w, RtFrameOut out,
                                                                         uint32_t *work_counter, unsigned long long *ray_counter,
-                                                                        uint32_t cap /* slots per ring, a power of two >= tune_inflight */) {
+                                                                        uint32_t cap /* slots per ring, a power of two >= tune_inflight */,
+                                                                        const uint32_t *__restrict__ order) {
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const unsigned lt = (1u << lane) - 1u;
@@ -922,6 +926,7 @@ __global__ void __launch_bounds__(kWfBlock, RT_EXT_MIN_BLOCKS) k_wf_flow(RtScene
     const RtBlockGeom g = rt_block_geom(p);
     uint32_t *rayq = w.queue[0] + (size_t)wid * cap, *hitq = w.queue[1] + (size_t)wid * cap;
     const uint32_t mask = cap - 1u;
+    const uint32_t n_chains = p.chains > 1u ? p.chains : 1u, n_pix = (uint32_t)p.cam.w * (uint32_t)p.cam.h;
     fill_perm_table();
     __syncthreads();
     uint32_t ray_head = 0, ray_tail = 0, hit_head = 0, hit_tail = 0; /* warp-uniform ring cursors */
@@ -942,18 +947,19 @@ __global__ void __launch_bounds__(kWfBlock, RT_EXT_MIN_BLOCKS) k_wf_flow(RtScene
     for (;;) {
         /* ---- claim + generate (K2 + first K3) ---- */
         while (more && inflight + 32u <= (uint32_t)p.tune_inflight) {
-            uint32_t blk = 0;
-            if (lane == 0) blk = atomicAdd(work_counter, 1u);
-            blk = __shfl_sync(full, blk, 0);
-            if (blk >= g.n_blocks) {
+            uint32_t item = 0; /* (block, chain) pairs, the chains of a block next to each other */
+            if (lane == 0) item = atomicAdd(work_counter, 1u);
+            item = __shfl_sync(full, item, 0);
+            if (item >= g.n_blocks * n_chains) {
                 more = false;
                 break;
             }
             uint32_t gp = 0;
-            bool live = wf_block_pixel(p, g, blk, lane, gp);
+            bool live = wf_block_pixel(p, g, item / n_chains, lane, gp, order);
             if (live) {
+                gp += (item % n_chains) * n_pix; /* virtual pixel */
                 live = rt_wf_generate_pixel(p, w, out, gp);
-                if (!live) wf_resolve_pixel(w, out, gp); /* no samples to trace */
+                if (!live && n_chains == 1u) wf_resolve_pixel(w, out, gp); /* no samples to trace */
             }
             const unsigned m = __ballot_sync(full, live);
             if (live) rayq[(ray_tail + (uint32_t)__popc(m & lt)) & mask] = gp;
@@ -987,7 +993,7 @@ __global__ void __launch_bounds__(kWfBlock, RT_EXT_MIN_BLOCKS) k_wf_flow(RtScene
             if ((uint32_t)lane < n) {
                 spix = hitq[(hit_head + (uint32_t)lane) & mask];
                 keep = rt_wf_shade_pixel(scene, p, w, out, spix);
-                if (!keep) wf_resolve_pixel(w, out, spix); /* the pixel's last sample: K6/K7 */
+                if (!keep && n_chains == 1u) wf_resolve_pixel(w, out, spix); /* the pixel's last sample: K6/K7 (chains: k_combine_chains) */
             }
             const unsigned mk = __ballot_sync(full, keep);
             if (keep) rayq[(ray_tail + (uint32_t)__popc(mk & lt)) & mask] = spix;
@@ -1045,6 +1051,28 @@ __global__ void k_resolve_owned(RtFrameParams p, const float4 *accum, const uint
         out.rgba8[i] = 0u;
     }
     out.rng[i] = rng_state[i];
+}
+
+/* sample chains: sum the chain planes of every owned pixel in chain order, resolve, store (also to the gather target) */
+__global__ void k_combine_chains(RtFrameParams p, const float4 *chain_accum, const uint32_t *chain_rng, RtFrameOut out) {
+    const uint32_t n_pix = (uint32_t)p.cam.w * (uint32_t)p.cam.h;
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_pix) return;
+    const int x = (int)(i % (uint32_t)p.cam.w), y = (int)(i / (uint32_t)p.cam.w);
+    if (!rt_owns_pixel(p, x, y)) return;
+    float4 s = chain_accum[i];
+    for (uint32_t c = 1; c < p.chains; c++) {
+        const float4 a = chain_accum[(size_t)c * n_pix + i];
+        s.x += a.x;
+        s.y += a.y;
+        s.z += a.z;
+        s.w += a.w;
+    }
+    out.accum[i] = s;
+    const uint32_t px = rt_resolve_pixel(s.x, s.y, s.z, s.w);
+    out.rgba8[i] = px;
+    if (out.gather) out.gather[i] = px;
+    out.rng[i] = chain_rng[i]; /* chain 0: the reference stream's state */
 }
 
 /* contraction self-test: (a*b)+c must be two roundings (DESIGN.md arithmetic contract) */
@@ -1150,8 +1178,9 @@ cudaError_t rt_launch_wf_persistent(cudaStream_t st, int grid, uint32_t cap, con
 }
 
 cudaError_t rt_launch_wf_flow(cudaStream_t st, int grid, uint32_t cap, const RtScene &scene, const RtFrameParams &p,
-                              const RtWavefrontState &w, const RtFrameOut &out, uint32_t *work_counter, unsigned long long *ray_counter) {
-    k_wf_flow<<<grid, kWfBlock, 0, st>>>(scene, p, w, out, work_counter, ray_counter, cap);
+                              const RtWavefrontState &w, const RtFrameOut &out, uint32_t *work_counter, unsigned long long *ray_counter,
+                              const uint32_t *order) {
+    k_wf_flow<<<grid, kWfBlock, 0, st>>>(scene, p, w, out, work_counter, ray_counter, cap, order);
     return cudaGetLastError();
 }
 
@@ -1201,6 +1230,14 @@ cudaError_t rt_launch_resolve_owned(cudaStream_t st, const RtFrameParams &p, con
     const uint32_t n_pix = (uint32_t)p.cam.w * (uint32_t)p.cam.h;
     if (n_pix == 0) return cudaSuccess;
     k_resolve_owned<<<(n_pix + 255) / 256, 256, 0, st>>>(p, (const float4 *)accum, rng_state, out);
+    return cudaGetLastError();
+}
+
+cudaError_t rt_launch_combine_chains(cudaStream_t st, const RtFrameParams &p, const float *chain_accum, const uint32_t *chain_rng,
+                                     const RtFrameOut &out) {
+    const uint32_t n_pix = (uint32_t)p.cam.w * (uint32_t)p.cam.h;
+    if (n_pix == 0) return cudaSuccess;
+    k_combine_chains<<<(n_pix + 255) / 256, 256, 0, st>>>(p, (const float4 *)chain_accum, chain_rng, out);
     return cudaGetLastError();
 }
 

@@ -7,6 +7,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <new>
+#include <chrono>
+#include <cstdio>
 #include <thread>
 
 #include "rt_internal.h"
@@ -128,6 +130,10 @@ struct rt_renderer {
     uint32_t *gather = nullptr;   /* tile shards: owned pixels are also stored here (peer memory) */
     bool gather_ipc = false;      /* gather was opened from an IPC handle (close it) */
     bool exported = false;        /* d_rgba8 is a gather destination: never clear foreign pixels */
+    float4 *d_chain_accum = nullptr; /* sample chains: one accumulation plane per chain ... */
+    uint32_t *d_chain_rng = nullptr; /* ... and (megakernel) one stream-state plane per chain */
+    uint32_t chain_planes = 0;       /* planes allocated (also the planes of the wavefront's per-pixel state) */
+    uint32_t last_chains = 1;
     const float4 *peer_accum[16] = {}; /* spp slices across processes: every rank's accumulation buffer (IPC mappings) */
     uint32_t peer_world = 0, peer_rank = 0;
     int tune_refill = 12; /* lanes that must run dry before a warp refills (RT_TUNE_REFILL overrides; 12-14 measured best) */
@@ -305,6 +311,8 @@ rt_status rt_scene_create(rt_context *ctx, const rt_scene_desc *desc, rt_scene *
     if (desc->texture_layer_count && !desc->texture_layers)
         return rt_set_error(ctx, RT_ERR_INVALID, "rt_scene_create", "texture_layers is NULL");
     RT_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    const bool trace = getenv("RT_TRACE") != nullptr; /* development: host-side phase times on stderr */
+    const auto t_begin = std::chrono::steady_clock::now();
 
     uint64_t n_verts = 0, n_idx = 0;
     for (uint32_t i = 0; i < desc->instance_count; i++) {
@@ -316,15 +324,14 @@ rt_status rt_scene_create(rt_context *ctx, const rt_scene_desc *desc, rt_scene *
             return rt_set_error(ctx, RT_ERR_INVALID, "rt_scene_create", "bad material type");
         if (in.material.albedo_image >= (int32_t)desc->texture_layer_count)
             return rt_set_error(ctx, RT_ERR_INVALID, "rt_scene_create", "albedo_image out of range");
-        uint32_t max_index = 0; /* branch-free so that the compiler vectorises it: 30 M indices at config 4 */
-        for (uint32_t k = 0; k < in.index_count; k++) max_index = in.indices[k] > max_index ? in.indices[k] : max_index;
-        if (in.index_count && max_index >= in.vertex_count) return rt_set_error(ctx, RT_ERR_INVALID, "rt_scene_create", "index out of range");
+        if (in.index_count && !in.vertex_count) return rt_set_error(ctx, RT_ERR_INVALID, "rt_scene_create", "index out of range");
         n_verts += in.vertex_count;
         n_idx += in.index_count;
     }
     if (n_idx >= 0xffffffffull || n_verts >= 0xffffffffull) /* index / vertex offsets are 32-bit (first_index, first_vertex) */
         return rt_set_error(ctx, RT_ERR_INVALID, "rt_scene_create", "scene too large (2^32 indices or vertices)");
 
+    const auto t_checked = std::chrono::steady_clock::now();
     rt_scene *s = new (std::nothrow) rt_scene();
     if (!s) return rt_set_error(ctx, RT_ERR_INVALID, "rt_scene_create", "out of memory");
     s->ctx = ctx;
@@ -364,6 +371,7 @@ rt_status rt_scene_create(rt_context *ctx, const rt_scene_desc *desc, rt_scene *
     };
     cudaError_t e;
     cudaStream_t stream = ctx->stream;
+    uint32_t *d_bad = nullptr, h_bad = 0;
     do {
         if ((e = rt_pool_alloc(ctx, (void **)&s->d_positions, n_verts * 3 * sizeof(float))) != cudaSuccess) { fail(e, "alloc positions"); break; }
         if ((e = rt_pool_alloc(ctx, (void **)&s->d_normals, n_verts * 3 * sizeof(float))) != cudaSuccess) { fail(e, "alloc normals"); break; }
@@ -387,6 +395,11 @@ rt_status rt_scene_create(rt_context *ctx, const rt_scene_desc *desc, rt_scene *
         }
         if (e != cudaSuccess) { fail(e, "copy geometry"); break; }
         if ((e = cudaMemcpyAsync(s->d_geom, s->h_geom.data(), s->h_geom.size() * sizeof(RtInstanceGeom), cudaMemcpyHostToDevice, stream)) != cudaSuccess) { fail(e, "copy geom"); break; }
+        /* index range check on the device, where the indices now are; the verdict is read after the upload has drained */
+        if ((e = rt_scratch(ctx, 1, 16, (void **)&d_bad)) != cudaSuccess) { fail(e, "alloc"); break; }
+        if ((e = cudaMemsetAsync(d_bad, 0, 4, stream)) != cudaSuccess) { fail(e, "memset"); break; }
+        if ((e = rt_launch_validate_indices(stream, s->d_indices, s->d_geom, s->n_inst, s->n_verts, n_idx, d_bad)) != cudaSuccess) { fail(e, "validate indices"); break; }
+        if ((e = cudaMemcpyAsync(&h_bad, d_bad, 4, cudaMemcpyDeviceToHost, stream)) != cudaSuccess) { fail(e, "validate indices"); break; }
         if ((e = cudaMemcpyAsync(s->d_inst, s->h_inst.data(), s->h_inst.size() * sizeof(RtInstance), cudaMemcpyHostToDevice, stream)) != cudaSuccess) { fail(e, "copy inst"); break; }
         /* texture array: RGBA8 512x512xN layered, point sampled, raw element reads (F13) */
         s->n_layers = desc->texture_layer_count;
@@ -416,8 +429,16 @@ rt_status rt_scene_create(rt_context *ctx, const rt_scene_desc *desc, rt_scene *
             td.normalizedCoords = 0;
             if ((e = cudaCreateTextureObject(&s->tex, &rd, &td, nullptr)) != cudaSuccess) { fail(e, "create texture object"); break; }
         }
+        const auto t_queued = std::chrono::steady_clock::now();
         if ((e = cudaStreamSynchronize(stream)) != cudaSuccess) { fail(e, "upload"); break; }
+        if (trace) {
+            const auto t_done = std::chrono::steady_clock::now();
+            auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+            fprintf(stderr, "[rt trace] rt_scene_create: validate %.2f ms, stage + enqueue %.2f ms, drain %.2f ms (%.1f MB)\n", ms(t_begin, t_checked),
+                    ms(t_checked, t_queued), ms(t_queued, t_done), (double)(n_verts * 32 + n_idx * 4) / 1e6);
+        }
     } while (0);
+    if (st == RT_OK && h_bad) st = rt_set_error(ctx, RT_ERR_INVALID, "rt_scene_create", "index out of range");
     if (st != RT_OK) {
         rt_scene_destroy(s);
         return st;
@@ -613,6 +634,8 @@ void rt_renderer_destroy(rt_renderer *r) {
     for (uint32_t *q : r->d_order) cudaFree(q);
     cudaFree(r->d_order_temp);
     cudaFree(r->d_region_cost);
+    cudaFree(r->d_chain_accum);
+    cudaFree(r->d_chain_rng);
     cudaFree(r->d_accum);
     cudaFree(r->d_rgba8);
     cudaFree(r->d_rng);
@@ -742,7 +765,10 @@ rt_status rt_render_frame(rt_renderer *r, const rt_scene *scene, const rt_camera
     if (sh.world > 1 && sh.rank >= sh.world) return rt_set_error(ctx, RT_ERR_INVALID, "rt_render_frame", "shard rank >= world");
     if (sh.world > 1 && sh.tile_size % 8 != 0) return rt_set_error(ctx, RT_ERR_INVALID, "rt_render_frame", "tile_size must be a multiple of 8");
     if (sh.world > 1 && sh.tile_size > 16384u) return rt_set_error(ctx, RT_ERR_INVALID, "rt_render_frame", "tile_size must be <= 16384");
-    if (params->flags & ~RT_RENDER_RESUME) return rt_set_error(ctx, RT_ERR_INVALID, "rt_render_frame", "unknown bits in rt_render_params.flags");
+    if (params->flags & ~(RT_RENDER_RESUME | RT_RENDER_ROULETTE)) return rt_set_error(ctx, RT_ERR_INVALID, "rt_render_frame", "unknown bits in rt_render_params.flags");
+    const uint32_t chains = params->sample_chains > 1u ? params->sample_chains : 1u;
+    if (chains > 16u) return rt_set_error(ctx, RT_ERR_INVALID, "rt_render_frame", "sample_chains must be <= 16");
+    if ((uint64_t)r->w * (uint64_t)r->h * chains > 0x7fffffffull) return rt_set_error(ctx, RT_ERR_INVALID, "rt_render_frame", "image size x sample_chains too large");
     RT_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
 
@@ -762,10 +788,12 @@ rt_status rt_render_frame(rt_renderer *r, const rt_scene *scene, const rt_camera
     p.tune_idle = r->tune_idle;
     p.tune_inflight = r->tune_inflight;
     p.resume = (params->flags & RT_RENDER_RESUME) ? 1 : 0;
+    p.roulette = (params->flags & RT_RENDER_ROULETTE) ? 1 : 0;
+    p.chains = chains;
     if (p.resume && !r->has_frame) return rt_set_error(ctx, RT_ERR_STATE, "rt_render_frame", "RT_RENDER_RESUME without a previous frame");
     if (p.resume && (r->last_scene != scene || memcmp(&r->last_camera, camera, sizeof(rt_camera)) != 0 || r->last_depth != params->max_depth ||
                      r->last_shard.rank != sh.rank || r->last_shard.world != sh.world || r->last_shard.tile_size != sh.tile_size ||
-                     r->last_shard.seed_salt != sh.seed_salt))
+                     r->last_shard.seed_salt != sh.seed_salt || r->last_chains != chains))
         return rt_set_error(ctx, RT_ERR_STATE, "rt_render_frame", "RT_RENDER_RESUME with a different scene, camera, depth or shard than the previous frame");
     RtFrameOut out;
     out.accum = r->d_accum;
@@ -775,6 +803,67 @@ rt_status rt_render_frame(rt_renderer *r, const rt_scene *scene, const rt_camera
     p.keep_foreign = r->exported ? 1 : 0;
     const size_t n = (size_t)r->w * (size_t)r->h;
     uint32_t launches = 0;
+    /* sample chains: the kernels work on `chains` planes of per-pixel state and k_combine_chains writes the frame */
+    RtFrameOut out_frame = out;
+    if (chains > 1u) {
+        if (r->chain_planes < chains) {
+            RT_CUDA_TRY(ctx, cudaStreamSynchronize(st));
+            cudaFree(r->d_chain_accum);
+            cudaFree(r->d_chain_rng);
+            r->d_chain_accum = nullptr;
+            r->d_chain_rng = nullptr;
+            r->chain_planes = 0;
+            r->has_frame = false;
+            if (p.resume) return rt_set_error(ctx, RT_ERR_STATE, "rt_render_frame", "RT_RENDER_RESUME with more sample chains than the previous frame");
+            RT_CUDA_TRY(ctx, dev_alloc(&r->d_chain_accum, n * chains));
+            RT_CUDA_TRY(ctx, dev_alloc(&r->d_chain_rng, n * chains));
+            if (r->kind == RT_WAVEFRONT) { /* the per-pixel ray state gets one plane per chain too */
+                cudaFree(r->wf.org); cudaFree(r->wf.dir); cudaFree(r->wf.att); cudaFree(r->wf.rad); cudaFree(r->wf.hit); cudaFree(r->wf.prog); cudaFree(r->wf.rng);
+                r->wf.org = nullptr; r->wf.dir = nullptr; r->wf.att = nullptr; r->wf.rad = nullptr; r->wf.hit = nullptr; r->wf.prog = nullptr; r->wf.rng = nullptr;
+                RT_CUDA_TRY(ctx, dev_alloc(&r->wf.org, n * chains));
+                RT_CUDA_TRY(ctx, dev_alloc(&r->wf.dir, n * chains));
+                RT_CUDA_TRY(ctx, dev_alloc(&r->wf.att, n * chains));
+                RT_CUDA_TRY(ctx, dev_alloc(&r->wf.rad, n * chains));
+                RT_CUDA_TRY(ctx, dev_alloc(&r->wf.hit, n * chains));
+                RT_CUDA_TRY(ctx, dev_alloc(&r->wf.prog, n * chains));
+                RT_CUDA_TRY(ctx, dev_alloc(&r->wf.rng, n * chains));
+            }
+            r->chain_planes = chains;
+        }
+        out.accum = r->d_chain_accum;
+        out.rng = r->d_chain_rng;
+    }
+
+    /* block order (both persistent kernels hand pixels out in 8x4 blocks from a global counter): the probe is a fixed cost
+     * (one low-occupancy path per block), the tail it removes grows with the length of a pixel's sequential chain:
+     * measured +10 % on C2 (64 spp), +1.5 % on C3, -1.5 % on C4 at 16 spp -> only from 32 spp per chain */
+    auto block_order = [&](const uint32_t **order) -> rt_status {
+        *order = nullptr;
+        const uint32_t n_blocks = rt_block_count(p);
+        if (!(r->block_order && p.spp >= 32 * chains && p.max_depth >= 2 && n_blocks >= 1024 &&
+              (uint64_t)r->w + sh.tile_size <= 65536u && (uint64_t)r->h + sh.tile_size <= 65536u)) /* block origins are packed 16 + 16 bits, partial edge tiles included */
+            return RT_OK;
+        if (n_blocks > r->order_capacity) { /* first frame (or a coarser tiling): (re)allocate */
+            RT_CUDA_TRY(ctx, cudaStreamSynchronize(st));
+            for (uint32_t *&q : r->d_order) {
+                cudaFree(q);
+                q = nullptr;
+            }
+            cudaFree(r->d_order_temp);
+            r->d_order_temp = nullptr;
+            r->order_capacity = 0;
+            for (uint32_t *&q : r->d_order) RT_CUDA_TRY(ctx, dev_alloc(&q, n_blocks));
+            RT_CUDA_TRY(ctx, rt_block_order_temp_bytes(n_blocks, &r->order_temp_bytes));
+            RT_CUDA_TRY(ctx, cudaMalloc(&r->d_order_temp, r->order_temp_bytes ? r->order_temp_bytes : 1));
+            if (!r->d_region_cost) RT_CUDA_TRY(ctx, dev_alloc(&r->d_region_cost, rt_region_count(r->w, r->h)));
+            r->order_capacity = n_blocks;
+        }
+        RT_CUDA_TRY(ctx, rt_launch_block_order(st, scene->view, p, r->d_region_cost, r->d_order[0], r->d_order[1], r->d_order[2], r->d_order[3],
+                                               r->d_order_temp, r->order_temp_bytes));
+        *order = r->d_order[3];
+        launches += 2;
+        return RT_OK;
+    };
 
     RT_CUDA_TRY(ctx, cudaEventRecord(ctx->ev0, st));
     RT_CUDA_TRY(ctx, cudaMemsetAsync(r->d_rays, 0, sizeof(unsigned long long), st));
@@ -785,39 +874,23 @@ rt_status rt_render_frame(rt_renderer *r, const rt_scene *scene, const rt_camera
             if (!r->exported) RT_CUDA_TRY(ctx, cudaMemsetAsync(r->d_rgba8, 0, n * 4, st));
             RT_CUDA_TRY(ctx, cudaMemsetAsync(r->d_rng, 0, n * 4, st));
         }
-        /* block order: the probe is a fixed cost (one low-occupancy path per block), the tail it removes grows
-         * with the length of a pixel's sequential chain: measured +10 % on C2 (64 spp), +1.5 % on C3, -1.5 % on
-         * C4 at 16 spp -> only from 32 spp */
+        if (chains > 1u) p.tune_ctx = 0; /* chains are implemented by the one-pixel-in-registers kernel */
         const uint32_t *order = nullptr;
-        const uint32_t n_blocks = rt_block_count(p);
-        if (r->block_order && p.spp >= 32 && p.max_depth >= 2 && n_blocks >= 1024 &&
-            (uint64_t)r->w + sh.tile_size <= 65536u && (uint64_t)r->h + sh.tile_size <= 65536u) { /* block origins are packed 16 + 16 bits, partial edge tiles included */
-            if (n_blocks > r->order_capacity) { /* first frame (or a coarser tiling): (re)allocate */
-                RT_CUDA_TRY(ctx, cudaStreamSynchronize(st));
-                for (uint32_t *&q : r->d_order) {
-                    cudaFree(q);
-                    q = nullptr;
-                }
-                cudaFree(r->d_order_temp);
-                r->d_order_temp = nullptr;
-                r->order_capacity = 0;
-                for (uint32_t *&q : r->d_order) RT_CUDA_TRY(ctx, dev_alloc(&q, n_blocks));
-                RT_CUDA_TRY(ctx, rt_block_order_temp_bytes(n_blocks, &r->order_temp_bytes));
-                RT_CUDA_TRY(ctx, cudaMalloc(&r->d_order_temp, r->order_temp_bytes ? r->order_temp_bytes : 1));
-                if (!r->d_region_cost) RT_CUDA_TRY(ctx, dev_alloc(&r->d_region_cost, rt_region_count(r->w, r->h)));
-                r->order_capacity = n_blocks;
-            }
-            RT_CUDA_TRY(ctx, rt_launch_block_order(st, scene->view, p, r->d_region_cost, r->d_order[0], r->d_order[1], r->d_order[2], r->d_order[3],
-                                                   r->d_order_temp, r->order_temp_bytes));
-            order = r->d_order[3];
-            launches += 2;
+        {
+            const rt_status os = block_order(&order);
+            if (os != RT_OK) return os;
         }
         RT_CUDA_TRY(ctx, rt_launch_megakernel(st, r->grid_mega, scene->view, p, out, r->d_work, r->d_rays, order));
         launches++;
-    } else if (r->wf_persist) {
+        if (chains > 1u) {
+            RT_CUDA_TRY(ctx, rt_launch_combine_chains(st, p, (const float *)r->d_chain_accum, r->d_chain_rng, out_frame));
+            launches++;
+        }
+    } else if (r->wf_persist || chains > 1u) {
         const uint32_t n_blocks = rt_block_count(p);
         uint32_t grid, cap;
-        if (r->wf_persist >= 2) { /* one ray ring + one hit ring per warp, a power of two >= the pixels a warp keeps in flight */
+        const bool flow = r->wf_persist >= 2 || chains > 1u; /* chains are implemented by the queue-driven form */
+        if (flow) { /* one ray ring + one hit ring per warp, a power of two >= the pixels a warp keeps in flight */
             grid = (uint32_t)r->grid_flow;
             cap = 32u;
             while (cap < (uint32_t)r->tune_inflight) cap <<= 1;
@@ -844,9 +917,16 @@ rt_status rt_render_frame(rt_renderer *r, const rt_scene *scene, const rt_camera
             RT_CUDA_TRY(ctx, cudaMemsetAsync(r->d_rng, 0, n * 4, st));
             RT_CUDA_TRY(ctx, cudaMemsetAsync(r->wf.rng, 0, n * 4, st));
         }
-        if (r->wf_persist >= 2) {
+        if (flow) {
             RT_CUDA_TRY(ctx, cudaMemsetAsync(r->d_work, 0, sizeof(uint32_t), st));
-            RT_CUDA_TRY(ctx, rt_launch_wf_flow(st, (int)grid, cap / (uint32_t)r->flow_warps, scene->view, p, r->wf, out, r->d_work, r->d_rays));
+            const uint32_t *order = nullptr;
+            const rt_status os = block_order(&order);
+            if (os != RT_OK) return os;
+            RT_CUDA_TRY(ctx, rt_launch_wf_flow(st, (int)grid, cap / (uint32_t)r->flow_warps, scene->view, p, r->wf, out, r->d_work, r->d_rays, order));
+            if (chains > 1u) {
+                RT_CUDA_TRY(ctx, rt_launch_combine_chains(st, p, (const float *)r->d_chain_accum, r->wf.rng, out_frame));
+                launches++;
+            }
         }
         else RT_CUDA_TRY(ctx, rt_launch_wf_persistent(st, (int)grid, cap, scene->view, p, r->wf, out, r->d_rays));
         launches++;
@@ -920,6 +1000,7 @@ rt_status rt_render_frame(rt_renderer *r, const rt_scene *scene, const rt_camera
     r->last_camera = *camera;
     r->last_shard = sh;
     r->last_depth = params->max_depth;
+    r->last_chains = chains;
 #ifdef RT_GPU_COUNTERS
     {
         unsigned long long c[2];

@@ -239,6 +239,7 @@ rt_status rt_group_render_frame(rt_group_renderer *r, const rt_group_scene *scen
         p.max_depth = params->max_depth;
         p.sample_count = params->sample_count;
         p.flags = params->flags;
+        p.sample_chains = params->sample_chains;
         const rt_status st = rt_render_frame(r->r[0], scene->scene[0], camera, &p, frame);
         return st == RT_OK ? st : group_error(g, st, std::string("rt_render_frame: ") + rt_last_error(g->ctx[0]));
     }
@@ -264,6 +265,7 @@ rt_status rt_group_render_frame(rt_group_renderer *r, const rt_group_scene *scen
         rt_render_params p = {};
         p.max_depth = params->max_depth;
         p.flags = params->flags;
+        p.sample_chains = params->sample_chains;
         p.shard.rank = i;
         p.shard.world = n_dev;
         if (tiles) {

@@ -79,6 +79,8 @@ inline void rt_pool_free(rt_context *ctx, void *p) {
     if (p) cudaFreeAsync(p, ctx->stream);
 }
 rt_status rt_build_bvh(rt_scene *s); /* bvh_build.cu */
+cudaError_t rt_launch_validate_indices(cudaStream_t st, const uint32_t *indices, const RtInstanceGeom *geom, uint32_t n_inst, uint32_t n_verts,
+                                       uint64_t n_idx, uint32_t *bad); /* bvh_build.cu */
 void rt_renderer_mark_exported(rt_renderer *r); /* rt_api.cu, for rt_group.cu */
 
 #define RT_CUDA_TRY(ctx, expr)                                                     \

@@ -27,7 +27,8 @@ cudaError_t rt_wf_persistent_grid(int sm_count, int *grid);
 /* queue-driven warps: one ray ring and one hit ring of `cap` (power of two >= tune_inflight) slots per warp */
 cudaError_t rt_wf_flow_grid(int sm_count, int *grid, int *warps_per_block);
 cudaError_t rt_launch_wf_flow(cudaStream_t st, int grid, uint32_t cap, const RtScene &scene, const RtFrameParams &p,
-                              const RtWavefrontState &w, const RtFrameOut &out, uint32_t *work_counter, unsigned long long *ray_counter);
+                              const RtWavefrontState &w, const RtFrameOut &out, uint32_t *work_counter, unsigned long long *ray_counter,
+                              const uint32_t *order /* NULL: enumeration order */);
 cudaError_t rt_launch_wf_persistent(cudaStream_t st, int grid, uint32_t cap, const RtScene &scene, const RtFrameParams &p,
                                     const RtWavefrontState &w, const RtFrameOut &out, unsigned long long *ray_counter);
 cudaError_t rt_launch_wf_generate(cudaStream_t st, int grid, const RtFrameParams &p, const RtWavefrontState &w,
@@ -41,6 +42,9 @@ cudaError_t rt_launch_resolve_owned(cudaStream_t st, const RtFrameParams &p, con
                                     const uint32_t *rng_state, const RtFrameOut &out);
 /* RT_GPU_COUNTERS builds: traversal steps since the last reset (zeros otherwise) */
 void rt_counters_read(unsigned long long out[2], bool reset);
+/* sample chains (rt_render_params.sample_chains > 1): sum of the chain planes -> accum / rgba8 / rng of the frame */
+cudaError_t rt_launch_combine_chains(cudaStream_t st, const RtFrameParams &p, const float *chain_accum, const uint32_t *chain_rng,
+                                     const RtFrameOut &out);
 /* reduce-scatter + resolve + gather over peer memory (rt_group.cu): pixels [first, first + count) summed over `world`
  * accumulation buffers in rank order; sum_out may be NULL */
 cudaError_t rt_launch_reduce_resolve_peer(cudaStream_t st, const float4 *const *accum, uint32_t world, uint32_t first, uint32_t count,

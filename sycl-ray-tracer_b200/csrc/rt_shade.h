@@ -239,7 +239,43 @@ struct RtFrameParams {
     int32_t tune_shade;     /* megakernel contexts: shade once this many lanes have a hit waiting ... */
     int32_t tune_idle;      /* ... or this many lanes can neither traverse nor switch */
     int32_t tune_inflight;  /* wavefront (queue-driven warps): pixels a warp keeps in flight, a multiple of 32 */
+    /* options that are NOT the reference's sampling order (off by default; PLAN.md:23-27 lists both as open) */
+    int32_t roulette;       /* RT_RENDER_ROULETTE: Russian roulette from the third bounce on */
+    uint32_t chains;        /* rt_render_params.sample_chains: independent sample chains per pixel (<= 1: one stream per pixel, F4) */
 };
+
+#define RT_ROULETTE_MIN_DEPTH 3u
+#define RT_CHAIN_SALT 0x9E3779B9u /* chain c of a pixel runs on the stream seed ^ c * RT_CHAIN_SALT (chain 0 = the reference stream) */
+
+/* What follows rt_shade_segment for one path segment (src/render_megakernel.cpp:41-62, src/render_wavefront.cpp:272-280):
+ * count the segment, cut the path at max_depth (survivors are black, F7), optionally play Russian roulette, and clamp a
+ * finished sample in the wavefront formulation (F9). Returns true when the path ended; `res` is then the sample.
+ * Russian roulette (optional, not in the reference): from the third bounce on the path survives with probability
+ * q = clamp(max(att), 0.05, 1) — ONE extra draw — and its attenuation is divided by q; a killed path is black. The
+ * caller quantises `att` afterwards (F6). */
+RT_HD bool rt_after_segment(const RtFrameParams &p, bool done, uint32_t &depth, f3 &att, XorShift32 &rng, f3 &res) {
+    depth++;
+    if (!done && depth == p.max_depth) { /* :62, survivors are black (F7) */
+        done = true;
+        res = mk3(0.0f, 0.0f, 0.0f);
+    }
+    if (!done && p.roulette && depth >= RT_ROULETTE_MIN_DEPTH) {
+        const float q = rt_min(rt_max(rt_max(rt_max(att.x, att.y), att.z), 0.05f), 1.0f);
+        if (rng.next() > q) {
+            done = true;
+            res = mk3(0.0f, 0.0f, 0.0f);
+        } else {
+            att = att * rt_div(1.0f, q);
+        }
+    }
+    if (done && p.clamp_samples) res = mk3(rt_clamp01(res.x), rt_clamp01(res.y), rt_clamp01(res.z)); /* :277 */
+    return done;
+}
+
+/* samples chain `c` of `chains` contributes to a pixel of `spp` samples (the first spp % chains chains take one more) */
+RT_HD uint32_t rt_chain_spp(uint32_t spp, uint32_t chains, uint32_t c) {
+    return chains <= 1u ? spp : spp / chains + (c < spp % chains ? 1u : 0u);
+}
 
 /* image-tile sharding: tile t (row major, tile_size^2 pixels) belongs to rank t % world */
 RT_HD bool rt_owns_pixel(const RtFrameParams &p, int x, int y) {
@@ -276,17 +312,12 @@ RT_HD f3 rt_megakernel_pixel(const RtScene &scene, const RtFrameParams &p, int x
         const RtHit h = rt_traverse(scene.bvh, r.org, r.dir, 0.0001f, INFINITY);
         f3 org = r.org, dir = r.dir, att = r.att, rad = r.rad, res = mk3(0.0f, 0.0f, 0.0f);
         bool done = rt_shade_segment(scene, h, rng, org, dir, att, rad, res);
+        done = rt_after_segment(p, done, depth, att, rng, res);
         r.org = org; /* src/render_megakernel.cpp:41-55: re-quantise the ray state (F6) */
         r.dir = round_half3(dir);
         r.att = round_half3(att);
         r.rad = round_half3(rad);
-        depth++;
-        if (!done && depth == p.max_depth) { /* :62, survivors are black (F7) */
-            done = true;
-            res = mk3(0.0f, 0.0f, 0.0f);
-        }
         if (done) {
-            if (p.clamp_samples) res = mk3(rt_clamp01(res.x), rt_clamp01(res.y), rt_clamp01(res.z));
             sum = sum + res;
             s++;
             need_ray = true;

@@ -46,32 +46,53 @@ RT_HD void rt_wf_store_ray(const RtWavefrontState &w, uint32_t pix, f3 org, f3 d
 
 /* K2 + first K3 (src/render_wavefront.cpp:62-74,106-124): seed, zero, first camera ray.
  * Returns true when the pixel enters the queue. */
+/* With sample chains (RtFrameParams.chains > 1, not the reference's order) the unit of work is a VIRTUAL pixel
+ * vp = chain * n_pix + pix: every per-pixel array (ray state, rng, accumulation) has `chains` planes, chain c runs its
+ * share of the samples on the stream seed ^ c * RT_CHAIN_SALT, and k_combine_chains sums the planes in chain order. */
+struct RtVirtualPixel {
+    uint32_t pix, chain, spp; /* image pixel, chain index, samples this chain contributes */
+};
+RT_HD RtVirtualPixel rt_virtual_pixel(const RtFrameParams &p, uint32_t vp) {
+    RtVirtualPixel v;
+    if (p.chains > 1u) {
+        const uint32_t n_pix = (uint32_t)p.cam.w * (uint32_t)p.cam.h;
+        v.chain = vp / n_pix;
+        v.pix = vp - v.chain * n_pix;
+    } else {
+        v.chain = 0u;
+        v.pix = vp;
+    }
+    v.spp = rt_chain_spp(p.spp, p.chains, v.chain);
+    return v;
+}
+
 RT_HD bool rt_wf_generate_pixel(const RtFrameParams &p, const RtWavefrontState &w, const RtFrameOut &out,
-                                uint32_t pix) {
-    const int x = (int)(pix % (uint32_t)p.cam.w), y = (int)(pix / (uint32_t)p.cam.w);
-    if (!p.resume) out.accum[pix] = rt_mk_float4(0.0f, 0.0f, 0.0f, 0.0f); /* the reference forgets combined_image (:56-57) */
+                                uint32_t vp) {
+    const RtVirtualPixel v = rt_virtual_pixel(p, vp);
+    const int x = (int)(v.pix % (uint32_t)p.cam.w), y = (int)(v.pix / (uint32_t)p.cam.w);
+    if (!p.resume) out.accum[vp] = rt_mk_float4(0.0f, 0.0f, 0.0f, 0.0f); /* the reference forgets combined_image (:56-57) */
     if (!rt_owns_pixel(p, x, y)) {
-        w.rng[pix] = 0u;
+        w.rng[vp] = 0u;
         return false;
     }
     XorShift32 rng;
-    rng.a = p.resume ? w.rng[pix] : (rt_pixel_seed(p.wavefront_seed, x, y, p.cam.w, p.cam.h) ^ p.seed_salt);
+    rng.a = p.resume ? w.rng[vp] : (rt_pixel_seed(p.wavefront_seed, x, y, p.cam.w, p.cam.h) ^ p.seed_salt ^ (v.chain * RT_CHAIN_SALT));
     bool live = false;
-    if (p.spp > 0 && p.max_depth > 0) {
+    if (v.spp > 0 && p.max_depth > 0) {
         const RtRayState r = rt_camera_ray(p.cam, x, y, rng);
-        rt_wf_store_ray(w, pix, r.org, r.dir, r.att, r.rad);
-        w.prog[pix] = rt_mk_uint2(0u, 0u);
+        rt_wf_store_ray(w, vp, r.org, r.dir, r.att, r.rad);
+        w.prog[vp] = rt_mk_uint2(0u, 0u);
         live = true;
     } else {
-        for (uint32_t s = 0; s < p.spp; s++) { /* depth 0: two draws per black sample */
+        for (uint32_t s = 0; s < v.spp; s++) { /* depth 0: two draws per black sample */
             rng.next();
             rng.next();
         }
-        rt_float4 a = p.resume ? out.accum[pix] : rt_mk_float4(0.0f, 0.0f, 0.0f, 0.0f);
-        a.w += (float)p.spp;
-        out.accum[pix] = a;
+        rt_float4 a = p.resume ? out.accum[vp] : rt_mk_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        a.w += (float)v.spp;
+        out.accum[vp] = a;
     }
-    w.rng[pix] = rng.a;
+    w.rng[vp] = rng.a;
     return live;
 }
 
@@ -86,7 +107,7 @@ RT_HD void rt_wf_extend_pixel(const RtScene &scene, const RtWavefrontState &w, u
 /* shade + connect + regenerate (the rest of K4, K5 and the next sample's K3,
  * src/render_wavefront.cpp:244-296,340-355). Returns true when the pixel stays queued. */
 RT_HD bool rt_wf_shade_pixel(const RtScene &scene, const RtFrameParams &p, const RtWavefrontState &w,
-                             const RtFrameOut &out, uint32_t pix) {
+                             const RtFrameOut &out, uint32_t pix /* virtual pixel */) {
     const rt_float4 o4 = w.org[pix];
     const rt_float4 h4 = w.hit[pix];
     RtHit h;
@@ -103,13 +124,8 @@ RT_HD bool rt_wf_shade_pixel(const RtScene &scene, const RtFrameParams &p, const
     f3 res = mk3(0.0f, 0.0f, 0.0f);
     bool keep;
     bool done = rt_shade_segment(scene, h, rng, org, dir, att, rad, res);
-    prog.y++;
-    if (!done && prog.y == p.max_depth) { /* :279-280 */
-        done = true;
-        res = mk3(0.0f, 0.0f, 0.0f);
-    }
+    done = rt_after_segment(p, done, prog.y, att, rng, res); /* :277-280 */
     if (done) {
-        if (p.clamp_samples) res = mk3(rt_clamp01(res.x), rt_clamp01(res.y), rt_clamp01(res.z)); /* :277 */
         rt_float4 a = out.accum[pix]; /* merge_samples, :340-355 */
         a.x += res.x;
         a.y += res.y;
@@ -118,9 +134,10 @@ RT_HD bool rt_wf_shade_pixel(const RtScene &scene, const RtFrameParams &p, const
         out.accum[pix] = a;
         prog.x++;
         prog.y = 0;
-        keep = prog.x < p.spp;
+        const RtVirtualPixel v = rt_virtual_pixel(p, pix);
+        keep = prog.x < v.spp;
         if (keep) { /* regenerate: this pixel's next sample */
-            const int x = (int)(pix % (uint32_t)p.cam.w), y = (int)(pix / (uint32_t)p.cam.w);
+            const int x = (int)(v.pix % (uint32_t)p.cam.w), y = (int)(v.pix / (uint32_t)p.cam.w);
             const RtRayState r = rt_camera_ray(p.cam, x, y, rng);
             rt_wf_store_ray(w, pix, r.org, r.dir, r.att, r.rad);
         }

@@ -67,12 +67,12 @@ class Scene:
                             prim.ctypes.data, u.ctypes.data, v.ctypes.data, t.ctypes.data)
         return dict(inst=inst, prim=prim, u=u, v=v, t=t)
 
-    def render(self, camera, kind, max_depth, spp, shard=None, resume=None):
+    def render(self, camera, kind, max_depth, spp, shard=None, resume=None, roulette=False):
         """resume = the dict a previous render() returned: continue it (RT_RENDER_RESUME)"""
         w, h = camera.img_size
         p = self.cap.rt_render_params()
         p.max_depth, p.sample_count = max_depth, spp
-        p.flags = self.cap.RT_RENDER_RESUME if resume else 0
+        p.flags = (self.cap.RT_RENDER_RESUME if resume else 0) | (self.cap.RT_RENDER_ROULETTE if roulette else 0)
         if shard:
             p.shard.rank, p.shard.world = shard.get("rank", 0), shard.get("world", 1)
             p.shard.tile_size, p.shard.seed_salt = shard.get("tile_size", 0), shard.get("seed_salt", 0)

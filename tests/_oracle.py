@@ -31,7 +31,7 @@ class orc_camera(C.Structure):
 class orc_render_params(C.Structure):
     _fields_ = [("mode", C.c_int32), ("max_depth", C.c_uint32), ("sample_count", C.c_uint32),
                 ("seed_salt", C.c_uint32), ("use_bvh", C.c_int32), ("threads", C.c_int32),
-                ("x0", C.c_int32), ("y0", C.c_int32), ("x1", C.c_int32), ("y1", C.c_int32)]
+                ("x0", C.c_int32), ("y0", C.c_int32), ("x1", C.c_int32), ("y1", C.c_int32), ("roulette", C.c_int32)]
 
 
 MODE_MEGAKERNEL, MODE_WAVEFRONT = 0, 1
@@ -115,10 +115,10 @@ class Scene:
                             inst.ctypes.data, prim.ctypes.data, u.ctypes.data, v.ctypes.data, t.ctypes.data)
         return dict(inst=inst, prim=prim, u=u, v=v, t=t)
 
-    def render(self, cam, mode, max_depth, spp, use_bvh=False, seed_salt=0, crop=None, threads=0):
+    def render(self, cam, mode, max_depth, spp, use_bvh=False, seed_salt=0, crop=None, threads=0, roulette=False):
         W, H = cam.img_size[0], cam.img_size[1]
         x0, y0, x1, y1 = crop if crop else (0, 0, W, H)
-        p = orc_render_params(mode, max_depth, spp, seed_salt, int(use_bvh), threads, x0, y0, x1, y1)
+        p = orc_render_params(mode, max_depth, spp, seed_salt, int(use_bvh), threads, x0, y0, x1, y1, int(roulette))
         ch, cw = y1 - y0, x1 - x0
         accum, rgba8 = np.empty((ch, cw, 4), np.float32), np.empty((ch, cw, 4), np.uint8)
         rng = np.empty((ch, cw), np.uint32)

@@ -372,6 +372,8 @@ void emu_intersect(const emu_scene *s, uint64_t n, const float *org, const float
 uint64_t emu_render(const emu_scene *s, int kind, const rt_camera *camera, const rt_render_params *params,
                     float *accum, uint8_t *rgba8, uint32_t *rng_out) {
     RtFrameParams p;
+    memset(&p, 0, sizeof(p));
+    p.roulette = (params->flags & RT_RENDER_ROULETTE) ? 1 : 0;
     p.cam.center = mk3(camera->center[0], camera->center[1], camera->center[2]);
     p.cam.pixel00 = mk3(camera->pixel00_loc[0], camera->pixel00_loc[1], camera->pixel00_loc[2]);
     p.cam.du = mk3(camera->pixel_delta_u[0], camera->pixel_delta_u[1], camera->pixel_delta_u[2]);
