@@ -30,7 +30,9 @@ def test_struct_layouts_match_the_header(pkg):
     assert C.sizeof(cap.rt_material) == 40
     assert C.sizeof(cap.rt_instance) == 4 * 8 + 8 + 64 + 40
     assert C.sizeof(cap.rt_camera) == 56
-    assert C.sizeof(cap.rt_render_params) == 28
+    assert C.sizeof(cap.rt_render_params) == 32
+    assert C.sizeof(cap.rt_group_params) == 24
+    assert C.sizeof(cap.rt_ipc_handle) == 64
     assert C.sizeof(cap.rt_frame) == 40
     assert C.sizeof(cap.rt_scene_stats) == 48
 
