@@ -102,15 +102,16 @@ __global__ void __launch_bounds__(128) k_block_cost(RtScene scene, RtFrameParams
             RtTravStacks ks;
             rt_trav_init(tv, org, dir, 0.0001f, INFINITY);
             cost += 2; /* ray set-up + shading, in units of one traversal step */
+            const RtRayTri rtri = rt_trav_ray_tri(tv);
             while (rt_trav_has_node(tv)) {
                 rt_trav_node_step(scene.bvh, tv, ks);
                 cost++;
                 while (rt_trav_has_tri(tv)) {
-                    rt_trav_tri_step(scene.bvh, tv, ks);
+                    rt_trav_tri_step(scene.bvh, tv, ks, rtri);
                     cost++;
                 }
             }
-            if (rt_shade_segment(scene, tv.best, rng, org, dir, att, rad, res)) break;
+            if (rt_shade_segment(scene, rt_trav_hit_noid(tv), rng, org, dir, att, rad, res)) break;
         }
         atomicAdd(region_cost + region_of(p, x0, y0), cost);
     }
@@ -239,42 +240,75 @@ __device__ __forceinline__ void traverse_phase(const RtBvh &bvh, RtTravState &tv
         const bool out = trav && rt_trav_tri_full(tv);
         if (!m_node || __popc(m_trav & ~m_node) >= thr || __any_sync(full, out)) break;
     }
-    for (;;) { /* drain: lanes that are out of nodes (or nearly out of triangle-stack room) must
-                  finish their triangles; every other lane with triangles pending joins in, and
-                  carries what is left to the next drain */
-        const bool tri = mode == kTraversing && rt_trav_has_tri(tv);
-        const bool must = tri && (!rt_trav_has_node(tv) || tv.tsp >= RT_TSTACK_SIZE - 2);
-        if (!__any_sync(full, must)) break;
-        if (tri) rt_trav_tri_step(bvh, tv, ks);
+    /* drain: lanes that are out of nodes (or nearly out of triangle-stack room) must finish their
+     * triangles; every other lane with triangles pending joins in, and carries what is left to the
+     * next drain. The nine-float shear form lives in registers only here (rt_traverse.h, RtTravState). */
+    {
+        bool tri = mode == kTraversing && rt_trav_has_tri(tv);
+        bool must = tri && (!rt_trav_has_node(tv) || tv.tsp >= RT_TSTACK_SIZE - 2);
+        if (__any_sync(full, must)) {
+            const RtRayTri rtri = rt_trav_ray_tri(tv);
+            do {
+                if (tri) rt_trav_tri_step(bvh, tv, ks, rtri);
+                tri = mode == kTraversing && rt_trav_has_tri(tv);
+                must = tri && (!rt_trav_has_node(tv) || tv.tsp >= RT_TSTACK_SIZE - 2);
+            } while (__any_sync(full, must));
+        }
     }
     if (mode == kTraversing && !rt_trav_has_node(tv)) mode = kHitPending;
 }
 
-#ifndef RT_PIXEL_ORDER
-#define RT_PIXEL_ORDER 0
-#endif
 #ifndef RT_MEGA_MIN_BLOCKS
 #define RT_MEGA_MIN_BLOCKS 8
 #endif
+/* Nine fp16 values in five registers. Between two bounces direction, attenuation and radiance ARE fp16 values
+ * (RayData, F6), so holding them packed across the traversal loses nothing: cvt.rn.f16x2.f32 rounds each half
+ * exactly like the scalar conversion of round_half3. */
+struct HalfRay {
+    uint32_t dxy, dz_ax, ayz, rxy, rz;
+};
+__device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
+    const __half2 h = __floats2half2_rn(lo, hi);
+    return *reinterpret_cast<const uint32_t *>(&h);
+}
+__device__ __forceinline__ float h_lo(uint32_t v) { return __half2float(__ushort_as_half((unsigned short)(v & 0xffffu))); }
+__device__ __forceinline__ float h_hi(uint32_t v) { return __half2float(__ushort_as_half((unsigned short)(v >> 16))); }
+__device__ __forceinline__ HalfRay pack_ray(f3 dir, f3 att, f3 rad) {
+    HalfRay h;
+    h.dxy = pack_h2(dir.x, dir.y);
+    h.dz_ax = pack_h2(dir.z, att.x);
+    h.ayz = pack_h2(att.y, att.z);
+    h.rxy = pack_h2(rad.x, rad.y);
+    h.rz = pack_h2(rad.z, 0.0f);
+    return h;
+}
+__device__ __forceinline__ f3 ray_dir(const HalfRay &h) { return mk3(h_lo(h.dxy), h_hi(h.dxy), h_lo(h.dz_ax)); }
+__device__ __forceinline__ f3 ray_att(const HalfRay &h) { return mk3(h_hi(h.dz_ax), h_lo(h.ayz), h_hi(h.ayz)); }
+__device__ __forceinline__ f3 ray_rad(const HalfRay &h) { return mk3(h_lo(h.rxy), h_hi(h.rxy), h_lo(h.rz)); }
+
+/* What a lane carries across the traversal loop is kept to 13 registers next to the traversal state (18): pixel
+ * coordinates in one word, sample and bounce counters, the stream, the running sum, the fp16 ray state packed
+ * (HalfRay), the ray counter in 32 bits; the ray origin lives in the traversal state only. Sample chains and the
+ * resume count are rare options: chains are a template parameter (no registers in the default kernel) and the count
+ * of earlier frames is re-read from the accumulation buffer when the pixel finishes. */
+template <bool CHAINS>
 __global__ void __launch_bounds__(kMegaBlock, RT_MEGA_MIN_BLOCKS) k_megakernel(RtScene scene, RtFrameParams p, RtFrameOut out,
                                                            uint32_t *work_counter, unsigned long long *ray_counter,
                                                            const uint32_t *__restrict__ order) {
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const RtBlockGeom g = rt_block_geom(p);
-    const uint32_t n_chains = p.chains > 1u ? p.chains : 1u;
+    const uint32_t n_chains = CHAINS ? p.chains : 1u;
     const uint32_t n_work = g.n_blocks * n_chains * 32u; /* pixel slots, 32 per (8x4 block, sample chain) */
     const size_t n_pix = (size_t)p.cam.w * (size_t)p.cam.h;
-    unsigned long long rays = 0;
+    uint32_t rays = 0; /* per lane: < 2^32 for any frame that finishes */
     int mode = kNeedPixel;
-    int x = 0, y = 0;
+    uint32_t xy = 0;
     uint32_t s = 0, depth = 0, chain = 0, spp_c = p.spp; /* sample chain of the lane's pixel, samples it contributes */
     XorShift32 rng;
     rng.a = 0;
     f3 sum = mk3(0.0f, 0.0f, 0.0f);
-    float base_count = 0.0f; /* samples accumulated by earlier frames (RT_RENDER_RESUME) */
-    RtRayState r;
-    r.org = r.dir = r.att = r.rad = sum;
+    HalfRay hr = pack_ray(sum, sum, sum);
     RtTravState tv;
     SmemStacks<kMegaBlock> ks;
 #if RT_SMEM_TRI || RT_SMEM_NODE
@@ -286,17 +320,16 @@ __global__ void __launch_bounds__(kMegaBlock, RT_MEGA_MIN_BLOCKS) k_megakernel(R
     tv.sp = 0;
     tv.tsp = 0;
     tv.ng_y = 0;
+    tv.org = sum;
 
     for (;;) {
         /* ---------------- regenerate ---------------- */
         if (mode == kHitPending) {
-            f3 org = r.org, dir = r.dir, att = r.att, rad = r.rad, res = mk3(0.0f, 0.0f, 0.0f);
-            bool done = rt_shade_segment(scene, tv.best, rng, org, dir, att, rad, res);
+            f3 org = tv.org, dir = ray_dir(hr), att = ray_att(hr), rad = ray_rad(hr), res = mk3(0.0f, 0.0f, 0.0f);
+            bool done = rt_shade_segment(scene, rt_trav_hit_noid(tv), rng, org, dir, att, rad, res);
             done = rt_after_segment(p, done, depth, att, rng, res);
-            r.org = org; /* src/render_megakernel.cpp:41-55: re-quantise the ray state (F6) */
-            r.dir = round_half3(dir);
-            r.att = round_half3(att);
-            r.rad = round_half3(rad);
+            tv.org = org;                 /* src/render_megakernel.cpp:41-55: re-quantise the ray state (F6) */
+            hr = pack_ray(dir, att, rad); /* fp32 -> fp16, round to nearest even */
             if (done) {
                 sum = sum + res;
                 s++;
@@ -307,24 +340,29 @@ __global__ void __launch_bounds__(kMegaBlock, RT_MEGA_MIN_BLOCKS) k_megakernel(R
         }
         for (;;) { /* warp-uniform: runs until no lane is waiting for a pixel */
             if (mode == kNeedRay) {
-                while (p.max_depth == 0 && s < spp_c) { /* the bounce loop never runs: black sample */
+                const int x = (int)(xy & 0xffffu), y = (int)(xy >> 16);
+                const uint32_t spp_l = CHAINS ? spp_c : p.spp;
+                while (p.max_depth == 0 && s < spp_l) { /* the bounce loop never runs: black sample */
                     rng.next();
                     rng.next();
                     s++;
                 }
-                if (s == spp_c) { /* pixel finished: :154-158 mean, gamma, image write */
-                    const size_t pix = (size_t)y * (size_t)p.cam.w + (size_t)x, vp = (size_t)chain * n_pix + pix;
-                    const float count = base_count + (float)spp_c;
+                if (s == spp_l) { /* pixel finished: :154-158 mean, gamma, image write */
+                    const size_t pix = (size_t)y * (size_t)p.cam.w + (size_t)x, vp = (CHAINS ? (size_t)chain * n_pix : 0) + pix;
+                    const float base_count = p.resume ? out.accum[vp].w : 0.0f; /* samples accumulated by earlier frames */
+                    const float count = base_count + (float)spp_l;
                     out.accum[vp] = make_float4(sum.x, sum.y, sum.z, count);
                     out.rng[vp] = rng.a;
-                    if (n_chains == 1u) { /* with sample chains k_combine_chains sums the planes and writes the image */
+                    if (!CHAINS) { /* with sample chains k_combine_chains sums the planes and writes the image */
                         const uint32_t px = rt_resolve_pixel(sum.x, sum.y, sum.z, count);
                         out.rgba8[pix] = px;
                         if (out.gather) out.gather[pix] = px; /* tile shards: straight into the destination rank's image */
                     }
                     mode = kNeedPixel;
                 } else {
-                    r = rt_camera_ray(p.cam, x, y, rng); /* 2 draws (F5) */
+                    const RtRayState r = rt_camera_ray(p.cam, x, y, rng); /* 2 draws (F5) */
+                    tv.org = r.org;
+                    hr = pack_ray(r.dir, r.att, r.rad);
                     depth = 0;
                     mode = kStart;
                 }
@@ -340,7 +378,7 @@ __global__ void __launch_bounds__(kMegaBlock, RT_MEGA_MIN_BLOCKS) k_megakernel(R
                 if (idx >= n_work) {
                     mode = kExhausted;
                 } else {
-                    const uint32_t in = idx & 31u, item = idx >> 5, blk = item / n_chains; /* (block, chain) pairs */
+                    const uint32_t in = idx & 31u, item = idx >> 5, blk = CHAINS ? item / n_chains : item; /* (block, chain) pairs */
                     uint32_t x0, y0;
                     if (order) { /* blocks sorted by decreasing cost class (k_block_cost) */
                         const uint32_t e = __ldg(order + blk);
@@ -349,21 +387,21 @@ __global__ void __launch_bounds__(kMegaBlock, RT_MEGA_MIN_BLOCKS) k_megakernel(R
                     } else {
                         rt_block_origin(p, g, blk, x0, y0);
                     }
-                    x = (int)(x0 + (in & 7u));
-                    y = (int)(y0 + (in >> 3));
+                    const int x = (int)(x0 + (in & 7u)), y = (int)(y0 + (in >> 3));
                     if (x < p.cam.w && y < p.cam.h && rt_owns_pixel(p, x, y)) {
-                        chain = item - blk * n_chains;
-                        spp_c = rt_chain_spp(p.spp, p.chains, chain);
+                        xy = (uint32_t)x | ((uint32_t)y << 16);
+                        if (CHAINS) {
+                            chain = item - blk * n_chains;
+                            spp_c = rt_chain_spp(p.spp, p.chains, chain);
+                        }
                         if (p.resume) { /* carry on where the previous frame stopped */
-                            const size_t vp = (size_t)chain * n_pix + (size_t)y * (size_t)p.cam.w + (size_t)x;
+                            const size_t vp = (CHAINS ? (size_t)chain * n_pix : 0) + (size_t)y * (size_t)p.cam.w + (size_t)x;
                             const float4 a = out.accum[vp];
                             rng.a = out.rng[vp];
                             sum = mk3(a.x, a.y, a.z);
-                            base_count = a.w;
                         } else {
-                            rng.a = rt_pixel_seed(p.wavefront_seed, x, y, p.cam.w, p.cam.h) ^ p.seed_salt ^ (chain * RT_CHAIN_SALT);
+                            rng.a = rt_pixel_seed(p.wavefront_seed, x, y, p.cam.w, p.cam.h) ^ p.seed_salt ^ (CHAINS ? chain * RT_CHAIN_SALT : 0u);
                             sum = mk3(0.0f, 0.0f, 0.0f);
-                            base_count = 0.0f;
                         }
                         s = 0;
                         mode = kNeedRay;
@@ -372,7 +410,7 @@ __global__ void __launch_bounds__(kMegaBlock, RT_MEGA_MIN_BLOCKS) k_megakernel(R
             }
         }
         if (mode == kStart) {
-            rt_trav_init(tv, r.org, r.dir, 0.0001f, INFINITY);
+            rt_trav_init(tv, tv.org, ray_dir(hr), 0.0001f, INFINITY);
             rays++;
             mode = kTraversing;
         }
@@ -381,9 +419,10 @@ __global__ void __launch_bounds__(kMegaBlock, RT_MEGA_MIN_BLOCKS) k_megakernel(R
         if (!act0) break; /* every lane is exhausted */
         traverse_phase(scene.bvh, tv, ks, mode, p.tune_refill);
     }
+    unsigned long long total = rays;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) rays += __shfl_xor_sync(full, rays, o);
-    if (lane == 0 && rays) atomicAdd(ray_counter, rays);
+    for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(full, total, o);
+    if (lane == 0 && total) atomicAdd(ray_counter, total);
 }
 
 /* ------------------------------------------------------------------------------ megakernel, K contexts per lane */
@@ -613,7 +652,7 @@ __global__ void __launch_bounds__(kMegaBlock, RT_MEGA_MIN_BLOCKS) k_megakernel_c
         }
         traverse_phase(scene.bvh, tv, ks, mode, p.tune_refill);
         if (mode == kHitPending) { /* park the hit; the lane switches at the top of the next round */
-            cx[opaque_index(cur * kCtxQ + 5)] = make_float4(tv.best.t, tv.best.u, tv.best.v, __uint_as_float(tv.best.tri));
+            cx[opaque_index(cur * kCtxQ + 5)] = make_float4(tv.t, tv.u, tv.v, __uint_as_float(tv.tri));
             st = (st & ~(7u << (3 * cur))) | ((uint32_t)cHit << (3 * cur));
             cur = -1;
         }
@@ -694,7 +733,7 @@ __global__ void __launch_bounds__(kWfBlock, RT_EXT_MIN_BLOCKS) k_wf_extend(RtSce
     tv.ng_y = 0;
     for (;;) {
         if (mode == kHitPending) {
-            w.hit[pix] = make_float4(tv.best.t, tv.best.u, tv.best.v, __uint_as_float(tv.best.tri));
+            w.hit[pix] = make_float4(tv.t, tv.u, tv.v, __uint_as_float(tv.tri));
             mode = kNeedPixel;
         }
         const unsigned need = __ballot_sync(full, mode == kNeedPixel);
@@ -829,7 +868,7 @@ __global__ void __launch_bounds__(kWfBlock, RT_EXT_MIN_BLOCKS) k_wf_persistent(R
             tv.ng_y = 0;
             for (;;) {
                 if (mode == kHitPending) {
-                    w.hit[pix] = make_float4(tv.best.t, tv.best.u, tv.best.v, __uint_as_float(tv.best.tri));
+                    w.hit[pix] = make_float4(tv.t, tv.u, tv.v, __uint_as_float(tv.tri));
                     mode = kNeedPixel;
                 }
                 const unsigned need = __ballot_sync(full, mode == kNeedPixel);
@@ -973,7 +1012,7 @@ __global__ void __launch_bounds__(kWfBlock, RT_EXT_MIN_BLOCKS) k_wf_flow(RtScene
             const unsigned m = __ballot_sync(full, fin);
             if (m) {
                 if (fin) {
-                    w.hit[pix] = make_float4(tv.best.t, tv.best.u, tv.best.v, __uint_as_float(tv.best.tri));
+                    w.hit[pix] = make_float4(tv.t, tv.u, tv.v, __uint_as_float(tv.tri));
                     hitq[(hit_tail + (uint32_t)__popc(m & lt)) & mask] = pix;
                     mode = kNeedPixel;
                 }
@@ -1102,7 +1141,7 @@ cudaError_t rt_megakernel_grid(int sm_count, int tune_ctx, int *grid) {
     case 2: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_megakernel_ctx<2>, kMegaBlock, 0); break;
     case 3: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_megakernel_ctx<3>, kMegaBlock, 0); break;
     case 4: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_megakernel_ctx<4>, kMegaBlock, 0); break;
-    default: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_megakernel, kMegaBlock, 0); break;
+    default: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_megakernel<false>, kMegaBlock, 0); break;
     }
     if (e != cudaSuccess) return e;
     if (per_sm < 1) per_sm = 1;
@@ -1118,7 +1157,10 @@ cudaError_t rt_launch_megakernel(cudaStream_t st, int grid, const RtScene &scene
     case 2: k_megakernel_ctx<2><<<grid, kMegaBlock, 0, st>>>(scene, p, out, work_counter, ray_counter, order); break;
     case 3: k_megakernel_ctx<3><<<grid, kMegaBlock, 0, st>>>(scene, p, out, work_counter, ray_counter, order); break;
     case 4: k_megakernel_ctx<4><<<grid, kMegaBlock, 0, st>>>(scene, p, out, work_counter, ray_counter, order); break;
-    default: k_megakernel<<<grid, kMegaBlock, 0, st>>>(scene, p, out, work_counter, ray_counter, order); break;
+    default:
+        if (p.chains > 1u) k_megakernel<true><<<grid, kMegaBlock, 0, st>>>(scene, p, out, work_counter, ray_counter, order);
+        else k_megakernel<false><<<grid, kMegaBlock, 0, st>>>(scene, p, out, work_counter, ray_counter, order);
+        break;
     }
     return cudaGetLastError();
 }

@@ -127,21 +127,40 @@ RT_HD void rt_ldg2(const rt_float4 *p, rt_float4 &a, rt_float4 &b) {
 #endif
 }
 
-/* byte j of w -> the float 1 + b * 2^-15, built with ONE byte permute (no I2F: the conversion
- * pipe is the narrowest one on sm_100a and 48 conversions per node visit made it the busiest):
- * 0x3F800000 | b << 8. The node test folds the "1 +" and the 2^-15 into its per-node constants. */
-template <int J, int UNIQ>
+/* global id of the triangle in leaf slot `slot` (RT_MISS -> RT_MISS: no hit yet loses every tie) */
+RT_HD uint32_t rt_tri_gid(const RtBvh &bvh, uint32_t slot) {
+    return slot == RT_MISS ? RT_MISS : rt_f2u(rt_ldg(bvh.tris + (size_t)slot * RT_TRI_VEC4 + 2).w);
+}
+
+/* byte j of w -> a float that encodes the quantised plane b, with ONE instruction and no I2F (the
+ * conversion pipe is the narrowest one on sm_100a; 48 conversions per node visit made it the busiest):
+ *   PRMT (ALU pipe): 0x3F800000 | b << 8         = 1 + b * 2^-15   one byte permute
+ *   IDP.4A (FMA pipe): 0x3F800000 + 128 * b      = 1 + b * 2^-16   dot product of the four bytes of w with
+ *                                                                  (0, .., 128, .., 0), accumulated onto 1.0f
+ * The node test folds the "1 +" and the 2^-15 / 2^-16 into its per-node constants. Which of the two an
+ * axis uses is a compile-time choice (RT_BYTE_IDP_MASK, bit a = axis a through IDP.4A): a node visit has
+ * ~150 ALU-pipe instructions (48 byte extractions, 32 FMNMX, selects, the hit mask) against ~75 on the FMA
+ * pipe, and both pipes take a warp instruction every other cycle, so the byte extractions are what can
+ * be moved to balance them (tools/microbench/pipe_bench.cu, profiles/README.md). */
+#ifndef RT_BYTE_IDP_MASK
+#define RT_BYTE_IDP_MASK 3 /* measured on B200 (slim state): x, y through IDP.4A, z through PRMT: C3 +0.6 / +2.5 %, C4 +0.8 / +2.7 % (megakernel / wavefront) over all-PRMT */
+#endif
+template <int J, int UNIQ, int IDP>
 RT_HD float rt_byte_to_unit(uint32_t w, uint32_t one_bits /* 0x3F800000, held in a register */) {
 #if RT_DEVICE_CODE
-    /* selector: byte0 <- one.b0, byte1 <- w.bJ, byte2 <- one.b2, byte3 <- one.b3. Only the low 16 bits
-     * of a PRMT selector are read; UNIQ makes every call site's constant different so that ptxas
-     * encodes it as an immediate instead of hoisting four shared selectors into registers and
-     * re-materialising them before each of the 48 permutes of a node test (measured: +48 moves). */
     uint32_t r;
-    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(w), "r"(one_bits), "n"(0x7604 | (J << 4) | (UNIQ << 16)));
+    if (IDP) {
+        asm("dp4a.u32.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(w), "n"(128u << (8 * J)), "r"(one_bits));
+    } else {
+        /* selector: byte0 <- one.b0, byte1 <- w.bJ, byte2 <- one.b2, byte3 <- one.b3. Only the low 16 bits
+         * of a PRMT selector are read; UNIQ makes every call site's constant different so that ptxas
+         * encodes it as an immediate instead of hoisting four shared selectors into registers and
+         * re-materialising them before each of the 48 permutes of a node test (measured: +48 moves). */
+        asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(w), "r"(one_bits), "n"(0x7604 | (J << 4) | (UNIQ << 16)));
+    }
     return __uint_as_float(r);
 #else
-    return rt_u2f(one_bits | (((w >> (8 * J)) & 0xffu) << 8));
+    return IDP ? rt_u2f(one_bits + (((w >> (8 * J)) & 0xffu) << 7)) : rt_u2f(one_bits | (((w >> (8 * J)) & 0xffu) << 8));
 #endif
 }
 /* PRMT takes one immediate: if the compiler sees both 0x3F800000 and the selector as constants it keeps
@@ -176,7 +195,7 @@ RT_HD float rt_shear(f3 p, f3 m) { return rt_fma(p.x, m.x, rt_fma(p.y, m.y, p.z 
 /* The direction-only part of the per-ray set-up (six IEEE divisions), separated so that the persistent
  * megakernel can compute it while it shades (many lanes active) and park it with the ray: starting the
  * traversal later is then a handful of loads and selects. code = kx | ky << 2 | kz << 4 | neg << 6 |
- * oct_inv << 9 (see RtRayBox). */
+ * oct_inv << 9 (see the wide-node test). */
 struct RtRayPre {
     f3 rcp;             /* 1 / dir with |dir| clamped away from 0 (box slabs) */
     float nSx, nSy, Sz; /* -dir[kx]/dir[kz], -dir[ky]/dir[kz], 1/dir[kz] (triangle shear) */
@@ -231,10 +250,12 @@ RT_HD RtRayTri rt_ray_tri_from_pre(f3 org, const RtRayPre &q) {
     return r;
 }
 
-/* Updates `best` when triangle (v0, v1, v2) is a closer hit (or an equal-t hit with a lower
- * id). Exactly the oracle's operation order. */
-RT_HD void rt_tri_test(const RtRayTri &r, f3 v0, f3 v1, f3 v2, uint32_t slot, uint32_t gid,
-                       float tnear, RtHit &best) {
+/* Updates the closest hit (t, u, v, slot) when triangle (v0, v1, v2) is closer, or equally far with a lower
+ * id. Exactly the oracle's operation order. The id of the current closest hit is only needed when the two
+ * distances are EQUAL (rare: coplanar duplicates, shared edges), so it is not carried in registers but
+ * re-read from the record of the current hit (third vertex, w). */
+RT_HD void rt_tri_test(const RtBvh &bvh, const RtRayTri &r, f3 v0, f3 v1, f3 v2, uint32_t slot, uint32_t gid, float tnear,
+                       float &best_t, float &best_u, float &best_v, uint32_t &best_tri) {
     const f3 A = v0 - r.org, B = v1 - r.org, C = v2 - r.org;
     const float Ax = rt_shear(A, r.mx), Ay = rt_shear(A, r.my);
     const float Bx = rt_shear(B, r.mx), By = rt_shear(B, r.my);
@@ -258,32 +279,19 @@ RT_HD void rt_tri_test(const RtRayTri &r, f3 v0, f3 v1, f3 v2, uint32_t slot, ui
     const float rcp = rt_div(1.0f, det);
     const float t = T * rcp;
     if (!(t > tnear)) return;
-    if (t < best.t || (t == best.t && gid < best.gid)) {
-        best.t = t;
-        best.u = V * rcp;
-        best.v = W * rcp;
-        best.tri = slot;
-        best.gid = gid;
+    if (t < best_t || (t == best_t && gid < rt_tri_gid(bvh, best_tri))) {
+        best_t = t;
+        best_u = V * rcp;
+        best_v = W * rcp;
+        best_tri = slot;
     }
 }
 
 /* ---- wide-node test ------------------------------------------------------------------ */
-struct RtRayBox {
-    f3 org;
-    f3 rcp;          /* 1 / dir with |dir| clamped away from 0 */
-    uint32_t neg;    /* bit0: dir.x < 0, bit1: dir.y < 0, bit2: dir.z < 0 */
-    uint32_t oct_inv; /* 7 - octant: the inner child in slot s has visiting priority s ^ oct_inv */
-};
-
-RT_HD RtRayBox rt_ray_box_from_pre(f3 org, const RtRayPre &q) {
-    RtRayBox r;
-    r.org = org;
-    r.rcp = q.rcp;
-    r.neg = (q.code >> 6) & 7u;
-    r.oct_inv = (q.code >> 9) & 7u;
-    return r;
-}
-
+/* The ray enters the node test as origin, 1 / dir (|dir| clamped away from 0) and oct_inv = 7 - octant,
+ * octant = (dir.x < 0) << 2 | (dir.y < 0) << 1 | (dir.z < 0): the inner child in slot s has visiting
+ * priority s ^ oct_inv, and a clear bit 2 / 1 / 0 of oct_inv means dir.x / y / z is negative (near and far
+ * planes swap). */
 /* bit i of x -> bit i ^ k (k = 0..7): the octant permutation of a byte of child-hit flags */
 RT_HD uint32_t rt_xor_perm8(uint32_t x, uint32_t k) {
     if (k & 1u) x = ((x & 0x55u) << 1) | ((x >> 1) & 0x55u);
@@ -308,9 +316,10 @@ RT_HD void rt_child_test(uint32_t nx, uint32_t ny, uint32_t nz, uint32_t fx, uin
                          float Sy, float Sz, float onx, float ony, float onz, float ofx, float ofy, float ofz,
                          float tmin, float tmax_pad, uint32_t one, uint32_t &hits) {
     float tnx, tny, tnz, tfx, tfy, tfz; /* near and far plane of one axis share the multiplier: one FFMA2 */
-    rt_fma2(rt_byte_to_unit<J, 1 + 0 + 6 * J + 24 * H>(nx, one), rt_byte_to_unit<J, 1 + 3 + 6 * J + 24 * H>(fx, one), Sx, onx, ofx, tnx, tfx);
-    rt_fma2(rt_byte_to_unit<J, 1 + 1 + 6 * J + 24 * H>(ny, one), rt_byte_to_unit<J, 1 + 4 + 6 * J + 24 * H>(fy, one), Sy, ony, ofy, tny, tfy);
-    rt_fma2(rt_byte_to_unit<J, 1 + 2 + 6 * J + 24 * H>(nz, one), rt_byte_to_unit<J, 1 + 5 + 6 * J + 24 * H>(fz, one), Sz, onz, ofz, tnz, tfz);
+    constexpr int IX = RT_BYTE_IDP_MASK & 1, IY = (RT_BYTE_IDP_MASK >> 1) & 1, IZ = (RT_BYTE_IDP_MASK >> 2) & 1;
+    rt_fma2(rt_byte_to_unit<J, 1 + 0 + 6 * J + 24 * H, IX>(nx, one), rt_byte_to_unit<J, 1 + 3 + 6 * J + 24 * H, IX>(fx, one), Sx, onx, ofx, tnx, tfx);
+    rt_fma2(rt_byte_to_unit<J, 1 + 1 + 6 * J + 24 * H, IY>(ny, one), rt_byte_to_unit<J, 1 + 4 + 6 * J + 24 * H, IY>(fy, one), Sy, ony, ofy, tny, tfy);
+    rt_fma2(rt_byte_to_unit<J, 1 + 2 + 6 * J + 24 * H, IZ>(nz, one), rt_byte_to_unit<J, 1 + 5 + 6 * J + 24 * H, IZ>(fz, one), Sz, onz, ofz, tnz, tfz);
     const float cmin = rt_max(rt_max3(tnx, tny, tnz), tmin);
     const float cmax = rt_min(rt_min3(tfx, tfy, tfz), tmax_pad);
     rt_or_if_le<1u << (4 * H + J)>(cmin, cmax, hits);
@@ -318,12 +327,12 @@ RT_HD void rt_child_test(uint32_t nx, uint32_t ny, uint32_t nz, uint32_t fx, uin
 
 /* four children (one 32-bit word of every quantised plane) */
 template <int H>
-RT_HD void rt_half_test(const RtRayBox &rb, uint32_t qlox, uint32_t qloy, uint32_t qloz, uint32_t qhix,
+RT_HD void rt_half_test(uint32_t oct_inv, uint32_t qlox, uint32_t qloy, uint32_t qloz, uint32_t qhix,
                         uint32_t qhiy, uint32_t qhiz, float Sx, float Sy, float Sz, float onx, float ony, float onz,
                         float ofx, float ofy, float ofz, float tmin, float tmax_pad, uint32_t one, uint32_t &hits) {
-    const uint32_t nx = (rb.neg & 1u) ? qhix : qlox, fx = (rb.neg & 1u) ? qlox : qhix;
-    const uint32_t ny = (rb.neg & 2u) ? qhiy : qloy, fy = (rb.neg & 2u) ? qloy : qhiy;
-    const uint32_t nz = (rb.neg & 4u) ? qhiz : qloz, fz = (rb.neg & 4u) ? qloz : qhiz;
+    const uint32_t nx = (oct_inv & 4u) ? qlox : qhix, fx = (oct_inv & 4u) ? qhix : qlox;
+    const uint32_t ny = (oct_inv & 2u) ? qloy : qhiy, fy = (oct_inv & 2u) ? qhiy : qloy;
+    const uint32_t nz = (oct_inv & 1u) ? qloz : qhiz, fz = (oct_inv & 1u) ? qhiz : qloz;
     rt_child_test<0, H>(nx, ny, nz, fx, fy, fz, Sx, Sy, Sz, onx, ony, onz, ofx, ofy, ofz, tmin, tmax_pad, one, hits);
     rt_child_test<1, H>(nx, ny, nz, fx, fy, fz, Sx, Sy, Sz, onx, ony, onz, ofx, ofy, ofz, tmin, tmax_pad, one, hits);
     rt_child_test<2, H>(nx, ny, nz, fx, fy, fz, Sx, Sy, Sz, onx, ony, onz, ofx, ofy, ofz, tmin, tmax_pad, one, hits);
@@ -332,32 +341,34 @@ RT_HD void rt_half_test(const RtRayBox &rb, uint32_t qlox, uint32_t qloy, uint32
 
 /* returns the hit flags of one wide node in SLOT order: bit s = the ray's interval [tmin, tmax_pad]
  * overlaps the (conservatively padded) box of slot s. Empty slots never hit (inverted boxes). */
-RT_HD uint32_t rt_node_test(const RtRayBox &rb, rt_uint4 n0, rt_uint4 n2, rt_uint4 n3, rt_uint4 n4, float tmin,
+RT_HD uint32_t rt_node_test(f3 org, f3 rcp, uint32_t oct_inv, rt_uint4 n0, rt_uint4 n2, rt_uint4 n3, rt_uint4 n4, float tmin,
                             float tmax_pad) {
     const float sx = rt_u2f((n0.w & 0xffu) << 23), sy = rt_u2f(((n0.w >> 8) & 0xffu) << 23),
                 sz = rt_u2f(((n0.w >> 16) & 0xffu) << 23);
     /* plane t = q*id + o with id = 2^e/d, o = (p - org)/d */
-    const float idx = sx * rb.rcp.x, idy = sy * rb.rcp.y, idz = sz * rb.rcp.z;
-    const float ox = (rt_u2f(n0.x) - rb.org.x) * rb.rcp.x, oy = (rt_u2f(n0.y) - rb.org.y) * rb.rcp.y,
-                oz = (rt_u2f(n0.z) - rb.org.z) * rb.rcp.z;
-    /* q enters as u = 1 + q*2^-15 (rt_byte_to_unit): t = u*S + (o - S), S = id * 2^15 (exact). */
-    const float Sx = idx * 32768.0f, Sy = idy * 32768.0f, Sz = idz * 32768.0f;
+    const float idx = sx * rcp.x, idy = sy * rcp.y, idz = sz * rcp.z;
+    const float ox = (rt_u2f(n0.x) - org.x) * rcp.x, oy = (rt_u2f(n0.y) - org.y) * rcp.y, oz = (rt_u2f(n0.z) - org.z) * rcp.z;
+    /* q enters as u = 1 + q*2^-k (rt_byte_to_unit; k = 15 for PRMT, 16 for IDP.4A): t = u*S + (o - S), S = id * 2^k (exact). */
+    constexpr float KX = (RT_BYTE_IDP_MASK & 1) ? 65536.0f : 32768.0f, KY = (RT_BYTE_IDP_MASK & 2) ? 65536.0f : 32768.0f,
+                    KZ = (RT_BYTE_IDP_MASK & 4) ? 65536.0f : 32768.0f;
+    const float Sx = idx * KX, Sy = idy * KY, Sz = idz * KZ;
     /* Conservative slabs. The sum cancels when the ray starts next to a plane that lies far from
      * the node origin p (|q*id|, |o| >> |t|), e.g. a bounce ray leaving an axis-aligned wall. The
      * roundings of o, of o - S and of the fma are bounded by 2^-24 * (3|o| + 2|S|) plus the three
      * roundings of the plain formula, 3 * 2^-24 * (255|id| + |o|); near planes are moved back and
-     * far planes forward by e = 2^-21 |o| + 2^-8 |id| (> the bound, ~0.4 % of a quantisation
+     * far planes forward by e = 2^-21 |o| + 2^(k-23) |id| (> the bound, 0.4 - 0.8 % of a quantisation
      * step), so rounding can never cull a box whose triangle the exact-difference triangle test
      * would accept. */
-    const float ex = rt_fma(fabsf(idx), 0.00390625f, fabsf(ox) * 4.76837158e-7f),
-                ey = rt_fma(fabsf(idy), 0.00390625f, fabsf(oy) * 4.76837158e-7f),
-                ez = rt_fma(fabsf(idz), 0.00390625f, fabsf(oz) * 4.76837158e-7f);
+    constexpr float PX = KX * 1.1920929e-7f, PY = KY * 1.1920929e-7f, PZ = KZ * 1.1920929e-7f; /* 2^(k-23) */
+    const float ex = rt_fma(fabsf(idx), PX, fabsf(ox) * 4.76837158e-7f),
+                ey = rt_fma(fabsf(idy), PY, fabsf(oy) * 4.76837158e-7f),
+                ez = rt_fma(fabsf(idz), PZ, fabsf(oz) * 4.76837158e-7f);
     const float onx = (ox - ex) - Sx, ony = (oy - ey) - Sy, onz = (oz - ez) - Sz;
     const float ofx = (ox + ex) - Sx, ofy = (oy + ey) - Sy, ofz = (oz + ez) - Sz;
     uint32_t hits = 0;
     const uint32_t one = rt_unit_bits();
-    rt_half_test<0>(rb, n2.x, n2.z, n3.x, n3.z, n4.x, n4.z, Sx, Sy, Sz, onx, ony, onz, ofx, ofy, ofz, tmin, tmax_pad, one, hits);
-    rt_half_test<1>(rb, n2.y, n2.w, n3.y, n3.w, n4.y, n4.w, Sx, Sy, Sz, onx, ony, onz, ofx, ofy, ofz, tmin, tmax_pad, one, hits);
+    rt_half_test<0>(oct_inv, n2.x, n2.z, n3.x, n3.z, n4.x, n4.z, Sx, Sy, Sz, onx, ony, onz, ofx, ofy, ofz, tmin, tmax_pad, one, hits);
+    rt_half_test<1>(oct_inv, n2.y, n2.w, n3.y, n3.w, n4.y, n4.w, Sx, Sy, Sz, onx, ony, onz, ofx, ofy, ofz, tmin, tmax_pad, one, hits);
     return hits;
 }
 
@@ -376,14 +387,33 @@ RT_HD uint32_t rt_node_test(const RtRayBox &rb, rt_uint4 n0, rt_uint4 n2, rt_uin
  * of nodes), then drain the pending triangles together. Deferring the triangle tests only delays the
  * shrinking of tmax; the closest hit (min t, then min id) does not depend on the test order. */
 #define RT_TSTACK_SIZE 8
+/* Kept small on purpose: the node test needs ~40 registers of its own (20 of node data), and whatever of
+ * this state does not fit next to it in the kernels' 64 registers is re-loaded from local memory on EVERY
+ * node visit (round 1: ten spill loads per visit, a quarter of the L1TEX sectors of the node loop). So the
+ * triangle shear is held as its three scalars + axis code (the nine-float form is rebuilt per triangle
+ * batch, rt_trav_ray_tri), the padded tmax is recomputed from the hit distance, the sign bits are read off
+ * oct_inv, and the closest hit's id (needed for exact-t ties only) is re-read from the triangle record. */
 struct RtTravState {
-    RtRayTri rt;
-    RtRayBox rb;
-    float tnear, tmax_pad;
-    RtHit best;
+    f3 org;
+    f3 rcp;             /* 1 / dir with |dir| clamped away from 0 */
+    float nSx, nSy, Sz; /* triangle shear (RtRayPre) */
+    uint32_t code;      /* RtRayPre::code: kx | ky << 2 | kz << 4 | neg << 6 | oct_inv << 9 */
+    float tnear;
+    float t, u, v;      /* closest hit so far (t = tfar: none) */
+    uint32_t tri;       /* its slot in the leaf-ordered triangle array, RT_MISS when nothing was hit */
     uint32_t ng_x, ng_y; /* current node group: (child base, child hit bits << 24 | imask) */
     int sp, tsp;
 };
+RT_HD uint32_t rt_trav_oct_inv(const RtTravState &s) { return (s.code >> 9) & 7u; }
+RT_HD RtRayTri rt_trav_ray_tri(const RtTravState &s) {
+    RtRayPre q;
+    q.rcp = s.rcp;
+    q.nSx = s.nSx;
+    q.nSy = s.nSy;
+    q.Sz = s.Sz;
+    q.code = s.code;
+    return rt_ray_tri_from_pre(s.org, q);
+}
 
 /* The dynamically indexed storage is kept apart from RtTravState so that the scalar state is
  * promoted to registers; entries are (base, bits) pairs packed in 64 bits (one access each).
@@ -403,15 +433,17 @@ struct RtTravStacks {
 RT_HD uint64_t rt_pack2(uint32_t x, uint32_t y) { return (uint64_t)x | ((uint64_t)y << 32); }
 
 RT_HD void rt_trav_init_pre(RtTravState &s, f3 org, const RtRayPre &pre, float tnear, float tfar) {
-    s.best.t = tfar;
-    s.best.u = 0.0f;
-    s.best.v = 0.0f;
-    s.best.tri = RT_MISS;
-    s.best.gid = RT_MISS;
-    s.rt = rt_ray_tri_from_pre(org, pre);
-    s.rb = rt_ray_box_from_pre(org, pre);
+    s.org = org;
+    s.rcp = pre.rcp;
+    s.nSx = pre.nSx;
+    s.nSy = pre.nSy;
+    s.Sz = pre.Sz;
+    s.code = pre.code;
     s.tnear = tnear;
-    s.tmax_pad = tfar * RT_BOX_PAD;
+    s.t = tfar;
+    s.u = 0.0f;
+    s.v = 0.0f;
+    s.tri = RT_MISS;
     s.sp = 0;
     s.tsp = 0;
     s.ng_x = 0;
@@ -436,7 +468,8 @@ RT_HD void rt_trav_node_step(const RtBvh &bvh, RtTravState &s, Stacks &k) {
         k.node_put(s.sp, rt_pack2(s.ng_x, s.ng_y));
         s.sp++;
     }
-    const uint32_t slot = ((uint32_t)bit - 24u) ^ s.rb.oct_inv;
+    const uint32_t oct_inv = rt_trav_oct_inv(s);
+    const uint32_t slot = ((uint32_t)bit - 24u) ^ oct_inv;
     const uint32_t rel = (uint32_t)rt_popc(imask & ~(0xffffffffu << slot));
     const rt_uint4 *np = bvh.nodes + (size_t)(s.ng_x + rel) * RT_NODE_VEC4;
     rt_uint4 n0, n1, n2, n3, n4;
@@ -450,11 +483,11 @@ RT_HD void rt_trav_node_step(const RtBvh &bvh, RtTravState &s, Stacks &k) {
     n4 = rt_ldg(np + 4);
 #endif
     RT_COUNT_NODE();
-    const uint32_t hits = rt_node_test(s.rb, n0, n2, n3, n4, s.tnear, s.tmax_pad);
+    const uint32_t hits = rt_node_test(s.org, s.rcp, oct_inv, n0, n2, n3, n4, s.tnear, s.t * RT_BOX_PAD);
     const uint32_t im = n0.w >> 24;
     const uint32_t leaf = hits & ~im;
     s.ng_x = n1.x;
-    s.ng_y = (k.perm(s.rb.oct_inv, hits & im) << 24) | im;
+    s.ng_y = (k.perm(oct_inv, hits & im) << 24) | im;
     if (leaf) {
         k.tri_put(s.tsp, rt_pack2(n1.y, (leaf << 24) | n1.z));
         s.tsp++;
@@ -468,9 +501,9 @@ RT_HD void rt_trav_node_step(const RtBvh &bvh, RtTravState &s, Stacks &k) {
 }
 
 /* precondition: rt_trav_has_tri(s). Tests ONE triangle of the top group: the lowest remaining
- * triangle position of the lowest hit leaf slot. */
+ * triangle position of the lowest hit leaf slot. rt = rt_trav_ray_tri(s), built once per batch of tests. */
 template <class Stacks>
-RT_HD void rt_trav_tri_step(const RtBvh &bvh, RtTravState &s, Stacks &k) {
+RT_HD void rt_trav_tri_step(const RtBvh &bvh, RtTravState &s, Stacks &k, const RtRayTri &rt) {
     const uint64_t e = k.tri_get(s.tsp - 1);
     const uint32_t base = (uint32_t)e;
     uint32_t w = (uint32_t)(e >> 32);
@@ -494,10 +527,29 @@ RT_HD void rt_trav_tri_step(const RtBvh &bvh, RtTravState &s, Stacks &k) {
     c = rt_ldg(tp + 2);
 #endif
     RT_COUNT_TRI();
-    const float before = s.best.t;
-    rt_tri_test(s.rt, mk3(a.x, a.y, a.z), mk3(b.x, b.y, b.z), mk3(c.x, c.y, c.z), tslot, rt_f2u(c.w), s.tnear,
-                s.best);
-    if (s.best.t != before) s.tmax_pad = s.best.t * RT_BOX_PAD;
+    rt_tri_test(bvh, rt, mk3(a.x, a.y, a.z), mk3(b.x, b.y, b.z), mk3(c.x, c.y, c.z), tslot, rt_f2u(c.w), s.tnear, s.t, s.u, s.v,
+                s.tri);
+}
+
+/* the closest hit without its id (all that shading needs) */
+RT_HD RtHit rt_trav_hit_noid(const RtTravState &s) {
+    RtHit h;
+    h.t = s.t;
+    h.u = s.u;
+    h.v = s.v;
+    h.tri = s.tri;
+    h.gid = 0;
+    return h;
+}
+/* the closest hit of a finished traversal; the id is read back from the triangle record */
+RT_HD RtHit rt_trav_hit(const RtBvh &bvh, const RtTravState &s) {
+    RtHit h;
+    h.t = s.t;
+    h.u = s.u;
+    h.v = s.v;
+    h.tri = s.tri;
+    h.gid = s.tri == RT_MISS ? RT_MISS : rt_f2u(rt_ldg(bvh.tris + (size_t)s.tri * RT_TRI_VEC4 + 2).w);
+    return h;
 }
 
 /* simple front-to-back traversal: triangles are tested right after the node that produced them */
@@ -505,11 +557,12 @@ RT_HD RtHit rt_traverse(const RtBvh &bvh, f3 org, f3 dir, float tnear, float tfa
     RtTravState s;
     RtTravStacks k;
     rt_trav_init(s, org, dir, tnear, tfar);
+    const RtRayTri rt = rt_trav_ray_tri(s);
     while (rt_trav_has_node(s)) {
         rt_trav_node_step(bvh, s, k);
-        while (rt_trav_has_tri(s)) rt_trav_tri_step(bvh, s, k);
+        while (rt_trav_has_tri(s)) rt_trav_tri_step(bvh, s, k, rt);
     }
-    return s.best;
+    return rt_trav_hit(bvh, s);
 }
 
 #endif /* RT_TRAVERSE_H */

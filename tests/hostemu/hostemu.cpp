@@ -571,11 +571,12 @@ extern "C" uint32_t emu_pixel_costs(const emu_scene *s, int wavefront_seed, cons
             RtTravStacks ks;
             rt_trav_init(tv, r.org, r.dir, 0.0001f, INFINITY);
             uint32_t nn = 0, nt = 0;
+            const RtRayTri rtri = rt_trav_ray_tri(tv);
             while (rt_trav_has_node(tv)) {
                 rt_trav_node_step(s->view.bvh, tv, ks);
                 nn++;
                 while (rt_trav_has_tri(tv)) {
-                    rt_trav_tri_step(s->view.bvh, tv, ks);
+                    rt_trav_tri_step(s->view.bvh, tv, ks, rtri);
                     nt++;
                 }
             }
@@ -586,7 +587,7 @@ extern "C" uint32_t emu_pixel_costs(const emu_scene *s, int wavefront_seed, cons
             }
             n++;
             f3 org = r.org, dir = r.dir, att = r.att, rad = r.rad, res;
-            const bool done = rt_shade_segment(s->view, tv.best, rng, org, dir, att, rad, res);
+            const bool done = rt_shade_segment(s->view, rt_trav_hit_noid(tv), rng, org, dir, att, rad, res);
             r.org = org;
             r.dir = round_half3(dir);
             r.att = round_half3(att);
