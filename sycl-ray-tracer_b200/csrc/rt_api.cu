@@ -136,7 +136,8 @@ struct rt_renderer {
     uint32_t last_chains = 1;
     const float4 *peer_accum[16] = {}; /* spp slices across processes: every rank's accumulation buffer (IPC mappings) */
     uint32_t peer_world = 0, peer_rank = 0;
-    int tune_refill = 12; /* lanes that must run dry before a warp refills (RT_TUNE_REFILL overrides; 12-14 measured best) */
+    int tune_refill = 14; /* lanes that must run dry before a warp refills (RT_TUNE_REFILL overrides; 8 / 10 / 12 / 14 / 16 measured on C3:
+                             3187 / 3306 / 3368 / 3391 / 3388 Mrays/s) */
     int tune_ctx = 0;     /* megakernel: parked ray contexts per lane (RT_MEGA_CTX 1-4 = k_megakernel_ctx; measured slower than the
                              one-pixel-in-registers kernel on C2/C3/C4, profiles/README.md) */
     int tune_inflight = 64; /* wavefront, queue-driven warps: pixels in flight per warp (RT_TUNE_INFLIGHT; measured 32 / 64 / 96 / 128 / 256 / 512:

@@ -4,7 +4,7 @@ usage: ncu_lines.py report.ncu-rep kernel_substring [cubin]"""
 import csv, collections, os, re, subprocess, sys, tempfile
 rep, kname = sys.argv[1], sys.argv[2]
 root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-so = os.path.join(root, "sycl-ray-tracer_b200", "librt_b200.so")
+so = os.environ.get("RT_LIB_PATH") or os.path.join(root, "sycl-ray-tracer_b200", "librt_b200.so")
 tmp = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", so], cwd=tmp, capture_output=True)
 lines = []

@@ -1,6 +1,13 @@
 """Summarise an .ncu-rep (read here, no GPU needed): key counters + SIMD-efficiency histogram + stall mix."""
 import csv, collections, subprocess, sys
+import re
 rep = sys.argv[1]
+# pipe utilisation (which of ALU / FMA / LSU / XU is busy) and the L1TEX wavefront counters
+EXTRA = re.compile(r"^(sm__inst_executed_pipe_[a-z0-9_]+\.avg\.pct_of_peak_sustained_active|sm__pipe_[a-z0-9_]+_cycles_active\.avg\.pct_of_peak_sustained_active|"
+                   r"l1tex__data_pipe_lsu_wavefronts(_mem_shared|_mem_lg)?\.sum|l1tex__lsu_writeback_active\.avg\.pct_of_peak_sustained_elapsed|"
+                   r"l1tex__data_bank_(reads|writes)\.avg\.pct_of_peak_sustained_elapsed|l1tex__t_sectors_pipe_lsu_mem_local_op_(ld|st)\.sum|"
+                   r"l1tex__t_requests_pipe_lsu_mem_local_op_(ld|st)\.sum|l1tex__t_sector_pipe_lsu_mem_local_op_ld_hit_rate\.pct|"
+                   r"l1tex__t_sector_pipe_lsu_mem_global_op_ld_hit_rate\.pct)$")
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(raw.splitlines()))
 hdr, units = rows[0], rows[1]
@@ -19,7 +26,7 @@ want = ["gpu__time_duration.sum", "launch__registers_per_thread", "launch__grid_
 for r in rows[2:]:
     print("==", r[hdr.index("Kernel Name")][:70])
     for h, u, v in zip(hdr, units, r):
-        if h in want:
+        if h in want or (EXTRA.search(h) and v not in ("", "0", "0.0")):
             print(f"  {h:72s} {v:>18s} {u}")
 src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(src.splitlines()))
