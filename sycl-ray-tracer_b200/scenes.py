@@ -9,6 +9,9 @@ scenes are identical across numpy versions and machines.
     cornell_scene()       C2  Cornell box + dielectric and metallic icospheres (~41 k triangles)
     sponza_scale_scene()  C3/C5  height-field floor + walls + 25 icospheres, textured (~261 k)
     big_mesh_scene(n)     C4  displaced height field, n x n cells (2236 -> 9,999,392 triangles)
+    stadium_scene()       a BVH-HOSTILE input (not one of BASELINE's configs): "teapots in a stadium" — 100 m architectural
+                              quads and 60 m long, 0.2 m wide diagonal beams next to 5,120-triangle props (~154 k triangles);
+                              what real glTF scenes hand to Embree's SAH builder (src/scene.cpp:406-439)
 """
 import numpy as np
 
@@ -267,6 +270,56 @@ def big_mesh_scene(cells=2236, seed=0x5EED0004):
     arrs = _cached(f"heightfield_{cells}_{seed:x}", mesh) if cells >= 1024 else mesh()
     I = [InstanceData(*arrs, None, Material.diffuse((0.7, 0.7, 0.7)))]
     return SceneData(I, None, (0.5, 0.7, 1.0), (0.0, 6.0, 49.0), (0.0, -0.08, -1.0), 1.5, f"heightfield_{cells}")
+
+
+def _beam(a, b, width, up=(0.0, 1.0, 0.0)):
+    """a flat strip from a to b, `width` wide: two long thin triangles"""
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    d = b - a
+    side = np.cross(d, np.asarray(up, np.float64))
+    if np.linalg.norm(side) < 1e-9:
+        side = np.cross(d, (1.0, 0.0, 0.0))
+    side *= 0.5 * width / np.linalg.norm(side)
+    n = np.cross(d, side)
+    n /= np.linalg.norm(n)
+    return quad(tuple(a - side), tuple(b - side), tuple(b + side), tuple(a + side), tuple(n), 8.0)
+
+
+def stadium_scene(n_props=30, prop_subdiv=4, n_beams=48, seed=0x5EED0006):
+    """The input that is hard for a Morton-ordered tree ("Tree quality vs Embree"): a 100 m x 100 m stadium whose
+    floor, walls and stands are a handful of huge triangles, crossed by `n_beams` long thin DIAGONAL strips (their boxes span
+    most of the scene), with `n_props` finely tessellated props (5,120 triangles, 0.3 - 0.9 m) standing on the pitch in front
+    of the camera. 30 props + 48 beams => 153,726 triangles, 70 % diffuse / 20 % metallic / 10 % dielectric props."""
+    st = _Stream(seed)
+    E, H = 50.0, 20.0
+    grey, green = (0.6, 0.6, 0.62), (0.25, 0.5, 0.22)
+    I = [InstanceData(*quad((-E, 0, E), (E, 0, E), (E, 0, -E), (-E, 0, -E), (0, 1, 0), 16.0), None, Material.diffuse(green))]
+    walls = [((-E, 0, -E), (E, 0, -E), (E, H, -E), (-E, H, -E), (0, 0, 1)), ((E, 0, E), (-E, 0, E), (-E, H, E), (E, H, E), (0, 0, -1)),
+             ((-E, 0, E), (-E, 0, -E), (-E, H, -E), (-E, H, E), (1, 0, 0)), ((E, 0, -E), (E, 0, E), (E, H, E), (E, H, -E), (-1, 0, 0))]
+    for p0, p1, p2, p3, n in walls:
+        I.append(InstanceData(*quad(p0, p1, p2, p3, n, 8.0), None, Material.diffuse(grey)))
+    # sloped stands behind the far goal and along one side: again two triangles each
+    I.append(InstanceData(*quad((-E, 0, -30.0), (E, 0, -30.0), (E, 12.0, -E), (-E, 12.0, -E), (0, 0.8, 0.6), 8.0), None, Material.diffuse((0.5, 0.45, 0.4))))
+    I.append(InstanceData(*quad((30.0, 0, E), (30.0, 0, -E), (E, 12.0, -E), (E, 12.0, E), (-0.6, 0.8, 0), 8.0), None, Material.diffuse((0.5, 0.45, 0.4))))
+    for k in range(n_beams):  # roof trusses and cables: corner to corner through the volume
+        a = (st.uniform(-E, E), st.uniform(8.0, H), st.uniform(-E, E))
+        ang, ln = st.uniform(0.0, 6.28318), st.uniform(40.0, 70.0)
+        b = (a[0] + ln * np.cos(ang), st.uniform(8.0, H), a[2] + ln * np.sin(ang))
+        b = (float(np.clip(b[0], -E, E)), b[1], float(np.clip(b[2], -E, E)))
+        I.append(InstanceData(*_beam(a, b, 0.2), None, Material.metallic((0.8, 0.8, 0.85), 0.3) if k % 3 == 0 else Material.diffuse((0.3, 0.3, 0.35))))
+    sp = icosphere(prop_subdiv)
+    for k in range(n_props):
+        r = st.uniform(0.3, 0.9)
+        x, z = st.uniform(-9.0, 9.0), st.uniform(-14.0, 4.0)
+        kind = st.uniform()
+        if kind < 0.7:
+            m = Material.diffuse((st.uniform(0.2, 0.9), st.uniform(0.2, 0.9), st.uniform(0.2, 0.9)))
+        elif kind < 0.9:
+            m = Material.metallic((st.uniform(0.6, 0.95), st.uniform(0.6, 0.95), st.uniform(0.6, 0.95)), st.uniform(0.0, 0.5))
+        else:
+            m = Material.dielectric(1.5)
+        I.append(InstanceData(*sp, trs((x, r * st.uniform(1.0, 1.8), z), (r, r, r), st.uniform(0, 6.28)), m))
+    return SceneData(I, None, (0.5, 0.7, 1.0), (0.0, 3.0, 14.0), (0.0, -0.12, -1.0), 1.5, "stadium")
 
 
 def random_soup(n_tris, seed=1, extent=1.0, instances=1):

@@ -355,3 +355,80 @@ def test_c4_style_half_million_triangles(pkg, oracle, app, scenes, kind):
     assert np.array_equal(f.accum[y0:y1, x0:x1].view(np.uint32), o["accum"].view(np.uint32))
     r.close()
     scene.close()
+
+
+@pytest.mark.parametrize("kind", [0, 1])
+@pytest.mark.parametrize("which", ["cornell", "sponza_scale"])
+def test_full_paths_1024spp_rmse_on_material_scenes(pkg, oracle, app, scenes, kind, which):
+    """north_star's full-path acceptance where the stream-consuming branches live (`reflectance > rng()`, `dot > 0`, textures,
+    emissive terminals): configs 2 and 3 at their full 1920x1080 size and 1024 spp on the GPU, a crop window through the
+    oracle. Tolerance: per-pixel linear mean RMSE <= 2e-3; it comes out 0 with bit-exact streams and ray-exact accumulation."""
+    if which == "cornell":
+        data, crop = scenes.cornell_scene(5), (1200, 760, 1232, 772)      # rim of the glass sphere + the wall behind it
+    else:
+        data, crop = scenes.sponza_scale_scene(), (948, 600, 972, 612)    # textured floor, spheres
+    spp = 1024
+    f, o, sub = _render_pair(pkg, oracle, app, data, 1920, 1080, 10, spp, kind, crop=crop)
+    mean_g, mean_o = sub(f.accum)[..., :3] / float(spp), o["accum"][..., :3] / float(spp)
+    rmse = float(np.sqrt(np.mean((mean_g - mean_o) ** 2)))
+    assert rmse <= 2e-3, rmse
+    assert np.array_equal(sub(f.rng_state), o["rng_state"])               # streams bit-exact after 1024 samples
+    assert np.array_equal(sub(f.accum).view(np.uint32), o["accum"].view(np.uint32)) and rmse == 0.0
+    assert np.array_equal(sub(f.rgba8), o["rgba8"])
+    assert (sub(f.accum)[..., 3] == spp).all()
+
+
+def test_c4_true_size_ten_million_triangles(pkg, oracle, app, scenes):
+    """config 4 at its OWN size: the 9,999,392-triangle height field (11-level wide tree, > 1 M nodes). 40 k random rays
+    through rt_intersect against the oracle's SAH BVH, then a crop of the 3840x2160 frame for both renderers."""
+    data = scenes.big_mesh_scene()
+    assert data.triangle_count == 9999392
+    scene = pkg.Scene(app, data)
+    st = scene.stats
+    assert st["triangle_count"] == 9999392 and st["node_count"] > 1000000
+    osc = oracle.Scene(data)
+    org, d = _rays(40000, 77, 50.0)
+    org[:, 1] = np.abs(org[:, 1]) * 0.2 + 1.0
+    g, o = pkg.intersect(app, scene, org, d), osc.intersect(org, d, use_bvh=True)
+    assert _check_hits(o, g) == 1.0 and np.array_equal(o["t"].view(np.uint32), g["t"].view(np.uint32))
+    assert 0.2 < (g["inst"] >= 0).mean() < 1.0
+    w, h, crop = 3840, 2160, (1900, 1300, 1964, 1332)
+    x0, y0, x1, y1 = crop
+    cam = pkg.Camera((w, h), data.camera_position, data.camera_direction, data.camera_focal_length)
+    for kind, cls in ((0, pkg.MegakernelRenderer), (1, pkg.WavefrontRenderer)):
+        r = cls(app, (w, h), None, 10, 2)
+        f = r.render_frame(cam, scene)
+        ref = osc.render(oracle.camera_for(data, w, h), kind, 10, 2, use_bvh=True, crop=crop)
+        assert np.array_equal(f.rng_state[y0:y1, x0:x1], ref["rng_state"])
+        assert np.array_equal(f.accum[y0:y1, x0:x1].view(np.uint32), ref["accum"].view(np.uint32))
+        assert np.array_equal(f.rgba8[y0:y1, x0:x1], ref["rgba8"])
+        r.close()
+    scene.close()
+
+
+@pytest.mark.parametrize("kind", [0, 1])
+def test_c5_4k_progressive_crop(pkg, oracle, app, scenes, kind):
+    """config 5's shape: the ~261 k-triangle scene at 3840x2160, rendered progressively as four resumed batches (3 + 2 + 2 + 1
+    samples); a crop of the final frame equals the oracle's one 8-sample frame in streams, accumulation and image"""
+    data = scenes.sponza_scale_scene()
+    w, h, crop = 3840, 2160, (1890, 1210, 1938, 1234)
+    x0, y0, x1, y1 = crop
+    scene = pkg.Scene(app, data)
+    cam = pkg.Camera((w, h), data.camera_position, data.camera_direction, data.camera_focal_length)
+    cls = pkg.MegakernelRenderer if kind == 0 else pkg.WavefrontRenderer
+    r = cls(app, (w, h), None, 10, 8)
+    rays = 0
+    for i, n in enumerate((3, 2, 2, 1)):
+        r.sample_count = n
+        f = r.render_frame(cam, scene, resume=i > 0)
+        rays += f.ray_count
+    r.sample_count = 8
+    one = r.render_frame(cam, scene)
+    assert rays == one.ray_count and np.array_equal(f.rgba8, one.rgba8) and np.array_equal(f.rng_state, one.rng_state)
+    o = oracle.Scene(data).render(oracle.camera_for(data, w, h), kind, 10, 8, use_bvh=True, crop=crop)
+    assert np.array_equal(f.rng_state[y0:y1, x0:x1], o["rng_state"])
+    assert np.array_equal(f.accum[y0:y1, x0:x1].view(np.uint32), o["accum"].view(np.uint32))
+    assert np.array_equal(f.rgba8[y0:y1, x0:x1], o["rgba8"])
+    assert (f.accum[..., 3] == 8).all()
+    r.close()
+    scene.close()
