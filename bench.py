@@ -53,6 +53,9 @@ WORKLOADS = {
     # RT_RENDER_RESUME) and split over the ranks by spp (4096 / N each): ~40 s per step on one GPU, so it is
     # an explicit --workload, not the default
     "c5_progressive_4k": ("sponza_scale_scene", {}, 3840, 2160, 4096, 10),
+    # not one of BASELINE.json's configs: the BVH-hostile scene (large architectural triangles next to dense props), for the
+    # tree-quality measurements of profiles/README.md
+    "stadium": ("stadium_scene", {}, 1920, 1080, 64, 10),
 }
 PROGRESSIVE = {"c5_progressive_4k": 256}  # default --batch-spp
 

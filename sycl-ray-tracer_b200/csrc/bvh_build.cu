@@ -2,8 +2,8 @@
  * bvh_build.cu — GPU BVH build for sm_100a: the rtcCommitScene replacement
  * (src/scene.cpp:101-107; per-primitive scenes :406-439; instances :483-507).
  *
- *   k_flatten -> k_morton -> cub radix sort (63-bit keys) -> k_karras -> k_fit
- *   -> per level { k_wide_select, cub exclusive scan, k_wide_emit }
+ *   k_flatten -> [k_split_count -> cub exclusive scan -> k_split_emit] -> k_morton -> cub radix sort (63-bit keys)
+ *   -> k_karras -> k_fit -> per level { k_wide_select, cub exclusive scan, k_wide_emit }
  *
  * The per-item logic lives in rt_build.h. Output: 80-byte compressed 8-wide nodes in BFS order
  * (children of a node contiguous), triangles (48 B) and shading records (64 B) in leaf order.
@@ -66,14 +66,55 @@ __global__ void k_init_bounds(int32_t *cb) {
     else if (threadIdx.x < 6) cb[threadIdx.x] = rt_float_to_ordered(-INFINITY);
 }
 
+/* triangle splitting (rt_build.h, "split"): edge-length threshold for doubling step `shift` */
+__global__ void k_split_len(RtBuild b, int shift, float *len2) { *len2 = rt_split_len2(b, shift); }
+
+/* references per triangle for that threshold, and how many MORE references than triangles that makes */
+__global__ void k_split_count(RtBuild b, const float *len2, uint32_t *counts, unsigned long long *extra) {
+    const uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t c = 0;
+    if (gid < b.n_tris) {
+        c = rt_split_count(b, gid, *len2);
+        counts[gid] = c;
+        c -= 1u;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(extra, (unsigned long long)c);
+}
+
+/* writes every triangle's references at its scanned offset; the centroid bounds become those of the references */
+__global__ void k_split_emit(RtBuild b, const float *len2, const uint32_t *offsets, uint32_t *ref_tri, rt_float4 *ref_lo, rt_float4 *ref_hi) {
+    const uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x;
+    f3 lo = mk3(INFINITY, INFINITY, INFINITY), hi = mk3(-INFINITY, -INFINITY, -INFINITY);
+    if (gid < b.n_tris) rt_split_emit(b, gid, *len2, offsets[gid], ref_tri, ref_lo, ref_hi, lo, hi);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        lo.x = fminf(lo.x, __shfl_xor_sync(0xffffffffu, lo.x, o));
+        lo.y = fminf(lo.y, __shfl_xor_sync(0xffffffffu, lo.y, o));
+        lo.z = fminf(lo.z, __shfl_xor_sync(0xffffffffu, lo.z, o));
+        hi.x = fmaxf(hi.x, __shfl_xor_sync(0xffffffffu, hi.x, o));
+        hi.y = fmaxf(hi.y, __shfl_xor_sync(0xffffffffu, hi.y, o));
+        hi.z = fmaxf(hi.z, __shfl_xor_sync(0xffffffffu, hi.z, o));
+    }
+    if ((threadIdx.x & 31) == 0 && lo.x <= hi.x) {
+        atomicMin(&b.cen_bounds[0], rt_float_to_ordered(lo.x));
+        atomicMin(&b.cen_bounds[1], rt_float_to_ordered(lo.y));
+        atomicMin(&b.cen_bounds[2], rt_float_to_ordered(lo.z));
+        atomicMax(&b.cen_bounds[3], rt_float_to_ordered(hi.x));
+        atomicMax(&b.cen_bounds[4], rt_float_to_ordered(hi.y));
+        atomicMax(&b.cen_bounds[5], rt_float_to_ordered(hi.z));
+    }
+}
+
 __global__ void k_morton(RtBuild b) {
     const uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x;
-    if (gid < b.n_tris) rt_morton_tri(b, gid);
+    if (gid < b.n_items) rt_morton_tri(b, gid);
 }
 
 __global__ void k_karras(RtBuild b) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i + 1 < b.n_tris) rt_karras_node(b, i);
+    if (i + 1 < b.n_items) rt_karras_node(b, i);
 }
 
 struct DeviceArrive {
@@ -87,7 +128,7 @@ struct DeviceArrive {
 
 __global__ void k_fit(RtBuild b) {
     const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j < b.n_tris) rt_fit_leaf(b, j, DeviceArrive());
+    if (j < b.n_items) rt_fit_leaf(b, j, DeviceArrive());
 }
 
 __global__ void k_wide_select(RtBuild b, uint32_t n_items) {
@@ -157,6 +198,7 @@ static rt_status build_bvh(rt_scene *s) {
         RT_CUDA_TRY(ctx, cudaStreamSynchronize(st));
         s->stats.node_count = 1;
         s->stats.wide_depth = 1;
+        s->n_items = 0;
         return RT_OK;
     }
 
@@ -175,63 +217,115 @@ static rt_status build_bvh(rt_scene *s) {
     uint32_t *items_a = nullptr, *items_b = nullptr;
     uint64_t *counts = nullptr, *offsets = nullptr;
     rt_uint4 *nodes_tmp = nullptr;
-    const size_t max_level_items = (size_t)n / 2 + 8; /* an inner wide node covers >= 2 triangles */
 
+    /* 1. flatten + centroid bounds */
     RT_CUDA_TRY(ctx, scratch.alloc(&b.wtris, (size_t)n * 3));
     RT_CUDA_TRY(ctx, scratch.alloc(&b.cen_bounds, 8));
-    RT_CUDA_TRY(ctx, scratch.alloc(&keys_in, n));
-    RT_CUDA_TRY(ctx, scratch.alloc(&keys_out, n));
-    RT_CUDA_TRY(ctx, scratch.alloc(&vals_in, n));
-    RT_CUDA_TRY(ctx, scratch.alloc(&vals_out, n));
-    RT_CUDA_TRY(ctx, scratch.alloc(&b.left, n));
-    RT_CUDA_TRY(ctx, scratch.alloc(&b.right, n));
-    RT_CUDA_TRY(ctx, scratch.alloc(&b.parent, (size_t)2 * n));
-    RT_CUDA_TRY(ctx, scratch.alloc(&b.range_first, n));
-    RT_CUDA_TRY(ctx, scratch.alloc(&b.range_last, n));
-    RT_CUDA_TRY(ctx, scratch.alloc(&b.box_lo, (size_t)2 * n));
-    RT_CUDA_TRY(ctx, scratch.alloc(&b.box_hi, (size_t)2 * n));
-    RT_CUDA_TRY(ctx, scratch.alloc(&b.flags, n));
-    RT_CUDA_TRY(ctx, scratch.alloc(&b.dp_cost, (size_t)4 * n));
-    RT_CUDA_TRY(ctx, scratch.alloc(&b.dp_dec, (size_t)4 * n));
+    k_init_bounds<<<1, 32, 0, st>>>(b.cen_bounds);
+    k_flatten<<<grid_for(n), kBlock, 0, st>>>(b);
+    RT_CUDA_TRY(ctx, cudaGetLastError());
+
+    /* 1b. OPTIONAL (RT_SPLIT=1 in the environment of rt_scene_commit): references for large triangles (rt_build.h "split").
+     * The threshold doubles until the extra references fit the budget. Off by default: measured with tools/tree_quality.py,
+     * early splitting trades triangle tests for MORE node visits on every scene tried (stadium, Cornell), while the size-class
+     * bit of the Morton key (rt_morton_tri) removes most of the LBVH's handicap on large triangles at no cost. */
+    uint32_t n_items = n;
+    if (getenv("RT_SPLIT") && atoi(getenv("RT_SPLIT")) > 0 && n > 1) {
+        uint32_t *split_counts = nullptr, *split_offsets = nullptr;
+        unsigned long long *d_extra = nullptr;
+        float *d_len2 = nullptr;
+        RT_CUDA_TRY(ctx, scratch.alloc(&split_counts, n));
+        RT_CUDA_TRY(ctx, scratch.alloc(&d_extra, 1));
+        RT_CUDA_TRY(ctx, scratch.alloc(&d_len2, 1));
+        const unsigned long long budget = std::max<unsigned long long>(n / 2, 65536ull);
+        unsigned long long extra = 0;
+        for (int shift = 0; shift <= 8; shift++) {
+            RT_CUDA_TRY(ctx, cudaMemsetAsync(d_extra, 0, sizeof(unsigned long long), st));
+            k_split_len<<<1, 1, 0, st>>>(b, shift, d_len2);
+            k_split_count<<<grid_for(n), kBlock, 0, st>>>(b, d_len2, split_counts, d_extra);
+            RT_CUDA_TRY(ctx, cudaGetLastError());
+            RT_CUDA_TRY(ctx, cudaMemcpyAsync(&extra, d_extra, sizeof(extra), cudaMemcpyDeviceToHost, st));
+            RT_CUDA_TRY(ctx, cudaStreamSynchronize(st));
+            if (extra <= budget) break;
+            if (shift == 8) extra = 0; /* give up: no references */
+        }
+        if (extra > 0 && (unsigned long long)n + extra < 0x7fffffffull) {
+            n_items = n + (uint32_t)extra;
+            uint32_t *ref_tri = nullptr;
+            rt_float4 *ref_lo = nullptr, *ref_hi = nullptr;
+            RT_CUDA_TRY(ctx, scratch.alloc(&split_offsets, n));
+            RT_CUDA_TRY(ctx, scratch.alloc(&ref_tri, n_items));
+            RT_CUDA_TRY(ctx, scratch.alloc(&ref_lo, n_items));
+            RT_CUDA_TRY(ctx, scratch.alloc(&ref_hi, n_items));
+            size_t tmp_bytes = 0;
+            RT_CUDA_TRY(ctx, cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, split_counts, split_offsets, (int)n, st));
+            void *tmp = nullptr;
+            RT_CUDA_TRY(ctx, scratch.alloc((uint8_t **)&tmp, tmp_bytes));
+            RT_CUDA_TRY(ctx, cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, split_counts, split_offsets, (int)n, st));
+            k_init_bounds<<<1, 32, 0, st>>>(b.cen_bounds);
+            k_split_emit<<<grid_for(n), kBlock, 0, st>>>(b, d_len2, split_offsets, ref_tri, ref_lo, ref_hi);
+            RT_CUDA_TRY(ctx, cudaGetLastError());
+            b.ref_tri = ref_tri;
+            b.ref_lo = ref_lo;
+            b.ref_hi = ref_hi;
+        }
+    }
+    b.n_items = n_items;
+    s->n_items = n_items;
+    const uint32_t m = n_items; /* leaves of the tree */
+    const size_t max_level_items = (size_t)m / 2 + 8; /* an inner wide node covers >= 2 leaves */
+
+    RT_CUDA_TRY(ctx, scratch.alloc(&keys_in, m));
+    RT_CUDA_TRY(ctx, scratch.alloc(&keys_out, m));
+    RT_CUDA_TRY(ctx, scratch.alloc(&vals_in, m));
+    RT_CUDA_TRY(ctx, scratch.alloc(&vals_out, m));
+    RT_CUDA_TRY(ctx, scratch.alloc(&b.left, m));
+    RT_CUDA_TRY(ctx, scratch.alloc(&b.right, m));
+    RT_CUDA_TRY(ctx, scratch.alloc(&b.parent, (size_t)2 * m));
+    RT_CUDA_TRY(ctx, scratch.alloc(&b.range_first, m));
+    RT_CUDA_TRY(ctx, scratch.alloc(&b.range_last, m));
+    RT_CUDA_TRY(ctx, scratch.alloc(&b.box_lo, (size_t)2 * m));
+    RT_CUDA_TRY(ctx, scratch.alloc(&b.box_hi, (size_t)2 * m));
+    RT_CUDA_TRY(ctx, scratch.alloc(&b.flags, m));
+    RT_CUDA_TRY(ctx, scratch.alloc(&b.dp_cost, (size_t)4 * m));
+    RT_CUDA_TRY(ctx, scratch.alloc(&b.dp_dec, (size_t)4 * m));
     RT_CUDA_TRY(ctx, scratch.alloc(&items_a, max_level_items));
     RT_CUDA_TRY(ctx, scratch.alloc(&items_b, max_level_items));
     RT_CUDA_TRY(ctx, scratch.alloc(&b.sel, max_level_items * 8));
     RT_CUDA_TRY(ctx, scratch.alloc(&counts, max_level_items));
     RT_CUDA_TRY(ctx, scratch.alloc(&offsets, max_level_items));
-    RT_CUDA_TRY(ctx, scratch.alloc(&nodes_tmp, (size_t)n * RT_NODE_VEC4));
-    RT_CUDA_TRY(ctx, rt_pool_alloc(ctx, (void **)&s->d_tris, (size_t)n * RT_TRI_VEC4 * sizeof(rt_float4)));
-    RT_CUDA_TRY(ctx, rt_pool_alloc(ctx, (void **)&s->d_shade, (size_t)n * 4 * sizeof(rt_float4)));
+    RT_CUDA_TRY(ctx, scratch.alloc(&nodes_tmp, (size_t)m * RT_NODE_VEC4));
+    RT_CUDA_TRY(ctx, rt_pool_alloc(ctx, (void **)&s->d_tris, (size_t)m * RT_TRI_VEC4 * sizeof(rt_float4)));
+    RT_CUDA_TRY(ctx, rt_pool_alloc(ctx, (void **)&s->d_shade, (size_t)m * 4 * sizeof(rt_float4)));
     b.tris = s->d_tris;
     b.shade = s->d_shade;
     b.nodes = nodes_tmp;
     b.counts = counts;
     b.offsets = offsets;
 
-    /* 1. flatten + centroid bounds, 2. Morton codes */
-    k_init_bounds<<<1, 32, 0, st>>>(b.cen_bounds);
-    k_flatten<<<grid_for(n), kBlock, 0, st>>>(b);
+    /* 2. Morton codes */
     b.keys = keys_in;
     b.vals = vals_in;
-    k_morton<<<grid_for(n), kBlock, 0, st>>>(b);
+    k_morton<<<grid_for(m), kBlock, 0, st>>>(b);
     RT_CUDA_TRY(ctx, cudaGetLastError());
 
     /* 3. radix sort by Morton code */
     {
         size_t tmp_bytes = 0;
         RT_CUDA_TRY(ctx, cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys_in, keys_out, vals_in,
-                                                         vals_out, (int)n, 0, 63, st));
+                                                         vals_out, (int)m, 0, 63, st));
         void *tmp = nullptr;
         RT_CUDA_TRY(ctx, scratch.alloc((uint8_t **)&tmp, tmp_bytes));
         RT_CUDA_TRY(ctx, cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys_in, keys_out, vals_in, vals_out,
-                                                         (int)n, 0, 63, st));
+                                                         (int)m, 0, 63, st));
     }
     b.keys = keys_out;
     b.vals = vals_out;
 
     /* 4. radix tree, 5. bottom-up boxes */
-    RT_CUDA_TRY(ctx, cudaMemsetAsync(b.flags, 0, (size_t)n * sizeof(uint32_t), st));
-    if (n > 1) k_karras<<<grid_for(n - 1), kBlock, 0, st>>>(b);
-    k_fit<<<grid_for(n), kBlock, 0, st>>>(b);
+    RT_CUDA_TRY(ctx, cudaMemsetAsync(b.flags, 0, (size_t)m * sizeof(uint32_t), st));
+    if (m > 1) k_karras<<<grid_for(m - 1), kBlock, 0, st>>>(b);
+    k_fit<<<grid_for(m), kBlock, 0, st>>>(b);
     RT_CUDA_TRY(ctx, cudaGetLastError());
 
     /* 6. collapse to the 8-wide compressed tree, one BFS level at a time */
@@ -271,7 +365,7 @@ static rt_status build_bvh(rt_scene *s) {
         cur = nxt;
         nxt = t;
     }
-    if (tri_cursor != n) return rt_set_error(ctx, RT_ERR_STATE, "rt_build_bvh", "triangle count mismatch");
+    if (tri_cursor != m) return rt_set_error(ctx, RT_ERR_STATE, "rt_build_bvh", "triangle count mismatch");
     if (depth > RT_STACK_SIZE - 2)
         return rt_set_error(ctx, RT_ERR_STATE, "rt_build_bvh", "wide tree deeper than the traversal stack");
 

@@ -469,8 +469,8 @@ rt_status rt_scene_commit(rt_scene *s) {
     s->view.tex = s->tex;
     s->view.n_layers = s->n_layers;
     s->view.sky = mk3(s->sky[0], s->sky[1], s->sky[2]);
-    s->stats.bvh_bytes = s->stats.node_count * (16ull * RT_NODE_VEC4) + (uint64_t)s->n_tris * (16ull * RT_TRI_VEC4);
-    s->stats.shading_bytes = (uint64_t)s->n_tris * 64ull + (uint64_t)s->n_inst * sizeof(RtInstance);
+    s->stats.bvh_bytes = s->stats.node_count * (16ull * RT_NODE_VEC4) + (uint64_t)s->n_items * (16ull * RT_TRI_VEC4);
+    s->stats.shading_bytes = (uint64_t)s->n_items * 64ull + (uint64_t)s->n_inst * sizeof(RtInstance);
     s->stats.max_leaf_tris = RT_LEAF_MAX;
     s->committed = true;
     return RT_OK;

@@ -4,7 +4,10 @@
  *
  *   flatten      instance transform applied to the geometry (one world-space triangle soup;
  *                Embree instead transforms the ray per instance, t/u/v are invariant)
- *   morton       63-bit Morton code of the triangle-AABB centroid
+ *   split        large triangles become several REFERENCES with the tight boxes of their pieces
+ *                (longest-edge bisection): the tree's leaves are references, the leaf records are copies
+ *                of the whole triangle, so hits are unchanged
+ *   morton       63-bit Morton code of the reference-AABB centroid
  *   (sort)       cub::DeviceRadixSort in bvh_build.cu
  *   karras       binary radix tree over the sorted codes (Karras, HPG 2012)
  *   fit          bottom-up AABB fit, one atomic flag per inner node
@@ -28,6 +31,10 @@ struct RtInstanceGeom {
 
 struct RtBuild {
     uint32_t n_tris, n_inst;
+    uint32_t n_items;       /* leaves of the tree: n_tris, or the number of references when triangles were split */
+    /* triangle splitting: null when no triangle was split (reference i = triangle i, box = the triangle's) */
+    const uint32_t *ref_tri;            /* n_items: global triangle id of a reference */
+    const rt_float4 *ref_lo, *ref_hi;   /* n_items: its box */
     /* concatenated instance geometry (object space) */
     const float *positions, *normals, *uvs;
     const uint32_t *indices;
@@ -109,6 +116,148 @@ RT_HD void rt_tri_box(const RtBuild &b, uint32_t gid, f3 &lo, f3 &hi) {
     hi = mk3(rt_max3(a.x, c.x, d.x), rt_max3(a.y, c.y, d.y), rt_max3(a.z, c.z, d.z));
 }
 
+/* ---- split: references of large triangles --------------------------------------------------------------------
+ * A Morton-ordered tree files a triangle under the cell of its box centre, so ONE long or large triangle (an
+ * architectural quad, a cable) drags a box as big as itself into a subtree of small neighbours, and every ray that
+ * crosses that box visits the subtree ("teapot in a stadium"; SAH builders such as Embree's, src/scene.cpp:406-439,
+ * avoid it by construction). Remedy: early split. A triangle whose longest edge exceeds `len` is bisected at the
+ * midpoint of its longest edge, recursively, and every piece becomes a REFERENCE (triangle id + box of the piece,
+ * clipped to the triangle's own box, padded by 8 ulp for the rounded midpoints). The tree is built over references;
+ * a leaf stores a copy of the WHOLE triangle (same id), so intersection results — closest t, ties by id — cannot
+ * change, a duplicate is merely tested twice. `len` = 2^-RT_SPLIT_TAU_LOG2 of the diagonal of the centroid bounds,
+ * doubled by the host until the extra references fit the budget (scenes made of large triangles only).
+ * OPT-IN (RT_SPLIT=1 at rt_scene_commit): on the scenes measured so far (tools/tree_quality.py) every threshold buys fewer
+ * triangle tests with MORE node visits — stadium 7.4 / 7.3 (visits / tests per ray) -> 7.5 / 6.5 at 1/4 of the diagonal,
+ * 8.9 / 5.7 at 1/8, 10.8 / 4.1 at 1/32; Cornell 3.8 / 2.8 -> 5.3 / 2.3 — and a node visit costs 2.5 triangle tests. */
+#ifndef RT_SPLIT_TAU_LOG2
+#define RT_SPLIT_TAU_LOG2 2
+#endif
+#define RT_SPLIT_MAX_DEPTH 14
+
+RT_HD void rt_load_wtri(const RtBuild &b, uint32_t gid, f3 v[3]) {
+    const rt_float4 a = b.wtris[(size_t)gid * 3], c = b.wtris[(size_t)gid * 3 + 1], d = b.wtris[(size_t)gid * 3 + 2];
+    v[0] = mk3(a.x, a.y, a.z);
+    v[1] = mk3(c.x, c.y, c.z);
+    v[2] = mk3(d.x, d.y, d.z);
+}
+RT_HD float rt_len2(f3 a, f3 c) {
+    const f3 d = a - c;
+    return (d.x * d.x + d.y * d.y) + d.z * d.z;
+}
+
+/* visits the pieces of triangle gid for edge-length threshold len2 (squared): emit(lo, hi) per piece; returns their
+ * number (1 = not split; then the one piece is the triangle's own box, unpadded) */
+template <class Emit>
+RT_HD uint32_t rt_split_visit(const RtBuild &b, uint32_t gid, float len2, Emit emit) {
+    f3 v[3];
+    rt_load_wtri(b, gid, v);
+    const f3 tlo = mk3(rt_min3(v[0].x, v[1].x, v[2].x), rt_min3(v[0].y, v[1].y, v[2].y), rt_min3(v[0].z, v[1].z, v[2].z));
+    const f3 thi = mk3(rt_max3(v[0].x, v[1].x, v[2].x), rt_max3(v[0].y, v[1].y, v[2].y), rt_max3(v[0].z, v[1].z, v[2].z));
+    const float e0 = rt_len2(v[0], v[1]), e1 = rt_len2(v[1], v[2]), e2 = rt_len2(v[2], v[0]);
+    if (!(len2 > 0.0f) || !(rt_max3(e0, e1, e2) > len2) || !(rt_max3(e0, e1, e2) < 3.0e38f)) { /* small, or not finite */
+        emit(tlo, thi);
+        return 1u;
+    }
+    const float pad = rt_max(rt_max3(fabsf(tlo.x), fabsf(tlo.y), fabsf(tlo.z)), rt_max3(fabsf(thi.x), fabsf(thi.y), fabsf(thi.z))) * 9.5367432e-7f;
+    f3 st[RT_SPLIT_MAX_DEPTH + 1][3];
+    int depth[RT_SPLIT_MAX_DEPTH + 1];
+    int sp = 0;
+    st[0][0] = v[0]; st[0][1] = v[1]; st[0][2] = v[2];
+    depth[0] = 0;
+    sp = 1;
+    uint32_t count = 0;
+    while (sp > 0) {
+        sp--;
+        const f3 a = st[sp][0], c = st[sp][1], d = st[sp][2];
+        const int dep = depth[sp];
+        const float l0 = rt_len2(a, c), l1 = rt_len2(c, d), l2 = rt_len2(d, a);
+        const float lm = rt_max3(l0, l1, l2);
+        if (lm > len2 && dep < RT_SPLIT_MAX_DEPTH) { /* bisect the longest edge (the first one on ties) */
+            f3 p, q, o; /* edge p-q, opposite vertex o */
+            if (l0 >= l1 && l0 >= l2) { p = a; q = c; o = d; }
+            else if (l1 >= l2) { p = c; q = d; o = a; }
+            else { p = d; q = a; o = c; }
+            const f3 m = mk3(0.5f * (p.x + q.x), 0.5f * (p.y + q.y), 0.5f * (p.z + q.z));
+            st[sp][0] = p; st[sp][1] = m; st[sp][2] = o; depth[sp] = dep + 1;
+            sp++;
+            st[sp][0] = m; st[sp][1] = q; st[sp][2] = o; depth[sp] = dep + 1;
+            sp++;
+            continue;
+        }
+        f3 lo = mk3(rt_min3(a.x, c.x, d.x) - pad, rt_min3(a.y, c.y, d.y) - pad, rt_min3(a.z, c.z, d.z) - pad);
+        f3 hi = mk3(rt_max3(a.x, c.x, d.x) + pad, rt_max3(a.y, c.y, d.y) + pad, rt_max3(a.z, c.z, d.z) + pad);
+        lo = mk3(rt_max(lo.x, tlo.x), rt_max(lo.y, tlo.y), rt_max(lo.z, tlo.z)); /* the triangle lies inside its own box */
+        hi = mk3(rt_min(hi.x, thi.x), rt_min(hi.y, thi.y), rt_min(hi.z, thi.z));
+        emit(lo, hi);
+        count++;
+    }
+    return count;
+}
+
+struct RtSplitCount {
+    RT_HD void operator()(f3, f3) const {}
+};
+RT_HD uint32_t rt_split_count(const RtBuild &b, uint32_t gid, float len2) { return rt_split_visit(b, gid, len2, RtSplitCount()); }
+
+/* writes the references of triangle gid from slot `first` on; returns the bounds of their centres in clo / chi */
+struct RtSplitEmit {
+    uint32_t *ref_tri;
+    rt_float4 *ref_lo, *ref_hi;
+    uint32_t gid, next;
+    f3 clo, chi;
+    RT_HD void operator()(f3 lo, f3 hi) {
+        ref_tri[next] = gid;
+        ref_lo[next] = rt_mk_float4(lo.x, lo.y, lo.z, 0.0f);
+        ref_hi[next] = rt_mk_float4(hi.x, hi.y, hi.z, 0.0f);
+        next++;
+        const f3 c = mk3(0.5f * (lo.x + hi.x), 0.5f * (lo.y + hi.y), 0.5f * (lo.z + hi.z));
+        clo = mk3(rt_min(clo.x, c.x), rt_min(clo.y, c.y), rt_min(clo.z, c.z));
+        chi = mk3(rt_max(chi.x, c.x), rt_max(chi.y, c.y), rt_max(chi.z, c.z));
+    }
+};
+struct RtSplitEmitRef { /* by reference, so that the visitor's state survives the by-value template argument */
+    RtSplitEmit *e;
+    RT_HD void operator()(f3 lo, f3 hi) const { (*e)(lo, hi); }
+};
+RT_HD void rt_split_emit(const RtBuild &b, uint32_t gid, float len2, uint32_t first, uint32_t *ref_tri, rt_float4 *ref_lo, rt_float4 *ref_hi,
+                         f3 &clo, f3 &chi) {
+    RtSplitEmit e;
+    e.ref_tri = ref_tri;
+    e.ref_lo = ref_lo;
+    e.ref_hi = ref_hi;
+    e.gid = gid;
+    e.next = first;
+    e.clo = mk3(INFINITY, INFINITY, INFINITY);
+    e.chi = mk3(-INFINITY, -INFINITY, -INFINITY);
+    RtSplitEmitRef r;
+    r.e = &e;
+    rt_split_visit(b, gid, len2, r);
+    clo = e.clo;
+    chi = e.chi;
+}
+/* edge length (squared) from which triangles are split, for doubling step `shift`: 0 when the scene has no extent */
+RT_HD float rt_split_len2(const RtBuild &b, int shift) {
+    float d2 = 0.0f;
+    for (int a = 0; a < 3; a++) {
+        const float e = rt_ordered_to_float(b.cen_bounds[3 + a]) - rt_ordered_to_float(b.cen_bounds[a]);
+        if (e > 0.0f && e < 3.0e38f) d2 += e * e;
+    }
+    const float k = rt_u2f((uint32_t)(127 - 2 * RT_SPLIT_TAU_LOG2 + 2 * shift) << 23); /* 4^(shift - tau) */
+    return d2 * k;
+}
+
+/* leaf item (reference) -> triangle id / box */
+RT_HD uint32_t rt_item_tri(const RtBuild &b, uint32_t item) { return b.ref_tri ? b.ref_tri[item] : item; }
+RT_HD void rt_item_box(const RtBuild &b, uint32_t item, f3 &lo, f3 &hi) {
+    if (b.ref_tri) {
+        const rt_float4 l = b.ref_lo[item], h = b.ref_hi[item];
+        lo = mk3(l.x, l.y, l.z);
+        hi = mk3(h.x, h.y, h.z);
+    } else {
+        rt_tri_box(b, item, lo, hi);
+    }
+}
+
 /* ---- morton ------------------------------------------------------------------------------ */
 /* 63-bit Morton code with an ADAPTIVE axis order (after Vinkler, Bittner, Havran, "Extended Morton
  * Codes for High Performance Bounding Volume Hierarchy Construction", HPG 2017): every bit splits the
@@ -116,9 +265,24 @@ RT_HD void rt_tri_box(const RtBuild &b, uint32_t gid, f3 &lo, f3 &hi) {
  * anisotropic scenes of the benchmark (height fields: x, z extent >> y) the plain interleave wastes a
  * third of the bits on an axis that does not separate anything. The axis sequence depends only on the
  * scene's centroid bounds, so every triangle derives the same sequence. */
-RT_HD void rt_morton_tri(const RtBuild &b, uint32_t gid) {
+/* SIZE CLASS: the top RT_SIZE_CLASS_BITS bits of the key hold a size class, so that items whose box is large against the
+ * scene (longest side > RT_SIZE_CLASS_T0 of the largest extent of the centroid bounds, next class RT_SIZE_CLASS_STEP times
+ * that) sort into their OWN subtree right under the root instead of inflating the boxes of a subtree of small neighbours —
+ * the "teapot in a stadium" case that SAH builders (Embree, src/scene.cpp:406-439) handle by construction. One bit at 1/16:
+ * node visits per ray 7.36 -> 6.09 on the stadium scene (a SAH-binned tree: 5.17), 3.77 -> 3.35 on Cornell (SAH 3.55),
+ * unchanged on C3 / C4 where no triangle is that large (tools/tree_quality.py, profiles/README.md). */
+#ifndef RT_SIZE_CLASS_BITS
+#define RT_SIZE_CLASS_BITS 1
+#endif
+#ifndef RT_SIZE_CLASS_T0
+#define RT_SIZE_CLASS_T0 0.0625f
+#endif
+#ifndef RT_SIZE_CLASS_STEP
+#define RT_SIZE_CLASS_STEP 4.0f
+#endif
+RT_HD void rt_morton_tri(const RtBuild &b, uint32_t gid /* leaf item */) {
     f3 lo, hi;
-    rt_tri_box(b, gid, lo, hi);
+    rt_item_box(b, gid, lo, hi);
     const float c[3] = {0.5f * (lo.x + hi.x), 0.5f * (lo.y + hi.y), 0.5f * (lo.z + hi.z)};
     float ext[3];
     uint32_t u[3];
@@ -131,7 +295,18 @@ RT_HD void rt_morton_tri(const RtBuild &b, uint32_t gid) {
         u[a] = (uint32_t)(f * 4294967296.0);
     }
     uint64_t code = 0;
-    for (int bit = 0; bit < 63; bit++) {
+    int cls_bits = RT_SIZE_CLASS_BITS;
+    float big = rt_max3(hi.x - lo.x, hi.y - lo.y, hi.z - lo.z), scene = rt_max3(ext[0], ext[1], ext[2]);
+    uint32_t cls = 0;
+    if (cls_bits > 0 && scene > 0.0f) {
+        float thr = scene * RT_SIZE_CLASS_T0;
+        const uint32_t top = (1u << cls_bits) - 1u;
+        while (cls < top && big > thr) {
+            cls++;
+            thr *= RT_SIZE_CLASS_STEP;
+        }
+    }
+    for (int bit = 0; bit < 63 - cls_bits; bit++) {
         int a = 0;
         if (ext[1] > ext[a]) a = 1;
         if (ext[2] > ext[a]) a = 2;
@@ -139,6 +314,7 @@ RT_HD void rt_morton_tri(const RtBuild &b, uint32_t gid) {
         ext[a] *= 0.5f;
         if (--pos[a] < 0) ext[a] = -1.0f; /* 32 bits of this axis used up */
     }
+    code |= (uint64_t)cls << (63 - cls_bits);
     b.keys[gid] = code;
     b.vals[gid] = gid;
 }
@@ -152,7 +328,7 @@ RT_HD int rt_delta(const uint64_t *keys, int n, int i, int j) {
 }
 
 RT_HD void rt_karras_node(const RtBuild &b, uint32_t iu) {
-    const int n = (int)b.n_tris, i = (int)iu;
+    const int n = (int)b.n_items, i = (int)iu;
     const uint64_t *keys = b.keys;
     const int d = (rt_delta(keys, n, i, i + 1) - rt_delta(keys, n, i, i - 1)) >= 0 ? 1 : -1;
     const int dmin = rt_delta(keys, n, i, i - d);
@@ -279,16 +455,16 @@ RT_HD uint32_t rt_dp_decision(const RtBuild &b, uint32_t id, int i) { /* byte i 
 /* ---- bottom-up fit + DP: called once per leaf; `arrive` returns the previous flag value -------- */
 template <class Arrive>
 RT_HD void rt_fit_leaf(const RtBuild &b, uint32_t j, Arrive arrive) {
-    const uint32_t leaf0 = b.n_tris - 1;
+    const uint32_t leaf0 = b.n_items - 1;
     f3 lo, hi;
-    rt_tri_box(b, b.vals[j], lo, hi);
+    rt_item_box(b, b.vals[j], lo, hi);
     rt_float4 l4, h4;
     l4.x = lo.x; l4.y = lo.y; l4.z = lo.z; l4.w = 0.0f;
     h4.x = hi.x; h4.y = hi.y; h4.z = hi.z; h4.w = 0.0f;
     rt_st_cg(&b.box_lo[leaf0 + j], l4);
     rt_st_cg(&b.box_hi[leaf0 + j], h4);
     rt_dp_leaf(b, leaf0 + j, l4, h4);
-    if (b.n_tris == 1) return;
+    if (b.n_items == 1) return;
     uint32_t node = b.parent[leaf0 + j];
     while (node != RT_MISS) {
         if (arrive(&b.flags[node]) == 0) return; /* first child to arrive: the sibling finishes */
@@ -305,12 +481,12 @@ RT_HD void rt_fit_leaf(const RtBuild &b, uint32_t j, Arrive arrive) {
 }
 
 /* ---- wide collapse ------------------------------------------------------------------------- */
-RT_HD bool rt_is_leaf_id(const RtBuild &b, uint32_t id) { return id >= b.n_tris - 1; }
+RT_HD bool rt_is_leaf_id(const RtBuild &b, uint32_t id) { return id >= b.n_items - 1; }
 RT_HD uint32_t rt_subtree_count(const RtBuild &b, uint32_t id) {
     return rt_is_leaf_id(b, id) ? 1u : b.range_last[id] - b.range_first[id] + 1u;
 }
 RT_HD uint32_t rt_subtree_first(const RtBuild &b, uint32_t id) {
-    return rt_is_leaf_id(b, id) ? id - (b.n_tris - 1) : b.range_first[id];
+    return rt_is_leaf_id(b, id) ? id - (b.n_items - 1) : b.range_first[id];
 }
 RT_HD float rt_box_area(const RtBuild &b, uint32_t id) {
     const rt_float4 lo = b.box_lo[id], hi = b.box_hi[id];
@@ -510,7 +686,7 @@ RT_HD void rt_wide_emit(const RtBuild &b, uint32_t item) {
             tmask |= ((1u << cnt) - 1u) << (3 * s); /* unary count; triangles follow in slot order */
             const uint32_t first = rt_subtree_first(b, id);
             for (uint32_t t = 0; t < cnt; t++) {
-                const uint32_t gid = b.vals[first + t];
+                const uint32_t gid = rt_item_tri(b, b.vals[first + t]);
                 const uint32_t slot = tri_base + tri_off + t;
                 b.tris[(size_t)slot * RT_TRI_VEC4] = b.wtris[(size_t)gid * 3];
                 b.tris[(size_t)slot * RT_TRI_VEC4 + 1] = b.wtris[(size_t)gid * 3 + 1];

@@ -46,6 +46,7 @@ struct rt_scene {
     rt_context *ctx = nullptr;
     bool committed = false;
     uint32_t n_inst = 0, n_tris = 0, n_verts = 0, n_indices = 0;
+    uint32_t n_items = 0; /* leaf records of the tree: n_tris + the extra references of split triangles (rt_build.h) */
     /* object-space geometry as uploaded (inputs of the build) */
     float *d_positions = nullptr, *d_normals = nullptr, *d_uvs = nullptr;
     uint32_t *d_indices = nullptr;

@@ -61,7 +61,7 @@ struct emu_scene {
     std::vector<uint8_t> tex;
     std::vector<rt_uint4> nodes;
     std::vector<rt_float4> tris, shade;
-    uint32_t n_tris = 0, n_nodes = 0, depth = 0;
+    uint32_t n_tris = 0, n_items = 0, n_nodes = 0, depth = 0;
     RtScene view;
 };
 
@@ -98,7 +98,7 @@ emu_scene *emu_scene_create(const rt_scene_desc *desc) {
         v0 += in.vertex_count;
         i0 += in.index_count;
     }
-    const uint32_t n = i0 / 3;
+    uint32_t n = i0 / 3;
     s->n_tris = n;
     if (desc->texture_layer_count)
         s->tex.assign(desc->texture_layers,
@@ -121,25 +121,75 @@ emu_scene *emu_scene_create(const rt_scene_desc *desc) {
         b.uvs = uv.data();
         b.indices = idx.data();
         b.geom = geom.data();
-        std::vector<rt_float4> wtris((size_t)n * 3), box_lo((size_t)2 * n), box_hi((size_t)2 * n);
+        std::vector<rt_float4> wtris((size_t)n * 3);
         std::vector<int32_t> cb(8);
-        std::vector<uint64_t> keys(n), keys_s(n);
-        std::vector<uint32_t> vals(n), vals_s(n), left(n), right(n), parent((size_t)2 * n), rf(n), rl(n), flags(n, 0);
         b.wtris = wtris.data();
         b.cen_bounds = cb.data();
-        for (int k = 0; k < 3; k++) {
-            cb[k] = rt_float_to_ordered(INFINITY);
-            cb[3 + k] = rt_float_to_ordered(-INFINITY);
-        }
+        auto reset_bounds = [&]() {
+            for (int k = 0; k < 3; k++) {
+                cb[k] = rt_float_to_ordered(INFINITY);
+                cb[3 + k] = rt_float_to_ordered(-INFINITY);
+            }
+        };
+        auto grow_bounds = [&](f3 lo, f3 hi) {
+            const float c0[3] = {lo.x, lo.y, lo.z}, c1[3] = {hi.x, hi.y, hi.z};
+            for (int k = 0; k < 3; k++) {
+                cb[k] = std::min(cb[k], rt_float_to_ordered(c0[k]));
+                cb[3 + k] = std::max(cb[3 + k], rt_float_to_ordered(c1[k]));
+            }
+        };
+        reset_bounds();
         for (uint32_t g = 0; g < n; g++) {
             f3 lo, hi;
             rt_flatten_tri(b, g, lo, hi);
-            const float c[3] = {0.5f * (lo.x + hi.x), 0.5f * (lo.y + hi.y), 0.5f * (lo.z + hi.z)};
-            for (int k = 0; k < 3; k++) {
-                cb[k] = std::min(cb[k], rt_float_to_ordered(c[k]));
-                cb[3 + k] = std::max(cb[3 + k], rt_float_to_ordered(c[k]));
+            const f3 c = mk3(0.5f * (lo.x + hi.x), 0.5f * (lo.y + hi.y), 0.5f * (lo.z + hi.z));
+            grow_bounds(c, c);
+        }
+        /* references for large triangles: the same steps as build_bvh (csrc/bvh_build.cu, 1b) */
+        std::vector<uint32_t> ref_tri;
+        std::vector<rt_float4> ref_lo, ref_hi;
+        uint32_t m = n;
+        if (getenv("RT_SPLIT") && atoi(getenv("RT_SPLIT")) > 0 && n > 1) {
+            std::vector<uint32_t> split_counts(n);
+            const unsigned long long budget = std::max<unsigned long long>(n / 2, 65536ull);
+            unsigned long long extra = 0;
+            float len2 = 0.0f;
+            for (int shift = 0; shift <= 8; shift++) {
+                len2 = rt_split_len2(b, shift);
+                extra = 0;
+                for (uint32_t g = 0; g < n; g++) {
+                    split_counts[g] = rt_split_count(b, g, len2);
+                    extra += split_counts[g] - 1u;
+                }
+                if (extra <= budget) break;
+                if (shift == 8) extra = 0;
+            }
+            if (extra > 0 && (unsigned long long)n + extra < 0x7fffffffull) {
+                m = n + (uint32_t)extra;
+                ref_tri.resize(m);
+                ref_lo.resize(m);
+                ref_hi.resize(m);
+                reset_bounds();
+                uint32_t first = 0;
+                for (uint32_t g = 0; g < n; g++) {
+                    f3 lo, hi;
+                    rt_split_emit(b, g, len2, first, ref_tri.data(), ref_lo.data(), ref_hi.data(), lo, hi);
+                    grow_bounds(lo, hi);
+                    first += split_counts[g];
+                }
+                b.ref_tri = ref_tri.data();
+                b.ref_lo = ref_lo.data();
+                b.ref_hi = ref_hi.data();
             }
         }
+        b.n_items = m;
+        s->n_items = m;
+        const uint32_t n_tris_in = n;
+        (void)n_tris_in;
+        n = m; /* from here on n = leaves of the tree (references) */
+        std::vector<rt_float4> box_lo((size_t)2 * n), box_hi((size_t)2 * n);
+        std::vector<uint64_t> keys(n), keys_s(n);
+        std::vector<uint32_t> vals(n), vals_s(n), left(n), right(n), parent((size_t)2 * n), rf(n), rl(n), flags(n, 0);
         b.keys = keys.data();
         b.vals = vals.data();
         for (uint32_t g = 0; g < n; g++) rt_morton_tri(b, g);
@@ -169,7 +219,7 @@ emu_scene *emu_scene_create(const rt_scene_desc *desc) {
             std::vector<float> clo((size_t)n * 3), chi((size_t)n * 3);
             for (uint32_t g = 0; g < n; g++) {
                 f3 lo, hi;
-                rt_tri_box(b, g, lo, hi);
+                rt_item_box(b, g, lo, hi);
                 clo[g * 3] = lo.x; clo[g * 3 + 1] = lo.y; clo[g * 3 + 2] = lo.z;
                 chi[g * 3] = hi.x; chi[g * 3 + 1] = hi.y; chi[g * 3 + 2] = hi.z;
             }
@@ -282,9 +332,15 @@ uint32_t emu_scene_depth(const emu_scene *s) { return s->depth; }
 
 /* structural check of the emitted tree. 0 = ok */
 int emu_scene_validate(const emu_scene *s) {
-    const uint32_t n = s->n_tris;
+    const uint32_t n = s->n_tris, m = s->n_items; /* triangles, leaf records (references of split triangles repeat the triangle) */
     if (n == 0) return 0;
-    std::vector<uint8_t> seen_tri(n, 0), seen_gid(n, 0), seen_node(s->n_nodes, 0);
+    std::vector<uint8_t> seen_tri(m, 0), seen_gid(n, 0), seen_node(s->n_nodes, 0);
+    std::vector<uint32_t> refs_of(n, 0);
+    for (uint32_t i = 0; i < m; i++) {
+        const uint32_t gid = rt_f2u(s->tris[(size_t)i * RT_TRI_VEC4 + 2].w);
+        if (gid >= n) return 7;
+        refs_of[gid]++;
+    }
     std::vector<uint32_t> stack = {0};
     seen_node[0] = 1;
     while (!stack.empty()) {
@@ -324,23 +380,31 @@ int emu_scene_validate(const emu_scene *s) {
                 if (cnt < 1 || cnt > 3 || unary != (1u << cnt) - 1u) return 5;
                 for (uint32_t t = 0; t < cnt; t++) {
                     const uint32_t tri = np[1].y + off + t;
-                    if (tri >= n || seen_tri[tri]) return 6;
+                    if (tri >= m || seen_tri[tri]) return 6;
                     seen_tri[tri] = 1;
                     const rt_float4 *tp = &s->tris[(size_t)tri * RT_TRI_VEC4];
                     const uint32_t gid = rt_f2u(tp[2].w);
-                    if (gid >= n || seen_gid[gid]) return 7;
+                    if (gid >= n || (seen_gid[gid] && refs_of[gid] == 1)) return 7;
                     seen_gid[gid] = 1;
+                    float tl[3] = {INFINITY, INFINITY, INFINITY}, th[3] = {-INFINITY, -INFINITY, -INFINITY};
                     for (int k = 0; k < 3; k++) {
                         const float v[3] = {tp[k].x, tp[k].y, tp[k].z};
-                        for (int a = 0; a < 3; a++)
-                            if (v[a] < lo[a] || v[a] > hi[a]) return 8;
+                        for (int a = 0; a < 3; a++) {
+                            if (refs_of[gid] == 1 && (v[a] < lo[a] || v[a] > hi[a])) return 8; /* an unsplit triangle lies inside its slot's box */
+                            tl[a] = std::min(tl[a], v[a]);
+                            th[a] = std::max(th[a], v[a]);
+                        }
                     }
+                    for (int a = 0; a < 3; a++) /* a reference's box is a piece of the triangle's box */
+                        if (th[a] < lo[a] || tl[a] > hi[a]) return 8;
                 }
             }
         }
     }
+    for (uint32_t i = 0; i < m; i++)
+        if (!seen_tri[i]) return 9;
     for (uint32_t i = 0; i < n; i++)
-        if (!seen_tri[i] || !seen_gid[i]) return 9;
+        if (!seen_gid[i]) return 9;
     for (uint32_t i = 0; i < s->n_nodes; i++)
         if (!seen_node[i]) return 10;
     return 0;

@@ -432,3 +432,38 @@ def test_c5_4k_progressive_crop(pkg, oracle, app, scenes, kind):
     assert (f.accum[..., 3] == 8).all()
     r.close()
     scene.close()
+
+
+@pytest.mark.parametrize("split", [False, True])
+def test_stadium_large_triangles_next_to_dense_detail(monkeypatch, pkg, oracle, app, scenes, split):
+    """the BVH-hostile scene on the GPU: size-class key bit (default build) and the optional reference split of large
+    triangles (RT_SPLIT=1 at rt_scene_commit) leave every hit and every pixel equal to the oracle's"""
+    if split:
+        monkeypatch.setenv("RT_SPLIT", "1")
+    else:
+        monkeypatch.delenv("RT_SPLIT", raising=False)
+    data = scenes.stadium_scene(n_props=8, prop_subdiv=3, n_beams=32)
+    scene = pkg.Scene(app, data)
+    osc = oracle.Scene(data)
+    rs = np.random.RandomState(3)
+    org = np.stack([rs.uniform(-45, 45, 40000), rs.uniform(0.5, 18, 40000), rs.uniform(-45, 45, 40000)], 1).astype(np.float32)
+    d = (rs.rand(40000, 3) - 0.5).astype(np.float32)
+    g, o = pkg.intersect(app, scene, org, d), osc.intersect(org, d, use_bvh=True)
+    assert _check_hits(o, g) == 1.0 and np.array_equal(o["t"].view(np.uint32), g["t"].view(np.uint32))
+    w, h, crop = 960, 540, (440, 250, 520, 290)
+    x0, y0, x1, y1 = crop
+    cam = pkg.Camera((w, h), data.camera_position, data.camera_direction, data.camera_focal_length)
+    for kind, cls in ((0, pkg.MegakernelRenderer), (1, pkg.WavefrontRenderer)):
+        r = cls(app, (w, h), None, 10, 4)
+        f = r.render_frame(cam, scene)
+        ref = osc.render(oracle.camera_for(data, w, h), kind, 10, 4, use_bvh=True, crop=crop)
+        assert np.array_equal(f.rng_state[y0:y1, x0:x1], ref["rng_state"])
+        assert np.array_equal(f.accum[y0:y1, x0:x1].view(np.uint32), ref["accum"].view(np.uint32))
+        assert np.array_equal(f.rgba8[y0:y1, x0:x1], ref["rgba8"])
+        r.close()
+    if split:
+        monkeypatch.delenv("RT_SPLIT")
+        plain = pkg.Scene(app, data)
+        assert scene.stats["bvh_bytes"] > plain.stats["bvh_bytes"]   # the references are there
+        plain.close()
+    scene.close()

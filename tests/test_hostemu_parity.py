@@ -210,3 +210,30 @@ def test_progressive_resume_on_the_cpu(pkg, oracle, hostemu, scenes, kind):
         assert rays == full["ray_count"]
         assert np.array_equal(f["accum"].view(np.uint32), full["accum"].view(np.uint32))
         assert np.array_equal(f["rgba8"], full["rgba8"]) and np.array_equal(f["rng_state"], full["rng_state"])
+
+
+@pytest.mark.parametrize("split", [False, True])
+def test_large_triangles_next_to_dense_detail(monkeypatch, oracle, hostemu, scenes, split):
+    """the BVH-hostile input (stadium: 100 m quads and 60 m diagonal strips next to finely tessellated props): the size-class
+    bit of the Morton key (default) and the optional early split of large triangles into references (RT_SPLIT=1) change the
+    TREE only — the tree stays structurally valid and every hit equals the brute-force oracle's, bit for bit"""
+    if split:
+        monkeypatch.setenv("RT_SPLIT", "1")
+    else:
+        monkeypatch.delenv("RT_SPLIT", raising=False)
+    data = scenes.stadium_scene(n_props=6, prop_subdiv=2, n_beams=24)
+    emu, orc = hostemu.Scene(data), oracle.Scene(data)
+    assert emu.validate() == 0
+    rs = np.random.RandomState(3)
+    org = np.stack([rs.uniform(-45, 45, 20000), rs.uniform(0.5, 18, 20000), rs.uniform(-45, 45, 20000)], 1).astype(np.float32)
+    d = (rs.rand(20000, 3) - 0.5).astype(np.float32)
+    a, b = orc.intersect(org, d, use_bvh=False), emu.intersect(org, d)
+    assert 0.5 < (a["inst"] >= 0).mean() < 0.9   # the stadium is open to the sky
+    for k in ("inst", "prim"):
+        assert np.array_equal(a[k], b[k]), k
+    for k in ("t", "u", "v"):
+        assert np.array_equal(a[k].view(np.uint32), b[k].view(np.uint32)), k
+    if split:  # the references really exist: more leaf records than triangles
+        monkeypatch.delenv("RT_SPLIT")
+        plain = hostemu.Scene(data)
+        assert emu.node_count != plain.node_count
