@@ -491,7 +491,11 @@ struct Decoder {
     }
 
     /* 8x8 inverse DCT, 12-bit fixed point; columns keep 2 extra bits, rows round with a 2^16 bias that
-     * also adds the +128 level shift */
+     * also adds the +128 level shift. ATTRIBUTION: this is the butterfly of stb_image v2.29 `stbi__idct_block` /
+     * STBI__IDCT_1D (Sean Barrett, public domain / MIT; the reference vendors it as deps/include/stb_image.h:2429-2523,
+     * itself derived from the IJG jidctint.c): bit-exact agreement with the bytes stb hands the reference forces the
+     * same fixed-point constants, the same order of additions and the same rounding biases, so the temporaries keep
+     * stb's names (t0..t3, p1..p5, x0..x3) to make the correspondence checkable. */
     static inline uint8_t clamp8(int x) { return (unsigned)x > 255u ? (x < 0 ? 0 : 255) : (uint8_t)x; }
     static inline int f2f(double x) { return (int)(x * 4096 + 0.5); }
     static void idct(uint8_t *out, int stride, const int16_t d[64]) {
