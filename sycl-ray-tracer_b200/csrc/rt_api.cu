@@ -127,6 +127,7 @@ struct rt_renderer {
     size_t order_temp_bytes = 0;
     uint32_t order_capacity = 0;
     int block_order = 1;          /* megakernel: hand blocks out by decreasing probed cost (RT_BLOCK_ORDER=0 disables) */
+    int block_order_min_spp = 32; /* ... from this many samples per pixel (RT_BLOCK_ORDER_MIN_SPP) */
     uint32_t *gather = nullptr;   /* tile shards: owned pixels are also stored here (peer memory) */
     bool gather_ipc = false;      /* gather was opened from an IPC handle (close it) */
     bool exported = false;        /* d_rgba8 is a gather destination: never clear foreign pixels */
@@ -562,6 +563,7 @@ rt_status rt_renderer_create(rt_context *ctx, rt_renderer_kind kind, int32_t wid
     r->h = height;
     if (const char *e = getenv("RT_TUNE_REFILL")) r->tune_refill = atoi(e) > 0 ? atoi(e) : r->tune_refill;
     if (const char *e = getenv("RT_BLOCK_ORDER")) r->block_order = atoi(e);
+    if (const char *e = getenv("RT_BLOCK_ORDER_MIN_SPP")) r->block_order_min_spp = atoi(e) > 0 ? atoi(e) : r->block_order_min_spp;
     if (const char *e = getenv("RT_WF_PERSIST")) r->wf_persist = atoi(e);
     if (const char *e = getenv("RT_TUNE_INFLIGHT")) r->tune_inflight = atoi(e) >= 32 && atoi(e) <= 65536 ? (atoi(e) + 31) / 32 * 32 : r->tune_inflight;
     if (const char *e = getenv("RT_MEGA_CTX")) r->tune_ctx = atoi(e) >= 0 && atoi(e) <= 4 ? atoi(e) : r->tune_ctx;
@@ -841,7 +843,7 @@ rt_status rt_render_frame(rt_renderer *r, const rt_scene *scene, const rt_camera
     auto block_order = [&](const uint32_t **order) -> rt_status {
         *order = nullptr;
         const uint32_t n_blocks = rt_block_count(p);
-        if (!(r->block_order && p.spp >= 32 * chains && p.max_depth >= 2 && n_blocks >= 1024 &&
+        if (!(r->block_order && p.spp >= (uint32_t)r->block_order_min_spp * chains && p.max_depth >= 2 && n_blocks >= 1024 &&
               (uint64_t)r->w + sh.tile_size <= 65536u && (uint64_t)r->h + sh.tile_size <= 65536u)) /* block origins are packed 16 + 16 bits, partial edge tiles included */
             return RT_OK;
         if (n_blocks > r->order_capacity) { /* first frame (or a coarser tiling): (re)allocate */
