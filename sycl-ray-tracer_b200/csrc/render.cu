@@ -223,7 +223,13 @@ struct SmemStacks {
 #endif
 };
 
-template <class Stacks>
+/* the megakernel extracts ALL plane bytes with IDP.4A (measured against x, y only: C3 3405 -> 3507, C2 6830 -> 6909,
+ * C4 4042 -> 4168 Mrays/s; the queue-driven wavefront kernel is 1 % faster with x, y only — its shading and queue code
+ * keeps the FMA pipe busier) */
+#ifndef RT_MEGA_IDP_MASK
+#define RT_MEGA_IDP_MASK 7
+#endif
+template <int MASK = RT_BYTE_IDP_MASK, class Stacks>
 __device__ __forceinline__ void traverse_phase(const RtBvh &bvh, RtTravState &tv, Stacks &ks, int &mode, int refill) {
     const unsigned full = 0xffffffffu;
     const bool trav = mode == kTraversing;
@@ -232,7 +238,7 @@ __device__ __forceinline__ void traverse_phase(const RtBvh &bvh, RtTravState &tv
      * exhausted) a finished lane must not wait for every other ray of its warp */
     const int thr = max(1, (__popc(m_trav) * refill + 31) >> 5);
     for (;;) {
-        if (trav && rt_trav_has_node(tv)) rt_trav_node_step(bvh, tv, ks);
+        if (trav && rt_trav_has_node(tv)) rt_trav_node_step<MASK>(bvh, tv, ks);
         const bool node = trav && rt_trav_has_node(tv);
         const unsigned m_node = __ballot_sync(full, node);
         /* leave when no lane has nodes left, `refill` lanes have run dry, or a lane's triangle stack
@@ -417,7 +423,7 @@ __global__ void __launch_bounds__(kMegaBlock, RT_MEGA_MIN_BLOCKS) k_megakernel(R
         /* ---------------- traverse ---------------- */
         const unsigned act0 = __ballot_sync(full, mode == kTraversing);
         if (!act0) break; /* every lane is exhausted */
-        traverse_phase(scene.bvh, tv, ks, mode, p.tune_refill);
+        traverse_phase<RT_MEGA_IDP_MASK>(scene.bvh, tv, ks, mode, p.tune_refill);
     }
     unsigned long long total = rays;
 #pragma unroll

@@ -311,12 +311,12 @@ RT_HD void rt_or_if_le(float a, float b, uint32_t &hits) {
 }
 
 /* one child: slot 4 * H + J, planes = byte J of the six quantised-plane words of half H */
-template <int J, int H>
+template <int J, int H, int MASK>
 RT_HD void rt_child_test(uint32_t nx, uint32_t ny, uint32_t nz, uint32_t fx, uint32_t fy, uint32_t fz, float Sx,
                          float Sy, float Sz, float onx, float ony, float onz, float ofx, float ofy, float ofz,
                          float tmin, float tmax_pad, uint32_t one, uint32_t &hits) {
     float tnx, tny, tnz, tfx, tfy, tfz; /* near and far plane of one axis share the multiplier: one FFMA2 */
-    constexpr int IX = RT_BYTE_IDP_MASK & 1, IY = (RT_BYTE_IDP_MASK >> 1) & 1, IZ = (RT_BYTE_IDP_MASK >> 2) & 1;
+    constexpr int IX = MASK & 1, IY = (MASK >> 1) & 1, IZ = (MASK >> 2) & 1;
     rt_fma2(rt_byte_to_unit<J, 1 + 0 + 6 * J + 24 * H, IX>(nx, one), rt_byte_to_unit<J, 1 + 3 + 6 * J + 24 * H, IX>(fx, one), Sx, onx, ofx, tnx, tfx);
     rt_fma2(rt_byte_to_unit<J, 1 + 1 + 6 * J + 24 * H, IY>(ny, one), rt_byte_to_unit<J, 1 + 4 + 6 * J + 24 * H, IY>(fy, one), Sy, ony, ofy, tny, tfy);
     rt_fma2(rt_byte_to_unit<J, 1 + 2 + 6 * J + 24 * H, IZ>(nz, one), rt_byte_to_unit<J, 1 + 5 + 6 * J + 24 * H, IZ>(fz, one), Sz, onz, ofz, tnz, tfz);
@@ -326,21 +326,22 @@ RT_HD void rt_child_test(uint32_t nx, uint32_t ny, uint32_t nz, uint32_t fx, uin
 }
 
 /* four children (one 32-bit word of every quantised plane) */
-template <int H>
+template <int H, int MASK>
 RT_HD void rt_half_test(uint32_t oct_inv, uint32_t qlox, uint32_t qloy, uint32_t qloz, uint32_t qhix,
                         uint32_t qhiy, uint32_t qhiz, float Sx, float Sy, float Sz, float onx, float ony, float onz,
                         float ofx, float ofy, float ofz, float tmin, float tmax_pad, uint32_t one, uint32_t &hits) {
     const uint32_t nx = (oct_inv & 4u) ? qlox : qhix, fx = (oct_inv & 4u) ? qhix : qlox;
     const uint32_t ny = (oct_inv & 2u) ? qloy : qhiy, fy = (oct_inv & 2u) ? qhiy : qloy;
     const uint32_t nz = (oct_inv & 1u) ? qloz : qhiz, fz = (oct_inv & 1u) ? qhiz : qloz;
-    rt_child_test<0, H>(nx, ny, nz, fx, fy, fz, Sx, Sy, Sz, onx, ony, onz, ofx, ofy, ofz, tmin, tmax_pad, one, hits);
-    rt_child_test<1, H>(nx, ny, nz, fx, fy, fz, Sx, Sy, Sz, onx, ony, onz, ofx, ofy, ofz, tmin, tmax_pad, one, hits);
-    rt_child_test<2, H>(nx, ny, nz, fx, fy, fz, Sx, Sy, Sz, onx, ony, onz, ofx, ofy, ofz, tmin, tmax_pad, one, hits);
-    rt_child_test<3, H>(nx, ny, nz, fx, fy, fz, Sx, Sy, Sz, onx, ony, onz, ofx, ofy, ofz, tmin, tmax_pad, one, hits);
+    rt_child_test<0, H, MASK>(nx, ny, nz, fx, fy, fz, Sx, Sy, Sz, onx, ony, onz, ofx, ofy, ofz, tmin, tmax_pad, one, hits);
+    rt_child_test<1, H, MASK>(nx, ny, nz, fx, fy, fz, Sx, Sy, Sz, onx, ony, onz, ofx, ofy, ofz, tmin, tmax_pad, one, hits);
+    rt_child_test<2, H, MASK>(nx, ny, nz, fx, fy, fz, Sx, Sy, Sz, onx, ony, onz, ofx, ofy, ofz, tmin, tmax_pad, one, hits);
+    rt_child_test<3, H, MASK>(nx, ny, nz, fx, fy, fz, Sx, Sy, Sz, onx, ony, onz, ofx, ofy, ofz, tmin, tmax_pad, one, hits);
 }
 
 /* returns the hit flags of one wide node in SLOT order: bit s = the ray's interval [tmin, tmax_pad]
  * overlaps the (conservatively padded) box of slot s. Empty slots never hit (inverted boxes). */
+template <int MASK>
 RT_HD uint32_t rt_node_test(f3 org, f3 rcp, uint32_t oct_inv, rt_uint4 n0, rt_uint4 n2, rt_uint4 n3, rt_uint4 n4, float tmin,
                             float tmax_pad) {
     const float sx = rt_u2f((n0.w & 0xffu) << 23), sy = rt_u2f(((n0.w >> 8) & 0xffu) << 23),
@@ -349,8 +350,7 @@ RT_HD uint32_t rt_node_test(f3 org, f3 rcp, uint32_t oct_inv, rt_uint4 n0, rt_ui
     const float idx = sx * rcp.x, idy = sy * rcp.y, idz = sz * rcp.z;
     const float ox = (rt_u2f(n0.x) - org.x) * rcp.x, oy = (rt_u2f(n0.y) - org.y) * rcp.y, oz = (rt_u2f(n0.z) - org.z) * rcp.z;
     /* q enters as u = 1 + q*2^-k (rt_byte_to_unit; k = 15 for PRMT, 16 for IDP.4A): t = u*S + (o - S), S = id * 2^k (exact). */
-    constexpr float KX = (RT_BYTE_IDP_MASK & 1) ? 65536.0f : 32768.0f, KY = (RT_BYTE_IDP_MASK & 2) ? 65536.0f : 32768.0f,
-                    KZ = (RT_BYTE_IDP_MASK & 4) ? 65536.0f : 32768.0f;
+    constexpr float KX = (MASK & 1) ? 65536.0f : 32768.0f, KY = (MASK & 2) ? 65536.0f : 32768.0f, KZ = (MASK & 4) ? 65536.0f : 32768.0f;
     const float Sx = idx * KX, Sy = idy * KY, Sz = idz * KZ;
     /* Conservative slabs. The sum cancels when the ray starts next to a plane that lies far from
      * the node origin p (|q*id|, |o| >> |t|), e.g. a bounce ray leaving an axis-aligned wall. The
@@ -367,8 +367,8 @@ RT_HD uint32_t rt_node_test(f3 org, f3 rcp, uint32_t oct_inv, rt_uint4 n0, rt_ui
     const float ofx = (ox + ex) - Sx, ofy = (oy + ey) - Sy, ofz = (oz + ez) - Sz;
     uint32_t hits = 0;
     const uint32_t one = rt_unit_bits();
-    rt_half_test<0>(oct_inv, n2.x, n2.z, n3.x, n3.z, n4.x, n4.z, Sx, Sy, Sz, onx, ony, onz, ofx, ofy, ofz, tmin, tmax_pad, one, hits);
-    rt_half_test<1>(oct_inv, n2.y, n2.w, n3.y, n3.w, n4.y, n4.w, Sx, Sy, Sz, onx, ony, onz, ofx, ofy, ofz, tmin, tmax_pad, one, hits);
+    rt_half_test<0, MASK>(oct_inv, n2.x, n2.z, n3.x, n3.z, n4.x, n4.z, Sx, Sy, Sz, onx, ony, onz, ofx, ofy, ofz, tmin, tmax_pad, one, hits);
+    rt_half_test<1, MASK>(oct_inv, n2.y, n2.w, n3.y, n3.w, n4.y, n4.w, Sx, Sy, Sz, onx, ony, onz, ofx, ofy, ofz, tmin, tmax_pad, one, hits);
     return hits;
 }
 
@@ -458,8 +458,9 @@ RT_HD bool rt_trav_has_node(const RtTravState &s) { return s.ng_y > 0x00ffffffu;
 RT_HD bool rt_trav_has_tri(const RtTravState &s) { return s.tsp > 0; }
 RT_HD bool rt_trav_tri_full(const RtTravState &s) { return s.tsp >= RT_TSTACK_SIZE; }
 
-/* precondition: rt_trav_has_node(s) && !rt_trav_tri_full(s) */
-template <class Stacks>
+/* precondition: rt_trav_has_node(s) && !rt_trav_tri_full(s). MASK = which axes extract their plane bytes with IDP.4A
+ * (rt_byte_to_unit): a per-kernel choice, the best split depends on what else the kernel keeps the two pipes busy with */
+template <int MASK, class Stacks>
 RT_HD void rt_trav_node_step(const RtBvh &bvh, RtTravState &s, Stacks &k) {
     const uint32_t imask = s.ng_y & 0xffu;
     const int bit = rt_bfind(s.ng_y);
@@ -483,7 +484,7 @@ RT_HD void rt_trav_node_step(const RtBvh &bvh, RtTravState &s, Stacks &k) {
     n4 = rt_ldg(np + 4);
 #endif
     RT_COUNT_NODE();
-    const uint32_t hits = rt_node_test(s.org, s.rcp, oct_inv, n0, n2, n3, n4, s.tnear, s.t * RT_BOX_PAD);
+    const uint32_t hits = rt_node_test<MASK>(s.org, s.rcp, oct_inv, n0, n2, n3, n4, s.tnear, s.t * RT_BOX_PAD);
     const uint32_t im = n0.w >> 24;
     const uint32_t leaf = hits & ~im;
     s.ng_x = n1.x;
@@ -498,6 +499,11 @@ RT_HD void rt_trav_node_step(const RtBvh &bvh, RtTravState &s, Stacks &k) {
         s.ng_x = (uint32_t)e;
         s.ng_y = (uint32_t)(e >> 32);
     }
+}
+
+template <class Stacks>
+RT_HD void rt_trav_node_step(const RtBvh &bvh, RtTravState &s, Stacks &k) {
+    rt_trav_node_step<RT_BYTE_IDP_MASK>(bvh, s, k);
 }
 
 /* precondition: rt_trav_has_tri(s). Tests ONE triangle of the top group: the lowest remaining
