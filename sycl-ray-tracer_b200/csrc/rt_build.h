@@ -128,7 +128,10 @@ RT_HD void rt_tri_box(const RtBuild &b, uint32_t gid, f3 &lo, f3 &hi) {
  * doubled by the host until the extra references fit the budget (scenes made of large triangles only).
  * OPT-IN (RT_SPLIT=1 at rt_scene_commit): on the scenes measured so far (tools/tree_quality.py) every threshold buys fewer
  * triangle tests with MORE node visits — stadium 7.4 / 7.3 (visits / tests per ray) -> 7.5 / 6.5 at 1/4 of the diagonal,
- * 8.9 / 5.7 at 1/8, 10.8 / 4.1 at 1/32; Cornell 3.8 / 2.8 -> 5.3 / 2.3 — and a node visit costs 2.5 triangle tests. */
+ * 8.9 / 5.7 at 1/8, 10.8 / 4.1 at 1/32; Cornell 3.8 / 2.8 -> 5.3 / 2.3 — and a node visit costs 2.5 triangle tests.
+ * KNOWN LIMIT: the exact, flat box of a piece of an axis-aligned 100 m wall culls the self-hit of a bounce ray whose exact
+ * crossing lies below tnear while the triangle test's rounding reports t just above it (a few paths per million differ from
+ * the brute-force definition, tests/test_gpu_parity.py); the unsplit wall sits in a coarsely quantised slot and is found. */
 #ifndef RT_SPLIT_TAU_LOG2
 #define RT_SPLIT_TAU_LOG2 2
 #endif
