@@ -144,7 +144,7 @@ __global__ void __launch_bounds__(128) k_block_key(RtFrameParams p, RtBlockGeom 
  *                (terminated-ray replacement, after Aila & Laine, HPG 2009).
  * The per-pixel arithmetic is the same as rt_megakernel_pixel (rt_shade.h), which the host
  * emulation and the oracle comparison exercise; only the scheduling differs. */
-enum { kNeedPixel = 0, kNeedRay = 1, kStart = 2, kTraversing = 3, kHitPending = 4, kExhausted = 5 };
+enum { kNeedPixel = 0, kNeedRay = 1, kStart = 2, kTraversing = 3, kHitPending = 4, kExhausted = 5, kWaitPart = 6 };
 
 /* Traverse phase shared by the megakernel and the wavefront extend kernel (warp-uniform control
  * flow): node steps for every lane with node work until `refill` lanes have run out of nodes, or
@@ -300,17 +300,21 @@ __device__ __forceinline__ f3 ray_rad(const HalfRay &h) { return mk3(h_lo(h.rxy)
 template <bool CHAINS>
 __global__ void __launch_bounds__(kMegaBlock, RT_MEGA_MIN_BLOCKS) k_megakernel(RtScene scene, RtFrameParams p, RtFrameOut out,
                                                            uint32_t *work_counter, unsigned long long *ray_counter,
-                                                           const uint32_t *__restrict__ order) {
+                                                           const uint32_t *__restrict__ order, const RtBlockGeom g /* = rt_block_geom(p), from the host: lives in the constant bank, not in registers */) {
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
-    const RtBlockGeom g = rt_block_geom(p);
-    const uint32_t n_chains = CHAINS ? p.chains : 1u;
-    const uint32_t n_work = g.n_blocks * n_chains * 32u; /* pixel slots, 32 per (8x4 block, sample chain) */
-    const size_t n_pix = (size_t)p.cam.w * (size_t)p.cam.h;
+    /* uniform quantities of the hand-out are macros over kernel parameters on purpose: named locals stayed in registers across
+     * the node loop and brought its spill re-loads back */
+#define N_CHAINS (CHAINS ? p.chains : 1u)
+#define N_PARTS (CHAINS ? 1u : p.n_parts)                    /* sample parts (RtFrameParams): all first parts, then all second parts, ... */
+#define N_SLOTS (g.n_blocks * N_CHAINS * 32u)                /* pixel slots of one part, 32 per (8x4 block, sample chain) */
+#define N_PIX ((size_t)p.cam.w * (size_t)p.cam.h)
     uint32_t rays = 0; /* per lane: < 2^32 for any frame that finishes */
     int mode = kNeedPixel;
     uint32_t xy = 0;
-    uint32_t s = 0, depth = 0, chain = 0, spp_c = p.spp; /* sample chain of the lane's pixel, samples it contributes */
+    uint32_t s = 0, depth = 0, chain = 0, spp_c = p.spp; /* sample chain of the lane's pixel, samples it contributes (CHAINS only) */
+    /* sample parts cost no register: the part index rides in the top two bits of the bounce counter, and a lane that waits
+     * for the previous part of its pixel (mode kWaitPart) keeps the work index in xy */
     XorShift32 rng;
     rng.a = 0;
     f3 sum = mk3(0.0f, 0.0f, 0.0f);
@@ -333,7 +337,11 @@ __global__ void __launch_bounds__(kMegaBlock, RT_MEGA_MIN_BLOCKS) k_megakernel(R
         if (mode == kHitPending) {
             f3 org = tv.org, dir = ray_dir(hr), att = ray_att(hr), rad = ray_rad(hr), res = mk3(0.0f, 0.0f, 0.0f);
             bool done = rt_shade_segment(scene, rt_trav_hit_noid(tv), rng, org, dir, att, rad, res);
-            done = rt_after_segment(p, done, depth, att, rng, res);
+            {
+                uint32_t d = depth & 0x3fffffffu;
+                done = rt_after_segment(p, done, d, att, rng, res);
+                depth = (depth & 0xc0000000u) | d;
+            }
             tv.org = org;                 /* src/render_megakernel.cpp:41-55: re-quantise the ray state (F6) */
             hr = pack_ray(dir, att, rad); /* fp32 -> fp16, round to nearest even */
             if (done) {
@@ -344,22 +352,28 @@ __global__ void __launch_bounds__(kMegaBlock, RT_MEGA_MIN_BLOCKS) k_megakernel(R
                 mode = kStart;
             }
         }
+        bool may_retry = mode == kWaitPart; /* ONE look per round: the previous part may be running in a lane of this very warp */
         for (;;) { /* warp-uniform: runs until no lane is waiting for a pixel */
             if (mode == kNeedRay) {
                 const int x = (int)(xy & 0xffffu), y = (int)(xy >> 16);
-                const uint32_t spp_l = CHAINS ? spp_c : p.spp;
+                const uint32_t part = CHAINS ? 0u : depth >> 30;
+                const uint32_t spp_l = CHAINS ? spp_c : p.part_end[part];
                 while (p.max_depth == 0 && s < spp_l) { /* the bounce loop never runs: black sample */
                     rng.next();
                     rng.next();
                     s++;
                 }
                 if (s == spp_l) { /* pixel finished: :154-158 mean, gamma, image write */
-                    const size_t pix = (size_t)y * (size_t)p.cam.w + (size_t)x, vp = (CHAINS ? (size_t)chain * n_pix : 0) + pix;
-                    const float base_count = p.resume ? out.accum[vp].w : 0.0f; /* samples accumulated by earlier frames */
-                    const float count = base_count + (float)spp_l;
+                    const size_t pix = (size_t)y * (size_t)p.cam.w + (size_t)x, vp = (CHAINS ? (size_t)chain * N_PIX : 0) + pix;
+                    const uint32_t first = part ? p.part_end[part - 1u] : 0u; /* this part added the samples [first, spp_l) */
+                    const float base_count = (p.resume || part) ? __ldcg(&out.accum[vp]).w : 0.0f; /* samples accumulated by earlier frames / parts */
+                    const float count = base_count + (float)(spp_l - first);
                     out.accum[vp] = make_float4(sum.x, sum.y, sum.z, count);
                     out.rng[vp] = rng.a;
-                    if (!CHAINS) { /* with sample chains k_combine_chains sums the planes and writes the image */
+                    if (!CHAINS && part + 1u < N_PARTS) { /* hand the pixel over to its next part: state first, then the flag */
+                        __threadfence();
+                        *(volatile uint32_t *)&out.part_done[pix] = part + 1u;
+                    } else if (!CHAINS) { /* with sample chains k_combine_chains sums the planes and writes the image */
                         const uint32_t px = rt_resolve_pixel(sum.x, sum.y, sum.z, count);
                         out.rgba8[pix] = px;
                         if (out.gather) out.gather[pix] = px; /* tile shards: straight into the destination rank's image */
@@ -369,22 +383,29 @@ __global__ void __launch_bounds__(kMegaBlock, RT_MEGA_MIN_BLOCKS) k_megakernel(R
                     const RtRayState r = rt_camera_ray(p.cam, x, y, rng); /* 2 draws (F5) */
                     tv.org = r.org;
                     hr = pack_ray(r.dir, r.att, r.rad);
-                    depth = 0;
+                    depth &= 0xc0000000u;
                     mode = kStart;
                 }
             }
+            /* a lane whose later part found the previous part unfinished looks again (it does not take a new slot) */
+            const bool retry = mode == kWaitPart && may_retry;
+            may_retry = false;
             const unsigned need = __ballot_sync(full, mode == kNeedPixel);
-            if (!need) break;
+            if (!need && !__any_sync(full, retry)) break;
             uint32_t base = 0;
-            const int leader = __ffs(need) - 1;
-            if (lane == leader) base = atomicAdd(work_counter, (uint32_t)__popc(need));
-            base = __shfl_sync(full, base, leader);
-            if (mode == kNeedPixel) {
-                const uint32_t idx = base + (uint32_t)__popc(need & ((1u << lane) - 1u));
-                if (idx >= n_work) {
+            if (need) {
+                const int leader = __ffs(need) - 1;
+                if (lane == leader) base = atomicAdd(work_counter, (uint32_t)__popc(need));
+                base = __shfl_sync(full, base, leader);
+            }
+            if (mode == kNeedPixel || retry) {
+                const uint32_t idx = retry ? xy : base + (uint32_t)__popc(need & ((1u << lane) - 1u));
+                mode = kNeedPixel;
+                if (idx >= N_SLOTS * N_PARTS) {
                     mode = kExhausted;
                 } else {
-                    const uint32_t in = idx & 31u, item = idx >> 5, blk = CHAINS ? item / n_chains : item; /* (block, chain) pairs */
+                    const uint32_t part = (CHAINS || N_PARTS == 1u) ? 0u : idx / N_SLOTS, slot = idx - part * N_SLOTS;
+                    const uint32_t in = slot & 31u, item = slot >> 5, blk = CHAINS ? item / N_CHAINS : item; /* (block, chain) pairs */
                     uint32_t x0, y0;
                     if (order) { /* blocks sorted by decreasing cost class (k_block_cost) */
                         const uint32_t e = __ldg(order + blk);
@@ -395,22 +416,30 @@ __global__ void __launch_bounds__(kMegaBlock, RT_MEGA_MIN_BLOCKS) k_megakernel(R
                     }
                     const int x = (int)(x0 + (in & 7u)), y = (int)(y0 + (in >> 3));
                     if (x < p.cam.w && y < p.cam.h && rt_owns_pixel(p, x, y)) {
-                        xy = (uint32_t)x | ((uint32_t)y << 16);
-                        if (CHAINS) {
-                            chain = item - blk * n_chains;
-                            spp_c = rt_chain_spp(p.spp, p.chains, chain);
-                        }
-                        if (p.resume) { /* carry on where the previous frame stopped */
-                            const size_t vp = (CHAINS ? (size_t)chain * n_pix : 0) + (size_t)y * (size_t)p.cam.w + (size_t)x;
-                            const float4 a = out.accum[vp];
-                            rng.a = out.rng[vp];
-                            sum = mk3(a.x, a.y, a.z);
+                        const size_t pix = (size_t)y * (size_t)p.cam.w + (size_t)x;
+                        if (part && *(volatile const uint32_t *)&out.part_done[pix] != part) {
+                            xy = idx; /* the previous part of this pixel is still running (in another lane): come back after the next traversal phase */
+                            mode = kWaitPart;
                         } else {
-                            rng.a = rt_pixel_seed(p.wavefront_seed, x, y, p.cam.w, p.cam.h) ^ p.seed_salt ^ (CHAINS ? chain * RT_CHAIN_SALT : 0u);
-                            sum = mk3(0.0f, 0.0f, 0.0f);
+                            xy = (uint32_t)x | ((uint32_t)y << 16);
+                            if (CHAINS) {
+                                chain = item - blk * N_CHAINS;
+                                spp_c = rt_chain_spp(p.spp, p.chains, chain);
+                            }
+                            depth = part << 30;
+                            if (p.resume || part) { /* carry on where the previous frame / part stopped */
+                                if (part) __threadfence(); /* the flag was read above: order the state loads after it */
+                                const size_t vp = (CHAINS ? (size_t)chain * N_PIX : 0) + pix;
+                                const float4 a = __ldcg(&out.accum[vp]);
+                                rng.a = __ldcg(&out.rng[vp]);
+                                sum = mk3(a.x, a.y, a.z);
+                            } else {
+                                rng.a = rt_pixel_seed(p.wavefront_seed, x, y, p.cam.w, p.cam.h) ^ p.seed_salt ^ (CHAINS ? chain * RT_CHAIN_SALT : 0u);
+                                sum = mk3(0.0f, 0.0f, 0.0f);
+                            }
+                            s = part ? p.part_end[part - 1u] : 0u;
+                            mode = kNeedRay;
                         }
-                        s = 0;
-                        mode = kNeedRay;
                     } /* else: padding / another rank's pixel, fetch again */
                 }
             }
@@ -422,13 +451,21 @@ __global__ void __launch_bounds__(kMegaBlock, RT_MEGA_MIN_BLOCKS) k_megakernel(R
         }
         /* ---------------- traverse ---------------- */
         const unsigned act0 = __ballot_sync(full, mode == kTraversing);
-        if (!act0) break; /* every lane is exhausted */
+        if (!act0) {
+            if (!__any_sync(full, mode == kWaitPart)) break; /* every lane is exhausted */
+            __nanosleep(500); /* only lanes waiting for a part that another warp is finishing: look again */
+            continue;
+        }
         traverse_phase<RT_MEGA_IDP_MASK>(scene.bvh, tv, ks, mode, p.tune_refill);
     }
     unsigned long long total = rays;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(full, total, o);
     if (lane == 0 && total) atomicAdd(ray_counter, total);
+#undef N_CHAINS
+#undef N_PARTS
+#undef N_SLOTS
+#undef N_PIX
 }
 
 /* ------------------------------------------------------------------------------ megakernel, K contexts per lane */
@@ -1164,8 +1201,8 @@ cudaError_t rt_launch_megakernel(cudaStream_t st, int grid, const RtScene &scene
     case 3: k_megakernel_ctx<3><<<grid, kMegaBlock, 0, st>>>(scene, p, out, work_counter, ray_counter, order); break;
     case 4: k_megakernel_ctx<4><<<grid, kMegaBlock, 0, st>>>(scene, p, out, work_counter, ray_counter, order); break;
     default:
-        if (p.chains > 1u) k_megakernel<true><<<grid, kMegaBlock, 0, st>>>(scene, p, out, work_counter, ray_counter, order);
-        else k_megakernel<false><<<grid, kMegaBlock, 0, st>>>(scene, p, out, work_counter, ray_counter, order);
+        if (p.chains > 1u) k_megakernel<true><<<grid, kMegaBlock, 0, st>>>(scene, p, out, work_counter, ray_counter, order, rt_block_geom(p));
+        else k_megakernel<false><<<grid, kMegaBlock, 0, st>>>(scene, p, out, work_counter, ray_counter, order, rt_block_geom(p));
         break;
     }
     return cudaGetLastError();

@@ -128,6 +128,8 @@ struct rt_renderer {
     uint32_t order_capacity = 0;
     int block_order = 1;          /* megakernel: hand blocks out by decreasing probed cost (RT_BLOCK_ORDER=0 disables) */
     int block_order_min_spp = 32; /* ... from this many samples per pixel (RT_BLOCK_ORDER_MIN_SPP) */
+    int sample_parts = 3;         /* megakernel: a pixel's samples are handed out in up to this many parts (RtFrameParams.n_parts; RT_SAMPLE_PARTS=1 disables) */
+    uint32_t *d_part_done = nullptr; /* per pixel: parts finished in the current frame */
     uint32_t *gather = nullptr;   /* tile shards: owned pixels are also stored here (peer memory) */
     bool gather_ipc = false;      /* gather was opened from an IPC handle (close it) */
     bool exported = false;        /* d_rgba8 is a gather destination: never clear foreign pixels */
@@ -563,6 +565,7 @@ rt_status rt_renderer_create(rt_context *ctx, rt_renderer_kind kind, int32_t wid
     r->h = height;
     if (const char *e = getenv("RT_TUNE_REFILL")) r->tune_refill = atoi(e) > 0 ? atoi(e) : r->tune_refill;
     if (const char *e = getenv("RT_BLOCK_ORDER")) r->block_order = atoi(e);
+    if (const char *e = getenv("RT_SAMPLE_PARTS")) r->sample_parts = atoi(e) >= 1 && atoi(e) <= 3 ? atoi(e) : r->sample_parts;
     if (const char *e = getenv("RT_BLOCK_ORDER_MIN_SPP")) r->block_order_min_spp = atoi(e) > 0 ? atoi(e) : r->block_order_min_spp;
     if (const char *e = getenv("RT_WF_PERSIST")) r->wf_persist = atoi(e);
     if (const char *e = getenv("RT_TUNE_INFLIGHT")) r->tune_inflight = atoi(e) >= 32 && atoi(e) <= 65536 ? (atoi(e) + 31) / 32 * 32 : r->tune_inflight;
@@ -643,6 +646,7 @@ void rt_renderer_destroy(rt_renderer *r) {
     cudaFree(r->d_rgba8);
     cudaFree(r->d_rng);
     cudaFree(r->d_work);
+    cudaFree(r->d_part_done);
     cudaFree(r->d_rays);
     cudaFree(r->d_counts);
     if (r->h_counts) cudaFreeHost(r->h_counts);
@@ -793,6 +797,8 @@ rt_status rt_render_frame(rt_renderer *r, const rt_scene *scene, const rt_camera
     p.resume = (params->flags & RT_RENDER_RESUME) ? 1 : 0;
     p.roulette = (params->flags & RT_RENDER_ROULETTE) ? 1 : 0;
     p.chains = chains;
+    p.n_parts = 1;
+    p.part_end[0] = p.part_end[1] = p.part_end[2] = p.spp;
     if (p.resume && !r->has_frame) return rt_set_error(ctx, RT_ERR_STATE, "rt_render_frame", "RT_RENDER_RESUME without a previous frame");
     if (p.resume && (r->last_scene != scene || memcmp(&r->last_camera, camera, sizeof(rt_camera)) != 0 || r->last_depth != params->max_depth ||
                      r->last_shard.rank != sh.rank || r->last_shard.world != sh.world || r->last_shard.tile_size != sh.tile_size ||
@@ -803,6 +809,7 @@ rt_status rt_render_frame(rt_renderer *r, const rt_scene *scene, const rt_camera
     out.rgba8 = r->d_rgba8;
     out.rng = r->d_rng;
     out.gather = (sh.world > 1 && sh.tile_size) ? r->gather : nullptr;
+    out.part_done = nullptr;
     p.keep_foreign = r->exported ? 1 : 0;
     const size_t n = (size_t)r->w * (size_t)r->h;
     uint32_t launches = 0;
@@ -878,6 +885,33 @@ rt_status rt_render_frame(rt_renderer *r, const rt_scene *scene, const rt_camera
             RT_CUDA_TRY(ctx, cudaMemsetAsync(r->d_rng, 0, n * 4, st));
         }
         if (chains > 1u) p.tune_ctx = 0; /* chains are implemented by the one-pixel-in-registers kernel */
+        /* sample parts (rt_shade.h, RtFrameParams): the frame ends with the longest chain handed out last, ~1.4 pixel chains
+         * after the work counter runs dry — 10 % of a 1080p frame at any spp, because a B200 keeps 151 k lanes busy and the
+         * frame has only 13.7 pixels per lane. Each part's tail is filled by the next part's work when
+         * (next part) / (this part) >= 1.43 * lanes / pixels, so the parts shrink geometrically by rho = 1.6 * lanes / pixels */
+        if (chains <= 1u && p.tune_ctx == 0 && r->sample_parts > 1 && p.spp >= 2u && p.max_depth >= 1u) {
+            const double lanes = (double)r->grid_mega * 128.0, pixels = (double)rt_block_count(p) * 32.0;
+            const double rho = std::min(0.5, std::max(1.0 / 64.0, 1.6 * lanes / std::max(pixels, 1.0)));
+            const uint32_t want = p.spp >= 3u && r->sample_parts >= 3 ? 3u : 2u;
+            const double norm = want == 3u ? 1.0 + rho + rho * rho : 1.0 + rho;
+            uint32_t c2 = want == 3u ? std::max(1u, (uint32_t)llround(p.spp * rho * rho / norm)) : 0u;
+            uint32_t c1 = std::max(1u, (uint32_t)llround(p.spp * rho / norm));
+            while (c1 + c2 >= p.spp) { /* tiny spp: keep at least one sample in the first part */
+                if (c1 > 1u) c1--;
+                else if (c2 > 1u) c2--;
+                else break;
+            }
+            if (c1 + c2 < p.spp) {
+                p.n_parts = want;
+                p.part_end[0] = p.spp - c1 - c2;
+                p.part_end[1] = p.spp - c2;
+                p.part_end[2] = p.spp;
+                if (want == 2u) p.part_end[1] = p.spp;
+                if (!r->d_part_done) RT_CUDA_TRY(ctx, dev_alloc(&r->d_part_done, n));
+                RT_CUDA_TRY(ctx, cudaMemsetAsync(r->d_part_done, 0, n * sizeof(uint32_t), st));
+                out.part_done = r->d_part_done;
+            }
+        }
         const uint32_t *order = nullptr;
         {
             const rt_status os = block_order(&order);

@@ -242,6 +242,13 @@ struct RtFrameParams {
     /* options that are NOT the reference's sampling order (off by default; PLAN.md:23-27 lists both as open) */
     int32_t roulette;       /* RT_RENDER_ROULETTE: Russian roulette from the third bounce on */
     uint32_t chains;        /* rt_render_params.sample_chains: independent sample chains per pixel (<= 1: one stream per pixel, F4) */
+    /* SAMPLE PARTS (scheduling only, results unchanged): a pixel's samples are handed out as n_parts work items, part k =
+     * samples [part_end[k-1], part_end[k]) of the SAME stream, continued through the frame buffers exactly like
+     * RT_RENDER_RESUME; all first parts are handed out before any second part. The frame's tail is then one LAST-part
+     * chain (a few samples) instead of one whole-pixel chain, and the tail of the long first parts is filled with the
+     * later parts of other pixels (profiles/README.md, "The tail of a frame"). */
+    uint32_t n_parts;       /* 1 .. 3 */
+    uint32_t part_end[3];   /* part_end[n_parts - 1] == spp */
 };
 
 #define RT_ROULETTE_MIN_DEPTH 3u

@@ -13,6 +13,7 @@ struct RtFrameOut {
     uint32_t *rgba8;  /* W*H */
     uint32_t *rng;    /* W*H: final xorshift state */
     uint32_t *gather; /* optional second destination of owned pixels' RGBA8 (peer memory, tile shards) */
+    uint32_t *part_done; /* W*H, sample parts (RtFrameParams.n_parts > 1): parts of the pixel's chain finished in this frame */
 };
 
 /* per-pixel ray state (Buffers, src/render_wavefront.hpp:10-37): fp32 origin padded to 16 B
