@@ -457,8 +457,12 @@ rt_status rt_scene_commit(rt_scene *s) {
     rt_context *ctx = s->ctx;
     if (s->committed) return rt_set_error(ctx, RT_ERR_STATE, "rt_scene_commit", "scene already committed (immutable)");
     RT_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    const auto t_commit = std::chrono::steady_clock::now();
     rt_status st = rt_build_bvh(s);
     if (st != RT_OK) return st;
+    if (getenv("RT_TRACE")) /* development: host time of the build against its device time (the difference is allocation and the per-level read-backs) */
+        fprintf(stderr, "[rt trace] rt_scene_commit: host %.2f ms, device %.2f ms\n",
+                std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_commit).count(), (double)s->stats.build_ms);
     /* the object-space inputs are no longer needed */
     rt_pool_free(ctx, s->d_positions); s->d_positions = nullptr;
     rt_pool_free(ctx, s->d_normals); s->d_normals = nullptr;
