@@ -81,9 +81,10 @@ __global__ void k_intersect(RtScene scene, const RtInstance *inst, uint64_t n, c
  * traversal steps it took to the block's 64x64-pixel region; blocks are then handed out by decreasing cost
  * class of their REGION (128 probes each: smooth, and neighbouring blocks stay together), image order
  * within a class. Scheduling only: results are bit-identical for any order. */
-constexpr uint32_t kRegion = 64;
+constexpr uint32_t kRegionMin = 8; /* the cost table is sized for the smallest region */
 __device__ __forceinline__ uint32_t region_of(const RtFrameParams &p, uint32_t x0, uint32_t y0) {
-    return (y0 / kRegion) * (((uint32_t)p.cam.w + kRegion - 1u) / kRegion) + x0 / kRegion;
+    const uint32_t rg = p.order_region;
+    return (y0 / rg) * (((uint32_t)p.cam.w + rg - 1u) / rg) + x0 / rg;
 }
 __global__ void __launch_bounds__(128) k_block_cost(RtScene scene, RtFrameParams p, RtBlockGeom g, uint32_t *region_cost, uint32_t *vals) {
     const uint32_t blk = blockIdx.x * blockDim.x + threadIdx.x;
@@ -95,6 +96,7 @@ __global__ void __launch_bounds__(128) k_block_cost(RtScene scene, RtFrameParams
         const int x = min((int)x0 + 3, p.cam.w - 1), y = min((int)y0 + 1, p.cam.h - 1);
         XorShift32 rng;
         rng.a = (((uint32_t)x * 0x9E3779B1u) ^ ((uint32_t)y * 0x85EBCA77u)) | 1u;
+        for (uint32_t probe = 0; probe < p.order_probes; probe++) {
         const RtRayState r = rt_camera_ray(p.cam, x, y, rng);
         f3 org = r.org, dir = r.dir, att = r.att, rad = r.rad, res;
         for (uint32_t depth = 0; depth < p.max_depth; depth++) {
@@ -112,6 +114,7 @@ __global__ void __launch_bounds__(128) k_block_cost(RtScene scene, RtFrameParams
                 }
             }
             if (rt_shade_segment(scene, rt_trav_hit_noid(tv), rng, org, dir, att, rad, res)) break;
+        }
         }
         atomicAdd(region_cost + region_of(p, x0, y0), cost);
     }
@@ -1229,7 +1232,7 @@ cudaError_t rt_block_order_temp_bytes(uint32_t n_blocks, size_t *bytes) {
                                                      (const uint32_t *)nullptr, (uint32_t *)nullptr, (int)n_blocks, 0, 8);
 }
 
-uint32_t rt_region_count(int w, int h) { return (((uint32_t)w + kRegion - 1u) / kRegion) * (((uint32_t)h + kRegion - 1u) / kRegion); }
+uint32_t rt_region_count(int w, int h) { return (((uint32_t)w + kRegionMin - 1u) / kRegionMin) * (((uint32_t)h + kRegionMin - 1u) / kRegionMin); }
 
 cudaError_t rt_launch_block_order(cudaStream_t st, const RtScene &scene, const RtFrameParams &p, uint32_t *region_cost, uint32_t *keys_in,
                                   uint32_t *keys_out, uint32_t *vals_in, uint32_t *vals_out, void *temp, size_t temp_bytes) {

@@ -128,6 +128,7 @@ struct rt_renderer {
     uint32_t order_capacity = 0;
     int block_order = 1;          /* megakernel: hand blocks out by decreasing probed cost (RT_BLOCK_ORDER=0 disables) */
     int block_order_min_spp = 32; /* ... from this many samples per pixel (RT_BLOCK_ORDER_MIN_SPP) */
+    int order_region = 32, order_probes = 1; /* cost-ordered hand-out: region side in pixels (RT_ORDER_REGION: 8 .. 256; 64 / 32 / 16 / 8 measured: 32 is +2 % on C2, neutral elsewhere), probe paths per block (RT_ORDER_PROBES: more than one never paid) */
     int sample_parts = 3;         /* megakernel: a pixel's samples are handed out in up to this many parts (RtFrameParams.n_parts; RT_SAMPLE_PARTS=1 disables) */
     uint32_t *d_part_done = nullptr; /* per pixel: parts finished in the current frame */
     uint32_t *gather = nullptr;   /* tile shards: owned pixels are also stored here (peer memory) */
@@ -569,6 +570,8 @@ rt_status rt_renderer_create(rt_context *ctx, rt_renderer_kind kind, int32_t wid
     r->h = height;
     if (const char *e = getenv("RT_TUNE_REFILL")) r->tune_refill = atoi(e) > 0 ? atoi(e) : r->tune_refill;
     if (const char *e = getenv("RT_BLOCK_ORDER")) r->block_order = atoi(e);
+    if (const char *e = getenv("RT_ORDER_REGION")) { const int v = atoi(e); if (v >= 8 && v <= 256 && (v & (v - 1)) == 0) r->order_region = v; }
+    if (const char *e = getenv("RT_ORDER_PROBES")) { const int v = atoi(e); if (v >= 1 && v <= 16) r->order_probes = v; }
     if (const char *e = getenv("RT_SAMPLE_PARTS")) r->sample_parts = atoi(e) >= 1 && atoi(e) <= 3 ? atoi(e) : r->sample_parts;
     if (const char *e = getenv("RT_BLOCK_ORDER_MIN_SPP")) r->block_order_min_spp = atoi(e) > 0 ? atoi(e) : r->block_order_min_spp;
     if (const char *e = getenv("RT_WF_PERSIST")) r->wf_persist = atoi(e);
@@ -802,6 +805,8 @@ rt_status rt_render_frame(rt_renderer *r, const rt_scene *scene, const rt_camera
     p.roulette = (params->flags & RT_RENDER_ROULETTE) ? 1 : 0;
     p.chains = chains;
     p.n_parts = 1;
+    p.order_region = (uint32_t)r->order_region;
+    p.order_probes = (uint32_t)r->order_probes;
     p.part_end[0] = p.part_end[1] = p.part_end[2] = p.spp;
     if (p.resume && !r->has_frame) return rt_set_error(ctx, RT_ERR_STATE, "rt_render_frame", "RT_RENDER_RESUME without a previous frame");
     if (p.resume && (r->last_scene != scene || memcmp(&r->last_camera, camera, sizeof(rt_camera)) != 0 || r->last_depth != params->max_depth ||

@@ -247,6 +247,8 @@ struct RtFrameParams {
      * RT_RENDER_RESUME; all first parts are handed out before any second part. The frame's tail is then one LAST-part
      * chain (a few samples) instead of one whole-pixel chain, and the tail of the long first parts is filled with the
      * later parts of other pixels (profiles/README.md, "The tail of a frame"). */
+    uint32_t order_region;  /* cost-ordered hand-out: side of the regions whose probed cost classes order the blocks (pixels, a power of two >= 8) */
+    uint32_t order_probes;  /* ... and throw-away probe paths per 8x4 block */
     uint32_t n_parts;       /* 1 .. 3 */
     uint32_t part_end[3];   /* part_end[n_parts - 1] == spp */
 };
