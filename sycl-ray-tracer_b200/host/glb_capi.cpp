@@ -55,6 +55,8 @@ int glb_image_decode(const uint8_t *data, size_t n, uint8_t *rgba_out, uint32_t 
         return 1;
     } catch (const std::exception &e) { g_err = e.what(); return 0; }
 }
+/* the 256-entry sRGB decode table of the bake (bake_resize.hpp), for the test that compares it with the reference's */
+void glb_srgb_decode_table(float *out256) { memcpy(out256, raytracer::glb::bake::tables().to_linear, 256 * sizeof(float)); }
 /* the bake's resize to one 512x512 RGBA8 layer (src/image_manager.hpp:52-62) */
 void glb_resize_to_layer(const uint8_t *rgba, uint32_t w, uint32_t h, uint8_t *out) {
     std::vector<uint8_t> src(rgba, rgba + (size_t)w * h * 4);

@@ -20,11 +20,9 @@
  *     focal = 1 / tan(yfov / 2) (:109-128);
  *   - images: every image is resized to 512x512 RGBA8 and baked into the layer array
  *     (src/image_manager.hpp:39-100). Embedded PNG and JPEG are decoded by image_codecs.hpp to exactly
- *     the bytes stb_image hands the reference. The 512x512 resize restates stb_image_resize2's DEFAULT filters
- *     (Catmull-Rom up, Mitchell down, alpha-weighted, linear light; resize_to_layer below) but NOT its float
- *     summation order: it is NOT pinned bit for bit — textures that are not already 512x512 come out within one
- *     code value of the reference's in < 2 % of the texels (tests/test_image_codecs.py); 512x512 inputs pass
- *     through untouched and are exact.
+ *     the bytes stb_image hands the reference, and bake_resize.hpp restates the arithmetic of the reference's
+ *     stbir_resize_uint8_srgb(..., 512, 512, 0, STBIR_RGBA) call operation for operation, so the baked layers are
+ *     the reference's bytes (tests/test_image_codecs.py, against the reference's own library).
  *
  * Explicit fallbacks where the reference relies on undefined behaviour (F15): a primitive without a
  * material -> diffuse 0.8 grey; no camera node -> position (0,0,0), direction (0,0,-1), focal 1. (The reference
@@ -34,6 +32,8 @@
 #pragma once
 
 #include <zlib.h>
+
+#include "bake_resize.hpp"
 
 #include <algorithm>
 #include <array>
@@ -246,114 +246,16 @@ inline bool png_write(const std::string &path, const uint8_t *rgba, uint32_t w, 
     return (bool)f;
 }
 
-/* Resize to one 512x512 layer the way the reference's bake does (stbir_resize_uint8_srgb(..., STBIR_RGBA),
- * src/image_manager.hpp:52-62) — stb_image_resize2's defaults, restated: colour in linear light (sRGB decode
- / encode), alpha linear and used as a weight ("fancy" alpha weighting: colour and alpha-weighted colour are
- * both filtered, the quotient weighted / alpha is the result unless the filtered alpha is below 2^-120, where the
- * plainly filtered colour is kept), edge clamp, separable polyphase filtering with the Catmull-Rom kernel along an axis that
- * is enlarged and the Mitchell-Netravali (B = C = 1/3) kernel, stretched by the scale, along one that is
- * reduced; every output tap set is normalised to sum 1. stb evaluates the same sums in single precision with
- * SIMD in a cost-chosen pass order and encodes sRGB through a table, so individual texels can differ by one
- * (rarely two) code values (tests/test_image_codecs.py measures it against the reference's output); an image
- * that already is 512x512 passes through untouched. */
-inline float resize_kernel_catmull_rom(float x) {
-    x = std::fabs(x);
-    if (x < 1.0f) return 1.0f - x * x * (2.5f - 1.5f * x);
-    if (x < 2.0f) return 2.0f - x * (4.0f + x * (0.5f * x - 2.5f));
-    return 0.0f;
-}
-inline float resize_kernel_mitchell(float x) {
-    x = std::fabs(x);
-    if (x < 1.0f) return (16.0f + x * x * (21.0f * x - 36.0f)) / 18.0f;
-    if (x < 2.0f) return (32.0f + x * (-60.0f + x * (36.0f - 7.0f * x))) / 18.0f;
-    return 0.0f;
-}
-struct ResizeTaps {
-    std::vector<int> first;               /* per output index: first input index (may be < 0: clamped when read) */
-    std::vector<std::vector<float>> w;    /* weights of first, first + 1, ... */
-};
-inline ResizeTaps resize_taps(int in_n, int out_n) {
-    ResizeTaps t;
-    t.first.resize(out_n);
-    t.w.resize(out_n);
-    const double scale = (double)out_n / (double)in_n;
-    for (int o = 0; o < out_n; o++) {
-        int lo, hi;
-        if (scale >= 1.0) { /* enlarge: kernel in input space, support 2 input pixels */
-            const double c = (o + 0.5) / scale;
-            lo = (int)std::floor(c - 2.0 + 0.5);
-            hi = (int)std::floor(c + 2.0 - 0.5);
-            for (int i = lo; i <= hi; i++) t.w[o].push_back(resize_kernel_catmull_rom((float)((i + 0.5) - c)));
-        } else { /* reduce: kernel in output space, support 2 output pixels = 2 / scale input pixels */
-            const double c = o + 0.5;
-            lo = (int)std::floor((c - 2.0) / scale - 0.5);
-            hi = (int)std::ceil((c + 2.0) / scale - 0.5);
-            for (int i = lo; i <= hi; i++) t.w[o].push_back(resize_kernel_mitchell((float)((i + 0.5) * scale - c)) * (float)scale);
-        }
-        t.first[o] = lo;
-        double sum = 0;
-        for (float v : t.w[o]) sum += v;
-        for (float &v : t.w[o]) v = (float)(v / sum);
-    }
-    return t;
-}
+/* Resize to one 512x512 layer exactly as the reference's bake does (stbir_resize_uint8_srgb(..., STBIR_RGBA),
+ * src/image_manager.hpp:52-62): bake_resize.hpp restates that call's single-precision arithmetic in its order, so the
+ * texels are the reference's bytes (tests/test_image_codecs.py compares them with the reference's own library). The
+ * reference resizes EVERY image, 512x512 ones included (both axes then point-sample, which is the identity), so they are
+ * passed through untouched. */
 inline std::vector<uint8_t> resize_to_layer(const std::vector<uint8_t> &src, uint32_t w, uint32_t h) {
     const uint32_t N = RT_TEX_SIZE;
     if (w == N && h == N) return src;
-    static float lin[256];
-    static bool lin_ready = false;
-    if (!lin_ready) {
-        for (int v = 0; v < 256; v++) {
-            const double c = v / 255.0;
-            lin[v] = (float)(c <= 0.04045 ? c / 12.92 : std::pow((c + 0.055) / 1.055, 2.4));
-        }
-        lin_ready = true;
-    }
-    const float tiny = std::ldexp(1.0f, -120);
-    /* decode to 7 planes per pixel: linear colour, alpha, alpha-weighted linear colour ("fancy" alpha weighting:
-     * where the filtered alpha vanishes the plainly filtered colour is kept instead of dividing by ~0) */
-    const int CH = 7;
-    std::vector<float> a((size_t)w * h * CH);
-    for (size_t i = 0; i < (size_t)w * h; i++) {
-        const float al = src[i * 4 + 3] / 255.0f;
-        for (int c = 0; c < 3; c++) {
-            a[i * CH + c] = lin[src[i * 4 + c]];
-            a[i * CH + 4 + c] = lin[src[i * 4 + c]] * al;
-        }
-        a[i * CH + 3] = al;
-    }
-    /* vertical pass: h -> N rows */
-    const ResizeTaps ty = resize_taps((int)h, (int)N), tx = resize_taps((int)w, (int)N);
-    std::vector<float> b((size_t)w * N * CH, 0.0f);
-    for (uint32_t y = 0; y < N; y++)
-        for (size_t k = 0; k < ty.w[y].size(); k++) {
-            const int sy = std::min(std::max(ty.first[y] + (int)k, 0), (int)h - 1);
-            const float wt = ty.w[y][k];
-            const float *in = &a[(size_t)sy * w * CH];
-            float *o = &b[(size_t)y * w * CH];
-            for (size_t i = 0; i < (size_t)w * CH; i++) o[i] += wt * in[i];
-        }
-    /* horizontal pass + encode */
     std::vector<uint8_t> out((size_t)N * N * 4);
-    for (uint32_t y = 0; y < N; y++)
-        for (uint32_t x = 0; x < N; x++) {
-            float acc[CH] = {0, 0, 0, 0, 0, 0, 0};
-            for (size_t k = 0; k < tx.w[x].size(); k++) {
-                const int sx = std::min(std::max(tx.first[x] + (int)k, 0), (int)w - 1);
-                const float wt = tx.w[x][k];
-                const float *in = &b[((size_t)y * w + sx) * CH];
-                for (int c = 0; c < CH; c++) acc[c] += wt * in[c];
-            }
-            uint8_t *o = &out[((size_t)y * N + x) * 4];
-            const float al = acc[3];
-            for (int c = 0; c < 3; c++) {
-                float l = al >= tiny ? acc[4 + c] / al : acc[c];
-                l = std::fmin(std::fmax(l, 0.0f), 1.0f);
-                const double e = l <= 0.0031308f ? l * 12.92 : 1.055 * std::pow((double)l, 1.0 / 2.4) - 0.055;
-                o[c] = (uint8_t)std::lround(std::fmin(std::fmax(e, 0.0), 1.0) * 255.0);
-            }
-            o[3] = (uint8_t)std::fmin(std::fmax(std::floor(al * 255.0f + 0.5f), 0.0f), 255.0f);
-        }
+    bake::resize_srgb_rgba(src.data(), (int)w, (int)h, out.data(), (int)N, (int)N);
     return out;
 }
 
