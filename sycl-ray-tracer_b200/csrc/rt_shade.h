@@ -141,8 +141,15 @@ RT_HD bool rt_shade_segment(const RtScene &s, const RtHit &h, XorShift32 &rng, f
     }
     const rt_float4 *sp = s.shade + (size_t)h.tri * 4;
     rt_float4 s0, s1, s2, s3;
+#if RT_USE_LDG256
     rt_ldg2(sp, s0, s1);
     rt_ldg2(sp + 2, s2, s3);
+#else
+    s0 = rt_ldg_hint<RT_SHADE_LD_HINT>(sp);
+    s1 = rt_ldg_hint<RT_SHADE_LD_HINT>(sp + 1);
+    s2 = rt_ldg_hint<RT_SHADE_LD_HINT>(sp + 2);
+    s3 = rt_ldg_hint<RT_SHADE_LD_HINT>(sp + 3);
+#endif
     const RtInstance &g = s.inst[rt_f2u(s3.w)];
     const float bx = h.u, by = h.v;
     const float bw = (1.0f - bx) - by;

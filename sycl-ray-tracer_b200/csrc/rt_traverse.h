@@ -105,6 +105,45 @@ RT_HD rt_float4 rt_ldg(const rt_float4 *p) {
 #endif
 }
 
+/* Cache-policy hints on the record fetches (compile-time experiments, profiles/README.md): triangle and shading records
+ * are read once per (ray, leaf) and compete in L1 with the nodes of the upper levels, which every ray of the warp re-reads.
+ *   RT_TRI_LD_HINT / RT_SHADE_LD_HINT: 0 = plain LDG.CONSTANT, 1 = L1::no_allocate, 2 = L1::evict_first
+ *   RT_NODE_LD_HINT: 0 = plain, 1 = L1::evict_last */
+#ifndef RT_TRI_LD_HINT
+#define RT_TRI_LD_HINT 0
+#endif
+#ifndef RT_SHADE_LD_HINT
+#define RT_SHADE_LD_HINT 0
+#endif
+#ifndef RT_NODE_LD_HINT
+#define RT_NODE_LD_HINT 0
+#endif
+template <int HINT>
+RT_HD rt_float4 rt_ldg_hint(const rt_float4 *p) {
+#if RT_DEVICE_CODE
+    if (HINT == 1) {
+        rt_float4 r;
+        asm("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+        return r;
+    }
+    if (HINT == 2) {
+        rt_float4 r;
+        asm("ld.global.nc.L1::evict_first.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+        return r;
+    }
+#endif
+    return rt_ldg(p);
+}
+RT_HD rt_uint4 rt_ldg_node(const rt_uint4 *p) {
+#if RT_DEVICE_CODE && RT_NODE_LD_HINT == 1
+    rt_uint4 r;
+    asm("ld.global.nc.L1::evict_last.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+#else
+    return rt_ldg(p);
+#endif
+}
+
 /* read-only 32-byte load of two consecutive 16-byte records (p must be 32-byte aligned) */
 RT_HD void rt_ldg2(const rt_uint4 *p, rt_uint4 &a, rt_uint4 &b) {
 #if RT_DEVICE_CODE && RT_USE_LDG256
@@ -474,14 +513,18 @@ RT_HD void rt_trav_node_step(const RtBvh &bvh, RtTravState &s, Stacks &k) {
     const uint32_t rel = (uint32_t)rt_popc(imask & ~(0xffffffffu << slot));
     const rt_uint4 *np = bvh.nodes + (size_t)(s.ng_x + rel) * RT_NODE_VEC4;
     rt_uint4 n0, n1, n2, n3, n4;
-    rt_ldg2(np, n0, n1);
-    rt_ldg2(np + 2, n2, n3);
 #if RT_USE_LDG256
     rt_uint4 n5;
+    rt_ldg2(np, n0, n1);
+    rt_ldg2(np + 2, n2, n3);
     rt_ldg2(np + 4, n4, n5);
     (void)n5;
 #else
-    n4 = rt_ldg(np + 4);
+    n0 = rt_ldg_node(np);
+    n1 = rt_ldg_node(np + 1);
+    n2 = rt_ldg_node(np + 2);
+    n3 = rt_ldg_node(np + 3);
+    n4 = rt_ldg_node(np + 4);
 #endif
     RT_COUNT_NODE();
     const uint32_t hits = rt_node_test<MASK>(s.org, s.rcp, oct_inv, n0, n2, n3, n4, s.tnear, s.t * RT_BOX_PAD);
@@ -524,13 +567,15 @@ RT_HD void rt_trav_tri_step(const RtBvh &bvh, RtTravState &s, Stacks &k, const R
     else s.tsp--;
     const rt_float4 *tp = bvh.tris + (size_t)tslot * RT_TRI_VEC4;
     rt_float4 a, b, c;
-    rt_ldg2(tp, a, b);
 #if RT_USE_LDG256
     rt_float4 d;
+    rt_ldg2(tp, a, b);
     rt_ldg2(tp + 2, c, d);
     (void)d;
 #else
-    c = rt_ldg(tp + 2);
+    a = rt_ldg_hint<RT_TRI_LD_HINT>(tp);
+    b = rt_ldg_hint<RT_TRI_LD_HINT>(tp + 1);
+    c = rt_ldg_hint<RT_TRI_LD_HINT>(tp + 2);
 #endif
     RT_COUNT_TRI();
     rt_tri_test(bvh, rt, mk3(a.x, a.y, a.z), mk3(b.x, b.y, b.z), mk3(c.x, c.y, c.z), tslot, rt_f2u(c.w), s.tnear, s.t, s.u, s.v,
