@@ -233,13 +233,17 @@ struct SmemStacks {
 #define RT_MEGA_IDP_MASK 7
 #endif
 template <int MASK = RT_BYTE_IDP_MASK, class Stacks>
-__device__ __forceinline__ void traverse_phase(const RtBvh &bvh, RtTravState &tv, Stacks &ks, int &mode, int refill) {
+__device__ __forceinline__ void traverse_phase(const RtBvh &bvh, RtTravState &tv, Stacks &ks, int &mode, int refill_carry /* tune_refill | tune_carry << 8 */) {
     const unsigned full = 0xffffffffu;
+    const int refill = refill_carry & 0xff, carry_cfg = refill_carry >> 8;
     const bool trav = mode == kTraversing;
     const unsigned m_trav = __ballot_sync(full, trav); /* does not change inside the node loop */
+    /* lanes that carried triangles over from the previous drain (tune_carry) have no nodes to begin with: they neither count as
+     * lanes that ran dry nor as lanes that could */
+    const unsigned m_run = __ballot_sync(full, trav && rt_trav_has_node(tv));
     /* the refill threshold scales with the lanes that still have work: in the drain of a frame (most lanes
      * exhausted) a finished lane must not wait for every other ray of its warp */
-    const int thr = max(1, (__popc(m_trav) * refill + 31) >> 5);
+    const int thr = max(1, (__popc(m_run) * refill + 31) >> 5);
     for (;;) {
         if (trav && rt_trav_has_node(tv)) rt_trav_node_step<MASK>(bvh, tv, ks);
         const bool node = trav && rt_trav_has_node(tv);
@@ -247,24 +251,32 @@ __device__ __forceinline__ void traverse_phase(const RtBvh &bvh, RtTravState &tv
         /* leave when no lane has nodes left, `refill` lanes have run dry, or a lane's triangle stack
          * is full (draining on a pending-triangle count instead was measured and never paid off) */
         const bool out = trav && rt_trav_tri_full(tv);
-        if (!m_node || __popc(m_trav & ~m_node) >= thr || __any_sync(full, out)) break;
+        if (!m_node || __popc(m_run & ~m_node) >= thr || __any_sync(full, out)) break;
     }
     /* drain: lanes that are out of nodes (or nearly out of triangle-stack room) must finish their
      * triangles; every other lane with triangles pending joins in, and carries what is left to the
-     * next drain. The nine-float shear form lives in registers only here (rt_traverse.h, RtTravState). */
+     * next drain. The nine-float shear form lives in registers only here (rt_traverse.h, RtTravState).
+     * tune_carry > 0: the drain's length is set by the lane with the MOST triangles pending while the others idle, so it stops
+     * once no more than `carry` lanes (scaled like the refill threshold) still have to finish; those lanes stay in the traversing
+     * state without nodes, sit out the next node loop and finish in the next drain, where other lanes' new triangles fill the
+     * warp. Every drain runs at least one round, so they always make progress; lanes short of stack room are never carried. */
     {
+        const int carry = (__popc(m_trav) * carry_cfg + 31) >> 5;
         bool tri = mode == kTraversing && rt_trav_has_tri(tv);
-        bool must = tri && (!rt_trav_has_node(tv) || tv.tsp >= RT_TSTACK_SIZE - 2);
-        if (__any_sync(full, must)) {
+        bool must_room = tri && tv.tsp >= RT_TSTACK_SIZE - 2, must_dry = tri && !rt_trav_has_node(tv);
+        if (__any_sync(full, must_room || must_dry)) {
             const RtRayTri rtri = rt_trav_ray_tri(tv);
+            bool again;
             do {
                 if (tri) rt_trav_tri_step(bvh, tv, ks, rtri);
                 tri = mode == kTraversing && rt_trav_has_tri(tv);
-                must = tri && (!rt_trav_has_node(tv) || tv.tsp >= RT_TSTACK_SIZE - 2);
-            } while (__any_sync(full, must));
+                must_room = tri && tv.tsp >= RT_TSTACK_SIZE - 2;
+                must_dry = tri && !rt_trav_has_node(tv);
+                again = __any_sync(full, must_room) || __popc(__ballot_sync(full, must_dry)) > carry; /* carry 0: while any lane must */
+            } while (again);
         }
     }
-    if (mode == kTraversing && !rt_trav_has_node(tv)) mode = kHitPending;
+    if (mode == kTraversing && !rt_trav_has_node(tv) && !rt_trav_has_tri(tv)) mode = kHitPending;
 }
 
 #ifndef RT_MEGA_MIN_BLOCKS
@@ -1071,7 +1083,7 @@ __global__ void __launch_bounds__(kWfBlock, RT_EXT_MIN_BLOCKS) k_wf_flow(RtScene
         for (;;) {
             const uint32_t n_hits = hit_tail - hit_head, n_rays = ray_tail - ray_head;
             const int n_idle = 32 - __popc(m_trav);
-            if (!(n_hits >= 32u || (n_hits > 0u && n_rays == 0u && (n_idle >= p.tune_refill || !m_trav)))) break;
+            if (!(n_hits >= 32u || (n_hits > 0u && n_rays == 0u && (n_idle >= (p.tune_refill & 0xff) || !m_trav)))) break;
             const uint32_t n = n_hits < 32u ? n_hits : 32u;
             bool keep = false;
             uint32_t spix = 0;

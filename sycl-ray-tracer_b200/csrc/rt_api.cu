@@ -140,8 +140,11 @@ struct rt_renderer {
     uint32_t last_chains = 1;
     const float4 *peer_accum[16] = {}; /* spp slices across processes: every rank's accumulation buffer (IPC mappings) */
     uint32_t peer_world = 0, peer_rank = 0;
-    int tune_refill = 14; /* lanes that must run dry before a warp refills (RT_TUNE_REFILL overrides; 8 / 10 / 12 / 14 / 16 measured on C3:
-                             3187 / 3306 / 3368 / 3391 / 3388 Mrays/s) */
+    int tune_refill = 16; /* lanes that must run dry before a warp refills (RT_TUNE_REFILL overrides; measured together with tune_carry,
+                             profiles/r02_ab_refill_carry.log: megakernel 16 / 2, queue-driven wavefront 12 / 3) */
+    int tune_carry = 2;   /* drain: lanes (of 32) that may carry unfinished triangles into the next drain instead of holding the
+                             warp (RT_TUNE_CARRY; render.cu traverse_phase). 0 / 1 / 2 / 3 / 4 / 8 on C3: 3502 / 3571 / 3580 / 3559 / 3524 /
+                             3359 Mrays/s, bit-identical images (profiles/r02_ab_drain_carry.log) */
     int tune_ctx = 0;     /* megakernel: parked ray contexts per lane (RT_MEGA_CTX 1-4 = k_megakernel_ctx; measured slower than the
                              one-pixel-in-registers kernel on C2/C3/C4, profiles/README.md) */
     int tune_inflight = 64; /* wavefront, queue-driven warps: pixels in flight per warp (RT_TUNE_INFLIGHT; measured 32 / 64 / 96 / 128 / 256 / 512:
@@ -575,12 +578,14 @@ rt_status rt_renderer_create(rt_context *ctx, rt_renderer_kind kind, int32_t wid
     if (const char *e = getenv("RT_SAMPLE_PARTS")) r->sample_parts = atoi(e) >= 1 && atoi(e) <= 3 ? atoi(e) : r->sample_parts;
     if (const char *e = getenv("RT_BLOCK_ORDER_MIN_SPP")) r->block_order_min_spp = atoi(e) > 0 ? atoi(e) : r->block_order_min_spp;
     if (const char *e = getenv("RT_WF_PERSIST")) r->wf_persist = atoi(e);
+    if (const char *e = getenv("RT_TUNE_CARRY")) r->tune_carry = atoi(e) >= 0 && atoi(e) <= 32 ? atoi(e) : r->tune_carry;
     if (const char *e = getenv("RT_TUNE_INFLIGHT")) r->tune_inflight = atoi(e) >= 32 && atoi(e) <= 65536 ? (atoi(e) + 31) / 32 * 32 : r->tune_inflight;
     if (const char *e = getenv("RT_MEGA_CTX")) r->tune_ctx = atoi(e) >= 0 && atoi(e) <= 4 ? atoi(e) : r->tune_ctx;
     if (const char *e = getenv("RT_TUNE_SHADE")) r->tune_shade = atoi(e) > 0 ? atoi(e) : r->tune_shade;
     if (const char *e = getenv("RT_TUNE_IDLE")) r->tune_idle = atoi(e) > 0 ? atoi(e) : r->tune_idle;
     if (kind == RT_MEGAKERNEL && r->tune_ctx > 0 && !getenv("RT_TUNE_REFILL")) r->tune_refill = 8;
-    if (kind == RT_WAVEFRONT && r->wf_persist >= 2 && !getenv("RT_TUNE_REFILL")) r->tune_refill = 14;
+    if (kind == RT_WAVEFRONT && !getenv("RT_TUNE_REFILL")) r->tune_refill = r->wf_persist >= 2 ? 12 : 14;
+    if (kind == RT_WAVEFRONT && !getenv("RT_TUNE_CARRY")) r->tune_carry = r->wf_persist >= 2 ? 3 : 2;
     const size_t n = (size_t)width * (size_t)height;
     cudaError_t e = cudaSuccess;
     do {
@@ -796,7 +801,7 @@ rt_status rt_render_frame(rt_renderer *r, const rt_scene *scene, const rt_camera
     p.tile_size = sh.tile_size;
     p.wavefront_seed = r->kind == RT_WAVEFRONT ? 1 : 0;
     p.clamp_samples = r->kind == RT_WAVEFRONT ? 1 : 0;
-    p.tune_refill = r->tune_refill;
+    p.tune_refill = (r->tune_refill & 0xff) | ((r->tune_ctx == 0 ? r->tune_carry : 0) << 8); /* packed: both reach traverse_phase as one kernel argument */
     p.tune_ctx = r->tune_ctx;
     p.tune_shade = r->tune_shade;
     p.tune_idle = r->tune_idle;

@@ -138,6 +138,14 @@ RT_HD float rt_div(float a, float b) {
     return a / b;
 #endif
 }
+/* v / 255.0f for v = 0 .. 255 (texel byte -> colour, src/material.hpp via the unorm8 read), correctly rounded without the
+ * IEEE-division sequence and its range check: q0 = v * RN(1/255), one FMA residual, one FMA correction (the last step of
+ * Markstein's division). Equal to v / 255.0f for all 256 inputs (tests/test_hostemu_parity.py checks every one). */
+RT_HD float rt_u8_to_unit(float v) {
+    const float rc = 0.0039215688593685627f; /* 0x3b808081 */
+    const float q0 = v * rc;
+    return rt_fma(rt_fma(-255.0f, q0, v), rc, q0);
+}
 RT_HD float rt_sqrt(float a) {
 #if RT_DEVICE_CODE
     return __fsqrt_rn(a);

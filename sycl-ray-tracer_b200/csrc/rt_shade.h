@@ -99,10 +99,10 @@ RT_HD f3 rt_texture_sample(const RtScene &s, int layer, float su, float sv) {
     int ix = rt_wrap_texel(su), iy = rt_wrap_texel(sv);
 #if RT_DEVICE_CODE
     uchar4 t = tex2DLayered<uchar4>(s.tex, (float)ix, (float)iy, layer);
-    return mk3(rt_div((float)t.x, 255.0f), rt_div((float)t.y, 255.0f), rt_div((float)t.z, 255.0f));
+    return mk3(rt_u8_to_unit((float)t.x), rt_u8_to_unit((float)t.y), rt_u8_to_unit((float)t.z));
 #else
     const uint8_t *p = s.tex_raw + (((size_t)layer * RT_TEX_DIM + (size_t)iy) * RT_TEX_DIM + (size_t)ix) * 4;
-    return mk3((float)p[0] / 255.0f, (float)p[1] / 255.0f, (float)p[2] / 255.0f);
+    return mk3(rt_u8_to_unit((float)p[0]), rt_u8_to_unit((float)p[1]), rt_u8_to_unit((float)p[2]));
 #endif
 }
 

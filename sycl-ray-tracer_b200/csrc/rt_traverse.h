@@ -263,12 +263,14 @@ RT_HD RtRayPre rt_ray_pre(f3 dir) {
     }
     r.nSx = -rt_div(sel3(dir, kx), dz);
     r.nSy = -rt_div(sel3(dir, ky), dz);
-    r.Sz = rt_div(1.0f, dz);
     const float tiny = 1e-20f;
     float dx = fabsf(dir.x) > tiny ? dir.x : copysignf(tiny, dir.x);
     float dy = fabsf(dir.y) > tiny ? dir.y : copysignf(tiny, dir.y);
     float dzz = fabsf(dir.z) > tiny ? dir.z : copysignf(tiny, dir.z);
     r.rcp = mk3(rt_div(1.0f, dx), rt_div(1.0f, dy), rt_div(1.0f, dzz));
+    /* 1 / dir[kz]: the dominant component is not clamped unless the direction vanishes altogether, so it IS the slab
+     * reciprocal of that axis (one IEEE division less per ray) */
+    r.Sz = fabsf(dz) > tiny ? sel3(r.rcp, kz) : rt_div(1.0f, dz);
     const uint32_t neg = (dx < 0.0f ? 1u : 0u) | (dy < 0.0f ? 2u : 0u) | (dzz < 0.0f ? 4u : 0u);
     /* slot s is visited in order of increasing (s ^ octant), octant = x<<2 | y<<1 | z sign bits */
     const uint32_t octant = (dx < 0.0f ? 4u : 0u) | (dy < 0.0f ? 2u : 0u) | (dzz < 0.0f ? 1u : 0u);

@@ -559,6 +559,14 @@ extern "C" uint32_t emu_trace_pixel(const emu_scene *s, int wavefront_seed, cons
     return n;
 }
 
+/* rt_u8_to_unit (rt_hd.h) and the direction-only ray set-up (rt_traverse.h) for the exhaustive / randomised checks */
+extern "C" float emu_u8_to_unit(int v) { return rt_u8_to_unit((float)v); }
+extern "C" void emu_ray_pre(const float *dir, float *out7, uint32_t *code) {
+    const RtRayPre q = rt_ray_pre(mk3(dir[0], dir[1], dir[2]));
+    out7[0] = q.rcp.x; out7[1] = q.rcp.y; out7[2] = q.rcp.z;
+    out7[3] = q.nSx; out7[4] = q.nSy; out7[5] = q.Sz;
+    *code = q.code;
+}
 extern "C" void emu_counters(unsigned long long *nodes, unsigned long long *tris, int reset) {
     *nodes = g_count_node;
     *tris = g_count_tri;

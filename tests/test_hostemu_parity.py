@@ -237,3 +237,43 @@ def test_large_triangles_next_to_dense_detail(monkeypatch, oracle, hostemu, scen
         monkeypatch.delenv("RT_SPLIT")
         plain = hostemu.Scene(data)
         assert emu.node_count != plain.node_count
+
+
+def test_texel_byte_to_unit_is_the_ieee_quotient_for_all_bytes(hostemu):
+    """rt_u8_to_unit (csrc/rt_hd.h: v * RN(1/255) + one FMA residual + one FMA correction, what the kernels use instead of the
+    IEEE division sequence) equals v / 255.0f, correctly rounded, for every byte"""
+    import ctypes as C
+    L = hostemu.lib()
+    L.emu_u8_to_unit.restype = C.c_float
+    L.emu_u8_to_unit.argtypes = [C.c_int]
+    got = np.array([L.emu_u8_to_unit(v) for v in range(256)], np.float32)
+    want = np.arange(256, dtype=np.float32) / np.float32(255.0)
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+
+
+def test_ray_setup_shares_the_dominant_axis_reciprocal(hostemu):
+    """rt_ray_pre (csrc/rt_traverse.h) takes 1 / dir[kz] of the triangle shear from the slab reciprocals instead of dividing
+    again: the six values equal the plainly divided ones bit for bit, also for axis-aligned, tiny and zero components"""
+    import ctypes as C
+    L = hostemu.lib()
+    L.emu_ray_pre.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    rs = np.random.RandomState(3)
+    dirs = (rs.rand(4000, 3).astype(np.float32) - np.float32(0.5))
+    dirs[::7] = dirs[::7].astype(np.float16).astype(np.float32)          # what the kernels really see (F6)
+    dirs[::11, 0] = 0.0
+    dirs[::13, 1] = -0.0
+    dirs[::17, :2] = 0.0
+    dirs[::19] *= np.float32(1e-22)
+    dirs[5] = (0.0, 0.0, 0.0)
+    tiny = np.float32(1e-20)
+    one = np.float32(1.0)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        for d in dirs:
+            out, code = np.zeros(7, np.float32), np.zeros(1, np.uint32)
+            L.emu_ray_pre(d.ctypes.data, out.ctypes.data, code.ctypes.data)
+            kx, ky, kz = int(code[0] & 3), int((code[0] >> 2) & 3), int((code[0] >> 4) & 3)
+            a = np.abs(d)
+            assert a[kz] == a.max() and sorted((kx, ky, kz)) == [0, 1, 2]
+            c = np.where(a > tiny, d, np.copysign(tiny, d)).astype(np.float32)
+            want = np.array([one / c[0], one / c[1], one / c[2], -(d[kx] / d[kz]), -(d[ky] / d[kz]), one / d[kz]], np.float32)
+            assert np.array_equal(out[:6].view(np.uint32), want.view(np.uint32)), (d, out[:6], want)

@@ -13,7 +13,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import bench
 pkg = importlib.import_module("sycl-ray-tracer_b200")
-KNOBS = ("RT_MEGA_CTX", "RT_TUNE_REFILL", "RT_TUNE_SHADE", "RT_TUNE_IDLE", "RT_BLOCK_ORDER", "RT_WF_PERSIST", "RT_SAMPLE_PARTS", "RT_TUNE_INFLIGHT", "RT_BLOCK_ORDER_MIN_SPP", "RT_ORDER_REGION", "RT_ORDER_PROBES")
+KNOBS = ("RT_MEGA_CTX", "RT_TUNE_REFILL", "RT_TUNE_SHADE", "RT_TUNE_IDLE", "RT_BLOCK_ORDER", "RT_WF_PERSIST", "RT_SAMPLE_PARTS", "RT_TUNE_INFLIGHT", "RT_BLOCK_ORDER_MIN_SPP", "RT_ORDER_REGION", "RT_ORDER_PROBES", "RT_TUNE_CARRY")
 ap = argparse.ArgumentParser()
 ap.add_argument("--workload", default="c3_sponza_scale")
 ap.add_argument("--renderer", default="megakernel")
