@@ -232,7 +232,13 @@ struct SmemStacks {
 #ifndef RT_MEGA_IDP_MASK
 #define RT_MEGA_IDP_MASK 7
 #endif
-template <int MASK = RT_BYTE_IDP_MASK, class Stacks>
+/* UNROLL = node steps per exit vote. Two votes, a population count and the branches are 17 of the ~285 instructions of a
+ * node-loop round; with two steps per round lanes that run dry in the first sit out the second. Measured (72 registers,
+ * profiles/r02_ab_regs_unroll.log): megakernel C3 3680 -> 3739, C2 7501 -> 7431; queue-driven wavefront C3 3611 -> 3603. */
+#ifndef RT_MEGA_NODE_UNROLL
+#define RT_MEGA_NODE_UNROLL 2
+#endif
+template <int MASK = RT_BYTE_IDP_MASK, int UNROLL = 1, class Stacks>
 __device__ __forceinline__ void traverse_phase(const RtBvh &bvh, RtTravState &tv, Stacks &ks, int &mode, int refill_carry /* tune_refill | tune_carry << 8 */) {
     const unsigned full = 0xffffffffu;
     const int refill = refill_carry & 0xff, carry_cfg = refill_carry >> 8;
@@ -246,6 +252,7 @@ __device__ __forceinline__ void traverse_phase(const RtBvh &bvh, RtTravState &tv
     const int thr = max(1, (__popc(m_run) * refill + 31) >> 5);
     for (;;) {
         if (trav && rt_trav_has_node(tv)) rt_trav_node_step<MASK>(bvh, tv, ks);
+        if (UNROLL == 2 && trav && rt_trav_has_node(tv) && !rt_trav_tri_full(tv)) rt_trav_node_step<MASK>(bvh, tv, ks);
         const bool node = trav && rt_trav_has_node(tv);
         const unsigned m_node = __ballot_sync(full, node);
         /* leave when no lane has nodes left, `refill` lanes have run dry, or a lane's triangle stack
@@ -279,8 +286,13 @@ __device__ __forceinline__ void traverse_phase(const RtBvh &bvh, RtTravState &tv
     if (mode == kTraversing && !rt_trav_has_node(tv) && !rt_trav_has_tri(tv)) mode = kHitPending;
 }
 
+/* resident CTAs per SM the megakernel is compiled for: 7 x 128 threads = 72 registers, no spills; 8 (64 registers) spills
+ * ~20 words of which two are re-loaded in every node visit, 6 (80 registers) has too few warps. Measured C3 / C2 / C4:
+ * 8: 3605 / 7326 / 4167, 7: 3685 / 7509 / 4258, 6: 3503 / 7292 / 4059 Mrays/s (profiles/r02_ab_stacktop_regs.log,
+ * r02_ab_regs_unroll.log). The queue-driven wavefront kernel stays at 4 x 256 threads / 64 registers (8 bytes of spill);
+ * 128 x 7, 128 x 6 and 256 x 3 are 5-8 % slower there. */
 #ifndef RT_MEGA_MIN_BLOCKS
-#define RT_MEGA_MIN_BLOCKS 8
+#define RT_MEGA_MIN_BLOCKS 7
 #endif
 /* Nine fp16 values in five registers. Between two bounces direction, attenuation and radiance ARE fp16 values
  * (RayData, F6), so holding them packed across the traversal loses nothing: cvt.rn.f16x2.f32 rounds each half
@@ -471,7 +483,7 @@ __global__ void __launch_bounds__(kMegaBlock, RT_MEGA_MIN_BLOCKS) k_megakernel(R
             __nanosleep(500); /* only lanes waiting for a part that another warp is finishing: look again */
             continue;
         }
-        traverse_phase<RT_MEGA_IDP_MASK>(scene.bvh, tv, ks, mode, p.tune_refill);
+        traverse_phase<RT_MEGA_IDP_MASK, RT_MEGA_NODE_UNROLL>(scene.bvh, tv, ks, mode, p.tune_refill);
     }
     unsigned long long total = rays;
 #pragma unroll

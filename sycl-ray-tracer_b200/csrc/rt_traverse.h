@@ -428,6 +428,11 @@ RT_HD uint32_t rt_node_test(f3 org, f3 rcp, uint32_t oct_inv, rt_uint4 n0, rt_ui
  * of nodes), then drain the pending triangles together. Deferring the triangle tests only delays the
  * shrinking of tmax; the closest hit (min t, then min id) does not depend on the test order. */
 #define RT_TSTACK_SIZE 8
+/* RT_STACK_TOP = 1 keeps the top of the node stack in two registers: a pop then is a register move and the load of the
+ * entry below it is off the critical path (popped group -> node address -> node fetch). Costs two registers. */
+#ifndef RT_STACK_TOP
+#define RT_STACK_TOP 0
+#endif
 /* Kept small on purpose: the node test needs ~40 registers of its own (20 of node data), and whatever of
  * this state does not fit next to it in the kernels' 64 registers is re-loaded from local memory on EVERY
  * node visit (round 1: ten spill loads per visit, a quarter of the L1TEX sectors of the node loop). So the
@@ -443,6 +448,9 @@ struct RtTravState {
     float t, u, v;      /* closest hit so far (t = tfar: none) */
     uint32_t tri;       /* its slot in the leaf-ordered triangle array, RT_MISS when nothing was hit */
     uint32_t ng_x, ng_y; /* current node group: (child base, child hit bits << 24 | imask) */
+#if RT_STACK_TOP
+    uint32_t top_x, top_y; /* the most recently deferred group, held in registers (top_y <= 0x00ffffff: none) */
+#endif
     int sp, tsp;
 };
 RT_HD uint32_t rt_trav_oct_inv(const RtTravState &s) { return (s.code >> 9) & 7u; }
@@ -487,6 +495,10 @@ RT_HD void rt_trav_init_pre(RtTravState &s, f3 org, const RtRayPre &pre, float t
     s.tri = RT_MISS;
     s.sp = 0;
     s.tsp = 0;
+#if RT_STACK_TOP
+    s.top_x = 0;
+    s.top_y = 0;
+#endif
     s.ng_x = 0;
     s.ng_y = 0x80000000u; /* the root, as the only child of a virtual group (imask 0: rank 0 for any slot) */
 }
@@ -507,8 +519,17 @@ RT_HD void rt_trav_node_step(const RtBvh &bvh, RtTravState &s, Stacks &k) {
     const int bit = rt_bfind(s.ng_y);
     s.ng_y &= ~(1u << bit);
     if (s.ng_y > 0x00ffffffu) { /* siblings still pending: keep the group for later */
+#if RT_STACK_TOP
+        if (s.top_y > 0x00ffffffu) {
+            k.node_put(s.sp, rt_pack2(s.top_x, s.top_y));
+            s.sp++;
+        }
+        s.top_x = s.ng_x;
+        s.top_y = s.ng_y;
+#else
         k.node_put(s.sp, rt_pack2(s.ng_x, s.ng_y));
         s.sp++;
+#endif
     }
     const uint32_t oct_inv = rt_trav_oct_inv(s);
     const uint32_t slot = ((uint32_t)bit - 24u) ^ oct_inv;
@@ -538,12 +559,26 @@ RT_HD void rt_trav_node_step(const RtBvh &bvh, RtTravState &s, Stacks &k) {
         k.tri_put(s.tsp, rt_pack2(n1.y, (leaf << 24) | n1.z));
         s.tsp++;
     }
+#if RT_STACK_TOP
+    if (s.ng_y <= 0x00ffffffu && s.top_y > 0x00ffffffu) { /* no child hit: next pending group, from registers */
+        s.ng_x = s.top_x;
+        s.ng_y = s.top_y;
+        s.top_y = 0;
+        if (s.sp > 0) { /* refill the register copy; nobody waits for this load */
+            s.sp--;
+            const uint64_t e = k.node_get(s.sp);
+            s.top_x = (uint32_t)e;
+            s.top_y = (uint32_t)(e >> 32);
+        }
+    }
+#else
     if (s.ng_y <= 0x00ffffffu && s.sp > 0) { /* no child hit: next pending group */
         s.sp--;
         const uint64_t e = k.node_get(s.sp);
         s.ng_x = (uint32_t)e;
         s.ng_y = (uint32_t)(e >> 32);
     }
+#endif
 }
 
 template <class Stacks>
