@@ -236,7 +236,13 @@ struct SmemStacks {
  * node-loop round; with two steps per round lanes that run dry in the first sit out the second. Measured (72 registers,
  * profiles/r02_ab_regs_unroll.log): megakernel C3 3680 -> 3739, C2 7501 -> 7431; queue-driven wavefront C3 3611 -> 3603. */
 #ifndef RT_MEGA_NODE_UNROLL
-#define RT_MEGA_NODE_UNROLL 2
+#define RT_MEGA_NODE_UNROLL 3
+#endif
+#ifndef RT_WF_NODE_UNROLL
+#define RT_WF_NODE_UNROLL 1
+#endif
+#ifndef RT_NODE_STEPS_ROLLED
+#define RT_NODE_STEPS_ROLLED 1
 #endif
 template <int MASK = RT_BYTE_IDP_MASK, int UNROLL = 1, class Stacks>
 __device__ __forceinline__ void traverse_phase(const RtBvh &bvh, RtTravState &tv, Stacks &ks, int &mode, int refill_carry /* tune_refill | tune_carry << 8 */) {
@@ -251,8 +257,16 @@ __device__ __forceinline__ void traverse_phase(const RtBvh &bvh, RtTravState &tv
      * exhausted) a finished lane must not wait for every other ray of its warp */
     const int thr = max(1, (__popc(m_run) * refill + 31) >> 5);
     for (;;) {
+#if RT_NODE_STEPS_ROLLED /* one copy of the node test, run UNROLL times */
+#pragma unroll 1
+        for (int u = 0; u < UNROLL; u++)
+            if (trav && rt_trav_has_node(tv) && !rt_trav_tri_full(tv)) rt_trav_node_step<MASK>(bvh, tv, ks);
+#else
         if (trav && rt_trav_has_node(tv)) rt_trav_node_step<MASK>(bvh, tv, ks);
-        if (UNROLL == 2 && trav && rt_trav_has_node(tv) && !rt_trav_tri_full(tv)) rt_trav_node_step<MASK>(bvh, tv, ks);
+#pragma unroll
+        for (int u = 1; u < UNROLL; u++)
+            if (trav && rt_trav_has_node(tv) && !rt_trav_tri_full(tv)) rt_trav_node_step<MASK>(bvh, tv, ks);
+#endif
         const bool node = trav && rt_trav_has_node(tv);
         const unsigned m_node = __ballot_sync(full, node);
         /* leave when no lane has nodes left, `refill` lanes have run dry, or a lane's triangle stack
@@ -1133,7 +1147,7 @@ __global__ void __launch_bounds__(kWfBlock, RT_EXT_MIN_BLOCKS) k_wf_flow(RtScene
             if (inflight == 0u && !more) break; /* every pixel this warp claimed has finished its samples */
             continue;
         }
-        traverse_phase(scene.bvh, tv, ks, mode, p.tune_refill);
+        traverse_phase<RT_BYTE_IDP_MASK, RT_WF_NODE_UNROLL>(scene.bvh, tv, ks, mode, p.tune_refill);
     }
     if (lane == 0 && rays) atomicAdd(ray_counter, rays);
 }
