@@ -200,6 +200,38 @@ def test_tile_shards_sum_to_unsharded(pkg, app, scenes):
     scene.close()
 
 
+@pytest.mark.parametrize("kind", ["megakernel", "wavefront"])
+def test_drain_and_refill_knobs_change_nothing(pkg, app, scenes, monkeypatch, kind):
+    """the drain carry-over (RT_TUNE_CARRY: lanes that may take unfinished triangles into the next drain) and the refill
+    threshold (RT_TUNE_REFILL) only decide WHEN a lane's triangles are tested: image, accumulation buffer, final stream states
+    and ray count equal the frame rendered with a carry of 0 (every drain runs to the end) at every setting, on a scene with
+    textures, all three materials and deep paths"""
+    data = scenes.sponza_scale_scene(32, 2, 9)
+    scene = pkg.Scene(app, data)
+    w, h = 192, 128
+    cam = pkg.Camera((w, h), data.camera_position, data.camera_direction, data.camera_focal_length)
+    cls = pkg.MegakernelRenderer if kind == "megakernel" else pkg.WavefrontRenderer
+    ref = None
+    for carry, refill in ((0, 14), (None, None), (1, 16), (5, 8), (12, 24), (32, 31), (3, 1)):
+        if carry is None:
+            monkeypatch.delenv("RT_TUNE_CARRY", raising=False)
+            monkeypatch.delenv("RT_TUNE_REFILL", raising=False)
+        else:
+            monkeypatch.setenv("RT_TUNE_CARRY", str(carry))
+            monkeypatch.setenv("RT_TUNE_REFILL", str(refill))
+        r = cls(app, (w, h), None, 8, 6)
+        f = r.render_frame(cam, scene)
+        got = (f.rgba8.copy(), f.accum.view(np.uint32).copy(), f.rng_state.copy(), f.ray_count)
+        r.close()
+        if ref is None:
+            ref = got
+            continue
+        assert got[3] == ref[3], (carry, refill)
+        for a, b in zip(got[:3], ref[:3]):
+            assert np.array_equal(a, b), (carry, refill)
+    scene.close()
+
+
 def test_cost_ordered_block_handout_changes_nothing(pkg, oracle, app, scenes, monkeypatch):
     """from 32 spp the megakernel hands its 8x4 pixel blocks out by decreasing probed cost (k_block_cost):
     scheduling only — every output equals the enumeration-order frame (RT_BLOCK_ORDER=0) and the oracle,
