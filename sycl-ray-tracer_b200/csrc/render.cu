@@ -238,13 +238,16 @@ struct SmemStacks {
 #ifndef RT_MEGA_NODE_UNROLL
 #define RT_MEGA_NODE_UNROLL 3
 #endif
+#ifndef RT_MEGA_NODE_NEAR /* within this many dry lanes of the refill threshold the vote is taken after every step again (0 = never) */
+#define RT_MEGA_NODE_NEAR 0
+#endif
 #ifndef RT_WF_NODE_UNROLL
 #define RT_WF_NODE_UNROLL 1
 #endif
 #ifndef RT_NODE_STEPS_ROLLED
 #define RT_NODE_STEPS_ROLLED 1
 #endif
-template <int MASK = RT_BYTE_IDP_MASK, int UNROLL = 1, class Stacks>
+template <int MASK = RT_BYTE_IDP_MASK, int UNROLL = 1, int NEAR = 0, class Stacks>
 __device__ __forceinline__ void traverse_phase(const RtBvh &bvh, RtTravState &tv, Stacks &ks, int &mode, int refill_carry /* tune_refill | tune_carry << 8 */) {
     const unsigned full = 0xffffffffu;
     const int refill = refill_carry & 0xff, carry_cfg = refill_carry >> 8;
@@ -256,10 +259,11 @@ __device__ __forceinline__ void traverse_phase(const RtBvh &bvh, RtTravState &tv
     /* the refill threshold scales with the lanes that still have work: in the drain of a frame (most lanes
      * exhausted) a finished lane must not wait for every other ray of its warp */
     const int thr = max(1, (__popc(m_run) * refill + 31) >> 5);
+    int steps = UNROLL;
     for (;;) {
-#if RT_NODE_STEPS_ROLLED /* one copy of the node test, run UNROLL times */
+#if RT_NODE_STEPS_ROLLED /* one copy of the node test, run `steps` times */
 #pragma unroll 1
-        for (int u = 0; u < UNROLL; u++)
+        for (int u = 0; u < steps; u++)
             if (trav && rt_trav_has_node(tv) && !rt_trav_tri_full(tv)) rt_trav_node_step<MASK>(bvh, tv, ks);
 #else
         if (trav && rt_trav_has_node(tv)) rt_trav_node_step<MASK>(bvh, tv, ks);
@@ -272,7 +276,9 @@ __device__ __forceinline__ void traverse_phase(const RtBvh &bvh, RtTravState &tv
         /* leave when no lane has nodes left, `refill` lanes have run dry, or a lane's triangle stack
          * is full (draining on a pending-triangle count instead was measured and never paid off) */
         const bool out = trav && rt_trav_tri_full(tv);
-        if (!m_node || __popc(m_run & ~m_node) >= thr || __any_sync(full, out)) break;
+        const int dry = __popc(m_run & ~m_node);
+        if (!m_node || dry >= thr || __any_sync(full, out)) break;
+        if (UNROLL > 1 && NEAR > 0) steps = thr - dry <= NEAR ? 1 : UNROLL; /* close to the refill threshold: vote after every step */
     }
     /* drain: lanes that are out of nodes (or nearly out of triangle-stack room) must finish their
      * triangles; every other lane with triangles pending joins in, and carries what is left to the
@@ -497,7 +503,7 @@ __global__ void __launch_bounds__(kMegaBlock, RT_MEGA_MIN_BLOCKS) k_megakernel(R
             __nanosleep(500); /* only lanes waiting for a part that another warp is finishing: look again */
             continue;
         }
-        traverse_phase<RT_MEGA_IDP_MASK, RT_MEGA_NODE_UNROLL>(scene.bvh, tv, ks, mode, p.tune_refill);
+        traverse_phase<RT_MEGA_IDP_MASK, RT_MEGA_NODE_UNROLL, RT_MEGA_NODE_NEAR>(scene.bvh, tv, ks, mode, p.tune_refill);
     }
     unsigned long long total = rays;
 #pragma unroll
