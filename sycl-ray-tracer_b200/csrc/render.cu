@@ -233,8 +233,12 @@ struct SmemStacks {
 #define RT_MEGA_IDP_MASK 7
 #endif
 /* UNROLL = node steps per exit vote. Two votes, a population count and the branches are 17 of the ~285 instructions of a
- * node-loop round; with two steps per round lanes that run dry in the first sit out the second. Measured (72 registers,
- * profiles/r02_ab_regs_unroll.log): megakernel C3 3680 -> 3739, C2 7501 -> 7431; queue-driven wavefront C3 3611 -> 3603. */
+ * node-loop round; with several steps per round a lane that runs dry in one sits out the rest. The steps run as a ROLLED loop
+ * over one copy of the node test (RT_NODE_STEPS_ROLLED): the megakernel is at the edge of the instruction cache, three
+ * unrolled copies (3248 instead of 2752 instructions) are 11 % slower than one step, the rolled loop is not. Measured at 72
+ * registers, C3 / C2 / C4 Mrays/s: 1 step 3680 / 7501 / 4255, 2 unrolled 3739 / 7431 / 4345, 3 rolled 3763 / 7746 / 4381,
+ * 4 rolled 3770 / 7721 (profiles/r02_ab_regs_unroll.log, r02_ab_rolled_steps.log); neutral for the queue-driven wavefront
+ * kernel (r02_ab_wf_rolled.log), which keeps one step. */
 #ifndef RT_MEGA_NODE_UNROLL
 #define RT_MEGA_NODE_UNROLL 3
 #endif
